@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched CartPole hot path on N B200s (one process per GPU).
+
+  python bench.py --gpus 1 --steps K --warmup W
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...        the reference's CPU path (CPU oracle, all host cores)
+
+A bench "step" is ONE launch of the fused random-policy rollout kernel: `--inner` env steps of every
+one of the `--num-envs` envs of this GPU (BASELINE.json configs[1]: CartPole-v1, 65 536 envs, random
+policy), with the whole trajectory (obs, reward, done, action = 25 B per env step) streamed to HBM.
+One step writes num_envs * inner * 25 B = 839 MB >> the 126 MB L2, so no L2 flush is needed.
+`e2e` is the same metric through the host-buffer C-ABI call (gymcuda_step) with pinned HOST action /
+obs / reward / done buffers: H2D + kernel + D2H inside the timed region, every step.
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_ROLLOUT = 25       # obs 16 + reward 4 + done 1 + action 4 written per env step
+ALGO_BYTES_STATE = 32         # state read + written once per launch, per env
+METRIC = "env-steps/sec"
+FALLBACK_HBM_GBS = 6650.0     # B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gymcuda", choices=["gymcuda", "reference"])
+    ap.add_argument("--env", default="CartPole-v1")
+    ap.add_argument("--num-envs", type=int, default=65536, help="envs per GPU (weak scaling)")
+    ap.add_argument("--inner", type=int, default=512, help="env steps per rollout launch")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cpu_rate(env_name, n, seconds, threads):
+    """The reference's CPU path restated (oracle F64 = C# double arithmetic), serial per-env loop split
+    over `threads` host threads, random actions pre-generated.  Returns (env-steps/s, sample text)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from helpers import KINDS
+    kind = KINDS[env_name]
+    o = O.OracleEnv(kind, n, seed=0, auto_reset=True, mode=O.MODE_F64)
+    o.set_threads(threads)
+    o.reset()
+    rng = np.random.default_rng(0)
+    d = o.d
+    acts = [rng.integers(0, d["act_n"], n).astype(np.int32) if d["act_n"] > 0
+            else rng.uniform(-1, 1, (n, d["act_dim"])).astype(np.float32) for _ in range(8)]
+    for i in range(3):
+        o.step(acts[i % 8])
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        o.step(acts[steps % 8]); steps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or steps >= 100000:
+            break
+    return n * steps / el, "%s, %d envs x %d batched steps in %.1f s, oracle F64 (C# double arithmetic), %d threads" % (
+        env_name, n, steps, el, threads)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is C#
+    (no dotnet/mono in this image) so oracle/_ref cannot be built; the CPU oracle port is timed."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.num_envs
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from helpers import KINDS
+    o = O.OracleEnv(KINDS[args.env], n, seed=0, auto_reset=True, mode=O.MODE_F64)
+    o.set_threads(cores)
+    o.reset()
+    rng = np.random.default_rng(0)
+    d = o.d
+    acts = [rng.integers(0, d["act_n"], n).astype(np.int32) if d["act_n"] > 0
+            else rng.uniform(-1, 1, (n, d["act_dim"])).astype(np.float32) for _ in range(8)]
+    inner = 16   # bounded sample per bench step: 16 batched steps of all n envs
+    for w in range(args.warmup):
+        for i in range(inner):
+            o.step(acts[i % 8])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for i in range(inner):
+            o.step(acts[i % 8])
+    el = time.perf_counter() - t0
+    value = n * inner * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s, %d envs, random policy, auto-reset" % (args.env, n),
+                   "sample_per_step": "%d batched steps of all %d envs" % (inner, n)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d steps, oracle F64 port of CartPoleEnv.Step (C# unavailable: no dotnet)" % (n, inner * args.steps)},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gymnet_b200 as G
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libgymcuda has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, K = args.num_envs, args.inner
+    env = G.make(args.env, n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True)
+    od, ad = env.obs_dim, env.act_dim
+    stream = torch.cuda.current_stream()
+    env.SetStream(stream.cuda_stream)
+    env.ResetBatch()
+
+    # trajectory buffers live in HBM (torch is only the allocator here)
+    t_obs = torch.empty((K, n, od), dtype=torch.float32, device=dev)
+    t_rew = torch.empty((K, n), dtype=torch.float32, device=dev)
+    t_done = torch.empty((K, n), dtype=torch.uint8, device=dev)
+    t_act = torch.empty((K, n, ad), dtype=torch.int32 if env.act_n > 0 else torch.float32, device=dev)
+
+    def launch():
+        env.RolloutRandomDevice(K, t_obs.data_ptr(), t_rew.data_ptr(), t_done.data_ptr(), t_act.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        launch()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for s in range(args.steps):
+        launch()
+        evs[s + 1].record(stream)
+    barrier()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop()
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = world * n * K * args.steps / (total_ms * 1e-3)
+
+    # ---- sanity: the timed launches really produced a trajectory
+    torch.cuda.synchronize()
+    dsum = int(t_done.sum().item())
+    assert 0 < dsum < K * n, "rollout produced no episode boundaries"
+
+    # ---- roofline of the dominant kernel (rollout_kernel), measured live with CUDA events
+    peak, peak_src = measured_peak()
+    launch_bytes = n * K * (od * 4 + 4 + 1 + ad * 4) + n * ALGO_BYTES_STATE
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    achieved = launch_bytes / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "rollout_kernel<%s>" % args.env,
+                "algorithmic_bytes_per_launch": launch_bytes,
+                "note": "bytes = env-steps x (obs+reward+done+action) + 32 B/env state; traffic from ncu --set full in profiles/"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("rollout_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through gymcuda_step (H2D actions, kernel, D2H obs/reward/done), every step
+    e2e_steps = args.e2e_steps
+    h_act = torch.empty((n, ad), dtype=t_act.dtype).pin_memory()
+    h_obs = torch.empty((n, od), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    rng = np.random.default_rng(rank)
+    if env.act_n > 0:
+        h_act.numpy()[:] = rng.integers(0, env.act_n, (n, ad))
+    else:
+        h_act.numpy()[:] = rng.uniform(-1, 1, (n, ad))
+    L = G._native.lib()
+
+    def e2e_step():
+        rc = L.gymcuda_step(env._h, C.c_void_p(h_act.data_ptr()), C.c_void_p(h_obs.data_ptr()),
+                            C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(L.gymcuda_last_error())
+
+    for _ in range(5):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = {"value": world * n * e2e_steps / e2e_s, "unit": "env-steps/s",
+           "h2d_bytes_per_step": n * ad * 4, "d2h_bytes_per_step": n * (od * 4 + 4 + 1),
+           "api": "gymcuda_step (host buffers, pinned)", "steps": e2e_steps}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port of the reference's CPU path
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, sample = oracle_cpu_rate(args.env, n, args.cpu_seconds, cores)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s, %d envs per GPU, random policy (in-kernel Philox), auto-reset; one step = one "
+                                   "fused rollout launch of %d env steps per env" % (args.env, n, K),
+                       "num_envs_per_gpu": n, "inner_steps": K, "parallelism": "independent env shards, no collective",
+                       "l2": "outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (launch_bytes / 1e6)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    env.Close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

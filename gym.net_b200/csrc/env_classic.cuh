@@ -1,0 +1,338 @@
+// Per-env device dynamics of the classic-control family.  One thread owns one env instance.
+//
+// Each env is a traits struct used by the generic step / reset / rollout kernels (kernels.cuh):
+//   SD, OD, AD, ACTN          state / observation / action widths, Discrete(n) or 0 for Box
+//   Vec                       the storage vector type of one env's state in HBM (float4 / float2)
+//   S                         register state
+//   load/store                one coalesced vector load/store per env
+//   reset(S&, Block)          Philox block -> initial state
+//   step(S&, Act, sbd)        transition + reward + termination
+//   obs(S, float*)            observation (OD floats)
+//
+// Arithmetic ("engine arithmetic v1"): float32 state and float32 math built from single IEEE
+// operations (detmath.cuh), with the termination test refined in double wherever float32 rounding
+// could flip it, so that `done` equals the reference's double-precision evaluation from the same
+// stored state.  Compiled with -fmad=false; fused operations are explicit.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "detmath.cuh"
+#include "philox.cuh"
+
+namespace gymcuda {
+
+struct StepOut { float reward; bool done; };
+
+// ------------------------------------------------------------------------------------------------
+// CartPole: src/Gym.Environments/Envs/Classic/CartPoleEnv.cs
+// ------------------------------------------------------------------------------------------------
+struct CartPole {
+    static constexpr int SD = 4, OD = 4, AD = 1, ACTN = 2, DEFAULT_LIMIT = 0;
+    static constexpr bool HAS_SBD = true;     // steps_beyond_done (CartPoleEnv.cs:41)
+    static constexpr bool REJECT_INVALID = false;  // Debug.Assert only (CartPoleEnv.cs:139)
+    using Vec = float4;
+    using Act = int32_t;
+    struct S { float x, x_dot, theta, theta_dot; };
+
+    // C# `const float` values (CartPoleEnv.cs:24-36), folded in float32 by the C# compiler.
+    static constexpr float GRAVITY = 9.8f;
+    static constexpr float FORCE_MAG = 10.0f;
+    static constexpr float TAU = 0.02f;
+    static constexpr float POLEMASS_LENGTH = 0.05000000074505806f;   // 0.1f * 0.5f
+    static constexpr float X_THRESHOLD = 2.4f;
+    static constexpr float THETA_THRESHOLD = 0.20943951606750488f;   // (float)(12*2*pi/360)
+    // derived, rounded once to float32
+    static constexpr float INV_TOTAL_MASS = 0.9090908765792847f;     // 1 / 1.100000023841858
+    static constexpr float K0 = 0.6666666865348816f;                 // length * 4/3
+    static constexpr float K1 = 0.04545454680919647f;                // length * masspole / total_mass
+    static constexpr float PML_OVER_M = 0.04545454680919647f;        // polemass_length / total_mass
+
+    __device__ static __forceinline__ S load(const void* base, int i) {
+        const float4 v = reinterpret_cast<const float4*>(base)[i];
+        return S{v.x, v.y, v.z, v.w};
+    }
+    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+        reinterpret_cast<float4*>(base)[i] = make_float4(s.x, s.x_dot, s.theta, s.theta_dot);
+    }
+    // CartPoleEnv.cs:65  state = uniform(-0.05, 0.05, 4)
+    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+        s.x = uniformf(-0.05f, 0.05f, b.w0);
+        s.x_dot = uniformf(-0.05f, 0.05f, b.w1);
+        s.theta = uniformf(-0.05f, 0.05f, b.w2);
+        s.theta_dot = uniformf(-0.05f, 0.05f, b.w3);
+    }
+    __device__ static __forceinline__ bool valid(Act a) { return a == 0 || a == 1; }
+
+    // CartPoleEnv.cs:137-186.  Accelerations (:146-151) in float32; the position updates (:154,:156)
+    // and the termination test (:167) with the reference's own double operations, so x, theta and
+    // `done` are exactly the reference's values from the same float32 state.
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t& sbd) {
+        const float force = (a == 1) ? FORCE_MAG : -FORCE_MAG;                         // :146
+        float sn, cs;
+        sincosf_det(s.theta, &sn, &cs);                                                // :147-148
+        const float t1 = (POLEMASS_LENGTH * s.theta_dot) * s.theta_dot;
+        const float temp = fmaf(t1, sn, force) * INV_TOTAL_MASS;                       // :149
+        const float den = fmaf(-K1, cs * cs, K0);
+        const float num = fmaf(GRAVITY, sn, -(cs * temp));
+        const float thetaacc = num / den;                                              // :150
+        const float xacc = fmaf(-(PML_OVER_M * thetaacc), cs, temp);                   // :151
+        const double xd = (double)s.x + (double)TAU * (double)s.x_dot;                 // :154
+        const double thd = (double)s.theta + (double)TAU * (double)s.theta_dot;        // :156
+        s.x_dot = fmaf(TAU, xacc, s.x_dot);                                            // :155
+        s.theta_dot = fmaf(TAU, thetaacc, s.theta_dot);                                // :157
+        s.x = (float)xd;
+        s.theta = (float)thd;
+        const bool done = (fabs(xd) > (double)X_THRESHOLD) | (fabs(thd) > (double)THETA_THRESHOLD);  // :167
+        float reward = 1.0f;                                                           // :170,:174
+        if (done) {
+            if (sbd == -1) sbd = 0;                                                    // :173
+            else { sbd += 1; reward = 0.0f; }                                          // :181-182
+        }
+        return StepOut{reward, done};
+    }
+    __device__ static __forceinline__ void obs(const S& s, float* o) {
+        o[0] = s.x; o[1] = s.x_dot; o[2] = s.theta; o[3] = s.theta_dot;                // :166,:185
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Pendulum-v1 (not in the reference, README.md:76; spec = upstream gym 0.26 pendulum.py)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float py_modf32(float a, float b) {   // Python float %, b > 0 (fmodf is exact)
+    float m = fmodf(a, b);
+    if (m != 0.0f) { if (m < 0.0f) m += b; } else m = 0.0f;
+    return m;
+}
+
+struct Pendulum {
+    static constexpr int SD = 2, OD = 3, AD = 1, ACTN = 0, DEFAULT_LIMIT = 200;
+    static constexpr bool HAS_SBD = false;
+    static constexpr bool REJECT_INVALID = true;
+    static constexpr float ACT_LOW = -2.0f, ACT_HIGH = 2.0f;
+    using Vec = float2;
+    using Act = float;
+    struct S { float th, thdot; };
+    __device__ static __forceinline__ S load(const void* base, int i) {
+        const float2 v = reinterpret_cast<const float2*>(base)[i];
+        return S{v.x, v.y};
+    }
+    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+        reinterpret_cast<float2*>(base)[i] = make_float2(s.th, s.thdot);
+    }
+    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+        constexpr float PI_F = 3.1415927410125732f;
+        s.th = uniformf(-PI_F, PI_F, b.w0);
+        s.thdot = uniformf(-1.0f, 1.0f, b.w1);
+    }
+    __device__ static __forceinline__ bool valid(Act a) { return a == a; }
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&) {
+        constexpr float PI_F = 3.1415927410125732f, TWO_PI_F = 6.2831854820251465f;
+        const float th = s.th, thdot = s.thdot;
+        const float u = clampf(a, -2.0f, 2.0f);
+        const float an = py_modf32(th + PI_F, TWO_PI_F) - PI_F;
+        const float costs = (an * an + 0.1f * (thdot * thdot)) + 0.001f * (u * u);
+        float sn, cs;
+        sincosf_det(th, &sn, &cs);
+        float newthdot = thdot + (15.0f * sn + 3.0f * u) * 0.05f;
+        newthdot = clampf(newthdot, -8.0f, 8.0f);
+        s.th = th + newthdot * 0.05f;
+        s.thdot = newthdot;
+        return StepOut{-costs, false};
+    }
+    __device__ static __forceinline__ void obs(const S& s, float* o) {
+        float sn, cs;
+        sincosf_det(s.th, &sn, &cs);
+        o[0] = cs; o[1] = sn; o[2] = s.thdot;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// MountainCar-v0 / MountainCarContinuous-v0 (not in the reference, README.md:74-75)
+// ------------------------------------------------------------------------------------------------
+template <bool CONTINUOUS>
+struct MountainCarT {
+    static constexpr int SD = 2, OD = 2, AD = 1, ACTN = CONTINUOUS ? 0 : 3;
+    static constexpr int DEFAULT_LIMIT = CONTINUOUS ? 999 : 200;
+    static constexpr bool HAS_SBD = false;
+    static constexpr bool REJECT_INVALID = true;
+    static constexpr float ACT_LOW = -1.0f, ACT_HIGH = 1.0f;
+    using Vec = float2;
+    using Act = typename std::conditional<CONTINUOUS, float, int32_t>::type;
+    struct S { float position, velocity; };
+    __device__ static __forceinline__ S load(const void* base, int i) {
+        const float2 v = reinterpret_cast<const float2*>(base)[i];
+        return S{v.x, v.y};
+    }
+    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+        reinterpret_cast<float2*>(base)[i] = make_float2(s.position, s.velocity);
+    }
+    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+        s.position = uniformf(-0.6f, -0.4f, b.w0);
+        s.velocity = 0.0f;
+    }
+    __device__ static __forceinline__ bool valid(Act a) {
+        if (CONTINUOUS) return a == a;
+        return a >= 0 && a < 3;
+    }
+    // upstream double-precision step, used only to refine `done` next to a threshold
+    __device__ static bool done_f64(float position0, float velocity0, Act a) {
+        double position = (double)position0, velocity = (double)velocity0;
+        if (CONTINUOUS) {
+            double force = (double)a;
+            force = force < -1.0 ? -1.0 : (force > 1.0 ? 1.0 : force);
+            velocity += force * 0.0015 - 0.0025 * cos(3 * position);
+        } else {
+            velocity += ((int)a - 1) * 0.001 + cos(3 * position) * (-0.0025);
+        }
+        velocity = velocity < -0.07 ? -0.07 : (velocity > 0.07 ? 0.07 : velocity);
+        position += velocity;
+        position = position < -1.2 ? -1.2 : (position > 0.6 ? 0.6 : position);
+        if (position == -1.2 && velocity < 0) velocity = 0;
+        return position >= (CONTINUOUS ? 0.45 : 0.5) && velocity >= 0.0;
+    }
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&) {
+        constexpr float MIN_POS = -1.2f, MAX_POS = 0.6f, MAX_SPEED = 0.07f;
+        constexpr float GOAL = CONTINUOUS ? 0.45f : 0.5f;
+        const float position = s.position, velocity = s.velocity;
+        float sn, cs;
+        sincosf_det(3.0f * position, &sn, &cs);
+        float push;
+        if (CONTINUOUS) push = clampf((float)a, -1.0f, 1.0f) * 0.0015f;
+        else push = (float)((int)a - 1) * 0.001f;
+        float nv = velocity + (push + cs * (-0.0025f));
+        nv = clampf(nv, -MAX_SPEED, MAX_SPEED);
+        float np = position + nv;
+        np = clampf(np, MIN_POS, MAX_POS);
+        if (np == MIN_POS && nv < 0.0f) nv = 0.0f;
+        bool done = np >= GOAL && nv >= 0.0f;
+        if (fabsf(np - GOAL) <= 1e-6f || fabsf(nv) <= 1e-7f) done = done_f64(position, velocity, a);
+        s.position = np;
+        s.velocity = nv;
+        float reward;
+        if (CONTINUOUS) {
+            reward = done ? 100.0f : 0.0f;
+            reward = reward - ((float)a * (float)a) * 0.1f;
+        } else {
+            reward = -1.0f;
+        }
+        return StepOut{reward, done};
+    }
+    __device__ static __forceinline__ void obs(const S& s, float* o) { o[0] = s.position; o[1] = s.velocity; }
+};
+using MountainCar = MountainCarT<false>;
+using MountainCarCont = MountainCarT<true>;
+
+// ------------------------------------------------------------------------------------------------
+// Acrobot-v1 (not in the reference, README.md:73; upstream acrobot.py, "book" dynamics, RK4, dt 0.2)
+// ------------------------------------------------------------------------------------------------
+template <class R> struct AcroMath;
+template <> struct AcroMath<double> {
+    __device__ static __forceinline__ void sc(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+    __device__ static __forceinline__ double cos_minus_half_pi(double x) { return cos(x - 3.14159265358979323846 / 2.0); }
+};
+template <> struct AcroMath<float> {
+    __device__ static __forceinline__ void sc(float x, float* s, float* c) { sincosf_det(x, s, c); }
+    __device__ static __forceinline__ float cos_minus_half_pi(float x) { float s, c; sincosf_det(x, &s, &c); return s; }
+};
+
+template <class R>
+__device__ __forceinline__ void acrobot_dsdt(const R s[4], R a, R out[4]) {
+    const R m1 = 1, m2 = 1, l1 = 1, lc1 = R(0.5), lc2 = R(0.5), I1 = 1, I2 = 1, g = R(9.8);
+    const R theta1 = s[0], theta2 = s[1], dtheta1 = s[2], dtheta2 = s[3];
+    R s2, c2;
+    AcroMath<R>::sc(theta2, &s2, &c2);
+    const R d1 = m1 * lc1 * lc1 + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * c2) + I1 + I2;
+    const R d2 = m2 * (lc2 * lc2 + l1 * lc2 * c2) + I2;
+    const R phi2 = m2 * lc2 * g * AcroMath<R>::cos_minus_half_pi(theta1 + theta2);
+    const R phi1 = -m2 * l1 * lc2 * dtheta2 * dtheta2 * s2 - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * s2 +
+                   (m1 * lc1 + m2 * l1) * g * AcroMath<R>::cos_minus_half_pi(theta1) + phi2;
+    const R ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * dtheta1 * dtheta1 * s2 - phi2) /
+                       (m2 * lc2 * lc2 + I2 - d2 * d2 / d1);
+    const R ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
+    out[0] = dtheta1; out[1] = dtheta2; out[2] = ddtheta1; out[3] = ddtheta2;
+}
+
+template <class R>
+__device__ __forceinline__ R acro_wrap(R x, R m, R M) {
+    const R diff = M - m;
+    if (!(fabs(x) < R(1e6))) return x;   // non-finite / absurd input: leave as is (never loops forever)
+    while (x > M) x = x - diff;
+    while (x < m) x = x + diff;
+    return x;
+}
+
+// integrates s in place; returns -cos(th1) - cos(th2 + th1) of the new state
+template <class R>
+__device__ __forceinline__ R acrobot_integrate(R s[4], int action) {
+    const R PI = R(3.14159265358979323846);
+    const R dt = R(0.2);
+    const R a = (R)(action - 1);
+    R k1[4], k2[4], k3[4], k4[4], y[4];
+    acrobot_dsdt<R>(s, a, k1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = s[i] + dt / 2 * k1[i];
+    acrobot_dsdt<R>(y, a, k2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = s[i] + dt / 2 * k2[i];
+    acrobot_dsdt<R>(y, a, k3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = s[i] + dt * k3[i];
+    acrobot_dsdt<R>(y, a, k4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = s[i] + dt / R(6.0) * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    y[0] = acro_wrap<R>(y[0], -PI, PI);
+    y[1] = acro_wrap<R>(y[1], -PI, PI);
+    const R MV1 = 4 * PI, MV2 = 9 * PI;
+    y[2] = y[2] < -MV1 ? -MV1 : (y[2] > MV1 ? MV1 : y[2]);
+    y[3] = y[3] < -MV2 ? -MV2 : (y[3] > MV2 ? MV2 : y[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = y[i];
+    R s1, c1, s12, c12;
+    AcroMath<R>::sc(y[0], &s1, &c1);
+    AcroMath<R>::sc(y[1] + y[0], &s12, &c12);
+    return -c1 - c12;
+}
+
+__device__ __noinline__ bool acrobot_done_f64(float s0, float s1, float s2, float s3, int action) {
+    double sd[4] = {(double)s0, (double)s1, (double)s2, (double)s3};
+    return acrobot_integrate<double>(sd, action) > 1.0;
+}
+
+struct Acrobot {
+    static constexpr int SD = 4, OD = 6, AD = 1, ACTN = 3, DEFAULT_LIMIT = 500;
+    static constexpr bool HAS_SBD = false;
+    static constexpr bool REJECT_INVALID = true;
+    using Vec = float4;
+    using Act = int32_t;
+    struct S { float v[4]; };
+    __device__ static __forceinline__ S load(const void* base, int i) {
+        const float4 v = reinterpret_cast<const float4*>(base)[i];
+        return S{{v.x, v.y, v.z, v.w}};
+    }
+    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+        reinterpret_cast<float4*>(base)[i] = make_float4(s.v[0], s.v[1], s.v[2], s.v[3]);
+    }
+    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+        s.v[0] = uniformf(-0.1f, 0.1f, b.w0);
+        s.v[1] = uniformf(-0.1f, 0.1f, b.w1);
+        s.v[2] = uniformf(-0.1f, 0.1f, b.w2);
+        s.v[3] = uniformf(-0.1f, 0.1f, b.w3);
+    }
+    __device__ static __forceinline__ bool valid(Act a) { return a >= 0 && a < 3; }
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&) {
+        const float o0 = s.v[0], o1 = s.v[1], o2 = s.v[2], o3 = s.v[3];
+        const float v = acrobot_integrate<float>(s.v, (int)a);
+        bool done = v > 1.0f;
+        if (fabsf(v - 1.0f) <= 2e-5f) done = acrobot_done_f64(o0, o1, o2, o3, (int)a);
+        return StepOut{done ? 0.0f : -1.0f, done};
+    }
+    __device__ static __forceinline__ void obs(const S& s, float* o) {
+        float s1, c1, s2, c2;
+        sincosf_det(s.v[0], &s1, &c1);
+        sincosf_det(s.v[1], &s2, &c2);
+        o[0] = c1; o[1] = s1; o[2] = c2; o[3] = s2; o[4] = s.v[2]; o[5] = s.v[3];
+    }
+};
+
+}  // namespace gymcuda

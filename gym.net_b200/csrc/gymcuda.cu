@@ -1,0 +1,684 @@
+// libgymcuda: C-ABI implementation (include/gymcuda.h).  Handle lifecycle, device memory,
+// kernel dispatch, host<->device copies, NCCL all-gather.  There is no CPU path in this file:
+// every compute entry point launches a CUDA kernel or fails with GYMCUDA_ECUDA.
+#include "../../include/gymcuda.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "kernels.cuh"
+#ifdef GYMCUDA_WITH_LUNAR
+#include "lunar.cuh"
+#endif
+
+using namespace gymcuda;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA,             \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily with dlopen so the library has no link-time dependency on it
+// ------------------------------------------------------------------------------------------------
+struct Id128 { char b[128]; };   // ncclUniqueId, passed by value
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+
+static int nccl_load(const char* path) {
+    if (g_nccl.lib) return GYMCUDA_OK;
+    const char* candidates[] = {path, getenv("GYMCUDA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* c : candidates) {
+        if (!c || !*c) continue;
+        h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(GYMCUDA_ENCCL, "cannot dlopen NCCL (tried path argument, $GYMCUDA_NCCL_LIB, libnccl.so.2): %s", dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+        dlclose(h);
+        return fail(GYMCUDA_ENCCL, "NCCL library is missing required symbols");
+    }
+    g_nccl.lib = h;
+    return GYMCUDA_OK;
+}
+
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        int _r = (expr);                                                                            \
+        if (_r != 0)                                                                                \
+            return fail(GYMCUDA_ENCCL, "%s failed: %s", #expr,                                      \
+                        g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error");          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct KindInfo { int sd, aux, od, ad, actn, default_limit; };
+
+static bool kind_info(int kind, KindInfo* ki) {
+    switch (kind) {
+        case GYMCUDA_CARTPOLE: *ki = {CartPole::SD, 2, CartPole::OD, CartPole::AD, CartPole::ACTN, CartPole::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_PENDULUM: *ki = {Pendulum::SD, 2, Pendulum::OD, Pendulum::AD, Pendulum::ACTN, Pendulum::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_MOUNTAINCAR: *ki = {MountainCar::SD, 2, MountainCar::OD, MountainCar::AD, MountainCar::ACTN, MountainCar::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_MOUNTAINCAR_CONT: *ki = {MountainCarCont::SD, 2, MountainCarCont::OD, MountainCarCont::AD, MountainCarCont::ACTN, MountainCarCont::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_ACROBOT: *ki = {Acrobot::SD, 2, Acrobot::OD, Acrobot::AD, Acrobot::ACTN, Acrobot::DEFAULT_LIMIT}; return true;
+#ifdef GYMCUDA_WITH_LUNAR
+        case GYMCUDA_LUNARLANDER: *ki = {LunarLander::SD, LunarLander::AUX, 8, 1, 4, 0}; return true;
+        case GYMCUDA_LUNARLANDER_CONT: *ki = {LunarLanderCont::SD, LunarLanderCont::AUX, 8, 2, 0, 0}; return true;
+#endif
+        default: return false;
+    }
+}
+
+struct gymcuda_env {
+    gymcuda_config cfg;
+    KindInfo ki;
+    int n, limit;
+    bool auto_reset, has_state;
+    uint64_t seed, t;
+    uint32_t seq;
+    cudaStream_t own_stream, stream;
+    // state
+    void* d_state;
+    int32_t *d_sbd, *d_ept, *d_seeds;
+    // I/O staging for the host-buffer entry points
+    void* d_actions;
+    float *d_obs, *d_reward;
+    uint8_t *d_done, *d_mask;
+    int32_t *d_done_idx, *d_done_count;
+    unsigned long long* d_stats;
+    const float* last_obs;   // device pointer of the most recent observations
+    // pinned scratch: [0..1] stats, [2] done_count
+    unsigned long long* h_small;
+    unsigned long long invalid_seen, env_steps;
+    // nccl
+    void* comm;
+    int rank, world;
+    size_t act_bytes() const { return (size_t)n * ki.ad * 4; }
+    size_t obs_bytes() const { return (size_t)n * ki.od * 4; }
+};
+
+static int check(const gymcuda_env* e) {
+    if (!e) return fail(GYMCUDA_EINVAL, "null gymcuda_env handle");
+    return GYMCUDA_OK;
+}
+#define ENTER(e)                                        \
+    do {                                                \
+        int _c = check(e);                              \
+        if (_c) return _c;                              \
+        CU_TRY(cudaSetDevice((e)->cfg.device));         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <class E>
+static cudaError_t launch_step(gymcuda_env* e, const StepArgs& a) {
+    const int grid = (e->n + STEP_BLOCK - 1) / STEP_BLOCK;
+    const bool ar = e->auto_reset, lim = e->limit > 0;
+    if (ar && lim) step_kernel<E, true, true><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
+    else if (ar) step_kernel<E, true, false><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
+    else if (lim) step_kernel<E, false, true><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
+    else step_kernel<E, false, false><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <class E>
+static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
+    const int grid = (e->n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
+    const bool ar = e->auto_reset, lim = e->limit > 0;
+    if (ar && lim) rollout_kernel<E, true, true><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    else if (ar) rollout_kernel<E, true, false><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    else if (lim) rollout_kernel<E, false, true><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    else rollout_kernel<E, false, false><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <class E>
+static cudaError_t launch_reset(gymcuda_env* e, const ResetArgs& a) {
+    reset_kernel<E><<<(e->n + 255) / 256, 256, 0, e->stream>>>(a);
+    return cudaGetLastError();
+}
+
+#ifdef GYMCUDA_WITH_LUNAR
+#define LUNAR_CASES(FN, ...)                                                      \
+    case GYMCUDA_LUNARLANDER: return lunar_##FN<LunarLander>(e, __VA_ARGS__);     \
+    case GYMCUDA_LUNARLANDER_CONT: return lunar_##FN<LunarLanderCont>(e, __VA_ARGS__);
+#else
+#define LUNAR_CASES(FN, ...)
+#endif
+
+#define DISPATCH(FN, ...)                                                                \
+    switch (e->cfg.env_kind) {                                                           \
+        case GYMCUDA_CARTPOLE: return launch_##FN<CartPole>(e, __VA_ARGS__);             \
+        case GYMCUDA_PENDULUM: return launch_##FN<Pendulum>(e, __VA_ARGS__);             \
+        case GYMCUDA_MOUNTAINCAR: return launch_##FN<MountainCar>(e, __VA_ARGS__);       \
+        case GYMCUDA_MOUNTAINCAR_CONT: return launch_##FN<MountainCarCont>(e, __VA_ARGS__); \
+        case GYMCUDA_ACROBOT: return launch_##FN<Acrobot>(e, __VA_ARGS__);               \
+        LUNAR_CASES(FN, __VA_ARGS__)                                                     \
+        default: return cudaErrorInvalidValue;                                           \
+    }
+
+static cudaError_t dispatch_step(gymcuda_env* e, const StepArgs& a) { DISPATCH(step, a) }
+static cudaError_t dispatch_rollout(gymcuda_env* e, const RolloutArgs& a) { DISPATCH(rollout, a) }
+static cudaError_t dispatch_reset(gymcuda_env* e, const ResetArgs& a) { DISPATCH(reset, a) }
+
+// ------------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gymcuda_version(void) { return GYMCUDA_VERSION; }
+const char* gymcuda_last_error(void) { return g_last_error.c_str(); }
+
+int gymcuda_device_count(int* count) {
+    if (!count) return fail(GYMCUDA_EINVAL, "count is null");
+    CU_TRY(cudaGetDeviceCount(count));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_config_default(gymcuda_config* cfg, int env_kind, int num_envs) {
+    if (!cfg) return fail(GYMCUDA_EINVAL, "cfg is null");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (uint32_t)sizeof(*cfg);
+    cfg->env_kind = env_kind;
+    cfg->num_envs = num_envs;
+    cfg->device = 0;
+    cfg->seed = 0;
+    cfg->flags = 0;
+    cfg->time_limit = 0;
+    cfg->gravity = -10.0f;          // LunarLanderEnv.cs:351
+    cfg->enable_wind = 0;
+    cfg->wind_power = 15.0f;        // :353
+    cfg->turbulence_power = 1.5f;   // :354
+    return GYMCUDA_OK;
+}
+
+int gymcuda_destroy(gymcuda_env* e) {
+    if (!e) return GYMCUDA_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_seeds);
+    cudaFree(e->d_actions); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done); cudaFree(e->d_mask);
+    cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats);
+    if (e->h_small) cudaFreeHost(e->h_small);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return GYMCUDA_OK;
+}
+
+static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
+    CU_TRY(cudaSetDevice(cfg->device));
+    CU_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    const size_t n = (size_t)e->n;
+#ifdef GYMCUDA_WITH_LUNAR
+    const size_t state_bytes = n * (size_t)e->ki.sd * 4 + n * (size_t)e->ki.aux * 4;
+#else
+    const size_t state_bytes = n * (size_t)e->ki.sd * 4;
+#endif
+    CU_TRY(cudaMalloc(&e->d_state, state_bytes));
+    CU_TRY(cudaMalloc(&e->d_sbd, n * 4));
+    CU_TRY(cudaMalloc(&e->d_ept, n * 4));
+    CU_TRY(cudaMalloc(&e->d_actions, e->act_bytes()));
+    CU_TRY(cudaMalloc(&e->d_obs, e->obs_bytes()));
+    CU_TRY(cudaMalloc(&e->d_reward, n * 4));
+    CU_TRY(cudaMalloc(&e->d_done, n));
+    CU_TRY(cudaMalloc(&e->d_mask, n));
+    CU_TRY(cudaMalloc(&e->d_done_idx, n * 4));
+    CU_TRY(cudaMalloc(&e->d_done_count, 2 * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&e->d_stats, 2 * sizeof(unsigned long long)));
+    CU_TRY(cudaHostAlloc((void**)&e->h_small, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU_TRY(cudaMemsetAsync(e->d_state, 0, state_bytes, e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_sbd, 0xff, n * 4, e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_ept, 0, n * 4, e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_done_count, 0, 2 * sizeof(int32_t), e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_stats, 0, 2 * sizeof(unsigned long long), e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_obs, 0, e->obs_bytes(), e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_create(const gymcuda_config* cfg, gymcuda_env** out) {
+    if (!cfg || !out) return fail(GYMCUDA_EINVAL, "cfg/out is null");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(gymcuda_config))
+        return fail(GYMCUDA_EINVAL, "gymcuda_config.struct_size %u != %zu (use gymcuda_config_default)", cfg->struct_size, sizeof(gymcuda_config));
+    KindInfo ki;
+    if (!kind_info(cfg->env_kind, &ki)) return fail(GYMCUDA_EINVAL, "unknown env_kind %d", cfg->env_kind);
+    if (cfg->num_envs <= 0) return fail(GYMCUDA_EINVAL, "num_envs must be > 0 (got %d)", cfg->num_envs);
+    if ((uint64_t)cfg->env_id_offset + (uint64_t)cfg->num_envs > 0x100000000ull)
+        return fail(GYMCUDA_EINVAL, "env_id_offset + num_envs exceeds 2^32");
+    // LunarLanderEnv ctor range checks (LunarLanderEnv.cs:396-407)
+    if (cfg->gravity < -12.0f || cfg->gravity > 0.0f) return fail(GYMCUDA_EINVAL, "Gravity must be between -12 and 0");
+    if (cfg->wind_power < 0.0f || cfg->wind_power > 20.0f) return fail(GYMCUDA_EINVAL, "wind_power value is recommended to be between 0.0 and 20.0");
+    if (cfg->turbulence_power < 0.0f || cfg->turbulence_power > 2.0f) return fail(GYMCUDA_EINVAL, "turbulence_power value is recommended to be between 0.0 and 2.0");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(GYMCUDA_ECUDA, "no CUDA device available (%s); libgymcuda has no CPU path", ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(GYMCUDA_EINVAL, "device %d out of range [0, %d)", cfg->device, ndev);
+
+    gymcuda_env* e = new (std::nothrow) gymcuda_env();
+    if (!e) return fail(GYMCUDA_ENOMEM, "host allocation failed");
+    std::memset(static_cast<void*>(e), 0, sizeof(*e));
+    e->cfg = *cfg;
+    e->ki = ki;
+    e->n = cfg->num_envs;
+    e->limit = cfg->time_limit == 0 ? ki.default_limit : (cfg->time_limit < 0 ? 0 : cfg->time_limit);
+    e->auto_reset = (cfg->flags & GYMCUDA_FLAG_AUTO_RESET) != 0;
+    e->seed = cfg->seed;
+    e->last_obs = nullptr;
+    int rc = create_impl(cfg, e);
+    if (rc != GYMCUDA_OK) { std::string keep = g_last_error; gymcuda_destroy(e); g_last_error = keep; return rc; }
+    e->last_obs = e->d_obs;
+    *out = e;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_num_envs(const gymcuda_env* e) { return e ? e->n : fail(GYMCUDA_EINVAL, "null handle"); }
+
+int gymcuda_space(const gymcuda_env* e, gymcuda_space_info* o) {
+    if (!e || !o) return fail(GYMCUDA_EINVAL, "null argument");
+    std::memset(o, 0, sizeof(*o));
+    o->obs_dim = e->ki.od; o->act_dim = e->ki.ad; o->act_n = e->ki.actn;
+    o->state_dim = e->ki.sd; o->aux_dim = e->ki.aux; o->time_limit = e->limit;
+    const float FMAX = std::numeric_limits<float>::max();
+    const float PI_F = 3.1415927410125732f;
+    auto set_obs = [&](std::initializer_list<float> hi) { int k = 0; for (float v : hi) { o->obs_high[k] = v; o->obs_low[k] = -v; ++k; } };
+    switch (e->cfg.env_kind) {
+        case GYMCUDA_CARTPOLE:   // CartPoleEnv.cs:46-48: high = [x_thr*2, float.Max, theta_thr*2, float.Max]
+            set_obs({4.800000190734863f, FMAX, 0.41887903213500977f, FMAX});
+            break;
+        case GYMCUDA_PENDULUM:
+            set_obs({1.0f, 1.0f, 8.0f});
+            o->act_low[0] = -2.0f; o->act_high[0] = 2.0f;
+            break;
+        case GYMCUDA_MOUNTAINCAR:
+        case GYMCUDA_MOUNTAINCAR_CONT:
+            o->obs_low[0] = -1.2f; o->obs_high[0] = 0.6f; o->obs_low[1] = -0.07f; o->obs_high[1] = 0.07f;
+            if (e->cfg.env_kind == GYMCUDA_MOUNTAINCAR_CONT) { o->act_low[0] = -1.0f; o->act_high[0] = 1.0f; }
+            break;
+        case GYMCUDA_ACROBOT:
+            set_obs({1.0f, 1.0f, 1.0f, 1.0f, 4.0f * PI_F, 9.0f * PI_F});
+            break;
+        case GYMCUDA_LUNARLANDER:
+        case GYMCUDA_LUNARLANDER_CONT: {   // LunarLanderEnv.cs:412-414
+            const float lo[8] = {-1.5f, -1.5f, -5.0f, -5.0f, -PI_F, -5.0f, 0.0f, 0.0f};
+            const float hi[8] = {1.5f, 1.5f, 5.0f, 5.0f, PI_F, 5.0f, 1.0f, 1.0f};
+            std::memcpy(o->obs_low, lo, sizeof(lo)); std::memcpy(o->obs_high, hi, sizeof(hi));
+            if (e->cfg.env_kind == GYMCUDA_LUNARLANDER_CONT) { o->act_low[0] = o->act_low[1] = -1.0f; o->act_high[0] = o->act_high[1] = 1.0f; }
+            break;
+        }
+    }
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// seeding
+// ------------------------------------------------------------------------------------------------
+int gymcuda_seed(gymcuda_env* e, uint64_t seed) {
+    ENTER(e);
+    e->seed = seed;
+    if (e->d_seeds) { CU_TRY(cudaStreamSynchronize(e->stream)); CU_TRY(cudaFree(e->d_seeds)); e->d_seeds = nullptr; }
+    return GYMCUDA_OK;
+}
+
+int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
+    ENTER(e);
+    if (!seeds) return fail(GYMCUDA_EINVAL, "seeds is null");
+    // VecEnv.Seed(int[]) throws ArgumentException on a length mismatch (VecEnv.cs:49)
+    if (n != e->n) return fail(GYMCUDA_EINVAL, "Number of seeds passed should be equals to number of environments");
+    if (!e->d_seeds) CU_TRY(cudaMalloc(&e->d_seeds, (size_t)n * 4));
+    CU_TRY(cudaMemcpyAsync(e->d_seeds, seeds, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset
+// ------------------------------------------------------------------------------------------------
+static int reset_impl(gymcuda_env* e, const uint8_t* d_mask, float* obs_host) {
+    ResetArgs a{};
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.mask = d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset;
+    a.seed = e->seed; a.t = e->t;
+    CU_TRY(dispatch_reset(e, a));
+    e->last_obs = e->d_obs;
+    if (obs_host) CU_TRY(cudaMemcpyAsync(obs_host, e->d_obs, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_reset(gymcuda_env* e, float* obs_out) {
+    ENTER(e);
+    int rc = reset_impl(e, nullptr, obs_out);
+    if (rc == GYMCUDA_OK) e->has_state = true;
+    return rc;
+}
+
+int gymcuda_reset_masked(gymcuda_env* e, const uint8_t* mask, float* obs_out) {
+    ENTER(e);
+    if (!mask) return fail(GYMCUDA_EINVAL, "mask is null");
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "reset_masked before the first full Reset()");
+    CU_TRY(cudaMemcpyAsync(e->d_mask, mask, (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+    return reset_impl(e, e->d_mask, obs_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------------
+static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int32_t bcast, float* d_obs,
+                       float* d_reward, uint8_t* d_done) {
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
+    StepArgs a{};
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
+    a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats;
+    a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
+    a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
+    CU_TRY(dispatch_step(e, a));
+    e->t += 1;
+    e->seq += 1;
+    e->env_steps += (unsigned long long)e->n;
+    e->last_obs = d_obs;
+    return GYMCUDA_OK;
+}
+
+static int step_finish_host(gymcuda_env* e, float* obs, float* reward, uint8_t* done) {
+    if (obs) CU_TRY(cudaMemcpyAsync(obs, e->d_obs, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
+    if (reward) CU_TRY(cudaMemcpyAsync(reward, e->d_reward, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (done) CU_TRY(cudaMemcpyAsync(done, e->d_done, (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    if (e->h_small[1] != e->invalid_seen) {
+        unsigned long long bad = e->h_small[1] - e->invalid_seen;
+        e->invalid_seen = e->h_small[1];
+        return fail(GYMCUDA_EACTION, "%llu action(s) invalid for this action space; those envs were not stepped", bad);
+    }
+    return GYMCUDA_OK;
+}
+
+int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward, uint8_t* done) {
+    ENTER(e);
+    if (!actions) return fail(GYMCUDA_EINVAL, "actions is null");
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
+    CU_TRY(cudaMemcpyAsync(e->d_actions, actions, e->act_bytes(), cudaMemcpyHostToDevice, e->stream));
+    int rc = step_launch(e, e->d_actions, 0, 0, e->d_obs, e->d_reward, e->d_done);
+    if (rc) return rc;
+    return step_finish_host(e, obs, reward, done);
+}
+
+int gymcuda_step_broadcast(gymcuda_env* e, int32_t action, float* obs, float* reward, uint8_t* done) {
+    ENTER(e);
+    if (e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "IVecEnv.Step(int action) needs a Discrete action space");
+    int rc = step_launch(e, nullptr, 1, action, e->d_obs, e->d_reward, e->d_done);
+    if (rc) return rc;
+    return step_finish_host(e, obs, reward, done);
+}
+
+int gymcuda_step_device(gymcuda_env* e, const void* d_actions, float* d_obs, float* d_reward, uint8_t* d_done) {
+    ENTER(e);
+    if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
+    return step_launch(e, d_actions, 0, 0, d_obs ? d_obs : e->d_obs, d_reward ? d_reward : e->d_reward,
+                       d_done ? d_done : e->d_done);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rollout
+// ------------------------------------------------------------------------------------------------
+int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, float* d_reward, uint8_t* d_done, void* d_actions) {
+    ENTER(e);
+    if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
+    RolloutArgs a{};
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats;
+    a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
+    CU_TRY(dispatch_rollout(e, a));
+    e->t += (uint64_t)k_steps;
+    e->env_steps += (unsigned long long)e->n * (unsigned long long)k_steps;
+    e->last_obs = nullptr;   // the current observations are not materialised; gymcuda_observe recomputes them
+    return GYMCUDA_OK;
+}
+
+int gymcuda_rollout_random(gymcuda_env* e, int k_steps, float* obs, float* reward, uint8_t* done, void* actions) {
+    ENTER(e);
+    if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
+    const size_t kn = (size_t)k_steps * (size_t)e->n;
+    float *d_obs = nullptr, *d_reward = nullptr; uint8_t* d_done = nullptr; void* d_act = nullptr;
+    int rc = GYMCUDA_OK;
+    auto cleanup = [&]() { cudaFree(d_obs); cudaFree(d_reward); cudaFree(d_done); cudaFree(d_act); };
+#define RB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    if (obs) RB_TRY(cudaMalloc(&d_obs, kn * e->ki.od * 4));
+    if (reward) RB_TRY(cudaMalloc(&d_reward, kn * 4));
+    if (done) RB_TRY(cudaMalloc(&d_done, kn));
+    if (actions) RB_TRY(cudaMalloc(&d_act, kn * e->ki.ad * 4));
+    rc = gymcuda_rollout_random_device(e, k_steps, d_obs, d_reward, d_done, d_act);
+    if (rc) { cleanup(); return rc; }
+    if (obs) RB_TRY(cudaMemcpyAsync(obs, d_obs, kn * e->ki.od * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (reward) RB_TRY(cudaMemcpyAsync(reward, d_reward, kn * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (done) RB_TRY(cudaMemcpyAsync(done, d_done, kn, cudaMemcpyDeviceToHost, e->stream));
+    if (actions) RB_TRY(cudaMemcpyAsync(actions, d_act, kn * e->ki.ad * 4, cudaMemcpyDeviceToHost, e->stream));
+    RB_TRY(cudaStreamSynchronize(e->stream));
+#undef RB_TRY
+    cleanup();
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// done compaction
+// ------------------------------------------------------------------------------------------------
+int gymcuda_done_indices(gymcuda_env* e, int32_t* idx, int32_t* count) {
+    ENTER(e);
+    if (!count) return fail(GYMCUDA_EINVAL, "count is null");
+    if (e->seq == 0) { *count = 0; return GYMCUDA_OK; }
+    int32_t* h = reinterpret_cast<int32_t*>(e->h_small + 2);
+    CU_TRY(cudaMemcpyAsync(h, e->d_done_count + ((e->seq - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    *count = *h;
+    if (idx && *count > 0) {
+        CU_TRY(cudaMemcpyAsync(idx, e->d_done_idx, (size_t)*count * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return GYMCUDA_OK;
+}
+
+int gymcuda_done_indices_device(gymcuda_env* e, const int32_t** d_idx, const int32_t** d_count) {
+    ENTER(e);
+    if (d_idx) *d_idx = e->d_done_idx;
+    if (d_count) *d_count = e->seq == 0 ? e->d_done_count : e->d_done_count + ((e->seq - 1) & 1);
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// snapshot / teacher forcing
+// ------------------------------------------------------------------------------------------------
+int gymcuda_get_state(gymcuda_env* e, float* state, int32_t* aux, uint64_t* t) {
+    ENTER(e);
+#ifdef GYMCUDA_WITH_LUNAR
+    if (e->cfg.env_kind >= GYMCUDA_LUNARLANDER) { int rc = lunar_get_state(e, state, aux); if (rc) return rc; if (t) *t = e->t; return GYMCUDA_OK; }
+#endif
+    if (state) CU_TRY(cudaMemcpyAsync(state, e->d_state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int32_t> sbd, ept;
+    if (aux) {
+        sbd.resize(e->n); ept.resize(e->n);
+        CU_TRY(cudaMemcpyAsync(sbd.data(), e->d_sbd, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(ept.data(), e->d_ept, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    if (aux) for (int i = 0; i < e->n; ++i) { aux[2 * i] = sbd[i]; aux[2 * i + 1] = ept[i]; }
+    if (t) *t = e->t;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, uint64_t t) {
+    ENTER(e);
+#ifdef GYMCUDA_WITH_LUNAR
+    if (e->cfg.env_kind >= GYMCUDA_LUNARLANDER) { int rc = lunar_set_state(e, state, aux); if (rc) return rc; e->t = t; e->has_state = true; e->last_obs = nullptr; return GYMCUDA_OK; }
+#endif
+    if (state) CU_TRY(cudaMemcpyAsync(e->d_state, state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyHostToDevice, e->stream));
+    std::vector<int32_t> sbd, ept;
+    if (aux) {
+        sbd.resize(e->n); ept.resize(e->n);
+        for (int i = 0; i < e->n; ++i) { sbd[i] = aux[2 * i]; ept[i] = aux[2 * i + 1]; }
+        CU_TRY(cudaMemcpyAsync(e->d_sbd, sbd.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->d_ept, ept.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->t = t;
+    e->has_state = true;
+    e->last_obs = nullptr;
+    return GYMCUDA_OK;
+}
+
+static int observe_device(gymcuda_env* e) {
+    // a masked reset with an all-zero mask only recomputes observations from the stored state
+    ResetArgs a{};
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    CU_TRY(cudaMemsetAsync(e->d_mask, 0, (size_t)e->n, e->stream));
+    a.mask = e->d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t;
+    CU_TRY(dispatch_reset(e, a));
+    e->last_obs = e->d_obs;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_observe(gymcuda_env* e, float* obs) {
+    ENTER(e);
+    if (!obs) return fail(GYMCUDA_EINVAL, "obs is null");
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "observe before Reset()");
+    int rc = observe_device(e);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(obs, e->d_obs, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
+    ENTER(e);
+    if (!out) return fail(GYMCUDA_EINVAL, "out is null");
+    CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    out->env_steps = e->env_steps;
+    out->episodes = e->h_small[0];
+    out->invalid_actions = e->h_small[1];
+    if (reset_counters) {
+        CU_TRY(cudaMemsetAsync(e->d_stats, 0, 2 * sizeof(unsigned long long), e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        e->env_steps = 0;
+        e->invalid_seen = 0;
+    }
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streams, pinned memory
+// ------------------------------------------------------------------------------------------------
+int gymcuda_set_stream(gymcuda_env* e, void* cuda_stream) {
+    ENTER(e);
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_sync(gymcuda_env* e) {
+    ENTER(e);
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(GYMCUDA_EINVAL, "ptr is null");
+    CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_host_free(void* ptr) {
+    if (ptr) CU_TRY(cudaFreeHost(ptr));
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL all-gather of observations
+// ------------------------------------------------------------------------------------------------
+int gymcuda_nccl_load(const char* path) { return nccl_load(path); }
+
+int gymcuda_nccl_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return fail(GYMCUDA_EINVAL, "id_out is null");
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    NCCL_TRY(g_nccl.GetUniqueId(id_out));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_comm_init(gymcuda_env* e, const uint8_t id[128], int rank, int world_size) {
+    ENTER(e);
+    if (!id || world_size <= 0 || rank < 0 || rank >= world_size) return fail(GYMCUDA_EINVAL, "bad rank/world_size");
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    Id128 uid;
+    std::memcpy(uid.b, id, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&e->comm, world_size, uid, rank));
+    e->rank = rank;
+    e->world = world_size;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_allgather_obs(gymcuda_env* e, const float* d_obs, float* d_out) {
+    ENTER(e);
+    if (!e->comm) return fail(GYMCUDA_ENCCL, "gymcuda_comm_init has not been called on this handle");
+    if (!d_out) return fail(GYMCUDA_EINVAL, "d_out is null");
+    const float* src = d_obs;
+    if (!src) {
+        if (!e->last_obs) { int rc = observe_device(e); if (rc) return rc; }
+        src = e->last_obs;
+    }
+    NCCL_TRY(g_nccl.AllGather(src, d_out, (size_t)e->n * e->ki.od, /* ncclFloat32 */ 7, e->comm, e->stream));
+    return GYMCUDA_OK;
+}
+
+}  // extern "C"

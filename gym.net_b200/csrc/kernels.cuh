@@ -1,0 +1,306 @@
+// Generic kernels of the engine: one thread = one env instance.
+//
+//   step_kernel     one env step per launch: coalesced vector load of the state, transition,
+//                   reward, termination, in-kernel auto-reset, coalesced stores, then warp-ballot +
+//                   block-scan compaction of the done mask (one atomicAdd per block).
+//                   Replaces the serial per-env loop of VecEnvWrapper.Step
+//                   (src/Gym/Envs/VecEnvWrapper.cs:22-24) over Env.Step (src/Gym/Envs/Env.cs:21).
+//   rollout_kernel  k fused steps of the random policy (Discrete.Sample / Box.Sample,
+//                   src/Gym/Spaces/Discrete.cs:27, src/Gym/Spaces/Box.cs:84): state stays in registers,
+//                   actions come from the per-env Philox stream, the trajectory is streamed to HBM
+//                   with evict-first stores.  This is the caller loop of the reference's tests
+//                   (tests/Gym.Tests/Envs/Classic/CartpoleEnvironment.cs:19-30) moved on-device.
+//   reset_kernel    Env.Reset for all / masked envs.
+//   observe_kernel  current observations without stepping.
+//
+// HBM layout (structure of arrays, all indexed by local env id):
+//   state   Vec[n]      float4 (CartPole, Acrobot) or float2 (Pendulum, MountainCar*)
+//   sbd     int32[n]    CartPole steps_beyond_done (touched only when auto-reset is off)
+//   ep_t    int32[n]    episode step counter (touched only when a time limit is set)
+//   seeds   int32[n]    optional per-env seeds (VecEnv.Seed(int[]))
+// No RNG state lives in memory: draws are functions of (seed, env id, t).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "env_classic.cuh"
+#include "philox.cuh"
+
+namespace gymcuda {
+
+struct StepArgs {
+    void* state;
+    int32_t* sbd;
+    int32_t* ep_t;
+    const int32_t* seeds;
+    const void* actions;
+    float* obs;
+    float* reward;
+    uint8_t* done;
+    int32_t* done_idx;                 // may be null
+    int32_t* done_count;               // [2], indexed by the parity of `seq`
+    unsigned long long* stats;         // [0] episodes finished, [1] invalid actions
+    int n;
+    uint32_t env_off;
+    uint64_t seed;
+    uint64_t t;
+    int limit;
+    int use_bcast;
+    int32_t bcast_action;
+    uint32_t seq;                      // step-launch sequence number of this handle
+};
+
+struct RolloutArgs {
+    void* state;
+    int32_t* sbd;
+    int32_t* ep_t;
+    const int32_t* seeds;
+    float* obs;        // [k][n][OD]   may be null
+    float* reward;     // [k][n]       may be null
+    uint8_t* done;     // [k][n]       may be null
+    void* actions;     // [k][n][AD]   may be null
+    unsigned long long* stats;
+    int n;
+    int k_steps;
+    uint32_t env_off;
+    uint64_t seed;
+    uint64_t t;
+    int limit;
+};
+
+struct ResetArgs {
+    void* state;
+    int32_t* sbd;
+    int32_t* ep_t;
+    const int32_t* seeds;
+    const uint8_t* mask;   // may be null = all
+    float* obs;            // may be null
+    int n;
+    uint32_t env_off;
+    uint64_t seed;
+    uint64_t t;
+};
+
+// ---------------------------------------------------------------- observation stores
+template <int OD, bool STREAM>
+__device__ __forceinline__ void store_obs(float* base, size_t env_index, const float* o) {
+    float* p = base + env_index * OD;
+    if (OD == 4) {
+        const float4 v = make_float4(o[0], o[1], o[2], o[3]);
+        if (STREAM) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
+    } else if (OD == 8) {
+        const float4 v0 = make_float4(o[0], o[1], o[2], o[3]), v1 = make_float4(o[4], o[5], o[6], o[7]);
+        if (STREAM) { __stcs(reinterpret_cast<float4*>(p), v0); __stcs(reinterpret_cast<float4*>(p) + 1, v1); }
+        else { reinterpret_cast<float4*>(p)[0] = v0; reinterpret_cast<float4*>(p)[1] = v1; }
+    } else if (OD % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < OD / 2; ++k) {
+            const float2 v = make_float2(o[2 * k], o[2 * k + 1]);
+            if (STREAM) __stcs(reinterpret_cast<float2*>(p) + k, v); else reinterpret_cast<float2*>(p)[k] = v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < OD; ++k) { if (STREAM) __stcs(p + k, o[k]); else p[k] = o[k]; }
+    }
+}
+
+// ---------------------------------------------------------------- actions
+template <class E> struct ActIO {
+    using Act = typename E::Act;
+    __device__ static __forceinline__ Act load(const void* base, int i) { return reinterpret_cast<const Act*>(base)[i]; }
+    __device__ static __forceinline__ Act bcast(int32_t a) { return (Act)a; }
+    __device__ static __forceinline__ void store(void* base, size_t idx, Act a) { __stcs(reinterpret_cast<Act*>(base) + idx, a); }
+};
+
+// Random policy: Discrete.Sample = randint(0, N) (Discrete.cs:27), Box.Sample = uniform(low, high) (Box.cs:84).
+// Draw t of env e comes from block (t >> SHIFT) of the ACTION stream; the block is regenerated only
+// when t crosses a block boundary (CartPole: once per 128 steps).
+template <class E, int ACTN = E::ACTN, int AD = E::AD> struct ActionGen;
+
+template <class E> struct ActionGen<E, 2, 1> {
+    Block b;
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
+        if (first || (t & 127) == 0) b = draw(seed, gid, t >> 7, STREAM_ACTION);
+        return (int32_t)((word(b, (uint32_t)(t >> 5) & 3u) >> (t & 31)) & 1u);
+    }
+};
+template <class E> struct ActionGen<E, 4, 1> {
+    Block b;
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
+        if (first || (t & 63) == 0) b = draw(seed, gid, t >> 6, STREAM_ACTION);
+        const uint32_t i = (uint32_t)(t & 63);
+        return (int32_t)((word(b, i >> 4) >> (2 * (i & 15))) & 3u);
+    }
+};
+template <class E> struct ActionGen<E, 3, 1> {
+    Block b;
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
+        if (first || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
+        return (int32_t)__umulhi(word(b, (uint32_t)t & 3u), 3u);
+    }
+};
+template <class E> struct ActionGen<E, 0, 1> {
+    Block b;
+    __device__ __forceinline__ float next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
+        if (first || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
+        return uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, (uint32_t)t & 3u));
+    }
+};
+template <class E> struct ActionGen<E, 0, 2> {
+    Block b;
+    __device__ __forceinline__ float2 next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
+        if (first || (t & 1) == 0) b = draw(seed, gid, t >> 1, STREAM_ACTION);
+        const uint32_t j = 2u * ((uint32_t)t & 1u);
+        return make_float2(uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, j)), uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, j + 1)));
+    }
+};
+
+__device__ __forceinline__ uint64_t seed_of(const int32_t* seeds, uint64_t seed, int i) {
+    return seeds ? (uint64_t)(uint32_t)seeds[i] : seed;
+}
+
+// ---------------------------------------------------------------- step
+constexpr int STEP_BLOCK = 128;
+
+template <class E, bool AUTO_RESET, bool LIMIT>
+__global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
+    using S = typename E::S;
+    using Act = typename E::Act;
+    const int i = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    bool done = false;
+    bool invalid = false;
+    if (i < p.n) {
+        S s = E::load(p.state, i);
+        const Act a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
+        int32_t sbd = -1;
+        if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
+        int32_t ept = 0;
+        if (LIMIT) ept = p.ep_t[i];
+        StepOut r{0.0f, false};
+        invalid = E::REJECT_INVALID && !E::valid(a);
+        if (!invalid) {
+            r = E::step(s, a, sbd);
+            if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }   // truncation folded into done
+            if (AUTO_RESET && r.done) {
+                E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, p.t + 1, STREAM_RESET));
+                sbd = -1;
+                ept = 0;
+            }
+            E::store(p.state, i, s);
+            if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
+            if (LIMIT) p.ep_t[i] = ept;
+        }
+        float o[E::OD];
+        E::obs(s, o);
+        store_obs<E::OD, false>(p.obs, (size_t)i, o);
+        p.reward[i] = r.reward;
+        p.done[i] = (uint8_t)r.done;
+        done = r.done;
+    }
+
+    // ---- done compaction: warp ballot + popc prefix -> block scan -> one atomicAdd per block
+    __shared__ int warp_cnt[STEP_BLOCK / 32];
+    __shared__ int block_base;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, done);
+    const unsigned mi = __ballot_sync(0xffffffffu, invalid);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    if (mi != 0 && lane == 0) atomicAdd(&p.stats[1], (unsigned long long)__popc(mi));
+    __syncthreads();
+    int warp_off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < STEP_BLOCK / 32; ++w) {
+        const int c = warp_cnt[w];
+        if (w < (int)warp) warp_off += c;
+        total += c;
+    }
+    int32_t* count = p.done_count + (p.seq & 1);
+    if (threadIdx.x == 0) {
+        int base = 0;
+        if (total > 0) {
+            base = atomicAdd(count, total);
+            atomicAdd(&p.stats[0], (unsigned long long)total);
+        }
+        block_base = base;
+        if (blockIdx.x == 0) p.done_count[(p.seq + 1) & 1] = 0;   // zero the next step's counter
+    }
+    if (p.done_idx != nullptr && total > 0) {
+        __syncthreads();
+        if (done) p.done_idx[block_base + warp_off + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+}
+
+// ---------------------------------------------------------------- fused random-policy rollout
+constexpr int ROLLOUT_BLOCK = 64;
+
+template <class E, bool AUTO_RESET, bool LIMIT>
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
+    using S = typename E::S;
+    const int i = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
+    unsigned episodes = 0;
+    if (i < p.n) {
+        S s = E::load(p.state, i);
+        int32_t sbd = -1;
+        if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
+        int32_t ept = 0;
+        if (LIMIT) ept = p.ep_t[i];
+        const uint64_t seed = seed_of(p.seeds, p.seed, i);
+        const uint32_t gid = p.env_off + (uint32_t)i;
+        ActionGen<E> gen;
+        const size_t n = (size_t)p.n;
+        for (int k = 0; k < p.k_steps; ++k) {
+            const uint64_t t = p.t + (uint64_t)k;
+            const typename E::Act a = gen.next(seed, gid, t, k == 0);
+            StepOut r = E::step(s, a, sbd);
+            if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }
+            if (r.done) {
+                episodes += 1;
+                if (AUTO_RESET) {
+                    E::reset(s, draw(seed, gid, t + 1, STREAM_RESET));
+                    sbd = -1;
+                    ept = 0;
+                }
+            }
+            const size_t idx = (size_t)k * n + (size_t)i;
+            if (p.obs) {
+                float o[E::OD];
+                E::obs(s, o);
+                store_obs<E::OD, true>(p.obs, idx, o);
+            }
+            if (p.reward) __stcs(p.reward + idx, r.reward);
+            if (p.done) __stcs(p.done + idx, (uint8_t)r.done);
+            if (p.actions) ActIO<E>::store(p.actions, idx, a);
+        }
+        E::store(p.state, i, s);
+        if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
+        if (LIMIT) p.ep_t[i] = ept;
+    }
+    // episodes finished: warp reduce, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) episodes += __shfl_xor_sync(0xffffffffu, episodes, o);
+    if ((threadIdx.x & 31) == 0 && episodes) atomicAdd(&p.stats[0], (unsigned long long)episodes);
+}
+
+// ---------------------------------------------------------------- reset / observe
+template <class E>
+__global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
+    using S = typename E::S;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    S s;
+    if (p.mask == nullptr || p.mask[i]) {
+        E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, p.t, STREAM_RESET));
+        E::store(p.state, i, s);
+        p.sbd[i] = -1;     // CartPoleEnv.cs:64
+        p.ep_t[i] = 0;
+    } else {
+        s = E::load(p.state, i);
+    }
+    if (p.obs) {
+        float o[E::OD];
+        E::obs(s, o);
+        store_obs<E::OD, false>(p.obs, (size_t)i, o);
+    }
+}
+
+}  // namespace gymcuda

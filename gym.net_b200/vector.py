@@ -1,0 +1,269 @@
+"""Gym.Environments.Vector -- the host-side mirror of the reference's Env / VecEnv surface for the
+batched CUDA path.  Python twin of csharp/Gym.Environments.Vector/CudaVecEnv.cs; both sit on the
+same C ABI (include/gymcuda.h).
+
+Reference members mirrored (paths relative to the reference):
+  Step {Observation, Reward, Done, Information}   src/Gym/Observations/Step.cs:7-20
+  VecEnv ctor / Reset / Step(int) / Seed / Close  src/Gym/Envs/VecEnv.cs:12-53, IVecEnv.cs:8-19
+  VecEnvWrapper.Step broadcast of one action      src/Gym/Envs/VecEnvWrapper.cs:22-24
+and extended with what a real VectorEnv needs (per-env actions, auto-reset, fused rollouts).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .spaces import Box, Discrete
+
+
+class Step:
+    """Gym.Observations.Step (Step.cs:7-29)."""
+
+    __slots__ = ("Observation", "Reward", "Done", "Information")
+
+    def __init__(self, observation=None, reward=0.0, done=False, information=None):
+        self.Observation, self.Reward, self.Done, self.Information = observation, reward, done, information
+
+    def __iter__(self):   # Deconstruct (Step.cs:22-27): var (obs, reward, done, info) = env.Step(a)
+        return iter((self.Observation, self.Reward, self.Done, self.Information))
+
+    def __repr__(self):
+        return "Reward: %s, Done: %s, Information: %s, Observation: %s" % (
+            self.Reward, self.Done, self.Information, self.Observation)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class CudaVecEnv:
+    """VecEnv over `num_envs` instances of one env family living on one GPU.
+
+    Source-compatible members: Reset() -> NDArray[], Step(int action) -> Step[] (broadcast),
+    Seed(int), Seed(int[]), Close(), ActionSpace, ObservationSpace, NumberOfEnvironments.
+    Batched members: ResetBatch(), StepBatch(actions) -> (obs, reward, done), RolloutRandom(k).
+    """
+
+    ENV_KIND = None
+
+    def __init__(self, num_envs, seed=0, device=0, env_id_offset=0, auto_reset=False, time_limit=0, **params):
+        if self.ENV_KIND is None:
+            raise TypeError("use a concrete family: CartPoleVecEnv, PendulumVecEnv, ...")
+        L = N.lib()
+        cfg = N.Config()
+        N.check(L.gymcuda_config_default(C.byref(cfg), self.ENV_KIND, int(num_envs)))
+        cfg.device, cfg.seed, cfg.env_id_offset = int(device), int(seed) & (2**64 - 1), int(env_id_offset)
+        cfg.flags = N.FLAG_AUTO_RESET if auto_reset else 0
+        cfg.time_limit = int(time_limit)
+        for k, v in params.items():   # gravity, enable_wind, wind_power, turbulence_power (LunarLanderEnv ctor)
+            if not hasattr(cfg, k):
+                raise TypeError("unknown env parameter %r" % k)
+            setattr(cfg, k, v)
+        h = C.c_void_p()
+        N.check(L.gymcuda_create(C.byref(cfg), C.byref(h)))
+        self._h, self._L = h, L
+        info = N.SpaceInfo()
+        N.check(L.gymcuda_space(h, C.byref(info)))
+        self.info = info
+        self.NumberOfEnvironments = int(num_envs)
+        self.obs_dim, self.act_dim, self.act_n = info.obs_dim, info.act_dim, info.act_n
+        self.state_dim, self.aux_dim, self.TimeLimit = info.state_dim, info.aux_dim, info.time_limit
+        low = np.array(info.obs_low[:self.obs_dim], np.float32)
+        high = np.array(info.obs_high[:self.obs_dim], np.float32)
+        self.ObservationSpace = Box(low, high, dtype=np.float32)
+        if self.act_n > 0:
+            self.ActionSpace = Discrete(self.act_n)
+        else:
+            self.ActionSpace = Box(np.array(info.act_low[:self.act_dim], np.float32),
+                                   np.array(info.act_high[:self.act_dim], np.float32), dtype=np.float32)
+        self.Metadata = {"render.modes": [], "video.frames_per_second": 50}
+        self.RewardRange = (-float("inf"), float("inf"))
+
+    # ---- lifecycle -------------------------------------------------------------------------------
+    def Close(self):
+        if getattr(self, "_h", None):
+            self._L.gymcuda_destroy(self._h)
+            self._h = None
+
+    CloseEnvironment = Close
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.Close()
+
+    # ---- Seed ------------------------------------------------------------------------------------
+    def Seed(self, seed):
+        """Seed(int) (VecEnv.cs:44-46) or Seed(int[]) (VecEnv.cs:48-53)."""
+        if np.isscalar(seed):
+            N.check(self._L.gymcuda_seed(self._h, int(seed) & (2**64 - 1)))
+        else:
+            s = np.ascontiguousarray(seed, dtype=np.int32)
+            N.check(self._L.gymcuda_seed_each(self._h, _ptr(s), int(s.size)))
+
+    # ---- batched API -----------------------------------------------------------------------------
+    def _out(self):
+        n = self.NumberOfEnvironments
+        return (np.empty((n, self.obs_dim), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8))
+
+    def ResetBatch(self, mask=None):
+        obs = np.empty((self.NumberOfEnvironments, self.obs_dim), np.float32)
+        if mask is None:
+            N.check(self._L.gymcuda_reset(self._h, _ptr(obs)))
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            if m.shape != (self.NumberOfEnvironments,):
+                raise ValueError("mask must have one entry per environment")
+            N.check(self._L.gymcuda_reset_masked(self._h, _ptr(m), _ptr(obs)))
+        return obs
+
+    def _actions(self, actions):
+        n = self.NumberOfEnvironments
+        if self.act_n > 0:
+            a = np.ascontiguousarray(actions, dtype=np.int32)
+            if a.shape != (n,):
+                raise ValueError("expected %d discrete actions" % n)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32).reshape(n, self.act_dim)
+        return a
+
+    def StepBatch(self, actions):
+        a = self._actions(actions)
+        obs, rew, done = self._out()
+        N.check(self._L.gymcuda_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
+        return obs, rew, done
+
+    def RolloutRandom(self, k_steps, want=("obs", "reward", "done", "actions")):
+        n, k = self.NumberOfEnvironments, int(k_steps)
+        obs = np.empty((k, n, self.obs_dim), np.float32) if "obs" in want else None
+        rew = np.empty((k, n), np.float32) if "reward" in want else None
+        done = np.empty((k, n), np.uint8) if "done" in want else None
+        act = None
+        if "actions" in want:
+            act = np.empty((k, n), np.int32) if self.act_n > 0 else np.empty((k, n, self.act_dim), np.float32)
+        N.check(self._L.gymcuda_rollout_random(self._h, k, _ptr(obs), _ptr(rew), _ptr(done), _ptr(act)))
+        return obs, rew, done, act
+
+    def DoneIndices(self):
+        cnt = C.c_int32()
+        idx = np.empty(self.NumberOfEnvironments, np.int32)
+        N.check(self._L.gymcuda_done_indices(self._h, _ptr(idx), C.byref(cnt)))
+        return idx[:cnt.value].copy()
+
+    def GetState(self):
+        n = self.NumberOfEnvironments
+        st = np.empty((n, self.state_dim), np.float32)
+        aux = np.empty((n, self.aux_dim), np.int32)
+        t = C.c_uint64()
+        N.check(self._L.gymcuda_get_state(self._h, _ptr(st), _ptr(aux), C.byref(t)))
+        return st, aux, t.value
+
+    def SetState(self, state, aux, t):
+        n = self.NumberOfEnvironments
+        st = np.ascontiguousarray(state, dtype=np.float32).reshape(n, self.state_dim)
+        ax = np.ascontiguousarray(aux, dtype=np.int32).reshape(n, self.aux_dim)
+        N.check(self._L.gymcuda_set_state(self._h, _ptr(st), _ptr(ax), int(t)))
+
+    def Observe(self):
+        obs = np.empty((self.NumberOfEnvironments, self.obs_dim), np.float32)
+        N.check(self._L.gymcuda_observe(self._h, _ptr(obs)))
+        return obs
+
+    def Stats(self, reset=False):
+        s = N.Stats()
+        N.check(self._L.gymcuda_get_stats(self._h, C.byref(s), 1 if reset else 0))
+        return {"env_steps": s.env_steps, "episodes": s.episodes, "invalid_actions": s.invalid_actions}
+
+    # ---- device-pointer API (torch tensors / raw pointers) ------------------------------------------
+    def SetStream(self, cuda_stream):
+        N.check(self._L.gymcuda_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def Sync(self):
+        N.check(self._L.gymcuda_sync(self._h))
+
+    def StepDevice(self, d_actions, d_obs, d_reward, d_done):
+        N.check(self._L.gymcuda_step_device(self._h, C.c_void_p(d_actions), C.c_void_p(d_obs or 0),
+                                            C.c_void_p(d_reward or 0), C.c_void_p(d_done or 0)))
+
+    def RolloutRandomDevice(self, k_steps, d_obs=0, d_reward=0, d_done=0, d_actions=0):
+        N.check(self._L.gymcuda_rollout_random_device(self._h, int(k_steps), C.c_void_p(d_obs or 0),
+                                                      C.c_void_p(d_reward or 0), C.c_void_p(d_done or 0),
+                                                      C.c_void_p(d_actions or 0)))
+
+    def CommInit(self, unique_id, rank, world_size):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        N.check(self._L.gymcuda_comm_init(self._h, buf, int(rank), int(world_size)))
+
+    def AllGatherObs(self, d_out, d_obs=0):
+        N.check(self._L.gymcuda_allgather_obs(self._h, C.c_void_p(d_obs or 0), C.c_void_p(d_out)))
+
+    # ---- source-compatible IVecEnv members -----------------------------------------------------------
+    def Reset(self):
+        """IVecEnv.Reset() -> NDArray[] (one observation array per env)."""
+        return list(self.ResetBatch())
+
+    def Step(self, action):
+        """IVecEnv.Step(int action) -> Step[]: ONE action broadcast to every env (VecEnvWrapper.cs:22-24)."""
+        if self.act_n == 0:
+            raise NotImplementedError("IVecEnv.Step(int) needs a Discrete action space; use StepBatch")
+        obs, rew, done = self._out()
+        N.check(self._L.gymcuda_step_broadcast(self._h, int(action), _ptr(obs), _ptr(rew), _ptr(done)))
+        return [Step(obs[i], float(rew[i]), bool(done[i]), None) for i in range(self.NumberOfEnvironments)]
+
+
+def nccl_unique_id():
+    buf = (C.c_uint8 * 128)()
+    N.check(N.lib().gymcuda_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class CartPoleVecEnv(CudaVecEnv):
+    """Batched Gym.Environments.Envs.Classic.CartPoleEnv (CartPoleEnv.cs)."""
+    ENV_KIND = N.CARTPOLE
+
+
+class PendulumVecEnv(CudaVecEnv):
+    ENV_KIND = N.PENDULUM
+
+
+class MountainCarVecEnv(CudaVecEnv):
+    ENV_KIND = N.MOUNTAINCAR
+
+
+class MountainCarContinuousVecEnv(CudaVecEnv):
+    ENV_KIND = N.MOUNTAINCAR_CONT
+
+
+class AcrobotVecEnv(CudaVecEnv):
+    ENV_KIND = N.ACROBOT
+
+
+class LunarLanderVecEnv(CudaVecEnv):
+    """Batched Gym.Environments.Envs.Aether.LunarLanderEnv (LunarLanderEnv.cs); continuous=True for the Box action space."""
+    ENV_KIND = N.LUNARLANDER
+
+    def __init__(self, num_envs, continuous=False, **kw):
+        self.ENV_KIND = N.LUNARLANDER_CONT if continuous else N.LUNARLANDER
+        self.ContinuousMode = bool(continuous)
+        super().__init__(num_envs, **kw)
+
+
+FAMILIES = {
+    "CartPole-v1": CartPoleVecEnv,
+    "Pendulum-v1": PendulumVecEnv,
+    "MountainCar-v0": MountainCarVecEnv,
+    "MountainCarContinuous-v0": MountainCarContinuousVecEnv,
+    "Acrobot-v1": AcrobotVecEnv,
+    "LunarLander-v2": LunarLanderVecEnv,
+}
+
+
+def make(name, num_envs, **kw):
+    return FAMILIES[name](num_envs, **kw)

@@ -1,0 +1,181 @@
+/* libgymcuda -- C ABI of the Blackwell-native vectorised environment engine.
+ *
+ * This is the drop-in boundary for ONE hot path of SciSharp/Gym.NET: the batched state transition,
+ * reward, termination (+ auto-reset and done compaction) of the classic-control environments and
+ * LunarLander.  The reference has no FFI for this path -- the seam is its managed API -- so every
+ * entry point below names the managed member it stands behind (paths relative to the reference):
+ *
+ *   Env.Reset / Env.Step / Env.Seed            src/Gym/Envs/Env.cs:20-29
+ *   IVecEnv.Reset / Step / Seed / Close        src/Gym/Envs/IVecEnv.cs:8-19, src/Gym/Envs/VecEnv.cs:39-53
+ *   VecEnvWrapper.Step (serial per-env loop)   src/Gym/Envs/VecEnvWrapper.cs:22-24
+ *   Step {Observation, Reward, Done, Info}     src/Gym/Observations/Step.cs:7-20
+ *   CartPoleEnv.Step / Reset / Seed            src/Gym.Environments/Envs/Classic/CartPoleEnv.cs:137-186, 63-67, 196-198
+ *   LunarLanderEnv.Step / Reset / Seed         src/Gym.Environments/Envs/Aether/LunarLanderEnv.cs:574-774, 489-572, 900-903
+ *   Discrete.Sample / Box.Sample (random policy) src/Gym/Spaces/Discrete.cs:17-28, src/Gym/Spaces/Box.cs:69-90
+ *
+ * The C# binding a maintainer adds ([DllImport("gymcuda")] + Gym.Environments.Vector.CudaVecEnv) is
+ * shown in INTEGRATION.md and shipped under csharp/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the boundary: every call returns
+ *     GYMCUDA_OK (0) or a negative gymcuda_status, and gymcuda_last_error() gives the text
+ *     (thread-local).  The C# shim maps GYMCUDA_EACTION -> InvalidActionError
+ *     (src/Gym/Exceptions/InvalidActionError.cs:7-10), GYMCUDA_EINVAL -> ArgumentException.
+ *   - one handle = one GPU = one CUDA stream; calls on a handle must be externally serialised
+ *     (reference Env instances are not thread-safe either); distinct handles may be used from
+ *     distinct threads or processes (one process per GPU).
+ *   - the library owns all device memory; the caller owns host buffers for the duration of a call.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with GYMCUDA_ECUDA.
+ *   - layouts: obs [num_envs][obs_dim] float32, reward [num_envs] float32, done [num_envs] uint8 (0/1),
+ *     discrete actions int32 [num_envs], box actions float32 [num_envs][act_dim];
+ *     rollout trajectories are [k_steps][num_envs][...] in the same element layouts.
+ */
+#ifndef GYMCUDA_H
+#define GYMCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GYMCUDA_VERSION 100 /* 0.1.0 */
+
+typedef enum gymcuda_status {
+    GYMCUDA_OK = 0,
+    GYMCUDA_EINVAL = -1,   /* bad argument                       -> ArgumentException   */
+    GYMCUDA_EACTION = -2,  /* action outside the action space    -> InvalidActionError  */
+    GYMCUDA_ECUDA = -3,    /* CUDA runtime / driver failure, or no device                */
+    GYMCUDA_ENCCL = -4,    /* NCCL failure or NCCL not loadable                          */
+    GYMCUDA_ENOMEM = -5,   /* device or host allocation failed                           */
+    GYMCUDA_ESTATE = -6    /* Step before Reset (CartPoleEnv.cs:40,141 would dereference null) */
+} gymcuda_status;
+
+typedef enum gymcuda_env_kind {
+    GYMCUDA_CARTPOLE = 0,          /* Gym.Environments.Envs.Classic.CartPoleEnv                     */
+    GYMCUDA_PENDULUM = 1,          /* north_star env, absent from the reference (README.md:76)      */
+    GYMCUDA_MOUNTAINCAR = 2,       /* north_star env, absent from the reference (README.md:75)      */
+    GYMCUDA_MOUNTAINCAR_CONT = 3,  /* north_star env, absent from the reference (README.md:74)      */
+    GYMCUDA_ACROBOT = 4,           /* north_star env, absent from the reference (README.md:73)      */
+    GYMCUDA_LUNARLANDER = 5,       /* Gym.Environments.Envs.Aether.LunarLanderEnv (discrete)         */
+    GYMCUDA_LUNARLANDER_CONT = 6   /* LunarLanderEnv(continuous: true)                              */
+} gymcuda_env_kind;
+
+enum {
+    GYMCUDA_FLAG_AUTO_RESET = 1u /* reset in-kernel at `done`; obs returned is the post-reset one */
+};
+
+typedef struct gymcuda_config {
+    uint32_t struct_size;   /* = sizeof(gymcuda_config); set by gymcuda_config_default            */
+    int32_t env_kind;       /* gymcuda_env_kind                                                    */
+    int32_t num_envs;       /* env instances held by THIS handle (this GPU's shard)                */
+    int32_t device;         /* CUDA device ordinal                                                 */
+    uint64_t seed;          /* Env.Seed; streams are keyed by (seed, global env id)                */
+    uint32_t env_id_offset; /* global id of local env 0: rank * num_envs for sharded batches       */
+    uint32_t flags;         /* GYMCUDA_FLAG_*                                                      */
+    int32_t time_limit;     /* 0 = env default (CartPole: none, like the reference), <0 none, >0 steps */
+    float gravity;          /* LunarLanderEnv ctor (LunarLanderEnv.cs:381): [-12, 0], default -10  */
+    int32_t enable_wind;    /* LunarLanderEnv ctor                                                  */
+    float wind_power;       /* [0, 20], default 15                                                 */
+    float turbulence_power; /* [0, 2], default 1.5                                                 */
+} gymcuda_config;
+
+typedef struct gymcuda_env gymcuda_env;
+
+typedef struct gymcuda_space_info {
+    int32_t obs_dim;       /* ObservationSpace = Box(low, high, float32) of this length           */
+    int32_t act_dim;       /* 1 for Discrete                                                      */
+    int32_t act_n;         /* Discrete(n); 0 when the action space is a Box                       */
+    int32_t state_dim;     /* float32 words per env in get_state/set_state                        */
+    int32_t aux_dim;       /* int32 words per env in get_state/set_state                          */
+    int32_t time_limit;    /* resolved limit (0 = none)                                           */
+    float obs_low[8], obs_high[8];
+    float act_low[2], act_high[2];
+} gymcuda_space_info;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int gymcuda_version(void);
+const char* gymcuda_last_error(void);
+int gymcuda_device_count(int* count);
+
+/* ---- lifecycle: new XxxEnv(...) / Env.CloseEnvironment / IVecEnv.Close ------------------------ */
+int gymcuda_config_default(gymcuda_config* cfg, int env_kind, int num_envs);
+int gymcuda_create(const gymcuda_config* cfg, gymcuda_env** out);
+int gymcuda_destroy(gymcuda_env* env);
+int gymcuda_space(const gymcuda_env* env, gymcuda_space_info* out);
+int gymcuda_num_envs(const gymcuda_env* env);
+
+/* ---- Env.Seed(int) / VecEnv.Seed(int[]) ----------------------------------------------------- */
+int gymcuda_seed(gymcuda_env* env, uint64_t seed);
+int gymcuda_seed_each(gymcuda_env* env, const int32_t* seeds, int n);
+
+/* ---- Env.Reset / IVecEnv.Reset --------------------------------------------------------------- */
+/* Host buffers; synchronous.  obs_out may be NULL. */
+int gymcuda_reset(gymcuda_env* env, float* obs_out);
+int gymcuda_reset_masked(gymcuda_env* env, const uint8_t* mask, float* obs_out);
+
+/* ---- Env.Step / IVecEnv.Step ------------------------------------------------------------------ */
+/* Host buffers; H2D(actions) -> kernel -> D2H(obs, reward, done); synchronous.
+ * Returns GYMCUDA_EACTION if any action was outside the action space of an env kind that rejects
+ * it (all but CartPole, whose reference only Debug.Asserts, CartPoleEnv.cs:139); those envs are
+ * left unstepped, the others step normally. */
+int gymcuda_step(gymcuda_env* env, const void* actions, float* obs, float* reward, uint8_t* done);
+/* Same, all pointers in device memory, asynchronous on the handle's stream; no copies. */
+int gymcuda_step_device(gymcuda_env* env, const void* d_actions, float* d_obs, float* d_reward,
+                        uint8_t* d_done);
+/* Broadcast of one action to every env: the shipped IVecEnv.Step(int action) (IVecEnv.cs:14). */
+int gymcuda_step_broadcast(gymcuda_env* env, int32_t action, float* obs, float* reward, uint8_t* done);
+
+/* ---- fused random-policy rollout (Discrete.Sample / Box.Sample inside the kernel) ------------- */
+/* k_steps env steps in ONE launch, state in registers, trajectory streamed out.  Every output
+ * pointer is optional (NULL = not written).  *_device: device pointers, asynchronous. */
+int gymcuda_rollout_random_device(gymcuda_env* env, int k_steps, float* d_obs, float* d_reward,
+                                  uint8_t* d_done, void* d_actions);
+int gymcuda_rollout_random(gymcuda_env* env, int k_steps, float* obs, float* reward, uint8_t* done,
+                           void* actions);
+
+/* ---- done compaction (valid after a step) ------------------------------------------------------ */
+/* Indices (local env ids, ascending within a thread block, block order unspecified) of the envs
+ * whose last step returned done, and their number.  idx may be NULL to fetch only the count. */
+int gymcuda_done_indices(gymcuda_env* env, int32_t* idx, int32_t* count);
+int gymcuda_done_indices_device(gymcuda_env* env, const int32_t** d_idx, const int32_t** d_count);
+
+/* ---- snapshot / teacher forcing ----------------------------------------------------------------- */
+/* state [num_envs][state_dim] float32, aux [num_envs][aux_dim] int32, t = global step counter. */
+int gymcuda_get_state(gymcuda_env* env, float* state, int32_t* aux, uint64_t* t);
+int gymcuda_set_state(gymcuda_env* env, const float* state, const int32_t* aux, uint64_t t);
+/* Current observations of all envs (no stepping). */
+int gymcuda_observe(gymcuda_env* env, float* obs);
+
+/* ---- episode statistics (accumulated on device by every step / rollout) ------------------------- */
+typedef struct gymcuda_stats {
+    uint64_t env_steps;      /* env steps executed                */
+    uint64_t episodes;       /* episodes finished (done returned) */
+    uint64_t invalid_actions;
+} gymcuda_stats;
+int gymcuda_get_stats(gymcuda_env* env, gymcuda_stats* out, int reset_counters);
+
+/* ---- streams, pinned memory -------------------------------------------------------------------- */
+/* Use the caller's CUDA stream (cudaStream_t) for every launch and copy; NULL restores the
+ * handle's own stream. */
+int gymcuda_set_stream(gymcuda_env* env, void* cuda_stream);
+int gymcuda_sync(gymcuda_env* env);
+int gymcuda_host_alloc(void** ptr, size_t bytes); /* pinned (page-locked) host memory */
+int gymcuda_host_free(void* ptr);
+
+/* ---- multi-GPU: optional all-gather of observations over NVLink (one process per GPU) ------- */
+/* Rank 0 calls gymcuda_nccl_unique_id and distributes the 128 bytes out of band; every rank then
+ * calls gymcuda_comm_init.  nccl_library_path may be NULL (default search: libnccl.so.2). */
+int gymcuda_nccl_load(const char* nccl_library_path);
+int gymcuda_nccl_unique_id(uint8_t id_out[128]);
+int gymcuda_comm_init(gymcuda_env* env, const uint8_t id[128], int rank, int world_size);
+/* Gathers every rank's current [num_envs][obs_dim] observations into d_out
+ * [world_size][num_envs][obs_dim] (device pointer), asynchronous on the handle's stream.
+ * d_obs == NULL gathers the observations of the last step/reset. */
+int gymcuda_allgather_obs(gymcuda_env* env, const float* d_obs, float* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYMCUDA_H */

@@ -1,0 +1,316 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle.
+
+T1  teacher-forced single step from random + adversarial float32 states:
+      vs ORACLE F64 (the reference's arithmetic): done bit-exact, reward exact/1e-5, state <= 1e-5
+      vs ORACLE F32 (engine arithmetic twin):     everything bit-exact
+T2  free-running rollouts with the in-kernel random policy + auto-reset vs the F32 twin, bit-exact,
+    and vs the F64 oracle teacher-forced along the trajectory.
+T3  the reference test's loop shape (i % 2 actions, reset on done; CartpoleEnvironment.cs:19-30).
+T4  invariances: sharding by env_id_offset, step-vs-rollout, k split.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import gymnet_b200 as G
+from helpers import KINDS, RTOL, STATE_SCALE, random_actions, random_states, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CLASSIC = ["CartPole-v1", "Pendulum-v1", "MountainCar-v0", "MountainCarContinuous-v0", "Acrobot-v1"]
+
+
+def adversarial_states(name, rng, n):
+    """States whose successor lands within a few float32 ulps of a termination threshold."""
+    s = random_states(name, rng, n)
+    if name == "CartPole-v1":
+        tau = np.float64(np.float32(0.02))
+        xthr, tthr = np.float64(np.float32(2.4)), np.float64(np.float32(12 * 2 * np.pi / 360))
+        k = n // 2
+        sign = rng.choice([-1.0, 1.0], size=k)
+        # x + tau*x_dot == +-x_thr up to a few ulps
+        s[:k, 0] = (sign * xthr - tau * s[:k, 1].astype(np.float64)).astype(np.float32)
+        jitter = rng.integers(-3, 4, size=k)
+        for j in range(k):
+            v = s[j, 0]
+            for _ in range(abs(int(jitter[j]))):
+                v = np.nextafter(v, np.float32(np.inf if jitter[j] > 0 else -np.inf), dtype=np.float32)
+            s[j, 0] = v
+        sign = rng.choice([-1.0, 1.0], size=n - k)
+        s[k:, 2] = (sign * tthr - tau * s[k:, 3].astype(np.float64)).astype(np.float32)
+    elif name in ("MountainCar-v0", "MountainCarContinuous-v0"):
+        goal = 0.5 if name == "MountainCar-v0" else 0.45
+        s[:, 1] = rng.uniform(0.0, 0.05, size=n).astype(np.float32)
+        s[:, 0] = (goal - s[:, 1] + rng.uniform(-2e-3, 2e-3, size=n)).astype(np.float32)
+    elif name == "Acrobot-v1":
+        # near the swing-up height: -cos(t1) - cos(t1+t2) ~ 1
+        t1 = rng.uniform(2.0, 2.2, size=n)
+        s[:, 0] = t1; s[:, 1] = rng.uniform(-0.3, 0.3, size=n)
+        s[:, 2:] = rng.uniform(-0.5, 0.5, size=(n, 2))
+        s = s.astype(np.float32)
+    return s
+
+
+def teacher_forced(name, states, actions, sbd=None):
+    n = len(states)
+    kind = KINDS[name]
+    aux = np.zeros((n, 2), np.int32)
+    aux[:, 0] = -1 if sbd is None else sbd
+    env = G.make(name, n, seed=3, auto_reset=False, time_limit=-1)
+    env.ResetBatch()
+    env.SetState(states, aux, 5)
+    obs, rew, done = env.StepBatch(actions)
+    st, ax, t = env.GetState()
+    assert t == 6
+    out = {"gpu": (obs, rew, done, st, ax)}
+    for mode in (O.MODE_F64_F32STORE, O.MODE_F32):
+        o = O.OracleEnv(kind, n, seed=3, auto_reset=False, time_limit=-1, mode=mode)
+        o.reset()
+        o.set_state(states.astype(np.float64), aux, 5)
+        oo, orr, od = o.step(actions)
+        ost, oax, _ = o.get_state()
+        out[mode] = (oo, orr, od, ost, oax)
+    env.Close()
+    return out
+
+
+@pytest.mark.parametrize("name", CLASSIC)
+@pytest.mark.parametrize("adversarial", [False, True])
+def test_t1_teacher_forced_single_step(name, adversarial):
+    rng = np.random.default_rng(11 + adversarial)
+    n = 1 << 18
+    states = adversarial_states(name, rng, n) if adversarial else random_states(name, rng, n)
+    env = G.make(name, 1)
+    actions = random_actions(env, rng, n)
+    env.Close()
+    sbd = rng.integers(-1, 3, size=n).astype(np.int32) if name == "CartPole-v1" else None
+    r = teacher_forced(name, states, actions, sbd)
+    obs, rew, done, st, ax = r["gpu"]
+    # --- vs the reference's arithmetic (F64, float32 store)
+    oo, orr, od, ost, oax = r[O.MODE_F64_F32STORE]
+    assert np.array_equal(done, od), "%d done flags differ from the F64 oracle" % int((done != od).sum())
+    assert np.array_equal(ax, oax)
+    assert rel_err(st, ost, STATE_SCALE[name]).max() <= RTOL
+    assert rel_err(obs, oo, 1.0).max() <= RTOL
+    assert rel_err(rew, orr, 1.0).max() <= RTOL
+    if adversarial and name != "Pendulum-v1":
+        assert 0 < done.sum() < n   # both outcomes are exercised next to the threshold
+    # --- vs the engine-arithmetic twin: bit for bit
+    oo, orr, od, ost, oax = r[O.MODE_F32]
+    assert np.array_equal(done, od) and np.array_equal(ax, oax)
+    assert np.array_equal(st, ost.astype(np.float32))
+    assert np.array_equal(obs, oo)
+    assert np.array_equal(rew, orr)
+
+
+@pytest.mark.parametrize("name", CLASSIC)
+def test_t2_free_running_rollout_bit_exact_vs_twin(name):
+    n, k = 4096, 600
+    env = G.make(name, n, seed=1234, auto_reset=True, env_id_offset=77)
+    o = O.OracleEnv(KINDS[name], n, seed=1234, auto_reset=True, env_id_offset=77, mode=O.MODE_F32)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    obs, rew, done, act = env.RolloutRandom(k)
+    oo, orr, od, oa = o.rollout_random(k)
+    assert np.array_equal(act, oa)
+    assert np.array_equal(done, od)
+    assert np.array_equal(rew, orr)
+    assert np.array_equal(obs, oo)
+    st, ax, t = env.GetState()
+    ost, oax, ot = o.get_state()
+    assert t == ot == k
+    assert np.array_equal(st, ost.astype(np.float32))
+    assert done.sum() > 0 or name == "MountainCarContinuous-v0"
+    assert env.Stats()["episodes"] == int(done.sum())
+    env.Close()
+
+
+@pytest.mark.parametrize("name", CLASSIC)
+def test_t2_trajectory_teacher_forced_vs_f64(name):
+    """Along a GPU trajectory, every transition agrees with the reference arithmetic: done bit-exact."""
+    n, k = 2048, 300
+    env = G.make(name, n, seed=5, auto_reset=True)
+    env.ResetBatch()
+    o = O.OracleEnv(KINDS[name], n, seed=5, auto_reset=True, mode=O.MODE_F64_F32STORE)
+    o.reset()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(k):
+        st, ax, t = env.GetState()
+        o.set_state(st.astype(np.float64), ax, t)
+        a = random_actions(env, rng, n)
+        obs, rew, done = env.StepBatch(a)
+        oo, orr, od = o.step(a)
+        assert np.array_equal(done, od)
+        nd = done == 0   # post-reset states are identical draws; compare the rest numerically
+        worst = max(worst, float(rel_err(obs[nd], oo[nd], 1.0).max(initial=0.0)))
+        assert np.array_equal(obs[~nd], oo[~nd])
+    assert worst <= RTOL
+    env.Close()
+
+
+def test_t3_reference_test_loop_shape():
+    """tests/Gym.Tests/Envs/Classic/CartpoleEnvironment.cs:19-30: 1000 iterations, Reset on done else Step(i % 2)."""
+    n = 64
+    env = G.CartPoleVecEnv(n, seed=0)
+    o = O.OracleEnv(O.CARTPOLE, n, seed=0, mode=O.MODE_F32)
+    done = np.ones(n, bool)
+    for i in range(1000):
+        if done.any():
+            m = done.astype(np.uint8)
+            assert np.array_equal(env.ResetBatch(mask=m), o.reset(mask=m))
+            done[:] = False
+        else:
+            a = np.full(n, i % 2, np.int32)
+            obs, rew, d = env.StepBatch(a)
+            oo, orr, od = o.step(a)
+            assert np.array_equal(obs, oo) and np.array_equal(rew, orr) and np.array_equal(d, od)
+            done = d.astype(bool)
+    env.Close()
+
+
+def test_ivecenv_surface_and_broadcast_step():
+    env = G.CartPoleVecEnv(8, seed=9)
+    obs = env.Reset()
+    assert len(obs) == 8 and obs[0].shape == (4,) and obs[0].dtype == np.float32
+    assert all(abs(v) <= 0.05 for o in obs for v in o)          # CartPoleEnv.cs:65
+    steps = env.Step(1)                                           # IVecEnv.Step(int action): broadcast
+    assert len(steps) == 8
+    ob, reward, done, info = steps[0]                             # Step.Deconstruct
+    assert reward == 1.0 and done is False and info is None
+    assert env.ActionSpace.N == 2 and env.ObservationSpace.Shape == (4,)
+    np.testing.assert_array_equal(env.ObservationSpace.High,
+                                  np.array([4.800000190734863, np.finfo(np.float32).max, 0.41887903213500977,
+                                            np.finfo(np.float32).max], np.float32))
+    env.Close()
+
+
+def test_cartpole_steps_beyond_done_quirk():
+    """CartPoleEnv.cs:168-183: reward 1 on the terminal step, then 0 with steps_beyond_done counting up."""
+    env = G.CartPoleVecEnv(2, seed=0, auto_reset=False)
+    env.ResetBatch()
+    st = np.array([[2.39, 3.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]], np.float32)
+    env.SetState(st, np.array([[-1, 0], [-1, 0]], np.int32), 0)
+    a = np.array([1, 1], np.int32)
+    _, r1, d1 = env.StepBatch(a)
+    _, r2, d2 = env.StepBatch(a)
+    _, r3, d3 = env.StepBatch(a)
+    assert list(d1) == [1, 0] and list(r1) == [1.0, 1.0]
+    assert d2[0] == 1 and r2[0] == 0.0 and d3[0] == 1 and r3[0] == 0.0
+    _, ax, _ = env.GetState()
+    assert ax[0, 0] == 2 and ax[1, 0] == -1
+    env.Close()
+
+
+def test_step_before_reset_is_estate():
+    env = G.CartPoleVecEnv(4)
+    with pytest.raises(G.GymCudaError) as ei:
+        env.StepBatch(np.zeros(4, np.int32))
+    assert ei.value.status == -6
+    env.Close()
+
+
+def test_invalid_actions():
+    # CartPole: Debug.Assert only (CartPoleEnv.cs:139): accepted, != 1 means "left"
+    env = G.CartPoleVecEnv(4, seed=1); env.ResetBatch()
+    o1, _, _ = env.StepBatch(np.array([7, 0, -3, 0], np.int32))
+    st, _, _ = env.GetState()
+    assert np.array_equal(st[0, 1] < 0, True) and st[0, 1] != 0
+    env.Close()
+    # the others reject: call returns EACTION (-> InvalidActionError), offending envs unstepped
+    env = G.AcrobotVecEnv(4, seed=1); before = env.ResetBatch()
+    with pytest.raises(G.InvalidActionError):
+        env.StepBatch(np.array([0, 3, 1, -1], np.int32))
+    after = env.Observe()
+    assert np.array_equal(after[1], before[1]) and np.array_equal(after[3], before[3])
+    assert not np.array_equal(after[0], before[0])
+    assert env.Stats()["invalid_actions"] == 2
+    env.Close()
+
+
+@pytest.mark.parametrize("name", ["CartPole-v1", "Acrobot-v1"])
+def test_t4_sharding_invariance(name):
+    """Global-env-id keyed streams: 2 shards of n/2 == 1 batch of n (what 8 GPUs rely on)."""
+    n, k = 2048, 200
+    full = G.make(name, n, seed=42, auto_reset=True)
+    full.ResetBatch()
+    fo, fr, fd, fa = full.RolloutRandom(k)
+    for part in range(2):
+        sh = G.make(name, n // 2, seed=42, auto_reset=True, env_id_offset=part * n // 2)
+        sh.ResetBatch()
+        so, sr, sd, sa = sh.RolloutRandom(k)
+        sl = slice(part * n // 2, (part + 1) * n // 2)
+        assert np.array_equal(so, fo[:, sl]) and np.array_equal(sd, fd[:, sl]) and np.array_equal(sa, fa[:, sl])
+        sh.Close()
+    full.Close()
+
+
+def test_t4_rollout_equals_repeated_step_and_k_split():
+    n = 1024
+    a_env = G.CartPoleVecEnv(n, seed=8, auto_reset=True); a_env.ResetBatch()
+    b_env = G.CartPoleVecEnv(n, seed=8, auto_reset=True); b_env.ResetBatch()
+    c_env = G.CartPoleVecEnv(n, seed=8, auto_reset=True); c_env.ResetBatch()
+    obs, rew, done, act = a_env.RolloutRandom(130)
+    parts = [b_env.RolloutRandom(k) for k in (1, 64, 65)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), obs)
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), done)
+    for t in range(130):
+        o, r, d = c_env.StepBatch(act[t])
+        assert np.array_equal(o, obs[t]) and np.array_equal(d, done[t]) and np.array_equal(r, rew[t])
+    for e in (a_env, b_env, c_env):
+        e.Close()
+
+
+def test_done_compaction_matches_mask():
+    n = 5000   # not a multiple of the block size: ragged tail
+    env = G.CartPoleVecEnv(n, seed=2, auto_reset=True); env.ResetBatch()
+    rng = np.random.default_rng(1)
+    seen = 0
+    for _ in range(60):
+        _, _, done = env.StepBatch(rng.integers(0, 2, n).astype(np.int32))
+        idx = env.DoneIndices()
+        assert np.array_equal(np.sort(idx), np.nonzero(done)[0])
+        seen += int(done.sum())
+    assert seen > 0 and env.Stats()["episodes"] == seen
+    env.Close()
+
+
+def test_seed_each_and_reseed():
+    n = 256
+    env = G.CartPoleVecEnv(n, seed=0)
+    o = O.OracleEnv(O.CARTPOLE, n, seed=0, mode=O.MODE_F32)
+    seeds = np.arange(1000, 1000 + n, dtype=np.int32)
+    env.Seed(seeds); o.seed_each(seeds)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    env.Seed(77); o.seed(77)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    with pytest.raises(ValueError):   # VecEnv.Seed(int[]) length check (VecEnv.cs:49)
+        env.Seed(np.arange(3, dtype=np.int32))
+    env.Close()
+
+
+@pytest.mark.parametrize("name,limit", [("Pendulum-v1", 200), ("MountainCar-v0", 200), ("Acrobot-v1", 500)])
+def test_time_limit_truncation(name, limit):
+    n = 512
+    env = G.make(name, n, seed=6, auto_reset=True); env.ResetBatch()
+    assert env.TimeLimit == limit
+    _, _, done, _ = env.RolloutRandom(limit + 1, want=("done",))
+    assert done[limit - 1].all() or name == "Acrobot-v1"
+    assert done[: limit - 1].sum() == 0 or name != "Pendulum-v1"
+    env.Close()
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 size (65 536 envs): size-independent properties of a long rollout."""
+    n, k = 65536, 256
+    env = G.CartPoleVecEnv(n, seed=0, auto_reset=True); env.ResetBatch()
+    obs, rew, done, act = env.RolloutRandom(k)
+    assert set(np.unique(act)) == {0, 1} and abs(act.mean() - 0.5) < 2e-3
+    assert (rew == 1.0).all()                       # auto-reset on: never steps beyond done
+    post = obs[done.astype(bool)]                   # observation returned at done is the post-reset one
+    assert np.abs(post).max() <= 0.05
+    alive = obs[~done.astype(bool)]
+    assert np.abs(alive[:, 0]).max() <= 2.4000001 and np.abs(alive[:, 2]).max() <= 0.2094396
+    lengths = k * n / max(1, done.sum())
+    assert 15 < lengths < 35                        # random-policy CartPole episodes last ~22 steps
+    assert env.Stats()["episodes"] == int(done.sum())
+    env.Close()
