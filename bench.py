@@ -97,57 +97,50 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_cpu_rate(env_name, n, seconds, threads):
-    """The reference's CPU path restated (oracle F64 = C# double arithmetic), serial per-env loop split
-    over `threads` host threads, random actions pre-generated.  Returns (env-steps/s, sample text)."""
+def _oracle_setup(env_name, n, threads, chunk):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     from helpers import KINDS
-    kind = KINDS[env_name]
-    o = O.OracleEnv(kind, n, seed=0, auto_reset=True, mode=O.MODE_F64)
+    o = O.OracleEnv(KINDS[env_name], n, seed=0, auto_reset=True, mode=O.MODE_F64)
     o.set_threads(threads)
     o.reset()
     rng = np.random.default_rng(0)
     d = o.d
-    acts = [rng.integers(0, d["act_n"], n).astype(np.int32) if d["act_n"] > 0
-            else rng.uniform(-1, 1, (n, d["act_dim"])).astype(np.float32) for _ in range(8)]
-    for i in range(3):
-        o.step(acts[i % 8])
-    steps, t0 = 0, time.perf_counter()
+    acts = (rng.integers(0, d["act_n"], (chunk, n)).astype(np.int32) if d["act_n"] > 0
+            else rng.uniform(-1, 1, (chunk, n, d["act_dim"])).astype(np.float32))
+    return o, acts
+
+
+def oracle_cpu_rate(env_name, n, seconds, threads, chunk=32):
+    """The reference's CPU path restated (oracle F64 = the C# double arithmetic of CartPoleEnv.Step),
+    per-env serial loops spread over `threads` host threads (the DistributedScheduler pool shape),
+    random actions pre-generated.  Returns (env-steps/s, sample text)."""
+    o, acts = _oracle_setup(env_name, n, threads, chunk)
+    o.step_many(acts)
+    calls, t0 = 0, time.perf_counter()
     while True:
-        o.step(acts[steps % 8]); steps += 1
+        o.step_many(acts); calls += 1
         el = time.perf_counter() - t0
-        if el >= seconds or steps >= 100000:
+        if el >= seconds or calls >= 100000:
             break
-    return n * steps / el, "%s, %d envs x %d batched steps in %.1f s, oracle F64 (C# double arithmetic), %d threads" % (
-        env_name, n, steps, el, threads)
+    return n * chunk * calls / el, "%s, %d envs x %d steps in %.1f s, oracle F64 port (C# double arithmetic), %d threads" % (
+        env_name, n, chunk * calls, el, threads)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is C#
-    (no dotnet/mono in this image) so oracle/_ref cannot be built; the CPU oracle port is timed."""
+    (no dotnet/mono in this image) so oracle/_ref cannot be built; the CPU oracle port is timed on
+    all host cores.  One bench step = `inner` batched steps of all num_envs envs (a bounded sample)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = args.num_envs
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    from helpers import KINDS
-    o = O.OracleEnv(KINDS[args.env], n, seed=0, auto_reset=True, mode=O.MODE_F64)
-    o.set_threads(cores)
-    o.reset()
-    rng = np.random.default_rng(0)
-    d = o.d
-    acts = [rng.integers(0, d["act_n"], n).astype(np.int32) if d["act_n"] > 0
-            else rng.uniform(-1, 1, (n, d["act_dim"])).astype(np.float32) for _ in range(8)]
-    inner = 16   # bounded sample per bench step: 16 batched steps of all n envs
-    for w in range(args.warmup):
-        for i in range(inner):
-            o.step(acts[i % 8])
+    n, inner = args.num_envs, 32
+    o, acts = _oracle_setup(args.env, n, cores, inner)
+    for w in range(max(1, args.warmup)):
+        o.step_many(acts)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        for i in range(inner):
-            o.step(acts[i % 8])
+        o.step_many(acts)
     el = time.perf_counter() - t0
     value = n * inner * args.steps / el
     line = {
@@ -186,7 +179,8 @@ def main():
     n, K = args.num_envs, args.inner
     env = G.make(args.env, n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True)
     od, ad = env.obs_dim, env.act_dim
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a real (non-NULL) stream: launches and events share it
+    torch.cuda.set_stream(stream)
     env.SetStream(stream.cuda_stream)
     env.ResetBatch()
 

@@ -100,11 +100,11 @@ struct KindInfo { int sd, aux, od, ad, actn, default_limit; };
 
 static bool kind_info(int kind, KindInfo* ki) {
     switch (kind) {
-        case GYMCUDA_CARTPOLE: *ki = {CartPole::SD, 2, CartPole::OD, CartPole::AD, CartPole::ACTN, CartPole::DEFAULT_LIMIT}; return true;
-        case GYMCUDA_PENDULUM: *ki = {Pendulum::SD, 2, Pendulum::OD, Pendulum::AD, Pendulum::ACTN, Pendulum::DEFAULT_LIMIT}; return true;
-        case GYMCUDA_MOUNTAINCAR: *ki = {MountainCar::SD, 2, MountainCar::OD, MountainCar::AD, MountainCar::ACTN, MountainCar::DEFAULT_LIMIT}; return true;
-        case GYMCUDA_MOUNTAINCAR_CONT: *ki = {MountainCarCont::SD, 2, MountainCarCont::OD, MountainCarCont::AD, MountainCarCont::ACTN, MountainCarCont::DEFAULT_LIMIT}; return true;
-        case GYMCUDA_ACROBOT: *ki = {Acrobot::SD, 2, Acrobot::OD, Acrobot::AD, Acrobot::ACTN, Acrobot::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_CARTPOLE: *ki = {CartPole::SD, 3, CartPole::OD, CartPole::AD, CartPole::ACTN, CartPole::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_PENDULUM: *ki = {Pendulum::SD, 3, Pendulum::OD, Pendulum::AD, Pendulum::ACTN, Pendulum::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_MOUNTAINCAR: *ki = {MountainCar::SD, 3, MountainCar::OD, MountainCar::AD, MountainCar::ACTN, MountainCar::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_MOUNTAINCAR_CONT: *ki = {MountainCarCont::SD, 3, MountainCarCont::OD, MountainCarCont::AD, MountainCarCont::ACTN, MountainCarCont::DEFAULT_LIMIT}; return true;
+        case GYMCUDA_ACROBOT: *ki = {Acrobot::SD, 3, Acrobot::OD, Acrobot::AD, Acrobot::ACTN, Acrobot::DEFAULT_LIMIT}; return true;
 #ifdef GYMCUDA_WITH_LUNAR
         case GYMCUDA_LUNARLANDER: *ki = {LunarLander::SD, LunarLander::AUX, 8, 1, 4, 0}; return true;
         case GYMCUDA_LUNARLANDER_CONT: *ki = {LunarLanderCont::SD, LunarLanderCont::AUX, 8, 2, 0, 0}; return true;
@@ -123,7 +123,7 @@ struct gymcuda_env {
     cudaStream_t own_stream, stream;
     // state
     void* d_state;
-    int32_t *d_sbd, *d_ept, *d_seeds;
+    int32_t *d_sbd, *d_ept, *d_episode, *d_seeds;
     // I/O staging for the host-buffer entry points
     void* d_actions;
     float *d_obs, *d_reward;
@@ -242,7 +242,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
-    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_seeds);
+    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds);
     cudaFree(e->d_actions); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done); cudaFree(e->d_mask);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats);
     if (e->h_small) cudaFreeHost(e->h_small);
@@ -264,6 +264,7 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMalloc(&e->d_state, state_bytes));
     CU_TRY(cudaMalloc(&e->d_sbd, n * 4));
     CU_TRY(cudaMalloc(&e->d_ept, n * 4));
+    CU_TRY(cudaMalloc(&e->d_episode, n * 4));
     CU_TRY(cudaMalloc(&e->d_actions, e->act_bytes()));
     CU_TRY(cudaMalloc(&e->d_obs, e->obs_bytes()));
     CU_TRY(cudaMalloc(&e->d_reward, n * 4));
@@ -276,6 +277,7 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMemsetAsync(e->d_state, 0, state_bytes, e->stream));
     CU_TRY(cudaMemsetAsync(e->d_sbd, 0xff, n * 4, e->stream));
     CU_TRY(cudaMemsetAsync(e->d_ept, 0, n * 4, e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_episode, 0, n * 4, e->stream));
     CU_TRY(cudaMemsetAsync(e->d_done_count, 0, 2 * sizeof(int32_t), e->stream));
     CU_TRY(cudaMemsetAsync(e->d_stats, 0, 2 * sizeof(unsigned long long), e->stream));
     CU_TRY(cudaMemsetAsync(e->d_obs, 0, e->obs_bytes(), e->stream));
@@ -364,7 +366,12 @@ int gymcuda_space(const gymcuda_env* e, gymcuda_space_info* o) {
 int gymcuda_seed(gymcuda_env* e, uint64_t seed) {
     ENTER(e);
     e->seed = seed;
-    if (e->d_seeds) { CU_TRY(cudaStreamSynchronize(e->stream)); CU_TRY(cudaFree(e->d_seeds)); e->d_seeds = nullptr; }
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    if (e->d_seeds) { CU_TRY(cudaFree(e->d_seeds)); e->d_seeds = nullptr; }
+    // a new generator restarts every stream (CartPoleEnv.cs:197 replaces the RandomState)
+    CU_TRY(cudaMemsetAsync(e->d_episode, 0, (size_t)e->n * 4, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->t = 0;
     return GYMCUDA_OK;
 }
 
@@ -375,7 +382,9 @@ int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
     if (n != e->n) return fail(GYMCUDA_EINVAL, "Number of seeds passed should be equals to number of environments");
     if (!e->d_seeds) CU_TRY(cudaMalloc(&e->d_seeds, (size_t)n * 4));
     CU_TRY(cudaMemcpyAsync(e->d_seeds, seeds, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_episode, 0, (size_t)e->n * 4, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
+    e->t = 0;
     return GYMCUDA_OK;
 }
 
@@ -384,7 +393,7 @@ int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
 // ------------------------------------------------------------------------------------------------
 static int reset_impl(gymcuda_env* e, const uint8_t* d_mask, float* obs_host) {
     ResetArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.mask = d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset;
     a.seed = e->seed; a.t = e->t;
     CU_TRY(dispatch_reset(e, a));
@@ -416,7 +425,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
                        float* d_reward, uint8_t* d_done) {
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
     StepArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
@@ -476,7 +485,7 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
     RolloutArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats;
     a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     CU_TRY(dispatch_rollout(e, a));
@@ -544,14 +553,15 @@ int gymcuda_get_state(gymcuda_env* e, float* state, int32_t* aux, uint64_t* t) {
     if (e->cfg.env_kind >= GYMCUDA_LUNARLANDER) { int rc = lunar_get_state(e, state, aux); if (rc) return rc; if (t) *t = e->t; return GYMCUDA_OK; }
 #endif
     if (state) CU_TRY(cudaMemcpyAsync(state, e->d_state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyDeviceToHost, e->stream));
-    std::vector<int32_t> sbd, ept;
+    std::vector<int32_t> sbd, ept, epi;
     if (aux) {
-        sbd.resize(e->n); ept.resize(e->n);
+        sbd.resize(e->n); ept.resize(e->n); epi.resize(e->n);
         CU_TRY(cudaMemcpyAsync(sbd.data(), e->d_sbd, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaMemcpyAsync(ept.data(), e->d_ept, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(epi.data(), e->d_episode, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
     }
     CU_TRY(cudaStreamSynchronize(e->stream));
-    if (aux) for (int i = 0; i < e->n; ++i) { aux[2 * i] = sbd[i]; aux[2 * i + 1] = ept[i]; }
+    if (aux) for (int i = 0; i < e->n; ++i) { aux[3 * i] = sbd[i]; aux[3 * i + 1] = ept[i]; aux[3 * i + 2] = epi[i]; }
     if (t) *t = e->t;
     return GYMCUDA_OK;
 }
@@ -562,12 +572,13 @@ int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, ui
     if (e->cfg.env_kind >= GYMCUDA_LUNARLANDER) { int rc = lunar_set_state(e, state, aux); if (rc) return rc; e->t = t; e->has_state = true; e->last_obs = nullptr; return GYMCUDA_OK; }
 #endif
     if (state) CU_TRY(cudaMemcpyAsync(e->d_state, state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyHostToDevice, e->stream));
-    std::vector<int32_t> sbd, ept;
+    std::vector<int32_t> sbd, ept, epi;
     if (aux) {
-        sbd.resize(e->n); ept.resize(e->n);
-        for (int i = 0; i < e->n; ++i) { sbd[i] = aux[2 * i]; ept[i] = aux[2 * i + 1]; }
+        sbd.resize(e->n); ept.resize(e->n); epi.resize(e->n);
+        for (int i = 0; i < e->n; ++i) { sbd[i] = aux[3 * i]; ept[i] = aux[3 * i + 1]; epi[i] = aux[3 * i + 2]; }
         CU_TRY(cudaMemcpyAsync(e->d_sbd, sbd.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
         CU_TRY(cudaMemcpyAsync(e->d_ept, ept.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->d_episode, epi.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
     }
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->t = t;
@@ -579,7 +590,7 @@ int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, ui
 static int observe_device(gymcuda_env* e) {
     // a masked reset with an all-zero mask only recomputes observations from the stored state
     ResetArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     CU_TRY(cudaMemsetAsync(e->d_mask, 0, (size_t)e->n, e->stream));
     a.mask = e->d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t;
     CU_TRY(dispatch_reset(e, a));

@@ -17,8 +17,12 @@
 //   state   Vec[n]      float4 (CartPole, Acrobot) or float2 (Pendulum, MountainCar*)
 //   sbd     int32[n]    CartPole steps_beyond_done (touched only when auto-reset is off)
 //   ep_t    int32[n]    episode step counter (touched only when a time limit is set)
+//   episode int32[n]    number of resets the env has had = index of its next RESET draw
+//                       (touched only by lanes that reset)
 //   seeds   int32[n]    optional per-env seeds (VecEnv.Seed(int[]))
-// No RNG state lives in memory: draws are functions of (seed, env id, t).
+// No generator state lives in memory: action draws are functions of (seed, env id, t), reset draws of
+// (seed, env id, episode ordinal) -- which is what lets the rollout kernel pre-generate the next
+// initial state and refill it for the whole warp at once instead of diverging at every `done`.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -32,6 +36,7 @@ struct StepArgs {
     void* state;
     int32_t* sbd;
     int32_t* ep_t;
+    int32_t* episode;
     const int32_t* seeds;
     const void* actions;
     float* obs;
@@ -54,6 +59,7 @@ struct RolloutArgs {
     void* state;
     int32_t* sbd;
     int32_t* ep_t;
+    int32_t* episode;
     const int32_t* seeds;
     float* obs;        // [k][n][OD]   may be null
     float* reward;     // [k][n]       may be null
@@ -72,6 +78,7 @@ struct ResetArgs {
     void* state;
     int32_t* sbd;
     int32_t* ep_t;
+    int32_t* episode;
     const int32_t* seeds;
     const uint8_t* mask;   // may be null = all
     float* obs;            // may be null
@@ -182,7 +189,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
             r = E::step(s, a, sbd);
             if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }   // truncation folded into done
             if (AUTO_RESET && r.done) {
-                E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, p.t + 1, STREAM_RESET));
+                const int32_t ep = p.episode[i];
+                E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, (uint64_t)(uint32_t)ep, STREAM_RESET));
+                p.episode[i] = ep + 1;
                 sbd = -1;
                 ept = 0;
             }
@@ -232,6 +241,12 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
 
 // ---------------------------------------------------------------- fused random-policy rollout
 constexpr int ROLLOUT_BLOCK = 64;
+constexpr int ROLLOUT_REFILL = 8;   // steps between warp-wide refills of the pre-generated reset state
+
+template <class E>
+__device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint32_t gid, int32_t ep) {
+    E::reset(next, draw(seed, gid, (uint64_t)(uint32_t)ep, STREAM_RESET));
+}
 
 template <class E, bool AUTO_RESET, bool LIMIT>
 __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
@@ -248,15 +263,28 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         const uint32_t gid = p.env_off + (uint32_t)i;
         ActionGen<E> gen;
         const size_t n = (size_t)p.n;
+        // next initial state, pre-generated: consumed at `done`, refilled for all lanes of the warp that
+        // need it every REFILL steps (one Philox evaluation per warp per refill instead of per done)
+        int32_t ep = 0;
+        if (AUTO_RESET) ep = p.episode[i];
+        S next = s;
+        bool have = false;
         for (int k = 0; k < p.k_steps; ++k) {
             const uint64_t t = p.t + (uint64_t)k;
+            if (AUTO_RESET && (k & (ROLLOUT_REFILL - 1)) == 0 && !have) {
+                E::reset(next, draw(seed, gid, (uint64_t)(uint32_t)ep, STREAM_RESET));
+                have = true;
+            }
             const typename E::Act a = gen.next(seed, gid, t, k == 0);
             StepOut r = E::step(s, a, sbd);
             if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }
             if (r.done) {
                 episodes += 1;
                 if (AUTO_RESET) {
-                    E::reset(s, draw(seed, gid, t + 1, STREAM_RESET));
+                    if (!have) reset_cold<E>(next, seed, gid, ep);   // second done before the refill: rare
+                    s = next;
+                    have = false;
+                    ep += 1;
                     sbd = -1;
                     ept = 0;
                 }
@@ -271,6 +299,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             if (p.done) __stcs(p.done + idx, (uint8_t)r.done);
             if (p.actions) ActIO<E>::store(p.actions, idx, a);
         }
+        if (AUTO_RESET) p.episode[i] = ep;
         E::store(p.state, i, s);
         if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
         if (LIMIT) p.ep_t[i] = ept;
@@ -289,8 +318,10 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
     if (i >= p.n) return;
     S s;
     if (p.mask == nullptr || p.mask[i]) {
-        E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, p.t, STREAM_RESET));
+        const int32_t ep = p.episode[i];
+        E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, (uint64_t)(uint32_t)ep, STREAM_RESET));
         E::store(p.state, i, s);
+        p.episode[i] = ep + 1;
         p.sbd[i] = -1;     // CartPoleEnv.cs:64
         p.ep_t[i] = 0;
     } else {

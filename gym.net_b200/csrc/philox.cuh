@@ -7,6 +7,8 @@
 //
 //   key = (seed_lo, global_env_id)
 //   ctr = (index_lo, index_hi, stream | sub << 8, seed_hi)
+// index: RESET = episode ordinal of the env (how many resets it has had), ACTION = block number
+// of the random-policy draw at global step t, DYNAMICS = global step t.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -158,7 +158,7 @@ int gymcuda_get_stats(gymcuda_env* env, gymcuda_stats* out, int reset_counters);
 
 /* ---- streams, pinned memory -------------------------------------------------------------------- */
 /* Use the caller's CUDA stream (cudaStream_t) for every launch and copy; NULL restores the
- * handle's own stream. */
+ * handle's own stream (to target the legacy default stream pass cudaStreamLegacy, not 0). */
 int gymcuda_set_stream(gymcuda_env* env, void* cuda_stream);
 int gymcuda_sync(gymcuda_env* env);
 int gymcuda_host_alloc(void** ptr, size_t bytes); /* pinned (page-locked) host memory */

@@ -25,11 +25,11 @@ using namespace oracle;
 
 struct KindInfo { int sd, ad, od, actd, actn, default_limit; };
 static const KindInfo KINDS[] = {
-    /* CARTPOLE         */ {4, 2, 4, 1, 2, 0},
-    /* PENDULUM         */ {2, 2, 3, 1, 0, 200},
-    /* MOUNTAINCAR      */ {2, 2, 2, 1, 3, 200},
-    /* MOUNTAINCAR_CONT */ {2, 2, 2, 1, 0, 999},
-    /* ACROBOT          */ {4, 2, 6, 1, 3, 500},
+    /* CARTPOLE         */ {4, 3, 4, 1, 2, 0},
+    /* PENDULUM         */ {2, 3, 3, 1, 0, 200},
+    /* MOUNTAINCAR      */ {2, 3, 2, 1, 3, 200},
+    /* MOUNTAINCAR_CONT */ {2, 3, 2, 1, 0, 999},
+    /* ACROBOT          */ {4, 3, 6, 1, 3, 500},
 #ifdef ORACLE_WITH_LUNAR
     /* LUNARLANDER      */ {lunar::STATE_DIM, lunar::AUX_DIM, 8, 1, 4, 0},
     /* LUNARLANDER_CONT */ {lunar::STATE_DIM, lunar::AUX_DIM, 8, 2, 0, 0},
@@ -44,7 +44,7 @@ struct oracle_env {
     KindInfo ki;
     std::vector<double> sd;      // F64 modes
     std::vector<float> sf;       // F32 mode
-    std::vector<int32_t> aux;    // [n][ad]: classic = {steps_beyond_done, episode_step}
+    std::vector<int32_t> aux;    // [n][ad]: classic = {steps_beyond_done, episode_step, episode ordinal}
     std::vector<int32_t> seeds;  // optional per-env seeds (VecEnv.Seed(int[]), src/Gym/Envs/VecEnv.cs:48-53)
 #ifdef ORACLE_WITH_LUNAR
     std::vector<lunar::Lander> landers;
@@ -86,8 +86,12 @@ static void write_obs(oracle_env* e, int i, float* obs) {
     }
 }
 
-// Reset of instance i; `index` is the t of the step that follows (RNG spec v1).
-static void reset_one(oracle_env* e, int i, uint64_t index) {
+// Reset of instance i: the RESET draw is indexed by the env's episode ordinal (RNG spec v1).
+static void reset_one(oracle_env* e, int i) {
+    int32_t* auxp = &e->aux[(size_t)i * e->ki.ad];
+    const int ORD = e->is_lunar() ? e->ki.ad - 1 : 2;
+    const uint64_t index = (uint64_t)(uint32_t)auxp[ORD];
+    auxp[ORD] += 1;
     const uint32_t gid = e->off + (uint32_t)i;
     const uint64_t seed = e->seed_of(i);
 #ifdef ORACLE_WITH_LUNAR
@@ -125,7 +129,8 @@ static void reset_one(oracle_env* e, int i, uint64_t index) {
 static bool action_valid(const oracle_env* e, int a) { return a >= 0 && a < e->ki.actn; }
 
 // One instance, one step.  Returns 1 if the action was invalid (instance left untouched).
-static int step_one(oracle_env* e, int i, const void* actions, float* obs, float* reward, uint8_t* done) {
+static int step_one_t(oracle_env* e, int i, const void* actions, float* obs, float* reward, uint8_t* done, uint64_t now) {
+    (void)now;   // used by the DYNAMICS stream of LunarLander only
     const KindInfo& ki = e->ki;
     int ia = 0; const float* fa = nullptr;
     if (ki.actn > 0) ia = ((const int32_t*)actions)[i];
@@ -137,9 +142,9 @@ static int step_one(oracle_env* e, int i, const void* actions, float* obs, float
     if (e->is_lunar()) {
         if (ki.actn > 0 && !action_valid(e, ia)) invalid = 1;   // LunarLanderEnv.cs:604-607 throws InvalidActionError
         else {
-            lunar::StepResult lr = lunar::step(e->landers[i], e->seed_of(i), e->off + (uint32_t)i, e->t, ia, fa);
+            lunar::StepResult lr = lunar::step(e->landers[i], e->seed_of(i), e->off + (uint32_t)i, now, ia, fa);
             r.reward = lr.reward; r.done = lr.done;
-            aux[1] += 1;
+            if (e->limit > 0) aux[1] += 1;
         }
     } else
 #endif
@@ -166,15 +171,22 @@ static int step_one(oracle_env* e, int i, const void* actions, float* obs, float
             }
             if (e->mode == ORACLE_MODE_F64_F32STORE)
                 for (int k = 0; k < ki.sd; ++k) d[k] = (double)(float)d[k];
-            aux[1] += 1;
+            if (e->limit > 0) aux[1] += 1;   // the episode-step counter exists only under a time limit
         }
     }
     if (!invalid && e->limit > 0 && aux[1] >= e->limit) r.done = 1;   // truncation folded into done
-    if (!invalid && r.done && (e->flags & ORACLE_FLAG_AUTO_RESET)) reset_one(e, i, e->t + 1);
+    if (!invalid && r.done && (e->flags & ORACLE_FLAG_AUTO_RESET)) reset_one(e, i);
     write_obs(e, i, obs);
     if (reward) reward[i] = r.reward;
     if (done) done[i] = r.done;
     return invalid;
+}
+
+static int step_one(oracle_env* e, int i, const void* actions, float* obs, float* reward, uint8_t* done) {
+    return step_one_t(e, i, actions, obs, reward, done, e->t);
+}
+static int step_one_at(oracle_env* e, int i, const void* actions, uint64_t now) {
+    return step_one_t(e, i, actions, nullptr, nullptr, nullptr, now);
 }
 
 template <class F>
@@ -219,19 +231,24 @@ oracle_env* oracle_create(int kind, int n, uint64_t seed, uint32_t off, uint32_t
 }
 
 void oracle_destroy(oracle_env* e) { delete e; }
-void oracle_seed(oracle_env* e, uint64_t seed) { e->seed = seed; e->seeds.clear(); }
-void oracle_seed_each(oracle_env* e, const int32_t* seeds) { e->seeds.assign(seeds, seeds + e->n); }
+static void restart_streams(oracle_env* e) {   // a new generator restarts every stream (CartPoleEnv.cs:197)
+    const int ORD = e->is_lunar() ? e->ki.ad - 1 : 2;
+    for (int i = 0; i < e->n; ++i) e->aux[(size_t)i * e->ki.ad + ORD] = 0;
+    e->t = 0;
+}
+void oracle_seed(oracle_env* e, uint64_t seed) { e->seed = seed; e->seeds.clear(); restart_streams(e); }
+void oracle_seed_each(oracle_env* e, const int32_t* seeds) { e->seeds.assign(seeds, seeds + e->n); restart_streams(e); }
 void oracle_set_threads(oracle_env* e, int threads) { e->threads = threads < 1 ? 1 : threads; }
 
 void oracle_reset(oracle_env* e, float* obs) {
     parallel_for(e->n, e->threads, [=](int lo, int hi) {
-        for (int i = lo; i < hi; ++i) { reset_one(e, i, e->t); write_obs(e, i, obs); }
+        for (int i = lo; i < hi; ++i) { reset_one(e, i); write_obs(e, i, obs); }
     });
 }
 
 void oracle_reset_masked(oracle_env* e, const uint8_t* mask, float* obs) {
     for (int i = 0; i < e->n; ++i) {
-        if (mask[i]) reset_one(e, i, e->t);
+        if (mask[i]) reset_one(e, i);
         write_obs(e, i, obs);
     }
 }
@@ -244,6 +261,24 @@ int oracle_step(oracle_env* e, const void* actions, float* obs, float* reward, u
         bad += c;
     });
     e->t += 1;
+    return bad.load();
+}
+
+// K steps with pre-generated actions [K][n][act_dim], no outputs: each host thread runs its slice of
+// independent envs through all K steps (one thread launch per call) -- the CPU-baseline timing loop.
+int oracle_step_many(oracle_env* e, int K, const void* actions) {
+    std::atomic<int> bad{0};
+    const size_t stride = (size_t)e->n * (e->ki.actn > 0 ? 1 : e->ki.actd) * 4;
+    const uint64_t t0 = e->t;
+    parallel_for(e->n, e->threads, [&](int lo, int hi) {
+        int c = 0;
+        for (int k = 0; k < K; ++k) {
+            const char* act = (const char*)actions + (size_t)k * stride;
+            for (int i = lo; i < hi; ++i) c += step_one_at(e, i, act, t0 + (uint64_t)k);
+        }
+        bad += c;
+    });
+    e->t = t0 + (uint64_t)K;
     return bad.load();
 }
 

@@ -51,6 +51,8 @@ void oracle_reset(oracle_env*, float* obs);
 void oracle_reset_masked(oracle_env*, const uint8_t* mask, float* obs);
 /* actions: int32[n] (discrete) or float[n*act_dim] (box).  Returns the number of invalid actions. */
 int oracle_step(oracle_env*, const void* actions, float* obs, float* reward, uint8_t* done);
+/* K steps with pre-generated actions [K][n][act_dim] and no outputs (CPU-baseline timing loop). */
+int oracle_step_many(oracle_env*, int k_steps, const void* actions);
 /* K steps of the random policy; any output pointer may be NULL.  Layouts [K][n][dim]. */
 void oracle_rollout_random(oracle_env*, int k_steps, float* obs, float* reward, uint8_t* done,
                            void* actions);

@@ -16,7 +16,7 @@
 // Addressing (one 128-bit block per call):
 //     key = (seed_lo, global_env_id)
 //     ctr = (index_lo, index_hi, stream | sub << 8, seed_hi)
-// stream 0 = RESET    index = t of the step that FOLLOWS the reset
+// stream 0 = RESET    index = episode ordinal of the env (number of resets it has had)
 // stream 1 = ACTION   index = block number of the random-policy draw (see action_*)
 // stream 2 = DYNAMICS index = t (LunarLander's two per-step dispersion draws)
 #pragma once

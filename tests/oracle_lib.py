@@ -44,6 +44,8 @@ def lib():
         L.oracle_reset_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.oracle_step.restype = C.c_int
+        L.oracle_step_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_step_many.restype = C.c_int
         L.oracle_rollout_random.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.oracle_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -119,6 +121,11 @@ class OracleEnv:
         bad = lib().oracle_step(self.h, _p(a), _p(obs), _p(rew), _p(done))
         self.invalid = bad
         return obs, rew, done
+
+    def step_many(self, actions):
+        """actions [K][n](,act_dim): K steps, no outputs (timing loop)."""
+        a = np.ascontiguousarray(actions, dtype=np.int32 if self.discrete else np.float32)
+        return lib().oracle_step_many(self.h, a.shape[0], _p(a))
 
     def rollout_random(self, k, want_obs=True):
         obs = np.empty((k, self.n, self.d["obs_dim"]), np.float32) if want_obs else None
