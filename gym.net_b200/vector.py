@@ -218,6 +218,17 @@ class CudaVecEnv:
         return [Step(obs[i], float(rew[i]), bool(done[i]), None) for i in range(self.NumberOfEnvironments)]
 
 
+def shard_envs(total_envs, rank, world_size):
+    """Contiguous shard of a global batch: (num_envs, env_id_offset) of `rank`.  Global env id =
+    env_id_offset + local id keys the Philox streams, so trajectories do not depend on the GPU count."""
+    if not (0 <= rank < world_size) or total_envs < world_size:
+        raise ValueError("bad shard request: total=%d rank=%d world=%d" % (total_envs, rank, world_size))
+    base, extra = divmod(int(total_envs), int(world_size))
+    n = base + (1 if rank < extra else 0)
+    off = rank * base + min(rank, extra)
+    return n, off
+
+
 def nccl_unique_id():
     buf = (C.c_uint8 * 128)()
     N.check(N.lib().gymcuda_nccl_unique_id(buf))

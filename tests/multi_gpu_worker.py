@@ -1,0 +1,39 @@
+"""torchrun worker of tests/test_gpu_multi.py: one process per GPU, independent env shards, then the
+optional NCCL all-gather of observations (gymcuda_allgather_obs).  torch.distributed only ships the
+128-byte ncclUniqueId between ranks."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gymnet_b200 as G  # noqa: E402
+
+
+def main():
+    out_dir = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    total = 4096
+    n, off = G.shard_envs(total, rank, world)
+    env = G.CartPoleVecEnv(n, seed=21, device=local, env_id_offset=off, auto_reset=True)
+    ids = [G.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    env.CommInit(ids[0], rank, world)
+    env.ResetBatch()
+    env.RolloutRandom(50, want=())
+    out = torch.empty((world, n, env.obs_dim), dtype=torch.float32, device="cuda")
+    env.AllGatherObs(out.data_ptr())        # observations recomputed from state, gathered over NVLink
+    env.Sync()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), out.cpu().numpy())
+    dist.barrier()
+    env.Close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
