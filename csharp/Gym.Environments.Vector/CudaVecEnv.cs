@@ -1,0 +1,138 @@
+// Gym.Environments.Vector.CudaVecEnv -- the drop-in VecEnv over libgymcuda.
+// Derives from the reference's VecEnv (src/Gym/Envs/VecEnv.cs:12-93) and keeps IVecEnv
+// (src/Gym/Envs/IVecEnv.cs:8-19) source-compatible: Reset() -> NDArray[], Step(int) -> Step[],
+// Seed(int), Seed(int[]), Close().  The batched overloads are what a learner should call.
+// NOT compiled here (no .NET SDK in the build image); mirrored 1:1 by gym.net_b200/vector.py, which
+// is what the parity tests drive.
+using System;
+using System.Collections.Generic;
+using Gym.Envs;
+using Gym.Observations;
+using Gym.Spaces;
+using NumSharp;
+
+namespace Gym.Environments.Vector {
+    public class CudaVecEnv : VecEnv, IDisposable {
+        private readonly GymCudaHandle _h;
+        private readonly GymCudaSpaceInfo _info;
+        private readonly float[] _obs, _reward;
+        private readonly byte[] _done;
+
+        public int ObsDim => _info.ObsDim;
+        public int ActDim => _info.ActDim;
+        public bool AutoReset { get; }
+
+        protected CudaVecEnv(GymCudaEnvKind kind, int numEnvs, Space observationSpace, Space actionSpace, ulong seed = 0,
+                             int device = 0, uint envIdOffset = 0, bool autoReset = false, int timeLimit = 0,
+                             Action<GymCudaConfigBox> configure = null)
+            : base(numEnvs, observationSpace, actionSpace) {
+            Native.Check(Native.gymcuda_config_default(out var cfg, (int) kind, numEnvs));
+            cfg.Seed = seed; cfg.Device = device; cfg.EnvIdOffset = envIdOffset; cfg.TimeLimit = timeLimit;
+            cfg.Flags = autoReset ? (uint) GymCudaFlags.AutoReset : 0u;
+            if (configure != null) { var box = new GymCudaConfigBox { Value = cfg }; configure(box); cfg = box.Value; }
+            Native.Check(Native.gymcuda_create(ref cfg, out _h));
+            Native.Check(Native.gymcuda_space(_h, out _info));
+            AutoReset = autoReset;
+            _obs = new float[numEnvs * _info.ObsDim];
+            _reward = new float[numEnvs];
+            _done = new byte[numEnvs];
+        }
+
+        // ---- IVecEnv -------------------------------------------------------------------------
+        public override NDArray[] Reset() {
+            Native.Check(Native.gymcuda_reset(_h, _obs));
+            return SplitObservations();
+        }
+
+        /// <summary>IVecEnv.Step(int action): ONE action broadcast to all envs (VecEnvWrapper.cs:22-24).</summary>
+        public override Step[] Step(int action) {
+            Native.Check(Native.gymcuda_step_broadcast(_h, action, _obs, _reward, _done));
+            var obs = SplitObservations();
+            var steps = new Step[NumberOfEnvironments];
+            for (int i = 0; i < steps.Length; i++) steps[i] = new Step(obs[i], _reward[i], _done[i] != 0, null);
+            return steps;
+        }
+
+        public override void Close() { _h.Dispose(); }
+        public void Dispose() { Close(); }
+
+        public new void Seed(int seed) { Native.Check(Native.gymcuda_seed(_h, (ulong) (uint) seed)); }
+        public new void Seed(int[] seed) { Native.Check(Native.gymcuda_seed_each(_h, seed, seed.Length)); }   // length check -> ArgumentException, as VecEnv.cs:49
+
+        // ---- batched API ---------------------------------------------------------------------
+        public (float[] obs, float[] reward, byte[] done) Step(int[] actions) {
+            Native.Check(Native.gymcuda_step(_h, actions, _obs, _reward, _done));
+            return (_obs, _reward, _done);
+        }
+        public (float[] obs, float[] reward, byte[] done) Step(float[] actions) {
+            Native.Check(Native.gymcuda_step(_h, actions, _obs, _reward, _done));
+            return (_obs, _reward, _done);
+        }
+        public float[] Reset(byte[] mask) { Native.Check(Native.gymcuda_reset_masked(_h, mask, _obs)); return _obs; }
+        public void RolloutRandom(int kSteps, float[] obs, float[] reward, byte[] done, int[] actions) {
+            Native.Check(Native.gymcuda_rollout_random(_h, kSteps, obs, reward, done, actions));
+        }
+        public int[] DoneIndices() {
+            var idx = new int[NumberOfEnvironments];
+            Native.Check(Native.gymcuda_done_indices(_h, idx, out int count));
+            Array.Resize(ref idx, count);
+            return idx;
+        }
+        public GymCudaStats Stats(bool reset = false) { Native.Check(Native.gymcuda_get_stats(_h, out var s, reset ? 1 : 0)); return s; }
+
+        private NDArray[] SplitObservations() {
+            var res = new NDArray[NumberOfEnvironments];
+            int d = _info.ObsDim;
+            for (int i = 0; i < res.Length; i++) {
+                var row = new float[d];
+                Array.Copy(_obs, i * d, row, 0, d);
+                res[i] = np.array(row);
+            }
+            return res;
+        }
+    }
+
+    public sealed class GymCudaConfigBox { public GymCudaConfig Value; }
+
+    /// <summary>Batched CartPoleEnv: spaces as CartPoleEnv.cs:46-48.</summary>
+    public sealed class CartPoleVecEnv : CudaVecEnv {
+        public CartPoleVecEnv(int numEnvs, ulong seed = 0, int device = 0, uint envIdOffset = 0, bool autoReset = false, int timeLimit = 0)
+            : base(GymCudaEnvKind.CartPole, numEnvs,
+                   new Box(-1 * High(), High(), np.float32), new Discrete(2), seed, device, envIdOffset, autoReset, timeLimit) { }
+        private static NDArray High() { return np.array(2.4f * 2, float.MaxValue, (float) (12 * 2 * Math.PI / 360) * 2, float.MaxValue); }
+    }
+
+    /// <summary>Batched LunarLanderEnv: spaces as LunarLanderEnv.cs:412-422.</summary>
+    public sealed class LunarLanderVecEnv : CudaVecEnv {
+        public LunarLanderVecEnv(int numEnvs, bool continuous = false, float gravity = -10f, bool enableWind = false,
+                                 float windPower = 15f, float turbulencePower = 1.5f, ulong seed = 0, int device = 0,
+                                 uint envIdOffset = 0, bool autoReset = false)
+            : base(continuous ? GymCudaEnvKind.LunarLanderContinuous : GymCudaEnvKind.LunarLander, numEnvs,
+                   new Box(np.array(new float[] {-1.5f, -1.5f, -5f, -5f, (float) -Math.PI, -5f, 0f, 0f}),
+                           np.array(new float[] {1.5f, 1.5f, 5f, 5f, (float) Math.PI, 5f, 1f, 1f})),
+                   continuous ? (Space) new Box(-1f, 1f, new Shape(2)) : new Discrete(4),
+                   seed, device, envIdOffset, autoReset, 0,
+                   c => { c.Value.Gravity = gravity; c.Value.EnableWind = enableWind ? 1 : 0; c.Value.WindPower = windPower; c.Value.TurbulencePower = turbulencePower; }) { }
+    }
+
+    public sealed class PendulumVecEnv : CudaVecEnv {
+        public PendulumVecEnv(int numEnvs, ulong seed = 0, int device = 0, uint envIdOffset = 0, bool autoReset = false, int timeLimit = 0)
+            : base(GymCudaEnvKind.Pendulum, numEnvs, new Box(np.array(-1f, -1f, -8f), np.array(1f, 1f, 8f), np.float32),
+                   new Box(-2f, 2f, new Shape(1)), seed, device, envIdOffset, autoReset, timeLimit) { }
+    }
+
+    public sealed class MountainCarVecEnv : CudaVecEnv {
+        public MountainCarVecEnv(int numEnvs, bool continuous = false, ulong seed = 0, int device = 0, uint envIdOffset = 0, bool autoReset = false, int timeLimit = 0)
+            : base(continuous ? GymCudaEnvKind.MountainCarContinuous : GymCudaEnvKind.MountainCar, numEnvs,
+                   new Box(np.array(-1.2f, -0.07f), np.array(0.6f, 0.07f), np.float32),
+                   continuous ? (Space) new Box(-1f, 1f, new Shape(1)) : new Discrete(3), seed, device, envIdOffset, autoReset, timeLimit) { }
+    }
+
+    public sealed class AcrobotVecEnv : CudaVecEnv {
+        public AcrobotVecEnv(int numEnvs, ulong seed = 0, int device = 0, uint envIdOffset = 0, bool autoReset = false, int timeLimit = 0)
+            : base(GymCudaEnvKind.Acrobot, numEnvs,
+                   new Box(np.array(-1f, -1f, -1f, -1f, (float) (-4 * Math.PI), (float) (-9 * Math.PI)),
+                           np.array(1f, 1f, 1f, 1f, (float) (4 * Math.PI), (float) (9 * Math.PI)), np.float32),
+                   new Discrete(3), seed, device, envIdOffset, autoReset, timeLimit) { }
+    }
+}

@@ -172,7 +172,8 @@ def test_t2_trajectory_teacher_forced_vs_f64(name):
         gs, _, _ = env.GetState()
         os_, _, _ = o.get_state()
         worst = max(worst, float(state_err(name, gs[nd], os_[nd]).max(initial=0.0)))
-        assert np.array_equal(obs[~nd], oo[~nd])
+        assert np.array_equal(gs[~nd], os_[~nd].astype(np.float32))      # same reset draws
+        assert np.abs(obs[~nd] - oo[~nd]).max(initial=0.0) <= RTOL        # obs of them: detmath vs libm cos/sin
         assert (np.abs(rew.astype(np.float64) - orr) <= reward_atol(name, st, orr)).all()
     assert worst <= RTOL
     env.Close()
