@@ -24,12 +24,17 @@ namespace gymcuda {
 
 struct StepOut { float reward; bool done; };
 
+// constructor arguments of the env (LunarLanderEnv.cs:381); unused by the classic-control family
+struct EnvParams { float gravity, wind_power, turbulence_power; int32_t use_wind; };
+
 // ------------------------------------------------------------------------------------------------
 // CartPole: src/Gym.Environments/Envs/Classic/CartPoleEnv.cs
 // ------------------------------------------------------------------------------------------------
 struct CartPole {
     static constexpr int SD = 4, OD = 4, AD = 1, ACTN = 2, DEFAULT_LIMIT = 0;
     static constexpr bool HAS_SBD = true;     // steps_beyond_done (CartPoleEnv.cs:41)
+    static constexpr bool PREGEN_RESET = true;   // rollout kernel pre-generates the next initial state
+    static constexpr int AUXW = 0;               // extra int32 words per env in HBM
     static constexpr bool REJECT_INVALID = false;  // Debug.Assert only (CartPoleEnv.cs:139)
     using Vec = float4;
     using Act = int32_t;
@@ -48,15 +53,16 @@ struct CartPole {
     static constexpr float K1 = 0.04545454680919647f;                // length * masspole / total_mass
     static constexpr float PML_OVER_M = 0.04545454680919647f;        // polemass_length / total_mass
 
-    __device__ static __forceinline__ S load(const void* base, int i) {
+    __device__ static __forceinline__ S load(const void* base, const int32_t*, int, int i, const EnvParams&) {
         const float4 v = reinterpret_cast<const float4*>(base)[i];
         return S{v.x, v.y, v.z, v.w};
     }
-    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+    __device__ static __forceinline__ void store(void* base, int32_t*, int, int i, const S& s) {
         reinterpret_cast<float4*>(base)[i] = make_float4(s.x, s.x_dot, s.theta, s.theta_dot);
     }
     // CartPoleEnv.cs:65  state = uniform(-0.05, 0.05, 4)
-    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+    __device__ static __forceinline__ void reset(S& s, uint64_t seed, uint32_t gid, uint32_t ordinal, uint64_t, const EnvParams&) {
+        const Block b = draw(seed, gid, (uint64_t)ordinal, STREAM_RESET);
         s.x = uniformf(-0.05f, 0.05f, b.w0);
         s.x_dot = uniformf(-0.05f, 0.05f, b.w1);
         s.theta = uniformf(-0.05f, 0.05f, b.w2);
@@ -67,7 +73,7 @@ struct CartPole {
     // CartPoleEnv.cs:137-186.  Accelerations (:146-151) in float32; the position updates (:154,:156)
     // and the termination test (:167) with the reference's own double operations, so x, theta and
     // `done` are exactly the reference's values from the same float32 state.
-    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t& sbd) {
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t& sbd, uint64_t, uint32_t, uint64_t) {
         const float force = (a == 1) ? FORCE_MAG : -FORCE_MAG;                         // :146
         float sn, cs;
         sincosf_det(s.theta, &sn, &cs);                                                // :147-148
@@ -108,25 +114,28 @@ __device__ __forceinline__ float py_modf32(float a, float b) {   // Python float
 struct Pendulum {
     static constexpr int SD = 2, OD = 3, AD = 1, ACTN = 0, DEFAULT_LIMIT = 200;
     static constexpr bool HAS_SBD = false;
+    static constexpr bool PREGEN_RESET = true;
+    static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
     static constexpr float ACT_LOW = -2.0f, ACT_HIGH = 2.0f;
     using Vec = float2;
     using Act = float;
     struct S { float th, thdot; };
-    __device__ static __forceinline__ S load(const void* base, int i) {
+    __device__ static __forceinline__ S load(const void* base, const int32_t*, int, int i, const EnvParams&) {
         const float2 v = reinterpret_cast<const float2*>(base)[i];
         return S{v.x, v.y};
     }
-    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+    __device__ static __forceinline__ void store(void* base, int32_t*, int, int i, const S& s) {
         reinterpret_cast<float2*>(base)[i] = make_float2(s.th, s.thdot);
     }
-    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+    __device__ static __forceinline__ void reset(S& s, uint64_t seed, uint32_t gid, uint32_t ordinal, uint64_t, const EnvParams&) {
+        const Block b = draw(seed, gid, (uint64_t)ordinal, STREAM_RESET);
         constexpr float PI_F = 3.1415927410125732f;
         s.th = uniformf(-PI_F, PI_F, b.w0);
         s.thdot = uniformf(-1.0f, 1.0f, b.w1);
     }
     __device__ static __forceinline__ bool valid(Act a) { return a == a; }
-    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&) {
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         constexpr float PI_F = 3.1415927410125732f, TWO_PI_F = 6.2831854820251465f;
         const float th = s.th, thdot = s.thdot;
         const float u = clampf(a, -2.0f, 2.0f);
@@ -155,19 +164,22 @@ struct MountainCarT {
     static constexpr int SD = 2, OD = 2, AD = 1, ACTN = CONTINUOUS ? 0 : 3;
     static constexpr int DEFAULT_LIMIT = CONTINUOUS ? 999 : 200;
     static constexpr bool HAS_SBD = false;
+    static constexpr bool PREGEN_RESET = true;
+    static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
     static constexpr float ACT_LOW = -1.0f, ACT_HIGH = 1.0f;
     using Vec = float2;
     using Act = typename std::conditional<CONTINUOUS, float, int32_t>::type;
     struct S { float position, velocity; };
-    __device__ static __forceinline__ S load(const void* base, int i) {
+    __device__ static __forceinline__ S load(const void* base, const int32_t*, int, int i, const EnvParams&) {
         const float2 v = reinterpret_cast<const float2*>(base)[i];
         return S{v.x, v.y};
     }
-    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+    __device__ static __forceinline__ void store(void* base, int32_t*, int, int i, const S& s) {
         reinterpret_cast<float2*>(base)[i] = make_float2(s.position, s.velocity);
     }
-    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+    __device__ static __forceinline__ void reset(S& s, uint64_t seed, uint32_t gid, uint32_t ordinal, uint64_t, const EnvParams&) {
+        const Block b = draw(seed, gid, (uint64_t)ordinal, STREAM_RESET);
         s.position = uniformf(-0.6f, -0.4f, b.w0);
         s.velocity = 0.0f;
     }
@@ -191,7 +203,7 @@ struct MountainCarT {
         if (position == -1.2 && velocity < 0) velocity = 0;
         return position >= (CONTINUOUS ? 0.45 : 0.5) && velocity >= 0.0;
     }
-    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&) {
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         constexpr float MIN_POS = -1.2f, MAX_POS = 0.6f, MAX_SPEED = 0.07f;
         constexpr float GOAL = CONTINUOUS ? 0.45f : 0.5f;
         const float position = s.position, velocity = s.velocity;
@@ -302,25 +314,28 @@ __device__ __noinline__ bool acrobot_done_f64(float s0, float s1, float s2, floa
 struct Acrobot {
     static constexpr int SD = 4, OD = 6, AD = 1, ACTN = 3, DEFAULT_LIMIT = 500;
     static constexpr bool HAS_SBD = false;
+    static constexpr bool PREGEN_RESET = true;
+    static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
     using Vec = float4;
     using Act = int32_t;
     struct S { float v[4]; };
-    __device__ static __forceinline__ S load(const void* base, int i) {
+    __device__ static __forceinline__ S load(const void* base, const int32_t*, int, int i, const EnvParams&) {
         const float4 v = reinterpret_cast<const float4*>(base)[i];
         return S{{v.x, v.y, v.z, v.w}};
     }
-    __device__ static __forceinline__ void store(void* base, int i, const S& s) {
+    __device__ static __forceinline__ void store(void* base, int32_t*, int, int i, const S& s) {
         reinterpret_cast<float4*>(base)[i] = make_float4(s.v[0], s.v[1], s.v[2], s.v[3]);
     }
-    __device__ static __forceinline__ void reset(S& s, const Block& b) {
+    __device__ static __forceinline__ void reset(S& s, uint64_t seed, uint32_t gid, uint32_t ordinal, uint64_t, const EnvParams&) {
+        const Block b = draw(seed, gid, (uint64_t)ordinal, STREAM_RESET);
         s.v[0] = uniformf(-0.1f, 0.1f, b.w0);
         s.v[1] = uniformf(-0.1f, 0.1f, b.w1);
         s.v[2] = uniformf(-0.1f, 0.1f, b.w2);
         s.v[3] = uniformf(-0.1f, 0.1f, b.w3);
     }
     __device__ static __forceinline__ bool valid(Act a) { return a >= 0 && a < 3; }
-    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&) {
+    __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         const float o0 = s.v[0], o1 = s.v[1], o2 = s.v[2], o3 = s.v[3];
         const float v = acrobot_integrate<float>(s.v, (int)a);
         bool done = v > 1.0f;

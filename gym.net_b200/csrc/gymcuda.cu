@@ -123,7 +123,9 @@ struct gymcuda_env {
     cudaStream_t own_stream, stream;
     // state
     void* d_state;
-    int32_t *d_sbd, *d_ept, *d_episode, *d_seeds;
+    int32_t *d_sbd, *d_ept, *d_episode, *d_seeds, *d_aux;
+    EnvParams prm;
+    int auxw;   // int32 words per env in d_aux (LunarLander only)
     // I/O staging for the host-buffer entry points
     void* d_actions;
     float *d_obs, *d_reward;
@@ -179,14 +181,14 @@ static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
 
 template <class E>
 static cudaError_t launch_reset(gymcuda_env* e, const ResetArgs& a) {
-    reset_kernel<E><<<(e->n + 255) / 256, 256, 0, e->stream>>>(a);
+    reset_kernel<E><<<(e->n + 127) / 128, 128, 0, e->stream>>>(a);
     return cudaGetLastError();
 }
 
 #ifdef GYMCUDA_WITH_LUNAR
 #define LUNAR_CASES(FN, ...)                                                      \
-    case GYMCUDA_LUNARLANDER: return lunar_##FN<LunarLander>(e, __VA_ARGS__);     \
-    case GYMCUDA_LUNARLANDER_CONT: return lunar_##FN<LunarLanderCont>(e, __VA_ARGS__);
+    case GYMCUDA_LUNARLANDER: return launch_##FN<LunarLander>(e, __VA_ARGS__);     \
+    case GYMCUDA_LUNARLANDER_CONT: return launch_##FN<LunarLanderCont>(e, __VA_ARGS__);
 #else
 #define LUNAR_CASES(FN, ...)
 #endif
@@ -205,6 +207,17 @@ static cudaError_t launch_reset(gymcuda_env* e, const ResetArgs& a) {
 static cudaError_t dispatch_step(gymcuda_env* e, const StepArgs& a) { DISPATCH(step, a) }
 static cudaError_t dispatch_rollout(gymcuda_env* e, const RolloutArgs& a) { DISPATCH(rollout, a) }
 static cudaError_t dispatch_reset(gymcuda_env* e, const ResetArgs& a) { DISPATCH(reset, a) }
+
+// constructor draws (LunarLander only): at create and whenever the generator is replaced by Seed()
+static cudaError_t dispatch_ctor(gymcuda_env* e, const ResetArgs& a) {
+#ifdef GYMCUDA_WITH_LUNAR
+    const int grid = (e->n + 127) / 128;
+    if (e->cfg.env_kind == GYMCUDA_LUNARLANDER) ctor_kernel<LunarLander><<<grid, 128, 0, e->stream>>>(a);
+    else if (e->cfg.env_kind == GYMCUDA_LUNARLANDER_CONT) ctor_kernel<LunarLanderCont><<<grid, 128, 0, e->stream>>>(a);
+#endif
+    (void)e; (void)a;
+    return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------------
 // library
@@ -242,7 +255,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
-    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds);
+    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux);
     cudaFree(e->d_actions); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done); cudaFree(e->d_mask);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats);
     if (e->h_small) cudaFreeHost(e->h_small);
@@ -256,12 +269,12 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     const size_t n = (size_t)e->n;
-#ifdef GYMCUDA_WITH_LUNAR
-    const size_t state_bytes = n * (size_t)e->ki.sd * 4 + n * (size_t)e->ki.aux * 4;
-#else
     const size_t state_bytes = n * (size_t)e->ki.sd * 4;
-#endif
     CU_TRY(cudaMalloc(&e->d_state, state_bytes));
+    if (e->auxw > 0) {
+        CU_TRY(cudaMalloc(&e->d_aux, n * (size_t)e->auxw * 4));
+        CU_TRY(cudaMemsetAsync(e->d_aux, 0, n * (size_t)e->auxw * 4, e->stream));
+    }
     CU_TRY(cudaMalloc(&e->d_sbd, n * 4));
     CU_TRY(cudaMalloc(&e->d_ept, n * 4));
     CU_TRY(cudaMalloc(&e->d_episode, n * 4));
@@ -281,6 +294,15 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMemsetAsync(e->d_done_count, 0, 2 * sizeof(int32_t), e->stream));
     CU_TRY(cudaMemsetAsync(e->d_stats, 0, 2 * sizeof(unsigned long long), e->stream));
     CU_TRY(cudaMemsetAsync(e->d_obs, 0, e->obs_bytes(), e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+static int run_ctor(gymcuda_env* e) {
+    ResetArgs a{};
+    a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
+    a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t;
+    CU_TRY(dispatch_ctor(e, a));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return GYMCUDA_OK;
 }
@@ -315,7 +337,10 @@ int gymcuda_create(const gymcuda_config* cfg, gymcuda_env** out) {
     e->auto_reset = (cfg->flags & GYMCUDA_FLAG_AUTO_RESET) != 0;
     e->seed = cfg->seed;
     e->last_obs = nullptr;
+    e->prm = EnvParams{cfg->gravity, cfg->wind_power, cfg->turbulence_power, cfg->enable_wind ? 1 : 0};
+    e->auxw = cfg->env_kind >= GYMCUDA_LUNARLANDER ? ki.aux - 2 : 0;
     int rc = create_impl(cfg, e);
+    if (rc == GYMCUDA_OK) rc = run_ctor(e);
     if (rc != GYMCUDA_OK) { std::string keep = g_last_error; gymcuda_destroy(e); g_last_error = keep; return rc; }
     e->last_obs = e->d_obs;
     *out = e;
@@ -372,7 +397,7 @@ int gymcuda_seed(gymcuda_env* e, uint64_t seed) {
     CU_TRY(cudaMemsetAsync(e->d_episode, 0, (size_t)e->n * 4, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->t = 0;
-    return GYMCUDA_OK;
+    return run_ctor(e);
 }
 
 int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
@@ -385,7 +410,7 @@ int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
     CU_TRY(cudaMemsetAsync(e->d_episode, 0, (size_t)e->n * 4, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->t = 0;
-    return GYMCUDA_OK;
+    return run_ctor(e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,7 +418,7 @@ int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
 // ------------------------------------------------------------------------------------------------
 static int reset_impl(gymcuda_env* e, const uint8_t* d_mask, float* obs_host) {
     ResetArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.mask = d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset;
     a.seed = e->seed; a.t = e->t;
     CU_TRY(dispatch_reset(e, a));
@@ -425,7 +450,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
                        float* d_reward, uint8_t* d_done) {
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
     StepArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
@@ -485,7 +510,7 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
     RolloutArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats;
     a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     CU_TRY(dispatch_rollout(e, a));
@@ -549,9 +574,21 @@ int gymcuda_done_indices_device(gymcuda_env* e, const int32_t** d_idx, const int
 // ------------------------------------------------------------------------------------------------
 int gymcuda_get_state(gymcuda_env* e, float* state, int32_t* aux, uint64_t* t) {
     ENTER(e);
-#ifdef GYMCUDA_WITH_LUNAR
-    if (e->cfg.env_kind >= GYMCUDA_LUNARLANDER) { int rc = lunar_get_state(e, state, aux); if (rc) return rc; if (t) *t = e->t; return GYMCUDA_OK; }
-#endif
+    if (e->auxw > 0) {   // LunarLander: device arrays are field-major [word][env]; the ABI is [env][word]
+        const size_t n = (size_t)e->n; const int sd = e->ki.sd, ad = e->ki.aux, aw = e->auxw;
+        std::vector<float> fs(n * sd); std::vector<int32_t> fa(n * aw), ept(n), epi(n);
+        CU_TRY(cudaMemcpyAsync(fs.data(), e->d_state, n * sd * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(fa.data(), e->d_aux, n * aw * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(ept.data(), e->d_ept, n * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(epi.data(), e->d_episode, n * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        for (size_t i = 0; i < n; ++i) {
+            if (state) for (int f = 0; f < sd; ++f) state[i * sd + f] = fs[(size_t)f * n + i];
+            if (aux) { for (int f = 0; f < aw; ++f) aux[i * ad + f] = fa[(size_t)f * n + i]; aux[i * ad + aw] = ept[i]; aux[i * ad + aw + 1] = epi[i]; }
+        }
+        if (t) *t = e->t;
+        return GYMCUDA_OK;
+    }
     if (state) CU_TRY(cudaMemcpyAsync(state, e->d_state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyDeviceToHost, e->stream));
     std::vector<int32_t> sbd, ept, epi;
     if (aux) {
@@ -568,9 +605,23 @@ int gymcuda_get_state(gymcuda_env* e, float* state, int32_t* aux, uint64_t* t) {
 
 int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, uint64_t t) {
     ENTER(e);
-#ifdef GYMCUDA_WITH_LUNAR
-    if (e->cfg.env_kind >= GYMCUDA_LUNARLANDER) { int rc = lunar_set_state(e, state, aux); if (rc) return rc; e->t = t; e->has_state = true; e->last_obs = nullptr; return GYMCUDA_OK; }
-#endif
+    if (e->auxw > 0) {
+        if (!state || !aux) return fail(GYMCUDA_EINVAL, "LunarLander set_state needs both state and aux");
+        const size_t n = (size_t)e->n; const int sd = e->ki.sd, ad = e->ki.aux, aw = e->auxw;
+        std::vector<float> fs(n * sd); std::vector<int32_t> fa(n * aw), ept(n), epi(n);
+        for (size_t i = 0; i < n; ++i) {
+            for (int f = 0; f < sd; ++f) fs[(size_t)f * n + i] = state[i * sd + f];
+            for (int f = 0; f < aw; ++f) fa[(size_t)f * n + i] = aux[i * ad + f];
+            ept[i] = aux[i * ad + aw]; epi[i] = aux[i * ad + aw + 1];
+        }
+        CU_TRY(cudaMemcpyAsync(e->d_state, fs.data(), n * sd * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->d_aux, fa.data(), n * aw * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->d_ept, ept.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->d_episode, epi.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        e->t = t; e->has_state = true; e->last_obs = nullptr;
+        return GYMCUDA_OK;
+    }
     if (state) CU_TRY(cudaMemcpyAsync(e->d_state, state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyHostToDevice, e->stream));
     std::vector<int32_t> sbd, ept, epi;
     if (aux) {
@@ -590,7 +641,7 @@ int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, ui
 static int observe_device(gymcuda_env* e) {
     // a masked reset with an all-zero mask only recomputes observations from the stored state
     ResetArgs a{};
-    a.state = e->d_state; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
+    a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     CU_TRY(cudaMemsetAsync(e->d_mask, 0, (size_t)e->n, e->stream));
     a.mask = e->d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t;
     CU_TRY(dispatch_reset(e, a));

@@ -1,7 +1,7 @@
 // Generic kernels of the engine: one thread = one env instance.
 //
-//   step_kernel     one env step per launch: coalesced vector load of the state, transition,
-//                   reward, termination, in-kernel auto-reset, coalesced stores, then warp-ballot +
+//   step_kernel     one env step per launch: coalesced load of the state, transition, reward,
+//                   termination, in-kernel auto-reset, coalesced stores, then warp-ballot +
 //                   block-scan compaction of the done mask (one atomicAdd per block).
 //                   Replaces the serial per-env loop of VecEnvWrapper.Step
 //                   (src/Gym/Envs/VecEnvWrapper.cs:22-24) over Env.Step (src/Gym/Envs/Env.cs:21).
@@ -10,11 +10,14 @@
 //                   actions come from the per-env Philox stream, the trajectory is streamed to HBM
 //                   with evict-first stores.  This is the caller loop of the reference's tests
 //                   (tests/Gym.Tests/Envs/Classic/CartpoleEnvironment.cs:19-30) moved on-device.
-//   reset_kernel    Env.Reset for all / masked envs.
-//   observe_kernel  current observations without stepping.
+//   reset_kernel    Env.Reset for all / masked envs; with an all-zero mask it only recomputes the
+//                   observations from the stored state.
+//   ctor_kernel     per-env constructor draws (LunarLander's wind phase, LunarLanderEnv.cs:409-410).
 //
 // HBM layout (structure of arrays, all indexed by local env id):
-//   state   Vec[n]      float4 (CartPole, Acrobot) or float2 (Pendulum, MountainCar*)
+//   state   classic: Vec[n], float4 (CartPole, Acrobot) or float2 (Pendulum, MountainCar*)
+//           LunarLander: float[SD][n] field-major (lunar.cuh)
+//   aux     LunarLander only: int32[AUXW][n] field-major (contact flags, limit states, manifold ids)
 //   sbd     int32[n]    CartPole steps_beyond_done (touched only when auto-reset is off)
 //   ep_t    int32[n]    episode step counter (touched only when a time limit is set)
 //   episode int32[n]    number of resets the env has had = index of its next RESET draw
@@ -34,6 +37,7 @@ namespace gymcuda {
 
 struct StepArgs {
     void* state;
+    int32_t* aux;
     int32_t* sbd;
     int32_t* ep_t;
     int32_t* episode;
@@ -53,10 +57,12 @@ struct StepArgs {
     int use_bcast;
     int32_t bcast_action;
     uint32_t seq;                      // step-launch sequence number of this handle
+    EnvParams prm;
 };
 
 struct RolloutArgs {
     void* state;
+    int32_t* aux;
     int32_t* sbd;
     int32_t* ep_t;
     int32_t* episode;
@@ -72,10 +78,12 @@ struct RolloutArgs {
     uint64_t seed;
     uint64_t t;
     int limit;
+    EnvParams prm;
 };
 
 struct ResetArgs {
     void* state;
+    int32_t* aux;
     int32_t* sbd;
     int32_t* ep_t;
     int32_t* episode;
@@ -86,6 +94,7 @@ struct ResetArgs {
     uint32_t env_off;
     uint64_t seed;
     uint64_t t;
+    EnvParams prm;
 };
 
 // ---------------------------------------------------------------- observation stores
@@ -112,10 +121,13 @@ __device__ __forceinline__ void store_obs(float* base, size_t env_index, const f
 }
 
 // ---------------------------------------------------------------- actions
+template <class Act> struct ActCast { __device__ static __forceinline__ Act from_int(int32_t a) { return (Act)a; } };
+template <> struct ActCast<float2> { __device__ static __forceinline__ float2 from_int(int32_t a) { return make_float2((float)a, 0.0f); } };
+
 template <class E> struct ActIO {
     using Act = typename E::Act;
     __device__ static __forceinline__ Act load(const void* base, int i) { return reinterpret_cast<const Act*>(base)[i]; }
-    __device__ static __forceinline__ Act bcast(int32_t a) { return (Act)a; }
+    __device__ static __forceinline__ Act bcast(int32_t a) { return ActCast<Act>::from_int(a); }
     __device__ static __forceinline__ void store(void* base, size_t idx, Act a) { __stcs(reinterpret_cast<Act*>(base) + idx, a); }
 };
 
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     bool done = false;
     bool invalid = false;
     if (i < p.n) {
-        S s = E::load(p.state, i);
+        S s = E::load(p.state, p.aux, p.n, i, p.prm);
         const Act a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
         int32_t sbd = -1;
         if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
@@ -186,16 +198,18 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         StepOut r{0.0f, false};
         invalid = E::REJECT_INVALID && !E::valid(a);
         if (!invalid) {
-            r = E::step(s, a, sbd);
+            const uint64_t seed = seed_of(p.seeds, p.seed, i);
+            const uint32_t gid = p.env_off + (uint32_t)i;
+            r = E::step(s, a, sbd, seed, gid, p.t);
             if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }   // truncation folded into done
             if (AUTO_RESET && r.done) {
                 const int32_t ep = p.episode[i];
-                E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, (uint64_t)(uint32_t)ep, STREAM_RESET));
+                E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
                 p.episode[i] = ep + 1;
                 sbd = -1;
                 ept = 0;
             }
-            E::store(p.state, i, s);
+            E::store(p.state, p.aux, p.n, i, s);
             if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
             if (LIMIT) p.ep_t[i] = ept;
         }
@@ -244,8 +258,8 @@ constexpr int ROLLOUT_BLOCK = 64;
 constexpr int ROLLOUT_REFILL = 8;   // steps between warp-wide refills of the pre-generated reset state
 
 template <class E>
-__device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint32_t gid, int32_t ep) {
-    E::reset(next, draw(seed, gid, (uint64_t)(uint32_t)ep, STREAM_RESET));
+__device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint32_t gid, int32_t ep, uint64_t t, const EnvParams& prm) {
+    E::reset(next, seed, gid, (uint32_t)ep, t, prm);
 }
 
 template <class E, bool AUTO_RESET, bool LIMIT>
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
     const int i = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
     unsigned episodes = 0;
     if (i < p.n) {
-        S s = E::load(p.state, i);
+        S s = E::load(p.state, p.aux, p.n, i, p.prm);
         int32_t sbd = -1;
         if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
         int32_t ept = 0;
@@ -267,23 +281,29 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         // need it every REFILL steps (one Philox evaluation per warp per refill instead of per done)
         int32_t ep = 0;
         if (AUTO_RESET) ep = p.episode[i];
-        S next = s;
+        constexpr bool PREGEN = AUTO_RESET && E::PREGEN_RESET;
+        S next;
+        if (PREGEN) next = s;
         bool have = false;
         for (int k = 0; k < p.k_steps; ++k) {
             const uint64_t t = p.t + (uint64_t)k;
-            if (AUTO_RESET && (k & (ROLLOUT_REFILL - 1)) == 0 && !have) {
-                E::reset(next, draw(seed, gid, (uint64_t)(uint32_t)ep, STREAM_RESET));
+            if (PREGEN && (k & (ROLLOUT_REFILL - 1)) == 0 && !have) {
+                E::reset(next, seed, gid, (uint32_t)ep, t, p.prm);
                 have = true;
             }
             const typename E::Act a = gen.next(seed, gid, t, k == 0);
-            StepOut r = E::step(s, a, sbd);
+            StepOut r = E::step(s, a, sbd, seed, gid, t);
             if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }
             if (r.done) {
                 episodes += 1;
                 if (AUTO_RESET) {
-                    if (!have) reset_cold<E>(next, seed, gid, ep);   // second done before the refill: rare
-                    s = next;
-                    have = false;
+                    if (PREGEN) {
+                        if (!have) reset_cold<E>(next, seed, gid, ep, t + 1, p.prm);   // second done before the refill: rare
+                        s = next;
+                        have = false;
+                    } else {
+                        E::reset(s, seed, gid, (uint32_t)ep, t + 1, p.prm);
+                    }
                     ep += 1;
                     sbd = -1;
                     ept = 0;
@@ -300,7 +320,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             if (p.actions) ActIO<E>::store(p.actions, idx, a);
         }
         if (AUTO_RESET) p.episode[i] = ep;
-        E::store(p.state, i, s);
+        E::store(p.state, p.aux, p.n, i, s);
         if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
         if (LIMIT) p.ep_t[i] = ept;
     }
@@ -310,28 +330,33 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
     if ((threadIdx.x & 31) == 0 && episodes) atomicAdd(&p.stats[0], (unsigned long long)episodes);
 }
 
-// ---------------------------------------------------------------- reset / observe
+// ---------------------------------------------------------------- reset / observe / ctor
 template <class E>
-__global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
+__global__ void __launch_bounds__(128) reset_kernel(const ResetArgs p) {
     using S = typename E::S;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    S s;
+    S s = E::load(p.state, p.aux, p.n, i, p.prm);
     if (p.mask == nullptr || p.mask[i]) {
         const int32_t ep = p.episode[i];
-        E::reset(s, draw(seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, (uint64_t)(uint32_t)ep, STREAM_RESET));
-        E::store(p.state, i, s);
+        E::reset(s, seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i, (uint32_t)ep, p.t, p.prm);
+        E::store(p.state, p.aux, p.n, i, s);
         p.episode[i] = ep + 1;
         p.sbd[i] = -1;     // CartPoleEnv.cs:64
         p.ep_t[i] = 0;
-    } else {
-        s = E::load(p.state, i);
     }
     if (p.obs) {
         float o[E::OD];
         E::obs(s, o);
         store_obs<E::OD, false>(p.obs, (size_t)i, o);
     }
+}
+
+template <class E>
+__global__ void __launch_bounds__(128) ctor_kernel(const ResetArgs p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    E::ctor(p.state, p.aux, p.n, i, seed_of(p.seeds, p.seed, i), p.env_off + (uint32_t)i);
 }
 
 }  // namespace gymcuda

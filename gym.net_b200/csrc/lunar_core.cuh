@@ -1,0 +1,921 @@
+// LunarLander on the GPU: one thread owns one lander (3 rigid bodies, 2 revolute joints, 11 static
+// terrain edges) and runs the whole World.Step of the reference for it.
+//
+// Restates Gym.Environments.Envs.Aether.LunarLanderEnv:
+//   src/Gym.Environments/Envs/Aether/LunarLanderEnv.cs:155-164   constants
+//   :181-302  LunarLanderBody (fuselage polygon, corner-anchored leg boxes, revolute joints)
+//   :305-346  ContactDetector ("last BeginContact wins" flags)
+//   :489-572  Reset (terrain, initial force, zero step)
+//   :574-774  Step (engines, World.Step(1/50, 180 velocity / 60 position iterations), obs, reward, done)
+// and, because the reference delegates all rigid-body arithmetic to the un-vendored NuGet package
+// Aether.Physics2D 1.6.1 (src/Gym.Environments/Gym.Environments.csproj:33), the published algorithm of
+// its Box2D-2.3 / Farseer-3.5 lineage specialised to this fixed topology: edge-vs-polygon manifolds
+// (b2CollideEdgeAndPolygon), sequential-impulse contact solver with block solver and warm starting,
+// revolute joint with motor + limit, island integration and sleeping.  Deviations are listed in
+// DESIGN.md ("LunarLander"): no TOI sub-stepping, inert particles skipped, fixed constraint order,
+// at most MAXC touching manifolds, float32 sin/cos (detmath).
+//
+// This kernel is bound by dependent float32 arithmetic (180 + 60 sequential solver iterations, about
+// 1e5 flop against ~0.8 KB of state per env step), not by HBM.
+//
+// HBM layout: field-major structure of arrays, word f of env i at state[f * n + i] (float) and
+// aux[f * n + i] (int32), so every load/store of the 32 lanes of a warp is one coalesced 128 B line.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "detmath.cuh"
+#include "philox.cuh"
+
+namespace gymcuda { namespace lunar {
+
+// ---------------------------------------------------------------- constants
+constexpr float SCALE = 30.0f;                       // :156
+constexpr float MAIN_ENGINE_POWER = 13.0f;           // :157
+constexpr float SIDE_ENGINE_POWER = 0.6f;            // :158
+constexpr float INITIAL_RANDOM = 1000.0f;            // :159
+constexpr float SIDE_ENGINE_HEIGHT = 14.0f;          // :160
+constexpr float SIDE_ENGINE_AWAY = 12.0f;            // :161
+constexpr float VIEW_W = 600.0f / 30.0f;             // VIEWPORT_W / SCALE
+constexpr float VIEW_H = 400.0f / 30.0f;             // VIEWPORT_H / SCALE
+constexpr float DT = 1.0f / 50.0f;                   // :721 (FPS = 50)
+constexpr float LEG_AWAY = 20.0f, LEG_DOWN = 18.0f;  // :186-187
+constexpr int CHUNKS = 11;                           // :503
+constexpr int NUM_EDGES = 11;                        // 10 terrain edges (:545-557) + the base edge (:541)
+constexpr int BASE_EDGE = 10;
+
+// Box2D-2.3 / Farseer-3.5 lineage settings
+constexpr float LINEAR_SLOP = 0.005f;
+constexpr float ANGULAR_SLOP = 0.03490658476948738f;          // 2/180*pi
+constexpr float POLYGON_RADIUS = 0.01f;                      // 2 * linearSlop
+constexpr float BAUMGARTE = 0.2f;
+constexpr float MAX_LINEAR_CORRECTION = 0.2f;
+constexpr float MAX_ANGULAR_CORRECTION = 0.13962633907794952f;  // 8/180*pi
+constexpr float MAX_TRANSLATION = 2.0f;
+constexpr float MAX_ROTATION = 1.5707963705062866f;          // 0.5*pi
+constexpr float VELOCITY_THRESHOLD = 1.0f;
+constexpr float TIME_TO_SLEEP = 0.5f;
+constexpr float LINEAR_SLEEP_TOL = 0.01f;
+constexpr float ANGULAR_SLEEP_TOL = 0.03490658476948738f;
+constexpr int VELOCITY_ITERATIONS = 180, POSITION_ITERATIONS = 60;   // :723-724
+constexpr float DEFAULT_FRICTION = 0.2f;
+
+constexpr int MAXC = 6;   // touching manifolds kept per lander
+
+// ---------------------------------------------------------------- small vector algebra (b2Math)
+struct V2 { float x, y; };
+__device__ __forceinline__ V2 mk(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ V2 operator-(V2 a) { return mk(-a.x, -a.y); }
+__device__ __forceinline__ V2 operator*(float s, V2 a) { return mk(s * a.x, s * a.y); }
+__device__ __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ V2 cross_sv(float s, V2 a) { return mk(-s * a.y, s * a.x); }
+__device__ __forceinline__ V2 cross_vs(V2 a, float s) { return mk(s * a.y, -s * a.x); }
+struct Rot { float s, c; };
+__device__ __forceinline__ Rot rot(float a) { Rot q; sincosf_det(a, &q.s, &q.c); return q; }
+__device__ __forceinline__ V2 rmul(Rot q, V2 v) { return mk(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
+__device__ __forceinline__ V2 rmulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ float minf(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float maxf(float a, float b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------- shapes (:189, :262-266), mass data
+// b2PolygonShape::Set order (gift-wrapped hull, CCW from the right-most lowest vertex) and
+// b2PolygonShape::ComputeMass evaluated once in float32 (tests/golden/make_golden.py documents how).
+struct Shape { int count; V2 v[6]; V2 n[6]; V2 centroid; float mass, inv_mass, inertia, inv_inertia, friction; };
+__constant__ Shape SHAPES[3] = {
+    {6,
+     {{0.5666666626930237f, -0.3333333432674408f}, {0.5666666626930237f, 0.0f}, {0.46666666865348816f, 0.5666666626930237f},
+      {-0.46666666865348816f, 0.5666666626930237f}, {-0.5666666626930237f, 0.0f}, {-0.5666666626930237f, -0.3333333432674408f}},
+     {{1.0f, 0.0f}, {0.9847835898399353f, 0.17378532886505127f}, {0.0f, 1.0f}, {-0.9847835898399353f, 0.17378532886505127f},
+      {-1.0f, 0.0f}, {0.0f, -1.0f}},
+     {0.0f, 0.10130719095468521f}, 4.816666603088379f, 0.20761245489120483f, 0.7838807106018066f, 1.275704264640808f, 0.1f},
+    {4,
+     {{0.06666667014360428f, 0.0f}, {0.06666667014360428f, 0.2666666805744171f}, {0.0f, 0.2666666805744171f}, {0.0f, 0.0f}, {0, 0}, {0, 0}},
+     {{1.0f, 0.0f}, {0.0f, 1.0f}, {-1.0f, 0.0f}, {0.0f, -1.0f}, {0, 0}, {0, 0}},
+     {0.03333333507180214f, 0.13333334028720856f}, 0.017777780070900917f, 56.24999237060547f, 0.00011193420505151153f, 8933.8193359375f, 0.2f},
+    {4,
+     {{0.06666667014360428f, 0.0f}, {0.06666667014360428f, 0.2666666805744171f}, {0.0f, 0.2666666805744171f}, {0.0f, 0.0f}, {0, 0}, {0, 0}},
+     {{1.0f, 0.0f}, {0.0f, 1.0f}, {-1.0f, 0.0f}, {0.0f, -1.0f}, {0, 0}, {0, 0}},
+     {0.03333333507180214f, 0.13333334028720856f}, 0.017777780070900917f, 56.24999237060547f, 0.00011193420505151153f, 8933.8193359375f, 0.2f},
+};
+
+// revolute joints fuselage <-> leg (:271-277): anchorA = (0,0), anchorB = (+-LEG_AWAY/S, LEG_DOWN/S),
+// referenceAngle = leg.Rotation - fuselage.Rotation at creation = -+0.05 (:259)
+struct JointDef { V2 anchor_b; float ref_angle, motor_speed, lower, upper; };
+__constant__ JointDef JOINTS[2] = {
+    {{-0.6666666865348816f, 0.6000000238418579f}, -0.05f, -0.3f, 0.4f, 0.9f},      // leg 0: (1*0.9 - 0.5, 1*0.9 + 0)
+    {{0.6666666865348816f, 0.6000000238418579f}, 0.05f, 0.3f, -0.9f, -0.4f},       // leg 1: (-0.9 + 0, -0.9 + 0.5)
+};
+constexpr float MAX_MOTOR_TORQUE = 40.0f;   // LEG_SPRING_TORQUE (:188, :274)
+enum { LIMIT_INACTIVE = 0, LIMIT_AT_LOWER = 1, LIMIT_AT_UPPER = 2, LIMIT_EQUAL = 3 };
+
+// ---------------------------------------------------------------- persistent state of one lander
+struct Body { V2 c; float a; V2 v; float w; float sleep_time; };
+struct Joint { float ix, iy, iz, motor; int32_t limit_state; };
+struct ContactSlot { int32_t pair; uint32_t key[2]; float ni[2], ti[2]; };   // pair = body * 16 + edge, -1 = free
+constexpr uint32_t NO_KEY = 0xffffffffu;
+
+enum : int32_t {
+    F_GAME_OVER = 1, F_LEG0 = 2, F_LEG1 = 4, F_FUSELAGE = 8, F_AWAKE = 16, F_FIRST_STEP = 32, F_CONTINUOUS = 64
+};
+
+struct Lander {
+    Body b[3];
+    Joint j[2];
+    ContactSlot c[MAXC];
+    float terrain[CHUNKS];     // smooth_y (:523-536)
+    float prev_shaping;        // float.MinValue sentinel after Reset (:498)
+    V2 force;                  // force accumulator of the fuselage (ApplyForce in Reset, :496)
+    float torque;
+    uint32_t touch[3];         // bit e of touch[body]: polygon `body` was touching edge e after the last Collide
+    int32_t flags;
+    int32_t wind_idx, torque_idx;
+    float gravity, wind_power, turbulence_power;
+    int32_t use_wind;
+    float obs[8];
+};
+
+constexpr int STATE_DIM = 21 + 8 + 4 * MAXC + CHUNKS + 1 + 3;        // 68
+constexpr int AUX_DIM = 3 + 1 + 2 + 3 * MAXC + 2 + 2;                  // touch[3], flags, limit[2], slots, wind idx, ep_t, episode
+
+__device__ __forceinline__ void zero_lander(Lander& L) {
+    for (int i = 0; i < 3; ++i) { L.b[i].c = mk(0.0f, 0.0f); L.b[i].a = 0.0f; L.b[i].v = mk(0.0f, 0.0f); L.b[i].w = 0.0f; L.b[i].sleep_time = 0.0f; L.touch[i] = 0u; }
+    for (int i = 0; i < 2; ++i) { L.j[i].ix = L.j[i].iy = L.j[i].iz = L.j[i].motor = 0.0f; L.j[i].limit_state = 0; }
+    for (int s = 0; s < MAXC; ++s) { L.c[s].pair = 0; L.c[s].key[0] = L.c[s].key[1] = 0u; L.c[s].ni[0] = L.c[s].ni[1] = L.c[s].ti[0] = L.c[s].ti[1] = 0.0f; }
+    for (int i = 0; i < CHUNKS; ++i) L.terrain[i] = 0.0f;
+    L.prev_shaping = 0.0f; L.force = mk(0.0f, 0.0f); L.torque = 0.0f; L.flags = 0;
+    L.wind_idx = 0; L.torque_idx = 0; L.gravity = 0.0f; L.wind_power = 0.0f; L.turbulence_power = 0.0f; L.use_wind = 0;
+    for (int i = 0; i < 8; ++i) L.obs[i] = 0.0f;
+}
+
+// ---------------------------------------------------------------- geometry helpers
+__device__ __forceinline__ void edge_points(const Lander& L, int e, V2* v1, V2* v2) {
+    if (e == BASE_EDGE) { *v1 = mk(0.0f, 0.0f); *v2 = mk(VIEW_W, 0.0f); return; }        // :541
+    const float cw = VIEW_W / (float)(CHUNKS - 1);                                        // :512
+    *v1 = mk(cw * (float)e, L.terrain[e]);                                                // :547-548
+    *v2 = mk(cw * (float)(e + 1), L.terrain[e + 1]);
+}
+__device__ __forceinline__ float edge_friction(int e) { return e == BASE_EDGE ? DEFAULT_FRICTION : 0.1f; }   // :550
+
+// ---------------------------------------------------------------- narrow phase: b2CollideEdgeAndPolygon
+struct ClipVertex { V2 v; uint32_t key; };
+__device__ __forceinline__ uint32_t make_key(int ia, int ib, int ta, int tb) { return (uint32_t)ia | ((uint32_t)ib << 8) | ((uint32_t)ta << 16) | ((uint32_t)tb << 24); }
+enum { FEAT_VERTEX = 0, FEAT_FACE = 1 };
+enum { MF_FACE_A = 1, MF_FACE_B = 2 };
+
+struct Manifold {
+    int type, count;
+    V2 local_normal, local_point;   // faceA: in the edge (world) frame; faceB: in the polygon's local frame
+    V2 lp[2];                       // faceA: polygon-local; faceB: world
+    uint32_t key[2];
+};
+
+__device__ __forceinline__ int clip_segment(ClipVertex out[2], const ClipVertex in[2], V2 normal, float offset, int vertex_index_a) {
+    int n = 0;
+    const float d0 = dot(normal, in[0].v) - offset;
+    const float d1 = dot(normal, in[1].v) - offset;
+    if (d0 <= 0.0f) out[n++] = in[0];
+    if (d1 <= 0.0f) out[n++] = in[1];
+    if (d0 * d1 < 0.0f) {
+        const float interp = d0 / (d0 - d1);
+        out[n].v = in[0].v + interp * (in[1].v - in[0].v);
+        out[n].key = make_key(vertex_index_a, (int)((in[0].key >> 8) & 0xff), FEAT_VERTEX, FEAT_FACE);
+        ++n;
+    }
+    return n;
+}
+
+// Edge A (static, identity transform, no adjacent vertices) vs polygon B with transform (p, q).
+__device__ __noinline__ void collide_edge_polygon(Manifold* m, V2 v1, V2 v2, const Shape& sh, V2 p, Rot q) {
+    m->count = 0;
+    m->type = 0;
+    const V2 centroid = rmul(q, sh.centroid) + p;
+    V2 edge1 = v2 - v1;
+    {   // b2Vec2::Normalize
+        const float len = sqrtf(edge1.x * edge1.x + edge1.y * edge1.y);
+        const float inv = 1.0f / len;
+        edge1 = mk(edge1.x * inv, edge1.y * inv);
+    }
+    const V2 normal1 = mk(edge1.y, -edge1.x);
+    const float offset1 = dot(normal1, centroid - v1);
+    const bool front = offset1 >= 0.0f;
+    V2 normal, lower, upper;
+    if (front) { normal = normal1; lower = -normal1; upper = -normal1; }
+    else { normal = -normal1; lower = normal1; upper = normal1; }
+    V2 vb[6], nb[6];
+    for (int i = 0; i < sh.count; ++i) { vb[i] = rmul(q, sh.v[i]) + p; nb[i] = rmul(q, sh.n[i]); }
+    const float radius = 2.0f * POLYGON_RADIUS;
+
+    // ComputeEdgeSeparation
+    float edge_sep = 3.4028234663852886e38f;
+    for (int i = 0; i < sh.count; ++i) { const float s = dot(normal, vb[i] - v1); if (s < edge_sep) edge_sep = s; }
+    if (edge_sep > radius) return;
+
+    // ComputePolygonSeparation
+    int poly_index = -1;
+    float poly_sep = -3.4028234663852886e38f;
+    bool poly_valid = false;
+    {
+        const V2 perp = mk(-normal.y, normal.x);
+        for (int i = 0; i < sh.count; ++i) {
+            const V2 n = -nb[i];
+            const float s1 = dot(n, vb[i] - v1);
+            const float s2 = dot(n, vb[i] - v2);
+            const float s = minf(s1, s2);
+            if (s > radius) { poly_valid = true; poly_index = i; poly_sep = s; break; }   // no collision
+            if (dot(n, perp) >= 0.0f) { if (dot(n - upper, normal) < -ANGULAR_SLOP) continue; }
+            else { if (dot(n - lower, normal) < -ANGULAR_SLOP) continue; }
+            if (s > poly_sep) { poly_valid = true; poly_index = i; poly_sep = s; }
+        }
+    }
+    if (poly_valid && poly_sep > radius) return;
+
+    const float k_relative_tol = 0.98f, k_absolute_tol = 0.001f;
+    const bool primary_is_edge = !poly_valid || !(poly_sep > k_relative_tol * edge_sep + k_absolute_tol);
+
+    ClipVertex ie[2];
+    int rf_i1, rf_i2;
+    V2 rf_v1, rf_v2, rf_normal;
+    if (primary_is_edge) {
+        m->type = MF_FACE_A;
+        int best = 0;
+        float best_value = dot(normal, nb[0]);
+        for (int i = 1; i < sh.count; ++i) { const float v = dot(normal, nb[i]); if (v < best_value) { best_value = v; best = i; } }
+        const int i1 = best, i2 = i1 + 1 < sh.count ? i1 + 1 : 0;
+        ie[0].v = vb[i1]; ie[0].key = make_key(0, i1, FEAT_FACE, FEAT_VERTEX);
+        ie[1].v = vb[i2]; ie[1].key = make_key(0, i2, FEAT_FACE, FEAT_VERTEX);
+        if (front) { rf_i1 = 0; rf_i2 = 1; rf_v1 = v1; rf_v2 = v2; rf_normal = normal1; }
+        else { rf_i1 = 1; rf_i2 = 0; rf_v1 = v2; rf_v2 = v1; rf_normal = -normal1; }
+    } else {
+        m->type = MF_FACE_B;
+        ie[0].v = v1; ie[0].key = make_key(0, poly_index, FEAT_VERTEX, FEAT_FACE);
+        ie[1].v = v2; ie[1].key = make_key(0, poly_index, FEAT_VERTEX, FEAT_FACE);
+        rf_i1 = poly_index; rf_i2 = rf_i1 + 1 < sh.count ? rf_i1 + 1 : 0;
+        rf_v1 = vb[rf_i1]; rf_v2 = vb[rf_i2]; rf_normal = nb[rf_i1];
+    }
+    const V2 side1 = mk(rf_normal.y, -rf_normal.x);
+    const V2 side2 = -side1;
+    const float side_off1 = dot(side1, rf_v1);
+    const float side_off2 = dot(side2, rf_v2);
+    ClipVertex c1[2], c2[2];
+    if (clip_segment(c1, ie, side1, side_off1, rf_i1) < 2) return;
+    if (clip_segment(c2, c1, side2, side_off2, rf_i2) < 2) return;
+    if (primary_is_edge) { m->local_normal = rf_normal; m->local_point = rf_v1; }
+    else { m->local_normal = sh.n[rf_i1]; m->local_point = sh.v[rf_i1]; }
+    int count = 0;
+    for (int i = 0; i < 2; ++i) {
+        const float separation = dot(rf_normal, c2[i].v - rf_v1);
+        if (separation <= radius) {
+            if (primary_is_edge) {
+                m->lp[count] = rmulT(q, c2[i].v - p);
+                m->key[count] = c2[i].key;
+            } else {
+                m->lp[count] = c2[i].v;
+                const uint32_t k = c2[i].key;   // swap A and B features
+                m->key[count] = make_key((int)((k >> 8) & 0xff), (int)(k & 0xff), (int)((k >> 24) & 0xff), (int)((k >> 16) & 0xff));
+            }
+            ++count;
+        }
+    }
+    m->count = count;
+}
+
+// ---------------------------------------------------------------- ContactDetector (:305-346)
+__device__ __forceinline__ void begin_contact(Lander& L, int body) {
+    L.flags &= ~(F_FUSELAGE | F_LEG0 | F_LEG1);          // :316, :324 clear every flag ...
+    if (body == 0) L.flags |= F_FUSELAGE;                // :317-320 ... then set the bodies of THIS contact
+    if (body == 1) L.flags |= F_LEG0;
+    if (body == 2) L.flags |= F_LEG1;
+}
+__device__ __forceinline__ void end_contact(Lander& L, int body) {
+    if (body == 1) L.flags &= ~F_LEG0;                   // :337-343 legs only; the fuselage flag is never cleared
+    if (body == 2) L.flags &= ~F_LEG1;
+}
+
+// ---------------------------------------------------------------- solver work structures
+struct VelPoint { V2 rb; float normal_impulse, tangent_impulse, normal_mass, tangent_mass, velocity_bias; };
+struct ActiveContact {
+    int body, edge, count;
+    Manifold m;
+    float friction;
+    V2 normal;
+    VelPoint p[2];
+    float k11, k12, k22, nm11, nm12, nm21, nm22;   // K and its inverse (block solver)
+};
+
+struct JointWork { V2 ra, rb; float m_exx, m_eyx, m_ezx, m_eyy, m_ezy, m_ezz, motor_mass; };
+
+__device__ __forceinline__ V2 solve22(float a11, float a12, float a21, float a22, V2 b) {   // b2Mat22::Solve / b2Mat33::Solve22
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = 1.0f / det;
+    return mk(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+
+// ---------------------------------------------------------------- World.Step(dt) for one lander
+__device__ __forceinline__ void set_awake(Lander& L, bool awake) {
+    if (awake) {
+        if (!(L.flags & F_AWAKE)) { L.flags |= F_AWAKE; for (int i = 0; i < 3; ++i) L.b[i].sleep_time = 0.0f; }
+    } else {
+        L.flags &= ~F_AWAKE;
+        for (int i = 0; i < 3; ++i) { L.b[i].sleep_time = 0.0f; L.b[i].v = mk(0.0f, 0.0f); L.b[i].w = 0.0f; }
+        L.force = mk(0.0f, 0.0f); L.torque = 0.0f;
+    }
+}
+
+__device__ __noinline__ void world_step(Lander& L) {
+    const float h = DT;
+    const float dt_ratio = (L.flags & F_FIRST_STEP) ? 0.0f : 1.0f;   // inv_dt0 * dt: 0 on a new World, then 50 * 0.02f = 1
+    ActiveContact ac[MAXC];
+    int nc = 0;
+
+    // ---- ContactManager.Collide: update every (polygon, edge) pair whose AABBs can overlap
+    if (L.flags & F_AWAKE) {
+        for (int body = 0; body < 3; ++body) {
+            const Shape& sh = SHAPES[body];
+            const Rot q = rot(L.b[body].a);
+            const V2 p = L.b[body].c - rmul(q, sh.centroid);
+            float xmin = 3.4028234663852886e38f, xmax = -3.4028234663852886e38f, ymin = 3.4028234663852886e38f;
+            for (int i = 0; i < sh.count; ++i) {
+                const V2 w = rmul(q, sh.v[i]) + p;
+                xmin = minf(xmin, w.x); xmax = maxf(xmax, w.x); ymin = minf(ymin, w.y);
+            }
+            const float margin = 0.1f;   // aabbExtension: a pair farther than this cannot be touching
+            uint32_t now = 0;
+            for (int e = 0; e < NUM_EDGES; ++e) {
+                V2 v1, v2;
+                edge_points(L, e, &v1, &v2);
+                const bool overlap = xmax + margin >= v1.x && xmin - margin <= v2.x &&
+                                     ymin - margin <= maxf(v1.y, v2.y);
+                Manifold m;
+                m.count = 0;
+                if (overlap) collide_edge_polygon(&m, v1, v2, sh, p, q);
+                const bool touching = m.count > 0 && nc < MAXC;
+                const bool was = (L.touch[body] >> e) & 1u;
+                if (touching) {
+                    now |= 1u << e;
+                    ActiveContact& c = ac[nc++];
+                    c.body = body; c.edge = e; c.count = m.count; c.m = m;
+                    for (int k = 0; k < 2; ++k) { c.p[k].normal_impulse = 0.0f; c.p[k].tangent_impulse = 0.0f; }
+                    // b2Contact::Update: match old manifold points by id, copy their impulses (warm start)
+                    const int32_t pair = body * 16 + e;
+                    for (int s = 0; s < MAXC; ++s) {
+                        if (L.c[s].pair != pair) continue;
+                        for (int k = 0; k < m.count; ++k)
+                            for (int o = 0; o < 2; ++o)
+                                if (L.c[s].key[o] != NO_KEY && L.c[s].key[o] == m.key[k]) {
+                                    c.p[k].normal_impulse = L.c[s].ni[o]; c.p[k].tangent_impulse = L.c[s].ti[o];
+                                }
+                    }
+                }
+                if (touching && !was) begin_contact(L, body);
+                if (!touching && was) end_contact(L, body);
+            }
+            L.touch[body] = now;
+        }
+    }
+
+    // ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1}
+    if (L.flags & F_AWAKE) {
+        V2 c[3], v[3];
+        float a[3], w[3];
+        const V2 gravity = mk(0.0f, L.gravity);
+        for (int i = 0; i < 3; ++i) {
+            c[i] = L.b[i].c; a[i] = L.b[i].a; v[i] = L.b[i].v; w[i] = L.b[i].w;
+            const V2 f = i == 0 ? L.force : mk(0.0f, 0.0f);
+            const float tq = i == 0 ? L.torque : 0.0f;
+            v[i] = v[i] + h * (gravity + SHAPES[i].inv_mass * f);
+            w[i] = w[i] + h * SHAPES[i].inv_inertia * tq;
+            v[i] = (1.0f / (1.0f + h * 0.0f)) * v[i];   // linear damping 0
+            w[i] = w[i] * (1.0f / (1.0f + h * 0.0f));
+        }
+
+        // contact solver: InitializeVelocityConstraints
+        for (int k = 0; k < nc; ++k) {
+            ActiveContact& cc = ac[k];
+            const int B = cc.body;
+            const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+            const Rot qB = rot(a[B]);
+            const V2 pB = c[B] - rmul(qB, SHAPES[B].centroid);
+            cc.friction = sqrtf(edge_friction(cc.edge) * SHAPES[B].friction);   // MixFriction
+            V2 normal, pts[2];
+            if (cc.m.type == MF_FACE_A) {
+                normal = cc.m.local_normal;
+                const V2 plane = cc.m.local_point;
+                for (int j = 0; j < cc.count; ++j) {
+                    const V2 clip = rmul(qB, cc.m.lp[j]) + pB;
+                    const V2 cA = clip + (POLYGON_RADIUS - dot(clip - plane, normal)) * normal;
+                    const V2 cB = clip - POLYGON_RADIUS * normal;
+                    pts[j] = 0.5f * (cA + cB);
+                }
+            } else {
+                normal = rmul(qB, cc.m.local_normal);
+                const V2 plane = rmul(qB, cc.m.local_point) + pB;
+                for (int j = 0; j < cc.count; ++j) {
+                    const V2 clip = cc.m.lp[j];
+                    const V2 cB = clip + (POLYGON_RADIUS - dot(clip - plane, normal)) * normal;
+                    const V2 cA = clip - POLYGON_RADIUS * normal;
+                    pts[j] = 0.5f * (cA + cB);
+                }
+                normal = -normal;
+            }
+            cc.normal = normal;
+            const V2 tangent = cross_vs(normal, 1.0f);
+            for (int j = 0; j < cc.count; ++j) {
+                VelPoint& vp = cc.p[j];
+                vp.normal_impulse = dt_ratio * vp.normal_impulse;
+                vp.tangent_impulse = dt_ratio * vp.tangent_impulse;
+                vp.rb = pts[j] - c[B];
+                const float rnB = cross(vp.rb, normal);
+                const float kn = mB + iB * rnB * rnB;
+                vp.normal_mass = kn > 0.0f ? 1.0f / kn : 0.0f;
+                const float rtB = cross(vp.rb, tangent);
+                const float kt = mB + iB * rtB * rtB;
+                vp.tangent_mass = kt > 0.0f ? 1.0f / kt : 0.0f;
+                vp.velocity_bias = 0.0f;   // restitution 0 (:242, :268)
+            }
+            if (cc.count == 2) {
+                const float rn1 = cross(cc.p[0].rb, normal), rn2 = cross(cc.p[1].rb, normal);
+                const float k11 = mB + iB * rn1 * rn1;
+                const float k22 = mB + iB * rn2 * rn2;
+                const float k12 = mB + iB * rn1 * rn2;
+                const float k_max_condition = 1000.0f;
+                if (k11 * k11 < k_max_condition * (k11 * k22 - k12 * k12)) {
+                    cc.k11 = k11; cc.k12 = k12; cc.k22 = k22;
+                    float det = k11 * k22 - k12 * k12;
+                    if (det != 0.0f) det = 1.0f / det;
+                    cc.nm11 = det * k22; cc.nm12 = -det * k12; cc.nm21 = -det * k12; cc.nm22 = det * k11;
+                } else {
+                    cc.count = 1;
+                }
+            }
+        }
+        // contact solver: WarmStart
+        for (int k = 0; k < nc; ++k) {
+            ActiveContact& cc = ac[k];
+            const int B = cc.body;
+            const V2 tangent = cross_vs(cc.normal, 1.0f);
+            for (int j = 0; j < cc.count; ++j) {
+                const V2 P = cc.p[j].normal_impulse * cc.normal + cc.p[j].tangent_impulse * tangent;
+                w[B] = w[B] + SHAPES[B].inv_inertia * cross(cc.p[j].rb, P);
+                v[B] = v[B] + SHAPES[B].inv_mass * P;
+            }
+        }
+        // joints: InitVelocityConstraints, island order leg1's joint, then leg0's
+        JointWork jw[2];
+        for (int jj = 0; jj < 2; ++jj) {
+            const int ji = 1 - jj;
+            const int A = 0, B = 1 + ji;
+            Joint& J = L.j[ji];
+            JointWork& W = jw[ji];
+            const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+            const Rot qA = rot(a[A]), qB = rot(a[B]);
+            W.ra = rmul(qA, mk(0.0f, 0.0f) - SHAPES[A].centroid);
+            W.rb = rmul(qB, JOINTS[ji].anchor_b - SHAPES[B].centroid);
+            W.m_exx = mA + mB + W.ra.y * W.ra.y * iA + W.rb.y * W.rb.y * iB;
+            W.m_eyx = -W.ra.y * W.ra.x * iA - W.rb.y * W.rb.x * iB;
+            W.m_ezx = -W.ra.y * iA - W.rb.y * iB;
+            W.m_eyy = mA + mB + W.ra.x * W.ra.x * iA + W.rb.x * W.rb.x * iB;
+            W.m_ezy = W.ra.x * iA + W.rb.x * iB;
+            W.m_ezz = iA + iB;
+            W.motor_mass = iA + iB;
+            if (W.motor_mass > 0.0f) W.motor_mass = 1.0f / W.motor_mass;
+            const float angle = a[B] - a[A] - JOINTS[ji].ref_angle;
+            if (fabsf(JOINTS[ji].upper - JOINTS[ji].lower) < 2.0f * ANGULAR_SLOP) {
+                J.limit_state = LIMIT_EQUAL;
+            } else if (angle <= JOINTS[ji].lower) {
+                if (J.limit_state != LIMIT_AT_LOWER) J.iz = 0.0f;
+                J.limit_state = LIMIT_AT_LOWER;
+            } else if (angle >= JOINTS[ji].upper) {
+                if (J.limit_state != LIMIT_AT_UPPER) J.iz = 0.0f;
+                J.limit_state = LIMIT_AT_UPPER;
+            } else {
+                J.limit_state = LIMIT_INACTIVE;
+                J.iz = 0.0f;
+            }
+            // warm start
+            J.ix = J.ix * dt_ratio; J.iy = J.iy * dt_ratio; J.iz = J.iz * dt_ratio; J.motor = J.motor * dt_ratio;
+            const V2 P = mk(J.ix, J.iy);
+            v[A] = v[A] - mA * P;
+            w[A] = w[A] - iA * (cross(W.ra, P) + J.motor + J.iz);
+            v[B] = v[B] + mB * P;
+            w[B] = w[B] + iB * (cross(W.rb, P) + J.motor + J.iz);
+        }
+
+        // velocity iterations
+        for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+            for (int jj = 0; jj < 2; ++jj) {
+                const int ji = 1 - jj;
+                const int A = 0, B = 1 + ji;
+                Joint& J = L.j[ji];
+                const JointWork& W = jw[ji];
+                const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+                // motor
+                if (J.limit_state != LIMIT_EQUAL) {
+                    const float Cdot = w[B] - w[A] - JOINTS[ji].motor_speed;
+                    float impulse = -W.motor_mass * Cdot;
+                    const float old_impulse = J.motor;
+                    const float max_impulse = h * MAX_MOTOR_TORQUE;
+                    J.motor = clampf(old_impulse + impulse, -max_impulse, max_impulse);
+                    impulse = J.motor - old_impulse;
+                    w[A] = w[A] - iA * impulse;
+                    w[B] = w[B] + iB * impulse;
+                }
+                if (J.limit_state != LIMIT_INACTIVE) {
+                    const V2 Cdot1 = v[B] + cross_sv(w[B], W.rb) - v[A] - cross_sv(w[A], W.ra);
+                    const float Cdot2 = w[B] - w[A];
+                    // impulse = -mass.Solve33(Cdot), mass symmetric: ex=(exx,eyx,ezx) ey=(eyx,eyy,ezy) ez=(ezx,ezy,ezz)
+                    const float exx = W.m_exx, exy = W.m_eyx, exz = W.m_ezx;
+                    const float eyx = W.m_eyx, eyy = W.m_eyy, eyz = W.m_ezy;
+                    const float ezx = W.m_ezx, ezy = W.m_ezy, ezz = W.m_ezz;
+                    const float bx = Cdot1.x, by = Cdot1.y, bz = Cdot2;
+                    // cross(ey, ez)
+                    const float c1x = eyy * ezz - eyz * ezy, c1y = eyz * ezx - eyx * ezz, c1z = eyx * ezy - eyy * ezx;
+                    float det = exx * c1x + exy * c1y + exz * c1z;
+                    if (det != 0.0f) det = 1.0f / det;
+                    const float sx = det * (bx * c1x + by * c1y + bz * c1z);
+                    // cross(b, ez)
+                    const float c2x = by * ezz - bz * ezy, c2y = bz * ezx - bx * ezz, c2z = bx * ezy - by * ezx;
+                    const float sy = det * (exx * c2x + exy * c2y + exz * c2z);
+                    // cross(ey, b)
+                    const float c3x = eyy * bz - eyz * by, c3y = eyz * bx - eyx * bz, c3z = eyx * by - eyy * bx;
+                    const float sz = det * (exx * c3x + exy * c3y + exz * c3z);
+                    float imx = -sx, imy = -sy, imz = -sz;
+                    if (J.limit_state == LIMIT_EQUAL) {
+                        J.ix += imx; J.iy += imy; J.iz += imz;
+                    } else {
+                        const float new_impulse = J.iz + imz;
+                        const bool release = J.limit_state == LIMIT_AT_LOWER ? new_impulse < 0.0f : new_impulse > 0.0f;
+                        if (release) {
+                            const V2 rhs = -Cdot1 + J.iz * mk(W.m_ezx, W.m_ezy);
+                            const V2 reduced = solve22(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, rhs);
+                            imx = reduced.x; imy = reduced.y; imz = -J.iz;
+                            J.ix += reduced.x; J.iy += reduced.y; J.iz = 0.0f;
+                        } else {
+                            J.ix += imx; J.iy += imy; J.iz += imz;
+                        }
+                    }
+                    const V2 P = mk(imx, imy);
+                    v[A] = v[A] - mA * P;
+                    w[A] = w[A] - iA * (cross(W.ra, P) + imz);
+                    v[B] = v[B] + mB * P;
+                    w[B] = w[B] + iB * (cross(W.rb, P) + imz);
+                } else {
+                    const V2 Cdot = v[B] + cross_sv(w[B], W.rb) - v[A] - cross_sv(w[A], W.ra);
+                    const V2 impulse = solve22(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, -Cdot);
+                    J.ix += impulse.x; J.iy += impulse.y;
+                    v[A] = v[A] - mA * impulse;
+                    w[A] = w[A] - iA * cross(W.ra, impulse);
+                    v[B] = v[B] + mB * impulse;
+                    w[B] = w[B] + iB * cross(W.rb, impulse);
+                }
+            }
+            for (int k = 0; k < nc; ++k) {
+                ActiveContact& cc = ac[k];
+                const int B = cc.body;
+                const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+                const V2 normal = cc.normal;
+                const V2 tangent = cross_vs(normal, 1.0f);
+                // friction first
+                for (int j = 0; j < cc.count; ++j) {
+                    VelPoint& vp = cc.p[j];
+                    const V2 dv = v[B] + cross_sv(w[B], vp.rb);
+                    const float vt = dot(dv, tangent);
+                    float lambda = vp.tangent_mass * (-vt);
+                    const float max_friction = cc.friction * vp.normal_impulse;
+                    const float new_impulse = clampf(vp.tangent_impulse + lambda, -max_friction, max_friction);
+                    lambda = new_impulse - vp.tangent_impulse;
+                    vp.tangent_impulse = new_impulse;
+                    const V2 P = lambda * tangent;
+                    v[B] = v[B] + mB * P;
+                    w[B] = w[B] + iB * cross(vp.rb, P);
+                }
+                if (cc.count == 1) {
+                    VelPoint& vp = cc.p[0];
+                    const V2 dv = v[B] + cross_sv(w[B], vp.rb);
+                    const float vn = dot(dv, normal);
+                    float lambda = -vp.normal_mass * (vn - vp.velocity_bias);
+                    const float new_impulse = maxf(vp.normal_impulse + lambda, 0.0f);
+                    lambda = new_impulse - vp.normal_impulse;
+                    vp.normal_impulse = new_impulse;
+                    const V2 P = lambda * normal;
+                    v[B] = v[B] + mB * P;
+                    w[B] = w[B] + iB * cross(vp.rb, P);
+                } else {
+                    VelPoint& cp1 = cc.p[0];
+                    VelPoint& cp2 = cc.p[1];
+                    const V2 aa = mk(cp1.normal_impulse, cp2.normal_impulse);
+                    const V2 dv1 = v[B] + cross_sv(w[B], cp1.rb);
+                    const V2 dv2 = v[B] + cross_sv(w[B], cp2.rb);
+                    float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+                    V2 b = mk(vn1 - cp1.velocity_bias, vn2 - cp2.velocity_bias);
+                    b = b - mk(cc.k11 * aa.x + cc.k12 * aa.y, cc.k12 * aa.x + cc.k22 * aa.y);
+                    V2 x;
+                    bool solved = false;
+                    // case 1: both active
+                    x = -mk(cc.nm11 * b.x + cc.nm12 * b.y, cc.nm21 * b.x + cc.nm22 * b.y);
+                    if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
+                    if (!solved) {   // case 2: x2 = 0
+                        x = mk(-cp1.normal_mass * b.x, 0.0f);
+                        vn2 = cc.k12 * x.x + b.y;
+                        if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
+                    }
+                    if (!solved) {   // case 3: x1 = 0
+                        x = mk(0.0f, -cp2.normal_mass * b.y);
+                        vn1 = cc.k12 * x.y + b.x;
+                        if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
+                    }
+                    if (!solved) {   // case 4: both zero
+                        x = mk(0.0f, 0.0f);
+                        if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
+                    }
+                    if (solved) {
+                        const V2 d = x - aa;
+                        const V2 P1 = d.x * normal, P2 = d.y * normal;
+                        v[B] = v[B] + mB * (P1 + P2);
+                        w[B] = w[B] + iB * (cross(cp1.rb, P1) + cross(cp2.rb, P2));
+                        cp1.normal_impulse = x.x;
+                        cp2.normal_impulse = x.y;
+                    }
+                }
+            }
+        }
+
+        // integrate positions
+        for (int i = 0; i < 3; ++i) {
+            const V2 translation = h * v[i];
+            if (dot(translation, translation) > MAX_TRANSLATION * MAX_TRANSLATION) {
+                const float ratio = MAX_TRANSLATION / sqrtf(dot(translation, translation));
+                v[i] = ratio * v[i];
+            }
+            const float rotation = h * w[i];
+            if (rotation * rotation > MAX_ROTATION * MAX_ROTATION) {
+                const float ratio = MAX_ROTATION / fabsf(rotation);
+                w[i] = w[i] * ratio;
+            }
+            c[i] = c[i] + h * v[i];
+            a[i] = a[i] + h * w[i];
+        }
+
+        // position iterations
+        bool position_solved = false;
+        for (int it = 0; it < POSITION_ITERATIONS; ++it) {
+            float min_separation = 0.0f;
+            for (int k = 0; k < nc; ++k) {
+                const ActiveContact& cc = ac[k];
+                const int B = cc.body;
+                const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+                for (int j = 0; j < cc.m.count; ++j) {
+                    const Rot qB = rot(a[B]);
+                    const V2 pB = c[B] - rmul(qB, SHAPES[B].centroid);
+                    V2 normal, point;
+                    float separation;
+                    if (cc.m.type == MF_FACE_A) {
+                        normal = cc.m.local_normal;
+                        const V2 plane = cc.m.local_point;
+                        const V2 clip = rmul(qB, cc.m.lp[j]) + pB;
+                        separation = dot(clip - plane, normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+                        point = clip;
+                    } else {
+                        normal = rmul(qB, cc.m.local_normal);
+                        const V2 plane = rmul(qB, cc.m.local_point) + pB;
+                        const V2 clip = cc.m.lp[j];
+                        separation = dot(clip - plane, normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+                        point = clip;
+                        normal = -normal;
+                    }
+                    const V2 rB = point - c[B];
+                    min_separation = minf(min_separation, separation);
+                    const float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
+                    const float rnB = cross(rB, normal);
+                    const float K = mB + iB * rnB * rnB;
+                    const float impulse = K > 0.0f ? -C / K : 0.0f;
+                    const V2 P = impulse * normal;
+                    c[B] = c[B] + mB * P;
+                    a[B] = a[B] + iB * cross(rB, P);
+                }
+            }
+            const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
+            bool joints_okay = true;
+            for (int jj = 0; jj < 2; ++jj) {
+                const int ji = 1 - jj;
+                const int A = 0, B = 1 + ji;
+                const Joint& J = L.j[ji];
+                const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+                float angular_error = 0.0f;
+                if (J.limit_state != LIMIT_INACTIVE) {
+                    const float angle = a[B] - a[A] - JOINTS[ji].ref_angle;
+                    float limit_impulse = 0.0f;
+                    const float motor_mass = jw[ji].motor_mass;
+                    if (J.limit_state == LIMIT_EQUAL) {
+                        const float C = clampf(angle - JOINTS[ji].lower, -MAX_ANGULAR_CORRECTION, MAX_ANGULAR_CORRECTION);
+                        limit_impulse = -motor_mass * C;
+                        angular_error = fabsf(C);
+                    } else if (J.limit_state == LIMIT_AT_LOWER) {
+                        float C = angle - JOINTS[ji].lower;
+                        angular_error = -C;
+                        C = clampf(C + ANGULAR_SLOP, -MAX_ANGULAR_CORRECTION, 0.0f);
+                        limit_impulse = -motor_mass * C;
+                    } else {
+                        float C = angle - JOINTS[ji].upper;
+                        angular_error = C;
+                        C = clampf(C - ANGULAR_SLOP, 0.0f, MAX_ANGULAR_CORRECTION);
+                        limit_impulse = -motor_mass * C;
+                    }
+                    a[A] = a[A] - iA * limit_impulse;
+                    a[B] = a[B] + iB * limit_impulse;
+                }
+                const Rot qA = rot(a[A]), qB = rot(a[B]);
+                const V2 rA = rmul(qA, mk(0.0f, 0.0f) - SHAPES[A].centroid);
+                const V2 rB = rmul(qB, JOINTS[ji].anchor_b - SHAPES[B].centroid);
+                const V2 C = c[B] + rB - c[A] - rA;
+                const float position_error = sqrtf(dot(C, C));
+                const float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+                const float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+                const float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+                const V2 impulse = -solve22(kxx, kxy, kxy, kyy, C);
+                c[A] = c[A] - mA * impulse;
+                a[A] = a[A] - iA * cross(rA, impulse);
+                c[B] = c[B] + mB * impulse;
+                a[B] = a[B] + iB * cross(rB, impulse);
+                joints_okay = joints_okay && (position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP);
+            }
+            if (contacts_okay && joints_okay) { position_solved = true; break; }
+        }
+
+        // copy back, store impulses (b2ContactSolver::StoreImpulses)
+        for (int i = 0; i < 3; ++i) { L.b[i].c = c[i]; L.b[i].a = a[i]; L.b[i].v = v[i]; L.b[i].w = w[i]; }
+        for (int s = 0; s < MAXC; ++s) {
+            ContactSlot& cs = L.c[s];
+            if (s < nc) {
+                cs.pair = ac[s].body * 16 + ac[s].edge;
+                for (int k = 0; k < 2; ++k) {
+                    const bool live = k < ac[s].m.count;
+                    cs.key[k] = live ? ac[s].m.key[k] : NO_KEY;
+                    cs.ni[k] = live ? ac[s].p[k].normal_impulse : 0.0f;
+                    cs.ti[k] = live ? ac[s].p[k].tangent_impulse : 0.0f;
+                }
+            } else {
+                cs.pair = -1; cs.key[0] = cs.key[1] = NO_KEY; cs.ni[0] = cs.ni[1] = cs.ti[0] = cs.ti[1] = 0.0f;
+            }
+        }
+
+        // sleeping (b2Island::Solve tail)
+        float min_sleep = 3.4028234663852886e38f;
+        const float lin_tol_sqr = LINEAR_SLEEP_TOL * LINEAR_SLEEP_TOL, ang_tol_sqr = ANGULAR_SLEEP_TOL * ANGULAR_SLEEP_TOL;
+        for (int i = 0; i < 3; ++i) {
+            if (L.b[i].w * L.b[i].w > ang_tol_sqr || dot(L.b[i].v, L.b[i].v) > lin_tol_sqr) {
+                L.b[i].sleep_time = 0.0f;
+                min_sleep = 0.0f;
+            } else {
+                L.b[i].sleep_time = L.b[i].sleep_time + h;
+                min_sleep = minf(min_sleep, L.b[i].sleep_time);
+            }
+        }
+        if (min_sleep >= TIME_TO_SLEEP && position_solved) set_awake(L, false);
+    }
+    // ClearForces
+    L.force = mk(0.0f, 0.0f);
+    L.torque = 0.0f;
+    L.flags &= ~F_FIRST_STEP;
+}
+
+// ---------------------------------------------------------------- Body.ApplyLinearImpulse(impulse, point)
+__device__ __forceinline__ void apply_linear_impulse(Lander& L, V2 impulse, V2 point) {
+    set_awake(L, true);
+    Body& f = L.b[0];
+    f.v = f.v + SHAPES[0].inv_mass * impulse;
+    f.w = f.w + SHAPES[0].inv_inertia * cross(point - f.c, impulse);
+}
+
+__device__ __forceinline__ void observe(const Lander& L, float* o) {   // LunarLanderEnv.cs:733-747
+    const Rot q1 = rot(L.b[0].a);
+    const V2 p1 = L.b[0].c - rmul(q1, SHAPES[0].centroid);
+    const float helipad_y = VIEW_H / 4.0f;                                                    // :517
+    o[0] = (p1.x - VIEW_W / 2.0f) / (VIEW_W / 2.0f);
+    o[1] = (p1.y - (helipad_y + LEG_DOWN / SCALE)) / (VIEW_H / 2.0f);
+    o[2] = L.b[0].v.x * ((VIEW_W / 2.0f) / 50.0f);
+    o[3] = L.b[0].v.y * ((VIEW_H / 2.0f) / 50.0f);
+    o[4] = L.b[0].a;
+    o[5] = 20.0f * L.b[0].w / 50.0f;
+    o[6] = (L.flags & F_LEG0) ? 1.0f : 0.0f;
+    o[7] = (L.flags & F_LEG1) ? 1.0f : 0.0f;
+}
+
+struct StepResult { float reward; uint8_t done; };
+
+// LunarLanderEnv.Step (:574-774).  `t` indexes the DYNAMICS stream (the two dispersion draws, :611-612).
+__device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action) {
+    const bool continuous = (L.flags & F_CONTINUOUS) != 0;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (continuous) { a0 = clampf(c_action[0], -1.0f, 1.0f); a1 = clampf(c_action[1], -1.0f, 1.0f); }   // :600
+    // wind (:588-596): only while no leg touches the ground
+    if (L.use_wind && !(L.flags & (F_LEG0 | F_LEG1))) {
+        const float wind_mag = (float)(tanh(sin(0.02 * L.wind_idx) + sin(3.14159265358979323846 * 0.01 * L.wind_idx))) * L.wind_power;
+        L.wind_idx += 1;
+        set_awake(L, true);
+        L.force = L.force + mk(wind_mag, 0.0f);
+        const float torque_mag = (float)(tanh(sin(0.02 * L.torque_idx) + sin(3.14159265358979323846 * 0.01 * L.torque_idx))) * L.turbulence_power;
+        L.torque_idx += 1;
+        L.torque = L.torque + torque_mag;
+    }
+    // fuselage pose: Body.Position is the body origin, Rotation the angle (:609, :657)
+    const Rot qf = rot(L.b[0].a);
+    const V2 pos0 = L.b[0].c - rmul(qf, SHAPES[0].centroid);
+    const V2 tip = mk(qf.s, qf.c);                   // :609
+    const V2 side = mk(-tip.y, tip.x);               // :610
+    const Block d = draw(seed, gid, t, STREAM_DYNAMICS);
+    const float disp_x = uniformf(-1.0f, 1.0f, d.w0) / SCALE;   // :611
+    const float disp_y = uniformf(-1.0f, 1.0f, d.w1) / SCALE;   // :612
+    bool fire_main, fire_thruster;
+    if (continuous) { fire_main = a0 > 0.0f; fire_thruster = fabsf(a1) > 0.5f; }          // :618-621
+    else { fire_main = i_action == 2; fire_thruster = i_action == 1 || i_action == 3; }      // :629-630
+    float m_power = 0.0f;
+    if (fire_main) {
+        m_power = continuous ? (clampf(a0, 0.0f, 1.0f) + 1.0f) * 0.5f : 1.0f;                 // :640, :652
+        const float ox = tip.x * (4.0f / SCALE + 2.0f * disp_x) + side.x * disp_y;            // :655
+        const float oy = -tip.y * (4.0f / SCALE + 2.0f * disp_x) - side.y * disp_y;           // :656
+        const V2 impulse_pos = pos0 + mk(ox, oy);                                             // :657
+        const V2 impulse = mk(-ox * MAIN_ENGINE_POWER * m_power, -oy * MAIN_ENGINE_POWER * m_power);   // :665
+        apply_linear_impulse(L, impulse, impulse_pos);                                        // :670
+    }
+    float s_power = 0.0f;
+    if (fire_thruster) {
+        float direction;
+        if (continuous) { direction = a1 < 0.0f ? -1.0f : 1.0f; s_power = clampf(fabsf(a1), 0.5f, 1.0f); }   // :683-684
+        else { direction = (float)i_action - 2.0f; s_power = 1.0f; }                          // :697-698
+        const float ox = tip.x * disp_x + side.x * (3.0f * disp_y + direction * SIDE_ENGINE_AWAY / SCALE);    // :700
+        const float oy = -tip.y * disp_x - side.y * (3.0f * disp_y + direction * SIDE_ENGINE_AWAY / SCALE);   // :701
+        const V2 impulse_pos = pos0 + mk(ox - tip.x * 17.0f / SCALE, oy + tip.y * SIDE_ENGINE_HEIGHT / SCALE);   // :702
+        const V2 impulse = mk(-ox * SIDE_ENGINE_POWER * s_power, -oy * SIDE_ENGINE_POWER * s_power);   // :709
+        apply_linear_impulse(L, impulse, impulse_pos);                                        // :714
+    }
+
+    world_step(L);                                                                            // :721-725
+    if (L.flags & F_FUSELAGE) L.flags |= F_GAME_OVER;                                         // :726-729
+
+    // observation (:733-747)
+    observe(L, L.obs);
+    const float px = L.obs[0], py = L.obs[1], vx = L.obs[2], vy = L.obs[3], angle = L.obs[4];
+    const float l0 = L.obs[6], l1 = L.obs[7];
+    // reward (:748-760)
+    float reward = 0.0f;
+    float shaping = -100.0f * sqrtf(px * px + py * py);
+    shaping += -100.0f * sqrtf(vx * vx + vy * vy);
+    shaping += -100.0f * fabsf(angle);
+    shaping += 10.0f * l0;
+    shaping += 10.0f * l1;
+    if (L.prev_shaping != -3.4028234663852886e38f) reward = shaping - L.prev_shaping;          // float.MinValue sentinel
+    L.prev_shaping = shaping;
+    reward -= m_power * 0.3f;
+    reward -= s_power * 0.03f;
+    uint8_t done = 0;
+    if ((L.flags & F_GAME_OVER) || px > 1.0f) { done = 1; reward = -100.0f; }                 // :762 one-sided: no `< -1` check
+    if (!(L.flags & F_AWAKE)) { done = 1; reward = 100.0f; }                                  // :767
+    return StepResult{reward, done};
+}
+
+// LunarLanderEnv.Reset (:489-572).  `index` = episode ordinal; draws: sub-block 0 = (fx, fy, h0, h1),
+// 1 = (h2..h5), 2 = (h6..h9), 3 = (h10, h11).  Ends with the zero step (:567-571) at step index `t`.
+__device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, uint64_t index, bool continuous, uint64_t t,
+                  float gravity, int use_wind, float wind_power, float turbulence_power) {
+    const int32_t wi = L.wind_idx, ti = L.torque_idx;   // drawn in the constructor, persist across episodes (:409-410)
+    zero_lander(L);
+    L.wind_idx = wi; L.torque_idx = ti;
+    L.gravity = gravity; L.use_wind = use_wind; L.wind_power = wind_power; L.turbulence_power = turbulence_power;
+    L.flags = F_AWAKE | F_FIRST_STEP | (continuous ? F_CONTINUOUS : 0);
+    for (int s = 0; s < MAXC; ++s) { L.c[s].pair = -1; L.c[s].key[0] = L.c[s].key[1] = NO_KEY; }
+    const Block b0 = draw(seed, gid, index, STREAM_RESET, 0), b1 = draw(seed, gid, index, STREAM_RESET, 1),
+                b2 = draw(seed, gid, index, STREAM_RESET, 2), b3 = draw(seed, gid, index, STREAM_RESET, 3);
+    L.force = mk(uniformf(-INITIAL_RANDOM, INITIAL_RANDOM, b0.w0), uniformf(-INITIAL_RANDOM, INITIAL_RANDOM, b0.w1));   // :496
+    L.prev_shaping = -3.4028234663852886e38f;                                                  // :498
+    float height[CHUNKS + 1];
+    const uint32_t hw[12] = {b0.w2, b0.w3, b1.w0, b1.w1, b1.w2, b1.w3, b2.w0, b2.w1, b2.w2, b2.w3, b3.w0, b3.w1};
+    for (int i = 0; i < CHUNKS + 1; ++i) height[i] = uniformf(0.0f, VIEW_H / 2.0f, hw[i]);   // :507
+    const int mid = CHUNKS / 2;
+    const float helipad_y = VIEW_H / 4.0f;
+    for (int i = mid - 2; i <= mid + 2; ++i) height[i] = helipad_y;                             // :518-522
+    for (int i = 0; i < CHUNKS; ++i) {
+        const float h1 = i > 0 ? height[i - 1] : 0.0f;                                         // :526-530
+        float y = 0.33f * (h1 + height[i] + height[i + 1]);                                    // :531
+        if (y > VIEW_H) y = VIEW_H / 4.0f;                                                     // :532-535
+        L.terrain[i] = y;
+    }
+    // bodies: created at the origin / (+-LEG_AWAY/S, 0) with rotation -+0.05 (:259-261), then moved by (W/2, H) (:561-565)
+    const V2 dv = mk(VIEW_W / 2.0f, VIEW_H);
+    for (int i = 0; i < 3; ++i) {
+        const float ang = i == 0 ? 0.0f : (i == 1 ? -0.05f : 0.05f);
+        const V2 origin = i == 0 ? mk(0.0f, 0.0f) : mk((i == 1 ? -1.0f : 1.0f) * LEG_AWAY / SCALE, 0.0f);
+        const V2 pos = origin + dv;
+        L.b[i].a = ang;
+        L.b[i].c = rmul(rot(ang), SHAPES[i].centroid) + pos;
+        L.b[i].v = mk(0.0f, 0.0f); L.b[i].w = 0.0f; L.b[i].sleep_time = 0.0f;
+    }
+    const float zero[2] = {0.0f, 0.0f};
+    step(L, seed, gid, t, 0, zero);                                                            // :567-571
+}
+
+
+}}  // namespace gymcuda::lunar

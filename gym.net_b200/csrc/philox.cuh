@@ -15,7 +15,7 @@
 
 namespace gymcuda {
 
-enum : uint32_t { STREAM_RESET = 0, STREAM_ACTION = 1, STREAM_DYNAMICS = 2 };
+enum : uint32_t { STREAM_RESET = 0, STREAM_ACTION = 1, STREAM_DYNAMICS = 2, STREAM_CTOR = 3 };
 
 struct Block { uint32_t w0, w1, w2, w3; };
 

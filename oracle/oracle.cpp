@@ -48,7 +48,11 @@ struct oracle_env {
     std::vector<int32_t> seeds;  // optional per-env seeds (VecEnv.Seed(int[]), src/Gym/Envs/VecEnv.cs:48-53)
 #ifdef ORACLE_WITH_LUNAR
     std::vector<lunar::Lander> landers;
+    float gravity = -10.0f, wind_power = 15.0f, turbulence_power = 1.5f;
+    int use_wind = 0;
 #endif
+    int EPT() const { return is_lunar() ? ki.ad - 2 : 1; }
+    int ORD() const { return is_lunar() ? ki.ad - 1 : 2; }
     bool is_lunar() const { return kind >= ORACLE_LUNARLANDER; }
     uint64_t seed_of(int i) const { return seeds.empty() ? seed : (uint64_t)(uint32_t)seeds[i]; }
 };
@@ -57,7 +61,7 @@ static void write_obs(oracle_env* e, int i, float* obs) {
     if (!obs) return;
     float* o = obs + (size_t)i * e->ki.od;
 #ifdef ORACLE_WITH_LUNAR
-    if (e->is_lunar()) { std::memcpy(o, e->landers[i].obs, sizeof(float) * 8); return; }
+    if (e->is_lunar()) { lunar::observe(e->landers[i], o); return; }
 #endif
     const bool f32 = e->mode == ORACLE_MODE_F32;
     const double* d = f32 ? nullptr : &e->sd[(size_t)i * e->ki.sd];
@@ -87,19 +91,21 @@ static void write_obs(oracle_env* e, int i, float* obs) {
 }
 
 // Reset of instance i: the RESET draw is indexed by the env's episode ordinal (RNG spec v1).
-static void reset_one(oracle_env* e, int i) {
+static void reset_one(oracle_env* e, int i, uint64_t next_t) {
     int32_t* auxp = &e->aux[(size_t)i * e->ki.ad];
-    const int ORD = e->is_lunar() ? e->ki.ad - 1 : 2;
-    const uint64_t index = (uint64_t)(uint32_t)auxp[ORD];
-    auxp[ORD] += 1;
+    const uint64_t index = (uint64_t)(uint32_t)auxp[e->ORD()];
+    auxp[e->ORD()] += 1;
+    auxp[e->EPT()] = 0;
     const uint32_t gid = e->off + (uint32_t)i;
     const uint64_t seed = e->seed_of(i);
 #ifdef ORACLE_WITH_LUNAR
     if (e->is_lunar()) {
-        lunar::reset(e->landers[i], seed, gid, index, e->kind == ORACLE_LUNARLANDER_CONT, e->mode);
+        lunar::reset(e->landers[i], seed, gid, index, e->kind == ORACLE_LUNARLANDER_CONT, next_t,
+                     e->gravity, e->use_wind, e->wind_power, e->turbulence_power);
         return;
     }
 #endif
+    (void)next_t;
     Block b = draw(seed, gid, index, STREAM_RESET);
     float v[4] = {0, 0, 0, 0};
     const float PI_F = 3.1415927410125732f;
@@ -122,15 +128,13 @@ static void reset_one(oracle_env* e, int i) {
         if (e->mode == ORACLE_MODE_F32) e->sf[(size_t)i * e->ki.sd + k] = v[k];
         else e->sd[(size_t)i * e->ki.sd + k] = (double)v[k];
     }
-    e->aux[(size_t)i * e->ki.ad + 0] = -1;   // steps_beyond_done = -1 (CartPoleEnv.cs:64)
-    e->aux[(size_t)i * e->ki.ad + 1] = 0;
+    auxp[0] = -1;   // steps_beyond_done = -1 (CartPoleEnv.cs:64)
 }
 
 static bool action_valid(const oracle_env* e, int a) { return a >= 0 && a < e->ki.actn; }
 
 // One instance, one step.  Returns 1 if the action was invalid (instance left untouched).
 static int step_one_t(oracle_env* e, int i, const void* actions, float* obs, float* reward, uint8_t* done, uint64_t now) {
-    (void)now;   // used by the DYNAMICS stream of LunarLander only
     const KindInfo& ki = e->ki;
     int ia = 0; const float* fa = nullptr;
     if (ki.actn > 0) ia = ((const int32_t*)actions)[i];
@@ -144,7 +148,7 @@ static int step_one_t(oracle_env* e, int i, const void* actions, float* obs, flo
         else {
             lunar::StepResult lr = lunar::step(e->landers[i], e->seed_of(i), e->off + (uint32_t)i, now, ia, fa);
             r.reward = lr.reward; r.done = lr.done;
-            if (e->limit > 0) aux[1] += 1;
+            if (e->limit > 0) aux[e->EPT()] += 1;
         }
     } else
 #endif
@@ -174,8 +178,8 @@ static int step_one_t(oracle_env* e, int i, const void* actions, float* obs, flo
             if (e->limit > 0) aux[1] += 1;   // the episode-step counter exists only under a time limit
         }
     }
-    if (!invalid && e->limit > 0 && aux[1] >= e->limit) r.done = 1;   // truncation folded into done
-    if (!invalid && r.done && (e->flags & ORACLE_FLAG_AUTO_RESET)) reset_one(e, i);
+    if (!invalid && e->limit > 0 && aux[e->EPT()] >= e->limit) r.done = 1;   // truncation folded into done
+    if (!invalid && r.done && (e->flags & ORACLE_FLAG_AUTO_RESET)) reset_one(e, i, now + 1);
     write_obs(e, i, obs);
     if (reward) reward[i] = r.reward;
     if (done) done[i] = r.done;
@@ -202,7 +206,26 @@ static void parallel_for(int n, int threads, F f) {
     for (auto& th : pool) th.join();
 }
 
+#ifdef ORACLE_WITH_LUNAR
+// LunarLanderEnv ctor (:409-410): _wind_idx / _torque_idx = randint(-9999, 9999), drawn once per generator
+static void lunar_ctor_draws(oracle_env* e) {
+    for (int i = 0; i < e->n; ++i) {
+        Block b = draw(e->seed_of(i), e->off + (uint32_t)i, 0, STREAM_CTOR);
+        e->landers[i].wind_idx = -9999 + (int32_t)(((uint64_t)b.w[0] * 19998u) >> 32);
+        e->landers[i].torque_idx = -9999 + (int32_t)(((uint64_t)b.w[1] * 19998u) >> 32);
+    }
+}
+#endif
+
 extern "C" {
+
+void oracle_set_lunar_params(oracle_env* e, float gravity, int use_wind, float wind_power, float turbulence_power) {
+#ifdef ORACLE_WITH_LUNAR
+    e->gravity = gravity; e->use_wind = use_wind; e->wind_power = wind_power; e->turbulence_power = turbulence_power;
+#else
+    (void)e; (void)gravity; (void)use_wind; (void)wind_power; (void)turbulence_power;
+#endif
+}
 
 int oracle_dims(int kind, int* sd, int* ad, int* od, int* actd, int* actn) {
     if (kind < 0 || kind >= NUM_KINDS) return -1;
@@ -223,18 +246,24 @@ oracle_env* oracle_create(int kind, int n, uint64_t seed, uint32_t off, uint32_t
     if (mode == ORACLE_MODE_F32) e->sf.assign((size_t)n * e->ki.sd, 0.0f);
     else e->sd.assign((size_t)n * e->ki.sd, 0.0);
     e->aux.assign((size_t)n * e->ki.ad, 0);
-    for (int i = 0; i < n; ++i) e->aux[(size_t)i * e->ki.ad] = -1;
+    if (!e->is_lunar()) for (int i = 0; i < n; ++i) e->aux[(size_t)i * e->ki.ad] = -1;
 #ifdef ORACLE_WITH_LUNAR
-    if (e->is_lunar()) e->landers.resize(n);
+    if (e->is_lunar()) {
+        e->landers.resize(n);
+        for (int i = 0; i < n; ++i) std::memset(&e->landers[i], 0, sizeof(lunar::Lander));
+        lunar_ctor_draws(e);
+    }
 #endif
     return e;
 }
 
 void oracle_destroy(oracle_env* e) { delete e; }
 static void restart_streams(oracle_env* e) {   // a new generator restarts every stream (CartPoleEnv.cs:197)
-    const int ORD = e->is_lunar() ? e->ki.ad - 1 : 2;
-    for (int i = 0; i < e->n; ++i) e->aux[(size_t)i * e->ki.ad + ORD] = 0;
+    for (int i = 0; i < e->n; ++i) e->aux[(size_t)i * e->ki.ad + e->ORD()] = 0;
     e->t = 0;
+#ifdef ORACLE_WITH_LUNAR
+    if (e->is_lunar()) lunar_ctor_draws(e);
+#endif
 }
 void oracle_seed(oracle_env* e, uint64_t seed) { e->seed = seed; e->seeds.clear(); restart_streams(e); }
 void oracle_seed_each(oracle_env* e, const int32_t* seeds) { e->seeds.assign(seeds, seeds + e->n); restart_streams(e); }
@@ -242,13 +271,13 @@ void oracle_set_threads(oracle_env* e, int threads) { e->threads = threads < 1 ?
 
 void oracle_reset(oracle_env* e, float* obs) {
     parallel_for(e->n, e->threads, [=](int lo, int hi) {
-        for (int i = lo; i < hi; ++i) { reset_one(e, i); write_obs(e, i, obs); }
+        for (int i = lo; i < hi; ++i) { reset_one(e, i, e->t); write_obs(e, i, obs); }
     });
 }
 
 void oracle_reset_masked(oracle_env* e, const uint8_t* mask, float* obs) {
     for (int i = 0; i < e->n; ++i) {
-        if (mask[i]) reset_one(e, i);
+        if (mask[i]) reset_one(e, i, e->t);
         write_obs(e, i, obs);
     }
 }
@@ -316,8 +345,13 @@ void oracle_get_state(oracle_env* e, double* state, int32_t* aux, uint64_t* t) {
     const size_t m = (size_t)e->n * e->ki.sd;
 #ifdef ORACLE_WITH_LUNAR
     if (e->is_lunar()) {
-        for (int i = 0; i < e->n; ++i) lunar::get_state(e->landers[i], state ? state + (size_t)i * e->ki.sd : nullptr,
-                                                        aux ? aux + (size_t)i * e->ki.ad : nullptr);
+        for (int i = 0; i < e->n; ++i) {
+            lunar::get_state(e->landers[i], state ? state + (size_t)i * e->ki.sd : nullptr, aux ? aux + (size_t)i * e->ki.ad : nullptr);
+            if (aux) {
+                aux[(size_t)i * e->ki.ad + e->EPT()] = e->aux[(size_t)i * e->ki.ad + e->EPT()];
+                aux[(size_t)i * e->ki.ad + e->ORD()] = e->aux[(size_t)i * e->ki.ad + e->ORD()];
+            }
+        }
         if (t) *t = e->t;
         return;
     }
@@ -331,7 +365,11 @@ void oracle_set_state(oracle_env* e, const double* state, const int32_t* aux, ui
     const size_t m = (size_t)e->n * e->ki.sd;
 #ifdef ORACLE_WITH_LUNAR
     if (e->is_lunar()) {
-        for (int i = 0; i < e->n; ++i) lunar::set_state(e->landers[i], state + (size_t)i * e->ki.sd, aux + (size_t)i * e->ki.ad);
+        for (int i = 0; i < e->n; ++i) {
+            lunar::set_state(e->landers[i], state + (size_t)i * e->ki.sd, aux + (size_t)i * e->ki.ad);
+            e->aux[(size_t)i * e->ki.ad + e->EPT()] = aux[(size_t)i * e->ki.ad + e->EPT()];
+            e->aux[(size_t)i * e->ki.ad + e->ORD()] = aux[(size_t)i * e->ki.ad + e->ORD()];
+        }
         e->t = t;
         return;
     }

@@ -46,6 +46,8 @@ int oracle_dims(int kind, int* state_dim, int* aux_dim, int* obs_dim, int* act_d
 void oracle_seed(oracle_env*, uint64_t seed);
 void oracle_seed_each(oracle_env*, const int32_t* seeds);
 void oracle_set_threads(oracle_env*, int threads);
+/* LunarLanderEnv ctor arguments (LunarLanderEnv.cs:381); call before the first reset. */
+void oracle_set_lunar_params(oracle_env*, float gravity, int use_wind, float wind_power, float turbulence_power);
 
 void oracle_reset(oracle_env*, float* obs);
 void oracle_reset_masked(oracle_env*, const uint8_t* mask, float* obs);

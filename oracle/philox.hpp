@@ -19,12 +19,13 @@
 // stream 0 = RESET    index = episode ordinal of the env (number of resets it has had)
 // stream 1 = ACTION   index = block number of the random-policy draw (see action_*)
 // stream 2 = DYNAMICS index = t (LunarLander's two per-step dispersion draws)
+// stream 3 = CTOR     index = 0 (LunarLander's wind / turbulence phase, drawn in its constructor)
 #pragma once
 #include <cstdint>
 
 namespace oracle {
 
-enum : uint32_t { STREAM_RESET = 0, STREAM_ACTION = 1, STREAM_DYNAMICS = 2 };
+enum : uint32_t { STREAM_RESET = 0, STREAM_ACTION = 1, STREAM_DYNAMICS = 2, STREAM_CTOR = 3 };
 
 struct Block { uint32_t w[4]; };
 

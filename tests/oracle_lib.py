@@ -40,6 +40,7 @@ def lib():
         L.oracle_seed.argtypes = [C.c_void_p, C.c_uint64]
         L.oracle_seed_each.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_lunar_params.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]
         L.oracle_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_reset_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 4
