@@ -244,9 +244,11 @@ def main():
     # ---- e2e: host buffers through gymcuda_step (H2D actions, kernel, D2H obs/reward/done), every step
     e2e_steps = args.e2e_steps
     h_act = torch.empty((n, ad), dtype=t_act.dtype).pin_memory()
-    h_obs = torch.empty((n, od), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    # obs | reward | done adjacent in one pinned block (what the C# shim pins): the library then needs one DMA
+    h_out = torch.empty((n * od * 4 + n * 4 + n,), dtype=torch.uint8).pin_memory()
+    h_obs = h_out[: n * od * 4].view(torch.float32).view(n, od)
+    h_rew = h_out[n * od * 4: n * od * 4 + n * 4].view(torch.float32)
+    h_done = h_out[n * od * 4 + n * 4:]
     rng = np.random.default_rng(rank)
     if env.act_n > 0:
         h_act.numpy()[:] = rng.integers(0, env.act_n, (n, ad))

@@ -128,8 +128,11 @@ struct gymcuda_env {
     int auxw;   // int32 words per env in d_aux (LunarLander only)
     // I/O staging for the host-buffer entry points
     void* d_actions;
+    uint8_t* d_out;          // obs | reward | done
     float *d_obs, *d_reward;
     uint8_t *d_done, *d_mask;
+    volatile int* h_invalid; // mapped pinned flag: set by the step kernel when it rejects an action
+    int* d_invalid_flag;
     int32_t *d_done_idx, *d_done_count;
     unsigned long long* d_stats;
     const float* last_obs;   // device pointer of the most recent observations
@@ -256,7 +259,8 @@ int gymcuda_destroy(gymcuda_env* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux);
-    cudaFree(e->d_actions); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done); cudaFree(e->d_mask);
+    cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
+    if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -279,9 +283,15 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMalloc(&e->d_ept, n * 4));
     CU_TRY(cudaMalloc(&e->d_episode, n * 4));
     CU_TRY(cudaMalloc(&e->d_actions, e->act_bytes()));
-    CU_TRY(cudaMalloc(&e->d_obs, e->obs_bytes()));
-    CU_TRY(cudaMalloc(&e->d_reward, n * 4));
-    CU_TRY(cudaMalloc(&e->d_done, n));
+    // obs | reward | done live in ONE allocation, in the order of the C ABI's out-parameters, so that a
+    // caller whose three host buffers are adjacent gets them with a single DMA
+    CU_TRY(cudaMalloc(&e->d_out, e->obs_bytes() + n * 4 + n));
+    e->d_obs = reinterpret_cast<float*>(e->d_out);
+    e->d_reward = reinterpret_cast<float*>(e->d_out + e->obs_bytes());
+    e->d_done = reinterpret_cast<uint8_t*>(e->d_out + e->obs_bytes() + n * 4);
+    CU_TRY(cudaHostAlloc((void**)&e->h_invalid, sizeof(int), cudaHostAllocMapped));
+    *e->h_invalid = 0;
+    CU_TRY(cudaHostGetDevicePointer((void**)&e->d_invalid_flag, (void*)e->h_invalid, 0));
     CU_TRY(cudaMalloc(&e->d_mask, n));
     CU_TRY(cudaMalloc(&e->d_done_idx, n * 4));
     CU_TRY(cudaMalloc(&e->d_done_count, 2 * sizeof(int32_t)));
@@ -452,7 +462,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     StepArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
-    a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats;
+    a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
     CU_TRY(dispatch_step(e, a));
@@ -464,12 +474,21 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
 }
 
 static int step_finish_host(gymcuda_env* e, float* obs, float* reward, uint8_t* done) {
-    if (obs) CU_TRY(cudaMemcpyAsync(obs, e->d_obs, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
-    if (reward) CU_TRY(cudaMemcpyAsync(reward, e->d_reward, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (done) CU_TRY(cudaMemcpyAsync(done, e->d_done, (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
-    CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    const size_t ob = e->obs_bytes(), n = (size_t)e->n;
+    const bool adjacent = obs && reward && done && reinterpret_cast<uint8_t*>(obs) + ob == reinterpret_cast<uint8_t*>(reward) &&
+                          reinterpret_cast<uint8_t*>(reward) + n * 4 == done;
+    if (adjacent) {
+        CU_TRY(cudaMemcpyAsync(obs, e->d_out, ob + n * 4 + n, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        if (obs) CU_TRY(cudaMemcpyAsync(obs, e->d_obs, ob, cudaMemcpyDeviceToHost, e->stream));
+        if (reward) CU_TRY(cudaMemcpyAsync(reward, e->d_reward, n * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (done) CU_TRY(cudaMemcpyAsync(done, e->d_done, n, cudaMemcpyDeviceToHost, e->stream));
+    }
     CU_TRY(cudaStreamSynchronize(e->stream));
-    if (e->h_small[1] != e->invalid_seen) {
+    if (*e->h_invalid) {   // written through mapped memory by the kernel: no extra copy on the common path
+        *e->h_invalid = 0;
+        CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
         unsigned long long bad = e->h_small[1] - e->invalid_seen;
         e->invalid_seen = e->h_small[1];
         return fail(GYMCUDA_EACTION, "%llu action(s) invalid for this action space; those envs were not stepped", bad);

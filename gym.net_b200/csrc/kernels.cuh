@@ -49,6 +49,7 @@ struct StepArgs {
     int32_t* done_idx;                 // may be null
     int32_t* done_count;               // [2], indexed by the parity of `seq`
     unsigned long long* stats;         // [0] episodes finished, [1] invalid actions
+    int* host_invalid;                 // mapped host flag raised when an action is rejected
     int n;
     uint32_t env_off;
     uint64_t seed;
@@ -228,7 +229,11 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     const unsigned m = __ballot_sync(0xffffffffu, done);
     const unsigned mi = __ballot_sync(0xffffffffu, invalid);
     if (lane == 0) warp_cnt[warp] = __popc(m);
-    if (mi != 0 && lane == 0) atomicAdd(&p.stats[1], (unsigned long long)__popc(mi));
+    if (mi != 0 && lane == 0) {
+        atomicAdd(&p.stats[1], (unsigned long long)__popc(mi));
+        *reinterpret_cast<volatile int*>(p.host_invalid) = 1;
+        __threadfence_system();
+    }
     __syncthreads();
     int warp_off = 0, total = 0;
 #pragma unroll
