@@ -131,6 +131,7 @@ struct gymcuda_env {
     uint8_t* d_out;          // obs | reward | done
     float *d_obs, *d_reward;
     uint8_t *d_done, *d_mask;
+    const void* alias_host[4]; void* alias_dev[4];   // cache of mapped_alias()
     volatile int* h_invalid; // mapped pinned flag: set by the step kernel when it rejects an action
     int* d_invalid_flag;
     int32_t *d_done_idx, *d_done_count;
@@ -473,6 +474,20 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     return GYMCUDA_OK;
 }
 
+// Device-visible alias of a host pointer if (and only if) it is page-locked memory mapped into the
+// device address space (cudaHostAlloc / cudaHostRegister / gymcuda_host_alloc), else null.
+static void* mapped_alias(gymcuda_env* e, const void* host, int slot) {
+    if (!host) return nullptr;
+    if (e->alias_host[slot] == host) return e->alias_dev[slot];
+    cudaPointerAttributes at;
+    void* dev = nullptr;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) dev = at.devicePointer;
+    else cudaGetLastError();   // pageable memory reports an error on old drivers: clear it
+    e->alias_host[slot] = host;
+    e->alias_dev[slot] = dev;
+    return dev;
+}
+
 static int step_finish_host(gymcuda_env* e, float* obs, float* reward, uint8_t* done) {
     const size_t ob = e->obs_bytes(), n = (size_t)e->n;
     const bool adjacent = obs && reward && done && reinterpret_cast<uint8_t*>(obs) + ob == reinterpret_cast<uint8_t*>(reward) &&
@@ -500,6 +515,21 @@ int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward,
     ENTER(e);
     if (!actions) return fail(GYMCUDA_EINVAL, "actions is null");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
+    // Zero-copy path: when all four host buffers are page-locked, the kernel reads the actions and
+    // writes obs / reward / done straight through their device aliases -- the H2D and D2H traffic
+    // crosses PCIe inside the step kernel, overlapped with the math, with no DMA set-up per buffer.
+    void* za = mapped_alias(e, actions, 0);
+    void* zo = mapped_alias(e, obs, 1);
+    void* zr = mapped_alias(e, reward, 2);
+    void* zd = mapped_alias(e, done, 3);
+    if (za && zo && zr && zd) {
+        int rc = step_launch(e, za, 0, 0, (float*)zo, (float*)zr, (uint8_t*)zd);
+        if (rc) return rc;
+        e->last_obs = nullptr;   // the observations were written to host memory only
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        if (*e->h_invalid) return step_finish_host(e, nullptr, nullptr, nullptr);
+        return GYMCUDA_OK;
+    }
     CU_TRY(cudaMemcpyAsync(e->d_actions, actions, e->act_bytes(), cudaMemcpyHostToDevice, e->stream));
     int rc = step_launch(e, e->d_actions, 0, 0, e->d_obs, e->d_reward, e->d_done);
     if (rc) return rc;
@@ -714,7 +744,7 @@ int gymcuda_sync(gymcuda_env* e) {
 
 int gymcuda_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(GYMCUDA_EINVAL, "ptr is null");
-    CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
     return GYMCUDA_OK;
 }
 

@@ -117,6 +117,9 @@ int gymcuda_reset_masked(gymcuda_env* env, const uint8_t* mask, float* obs_out);
 
 /* ---- Env.Step / IVecEnv.Step ------------------------------------------------------------------ */
 /* Host buffers; H2D(actions) -> kernel -> D2H(obs, reward, done); synchronous.
+ * Pageable buffers are staged with cudaMemcpyAsync (one DMA for obs|reward|done when they are adjacent);
+ * page-locked buffers (gymcuda_host_alloc, cudaHostAlloc, cudaHostRegister, GCHandle-pinned + registered)
+ * are read and written by the kernel directly over PCIe (zero-copy), which is the fast path.
  * Returns GYMCUDA_EACTION if any action was outside the action space of an env kind that rejects
  * it (all but CartPole, whose reference only Debug.Asserts, CartPoleEnv.cs:139); those envs are
  * left unstepped, the others step normally. */

@@ -345,3 +345,34 @@ def test_full_size_config2_properties():
     assert 15 < lengths < 35                        # random-policy CartPole episodes last ~22 steps
     assert env.Stats()["episodes"] == int(done.sum())
     env.Close()
+
+
+def test_zero_copy_pinned_buffers_match_staged_copies():
+    """gymcuda_step with page-locked host buffers (kernel reads/writes them over PCIe) == pageable path."""
+    import ctypes as C
+    from gymnet_b200 import _native as N
+    n = 3000
+    L = N.lib()
+    a_env = G.CartPoleVecEnv(n, seed=4, auto_reset=True); a_env.ResetBatch()
+    b_env = G.CartPoleVecEnv(n, seed=4, auto_reset=True); b_env.ResetBatch()
+    nbytes = n * 4 + n * 16 + n * 4 + n
+    ptr = C.c_void_p()
+    N.check(L.gymcuda_host_alloc(C.byref(ptr), nbytes))
+    buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+    raw = np.frombuffer(buf, dtype=np.uint8)
+    act = raw[: n * 4].view(np.int32)
+    obs = raw[n * 4: n * 20].view(np.float32).reshape(n, 4)
+    rew = raw[n * 20: n * 24].view(np.float32)
+    done = raw[n * 24:]
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        a = rng.integers(0, 2, n).astype(np.int32)
+        act[:] = a
+        N.check(L.gymcuda_step(a_env._h, C.c_void_p(act.ctypes.data), C.c_void_p(obs.ctypes.data),
+                               C.c_void_p(rew.ctypes.data), C.c_void_p(done.ctypes.data)))
+        o, r, d = b_env.StepBatch(a)
+        assert np.array_equal(obs, o) and np.array_equal(rew, r) and np.array_equal(done, d)
+    assert np.array_equal(a_env.Observe(), b_env.Observe())
+    del act, obs, rew, done, raw, buf
+    N.check(L.gymcuda_host_free(ptr))
+    a_env.Close(); b_env.Close()
