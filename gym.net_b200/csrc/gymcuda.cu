@@ -172,14 +172,20 @@ static cudaError_t launch_step(gymcuda_env* e, const StepArgs& a) {
     return cudaGetLastError();
 }
 
+template <class E, bool ALL_OUT>
+static void launch_rollout_variant(gymcuda_env* e, const RolloutArgs& a, int grid) {
+    const bool ar = e->auto_reset, lim = e->limit > 0;
+    if (ar && lim) rollout_kernel<E, true, true, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    else if (ar) rollout_kernel<E, true, false, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    else if (lim) rollout_kernel<E, false, true, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    else rollout_kernel<E, false, false, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+}
+
 template <class E>
 static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
     const int grid = (e->n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
-    const bool ar = e->auto_reset, lim = e->limit > 0;
-    if (ar && lim) rollout_kernel<E, true, true><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
-    else if (ar) rollout_kernel<E, true, false><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
-    else if (lim) rollout_kernel<E, false, true><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
-    else rollout_kernel<E, false, false><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    if (a.obs && a.reward && a.done && a.actions) launch_rollout_variant<E, true>(e, a, grid);
+    else launch_rollout_variant<E, false>(e, a, grid);
     return cudaGetLastError();
 }
 

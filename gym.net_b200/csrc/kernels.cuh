@@ -267,7 +267,9 @@ __device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint
     E::reset(next, seed, gid, (uint32_t)ep, t, prm);
 }
 
-template <class E, bool AUTO_RESET, bool LIMIT>
+// ALL_OUT: every trajectory pointer is non-null (the benchmark / learner case): the stores are
+// unconditional and addressed by four running pointers instead of per-step 64-bit index arithmetic.
+template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT>
 __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
     using S = typename E::S;
     const int i = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
@@ -290,6 +292,10 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         S next;
         if (PREGEN) next = s;
         bool have = false;
+        float* po = p.obs + (size_t)i * E::OD;
+        float* pr = p.reward + i;
+        uint8_t* pd = p.done + i;
+        typename E::Act* pa = reinterpret_cast<typename E::Act*>(p.actions) + i;
         for (int k = 0; k < p.k_steps; ++k) {
             const uint64_t t = p.t + (uint64_t)k;
             if (PREGEN && (k & (ROLLOUT_REFILL - 1)) == 0 && !have) {
@@ -314,15 +320,25 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                     ept = 0;
                 }
             }
-            const size_t idx = (size_t)k * n + (size_t)i;
-            if (p.obs) {
+            if (ALL_OUT) {
                 float o[E::OD];
                 E::obs(s, o);
-                store_obs<E::OD, true>(p.obs, idx, o);
+                store_obs<E::OD, true>(po, 0, o);
+                __stcs(pr, r.reward);
+                __stcs(pd, (uint8_t)r.done);
+                __stcs(pa, a);
+                po += n * E::OD; pr += n; pd += n; pa += n;
+            } else {
+                const size_t idx = (size_t)k * n + (size_t)i;
+                if (p.obs) {
+                    float o[E::OD];
+                    E::obs(s, o);
+                    store_obs<E::OD, true>(p.obs, idx, o);
+                }
+                if (p.reward) __stcs(p.reward + idx, r.reward);
+                if (p.done) __stcs(p.done + idx, (uint8_t)r.done);
+                if (p.actions) ActIO<E>::store(p.actions, idx, a);
             }
-            if (p.reward) __stcs(p.reward + idx, r.reward);
-            if (p.done) __stcs(p.done + idx, (uint8_t)r.done);
-            if (p.actions) ActIO<E>::store(p.actions, idx, a);
         }
         if (AUTO_RESET) p.episode[i] = ep;
         E::store(p.state, p.aux, p.n, i, s);

@@ -314,6 +314,11 @@ __device__ __forceinline__ V2 solve22(float a11, float a12, float a21, float a22
     return mk(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
 }
 
+// Body-indexed access with a run-time body index, written as selects over compile-time indices so that
+// the per-body arrays stay in registers (a dynamically indexed array would be demoted to local memory).
+#define GETB(arr, B) ((B) == 0 ? arr[0] : ((B) == 1 ? arr[1] : arr[2]))
+#define SETB(arr, B, val) do { if ((B) == 0) arr[0] = (val); else if ((B) == 1) arr[1] = (val); else arr[2] = (val); } while (0)
+
 // ---------------------------------------------------------------- World.Step(dt) for one lander
 __device__ __forceinline__ void set_awake(Lander& L, bool awake) {
     if (awake) {
@@ -381,7 +386,9 @@ __device__ __noinline__ void world_step(Lander& L) {
     if (L.flags & F_AWAKE) {
         V2 c[3], v[3];
         float a[3], w[3];
+        Joint Jl[2] = {L.j[0], L.j[1]};   // joint accumulators live in registers during the iterations
         const V2 gravity = mk(0.0f, L.gravity);
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
             c[i] = L.b[i].c; a[i] = L.b[i].a; v[i] = L.b[i].v; w[i] = L.b[i].w;
             const V2 f = i == 0 ? L.force : mk(0.0f, 0.0f);
@@ -396,9 +403,10 @@ __device__ __noinline__ void world_step(Lander& L) {
         for (int k = 0; k < nc; ++k) {
             ActiveContact& cc = ac[k];
             const int B = cc.body;
+            V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
             const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
-            const Rot qB = rot(a[B]);
-            const V2 pB = c[B] - rmul(qB, SHAPES[B].centroid);
+            const Rot qB = rot(aB);
+            const V2 pB = cB - rmul(qB, SHAPES[B].centroid);
             cc.friction = sqrtf(edge_friction(cc.edge) * SHAPES[B].friction);   // MixFriction
             V2 normal, pts[2];
             if (cc.m.type == MF_FACE_A) {
@@ -427,7 +435,7 @@ __device__ __noinline__ void world_step(Lander& L) {
                 VelPoint& vp = cc.p[j];
                 vp.normal_impulse = dt_ratio * vp.normal_impulse;
                 vp.tangent_impulse = dt_ratio * vp.tangent_impulse;
-                vp.rb = pts[j] - c[B];
+                vp.rb = pts[j] - cB;
                 const float rnB = cross(vp.rb, normal);
                 const float kn = mB + iB * rnB * rnB;
                 vp.normal_mass = kn > 0.0f ? 1.0f / kn : 0.0f;
@@ -456,19 +464,22 @@ __device__ __noinline__ void world_step(Lander& L) {
         for (int k = 0; k < nc; ++k) {
             ActiveContact& cc = ac[k];
             const int B = cc.body;
+            V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
             const V2 tangent = cross_vs(cc.normal, 1.0f);
             for (int j = 0; j < cc.count; ++j) {
                 const V2 P = cc.p[j].normal_impulse * cc.normal + cc.p[j].tangent_impulse * tangent;
-                w[B] = w[B] + SHAPES[B].inv_inertia * cross(cc.p[j].rb, P);
-                v[B] = v[B] + SHAPES[B].inv_mass * P;
+                wB = wB + SHAPES[B].inv_inertia * cross(cc.p[j].rb, P);
+                vB = vB + SHAPES[B].inv_mass * P;
             }
+            SETB(v, B, vB); SETB(w, B, wB); SETB(c, B, cB); SETB(a, B, aB);
         }
         // joints: InitVelocityConstraints, island order leg1's joint, then leg0's
         JointWork jw[2];
+#pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
             const int ji = 1 - jj;
             const int A = 0, B = 1 + ji;
-            Joint& J = L.j[ji];
+            Joint& J = Jl[ji];
             JointWork& W = jw[ji];
             const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
             const Rot qA = rot(a[A]), qB = rot(a[B]);
@@ -506,10 +517,11 @@ __device__ __noinline__ void world_step(Lander& L) {
 
         // velocity iterations
         for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+#pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int ji = 1 - jj;
                 const int A = 0, B = 1 + ji;
-                Joint& J = L.j[ji];
+                Joint& J = Jl[ji];
                 const JointWork& W = jw[ji];
                 const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 // motor
@@ -575,13 +587,14 @@ __device__ __noinline__ void world_step(Lander& L) {
             for (int k = 0; k < nc; ++k) {
                 ActiveContact& cc = ac[k];
                 const int B = cc.body;
+                V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
                 const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 const V2 normal = cc.normal;
                 const V2 tangent = cross_vs(normal, 1.0f);
                 // friction first
                 for (int j = 0; j < cc.count; ++j) {
                     VelPoint& vp = cc.p[j];
-                    const V2 dv = v[B] + cross_sv(w[B], vp.rb);
+                    const V2 dv = vB + cross_sv(wB, vp.rb);
                     const float vt = dot(dv, tangent);
                     float lambda = vp.tangent_mass * (-vt);
                     const float max_friction = cc.friction * vp.normal_impulse;
@@ -589,26 +602,26 @@ __device__ __noinline__ void world_step(Lander& L) {
                     lambda = new_impulse - vp.tangent_impulse;
                     vp.tangent_impulse = new_impulse;
                     const V2 P = lambda * tangent;
-                    v[B] = v[B] + mB * P;
-                    w[B] = w[B] + iB * cross(vp.rb, P);
+                    vB = vB + mB * P;
+                    wB = wB + iB * cross(vp.rb, P);
                 }
                 if (cc.count == 1) {
                     VelPoint& vp = cc.p[0];
-                    const V2 dv = v[B] + cross_sv(w[B], vp.rb);
+                    const V2 dv = vB + cross_sv(wB, vp.rb);
                     const float vn = dot(dv, normal);
                     float lambda = -vp.normal_mass * (vn - vp.velocity_bias);
                     const float new_impulse = maxf(vp.normal_impulse + lambda, 0.0f);
                     lambda = new_impulse - vp.normal_impulse;
                     vp.normal_impulse = new_impulse;
                     const V2 P = lambda * normal;
-                    v[B] = v[B] + mB * P;
-                    w[B] = w[B] + iB * cross(vp.rb, P);
+                    vB = vB + mB * P;
+                    wB = wB + iB * cross(vp.rb, P);
                 } else {
                     VelPoint& cp1 = cc.p[0];
                     VelPoint& cp2 = cc.p[1];
                     const V2 aa = mk(cp1.normal_impulse, cp2.normal_impulse);
-                    const V2 dv1 = v[B] + cross_sv(w[B], cp1.rb);
-                    const V2 dv2 = v[B] + cross_sv(w[B], cp2.rb);
+                    const V2 dv1 = vB + cross_sv(wB, cp1.rb);
+                    const V2 dv2 = vB + cross_sv(wB, cp2.rb);
                     float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
                     V2 b = mk(vn1 - cp1.velocity_bias, vn2 - cp2.velocity_bias);
                     b = b - mk(cc.k11 * aa.x + cc.k12 * aa.y, cc.k12 * aa.x + cc.k22 * aa.y);
@@ -634,16 +647,18 @@ __device__ __noinline__ void world_step(Lander& L) {
                     if (solved) {
                         const V2 d = x - aa;
                         const V2 P1 = d.x * normal, P2 = d.y * normal;
-                        v[B] = v[B] + mB * (P1 + P2);
-                        w[B] = w[B] + iB * (cross(cp1.rb, P1) + cross(cp2.rb, P2));
+                        vB = vB + mB * (P1 + P2);
+                        wB = wB + iB * (cross(cp1.rb, P1) + cross(cp2.rb, P2));
                         cp1.normal_impulse = x.x;
                         cp2.normal_impulse = x.y;
                     }
                 }
+                SETB(v, B, vB); SETB(w, B, wB); SETB(c, B, cB); SETB(a, B, aB);
             }
         }
 
         // integrate positions
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
             const V2 translation = h * v[i];
             if (dot(translation, translation) > MAX_TRANSLATION * MAX_TRANSLATION) {
@@ -666,10 +681,11 @@ __device__ __noinline__ void world_step(Lander& L) {
             for (int k = 0; k < nc; ++k) {
                 const ActiveContact& cc = ac[k];
                 const int B = cc.body;
+                V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
                 const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 for (int j = 0; j < cc.m.count; ++j) {
-                    const Rot qB = rot(a[B]);
-                    const V2 pB = c[B] - rmul(qB, SHAPES[B].centroid);
+                    const Rot qB = rot(aB);
+                    const V2 pB = cB - rmul(qB, SHAPES[B].centroid);
                     V2 normal, point;
                     float separation;
                     if (cc.m.type == MF_FACE_A) {
@@ -686,23 +702,25 @@ __device__ __noinline__ void world_step(Lander& L) {
                         point = clip;
                         normal = -normal;
                     }
-                    const V2 rB = point - c[B];
+                    const V2 rB = point - cB;
                     min_separation = minf(min_separation, separation);
                     const float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
                     const float rnB = cross(rB, normal);
                     const float K = mB + iB * rnB * rnB;
                     const float impulse = K > 0.0f ? -C / K : 0.0f;
                     const V2 P = impulse * normal;
-                    c[B] = c[B] + mB * P;
-                    a[B] = a[B] + iB * cross(rB, P);
+                    cB = cB + mB * P;
+                    aB = aB + iB * cross(rB, P);
                 }
+                SETB(v, B, vB); SETB(w, B, wB); SETB(c, B, cB); SETB(a, B, aB);
             }
             const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
             bool joints_okay = true;
+#pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int ji = 1 - jj;
                 const int A = 0, B = 1 + ji;
-                const Joint& J = L.j[ji];
+                const Joint& J = Jl[ji];
                 const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 float angular_error = 0.0f;
                 if (J.limit_state != LIMIT_INACTIVE) {
@@ -746,7 +764,9 @@ __device__ __noinline__ void world_step(Lander& L) {
         }
 
         // copy back, store impulses (b2ContactSolver::StoreImpulses)
+#pragma unroll
         for (int i = 0; i < 3; ++i) { L.b[i].c = c[i]; L.b[i].a = a[i]; L.b[i].v = v[i]; L.b[i].w = w[i]; }
+        L.j[0] = Jl[0]; L.j[1] = Jl[1];
         for (int s = 0; s < MAXC; ++s) {
             ContactSlot& cs = L.c[s];
             if (s < nc) {
@@ -765,6 +785,7 @@ __device__ __noinline__ void world_step(Lander& L) {
         // sleeping (b2Island::Solve tail)
         float min_sleep = 3.4028234663852886e38f;
         const float lin_tol_sqr = LINEAR_SLEEP_TOL * LINEAR_SLEEP_TOL, ang_tol_sqr = ANGULAR_SLEEP_TOL * ANGULAR_SLEEP_TOL;
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
             if (L.b[i].w * L.b[i].w > ang_tol_sqr || dot(L.b[i].v, L.b[i].v) > lin_tol_sqr) {
                 L.b[i].sleep_time = 0.0f;
