@@ -12,6 +12,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gymnet_b200 as G  # noqa: E402
 
 
+def _second_id(rank):
+    ids = [G.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    return ids[0]
+
+
 def main():
     out_dir = sys.argv[1]
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -32,6 +38,24 @@ def main():
         np.save(os.path.join(out_dir, "gathered.npy"), out.cpu().numpy())
     dist.barrier()
     env.Close()
+    # config 5 shape: LunarLander shards, one step, obs all-gather of the step's observations
+    n2, off2 = G.shard_envs(2048, rank, world)
+    ll = G.LunarLanderVecEnv(n2, seed=5, device=local, env_id_offset=off2, auto_reset=True)
+    ll.CommInit(_second_id(rank), rank, world)
+    ll.ResetBatch()
+    d_obs = torch.empty((n2, 8), dtype=torch.float32, device="cuda")
+    d_rew = torch.empty((n2,), dtype=torch.float32, device="cuda")
+    d_done = torch.empty((n2,), dtype=torch.uint8, device="cuda")
+    acts = torch.full((n2,), 2, dtype=torch.int32, device="cuda")
+    for _ in range(20):
+        ll.StepDevice(acts.data_ptr(), d_obs.data_ptr(), d_rew.data_ptr(), d_done.data_ptr())
+    out2 = torch.empty((world, n2, 8), dtype=torch.float32, device="cuda")
+    ll.AllGatherObs(out2.data_ptr(), d_obs.data_ptr())
+    ll.Sync()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered_lunar.npy"), out2.cpu().numpy())
+    dist.barrier()
+    ll.Close()
     dist.destroy_process_group()
 
 
