@@ -84,6 +84,10 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_nccl_unique_id(byte[] id128);
         [DllImport(Lib)] internal static extern int gymcuda_comm_init(GymCudaHandle env, byte[] id128, int rank, int worldSize);
         [DllImport(Lib)] internal static extern int gymcuda_allgather_obs(GymCudaHandle env, IntPtr dObs, IntPtr dOut);
+        [DllImport(Lib)] internal static extern int gymcuda_gather_create(GymCudaHandle env, int rank, int worldSize, byte[] handle64);
+        [DllImport(Lib)] internal static extern int gymcuda_gather_open(GymCudaHandle env, byte[] handles);
+        [DllImport(Lib)] internal static extern int gymcuda_step_gather_device(GymCudaHandle env, IntPtr dActions, IntPtr dReward, IntPtr dDone, out IntPtr dGathered);
+        [DllImport(Lib)] internal static extern int gymcuda_gather_wait(GymCudaHandle env);
 
         /// <summary>Error convention of the boundary: status code -> the reference's exception types.</summary>
         internal static void Check(int status) {

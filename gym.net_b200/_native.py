@@ -73,6 +73,10 @@ SYMBOLS = {
     "gymcuda_nccl_unique_id": (_I, [_VP]),
     "gymcuda_comm_init": (_I, [_VP, _VP, _I, _I]),
     "gymcuda_allgather_obs": (_I, [_VP, _VP, _VP]),
+    "gymcuda_gather_create": (_I, [_VP, _I, _I, _VP]),
+    "gymcuda_gather_open": (_I, [_VP, _VP]),
+    "gymcuda_step_gather_device": (_I, [_VP, _VP, _VP, _VP, C.POINTER(_VP)]),
+    "gymcuda_gather_wait": (_I, [_VP]),
 }
 
 

@@ -143,6 +143,12 @@ struct gymcuda_env {
     // nccl
     void* comm;
     int rank, world;
+    // fused gather over peer memory
+    int g_world, g_rank;
+    uint32_t g_seq;
+    uint8_t* g_local;                 // [2][world][n][od] floats, then flags[world] u32, then block counter
+    size_t g_flags_off, g_counter_off;
+    void* g_peer[MAX_PEERS];          // mapped base of every rank's g_local (own entry = g_local)
     size_t act_bytes() const { return (size_t)n * ki.ad * 4; }
     size_t obs_bytes() const { return (size_t)n * ki.od * 4; }
 };
@@ -264,6 +270,8 @@ int gymcuda_destroy(gymcuda_env* e) {
     if (!e) return GYMCUDA_OK;
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (int r = 0; r < e->g_world; ++r) if (e->g_peer[r] && r != e->g_rank) cudaIpcCloseMemHandle(e->g_peer[r]);
+    cudaFree(e->g_local);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux);
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
@@ -464,7 +472,7 @@ int gymcuda_reset_masked(gymcuda_env* e, const uint8_t* mask, float* obs_out) {
 // step
 // ------------------------------------------------------------------------------------------------
 static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int32_t bcast, float* d_obs,
-                       float* d_reward, uint8_t* d_done) {
+                       float* d_reward, uint8_t* d_done, bool gather = false) {
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
     StepArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
@@ -472,6 +480,15 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
+    if (gather) {
+        e->g_seq += 1;
+        a.world = e->g_world; a.rank = e->g_rank; a.gseq = e->g_seq;
+        for (int r = 0; r < e->g_world; ++r) {
+            a.peer_obs[r] = reinterpret_cast<float*>(e->g_peer[r]);
+            a.peer_flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(e->g_peer[r]) + e->g_flags_off);
+        }
+        a.block_counter = reinterpret_cast<unsigned*>(e->g_local + e->g_counter_off);
+    }
     CU_TRY(dispatch_step(e, a));
     e->t += 1;
     e->seq += 1;
@@ -795,6 +812,63 @@ int gymcuda_allgather_obs(gymcuda_env* e, const float* d_obs, float* d_out) {
         src = e->last_obs;
     }
     NCCL_TRY(g_nccl.AllGather(src, d_out, (size_t)e->n * e->ki.od, /* ncclFloat32 */ 7, e->comm, e->stream));
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused step + observation gather over peer memory
+// ------------------------------------------------------------------------------------------------
+int gymcuda_gather_create(gymcuda_env* e, int rank, int world_size, uint8_t handle_out[64]) {
+    ENTER(e);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!handle_out || world_size <= 0 || world_size > MAX_PEERS || rank < 0 || rank >= world_size)
+        return fail(GYMCUDA_EINVAL, "bad rank/world_size (at most %d ranks: the GPUs of one box)", MAX_PEERS);
+    if (e->g_local) return fail(GYMCUDA_EINVAL, "gather buffer already created");
+    const size_t obs_bytes = 2 * (size_t)world_size * e->obs_bytes();
+    e->g_flags_off = (obs_bytes + 255) & ~(size_t)255;
+    e->g_counter_off = e->g_flags_off + 256;
+    CU_TRY(cudaMalloc(&e->g_local, e->g_counter_off + 256));
+    CU_TRY(cudaMemset(e->g_local, 0, e->g_counter_off + 256));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, e->g_local));
+    std::memcpy(handle_out, &h, 64);
+    e->g_world = world_size; e->g_rank = rank; e->g_seq = 0;
+    for (int r = 0; r < MAX_PEERS; ++r) e->g_peer[r] = nullptr;
+    e->g_peer[rank] = e->g_local;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_gather_open(gymcuda_env* e, const uint8_t* handles) {
+    ENTER(e);
+    if (!e->g_local) return fail(GYMCUDA_EINVAL, "call gymcuda_gather_create first");
+    if (!handles) return fail(GYMCUDA_EINVAL, "handles is null");
+    for (int r = 0; r < e->g_world; ++r) {
+        if (r == e->g_rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * 64, 64);
+        CU_TRY(cudaIpcOpenMemHandle(&e->g_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    return GYMCUDA_OK;
+}
+
+int gymcuda_step_gather_device(gymcuda_env* e, const void* d_actions, float* d_reward, uint8_t* d_done, const float** d_gathered) {
+    ENTER(e);
+    if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
+    if (!e->g_local) return fail(GYMCUDA_EINVAL, "gather buffer not created");
+    for (int r = 0; r < e->g_world; ++r) if (!e->g_peer[r]) return fail(GYMCUDA_EINVAL, "gymcuda_gather_open has not mapped rank %d", r);
+    int rc = step_launch(e, d_actions, 0, 0, nullptr, d_reward ? d_reward : e->d_reward, d_done ? d_done : e->d_done, true);
+    if (rc) return rc;
+    const float* base = reinterpret_cast<const float*>(e->g_local) + (size_t)(e->g_seq & 1u) * e->g_world * (size_t)e->n * e->ki.od;
+    e->last_obs = base + (size_t)e->g_rank * (size_t)e->n * e->ki.od;
+    if (d_gathered) *d_gathered = base;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_gather_wait(gymcuda_env* e) {
+    ENTER(e);
+    if (!e->g_local) return fail(GYMCUDA_EINVAL, "gather buffer not created");
+    gather_wait_kernel<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->g_local + e->g_flags_off), e->g_world, e->g_seq);
+    CU_TRY(cudaGetLastError());
     return GYMCUDA_OK;
 }
 

@@ -35,6 +35,8 @@
 
 namespace gymcuda {
 
+constexpr int MAX_PEERS = 8;   // GPUs of one NVSwitch box
+
 struct StepArgs {
     void* state;
     int32_t* aux;
@@ -59,6 +61,12 @@ struct StepArgs {
     int32_t bcast_action;
     uint32_t seq;                      // step-launch sequence number of this handle
     EnvParams prm;
+    // fused observation gather over NVLink peer memory (world == 0: off)
+    int world, rank;
+    uint32_t gseq;                     // gather sequence number (parity selects the double buffer)
+    float* peer_obs[MAX_PEERS];        // every rank's gather buffer [2][world][n][OD], mapped with cudaIpc
+    uint32_t* peer_flags[MAX_PEERS];   // every rank's arrival flags [world]
+    unsigned* block_counter;           // last-block detection
 };
 
 struct RolloutArgs {
@@ -216,7 +224,11 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         }
         float o[E::OD];
         E::obs(s, o);
-        store_obs<E::OD, false>(p.obs, (size_t)i, o);
+        if (p.obs) store_obs<E::OD, false>(p.obs, (size_t)i, o);
+        // step + all-gather in one kernel: the observation goes straight into slot `rank` of EVERY rank's
+        // gather buffer with peer stores over NVLink (the local copy is just the peer == rank case)
+        for (int r = 0; r < p.world; ++r)
+            store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
         p.reward[i] = r.reward;
         p.done[i] = (uint8_t)r.done;
         done = r.done;
@@ -256,6 +268,31 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         __syncthreads();
         if (done) p.done_idx[block_base + warp_off + __popc(m & ((1u << lane) - 1u))] = i;
     }
+    // ---- gather signal: once the LAST block's peer stores are fenced, publish gseq in every rank's flag word
+    if (p.world > 0) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(p.block_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *p.block_counter = 0u;
+                __threadfence_system();
+                for (int r = 0; r < p.world; ++r) *reinterpret_cast<volatile uint32_t*>(p.peer_flags[r] + p.rank) = p.gseq;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// Waits (on the consumer's stream) until every rank's observations of gather step `gseq` have landed in
+// this rank's buffer: one thread per peer spins on that peer's arrival flag.
+__global__ void gather_wait_kernel(const uint32_t* flags, int world, uint32_t gseq) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        const volatile uint32_t* f = flags + r;
+        while ((int32_t)(*f - gseq) < 0) { __nanosleep(64); }
+    }
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------- fused random-policy rollout

@@ -204,6 +204,27 @@ class CudaVecEnv:
     def AllGatherObs(self, d_out, d_obs=0):
         N.check(self._L.gymcuda_allgather_obs(self._h, C.c_void_p(d_obs or 0), C.c_void_p(d_out)))
 
+    # ---- fused step + obs gather over NVLink peer memory -----------------------------------------------
+    def GatherCreate(self, rank, world_size):
+        buf = (C.c_uint8 * 64)()
+        N.check(self._L.gymcuda_gather_create(self._h, int(rank), int(world_size), buf))
+        return bytes(buf)
+
+    def GatherOpen(self, handles):
+        blob = b"".join(bytes(h) for h in handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        N.check(self._L.gymcuda_gather_open(self._h, buf))
+
+    def StepGatherDevice(self, d_actions, d_reward=0, d_done=0):
+        """Step + all-gather in one kernel; returns the device pointer of this rank's [world][n][obs_dim] view."""
+        out = C.c_void_p()
+        N.check(self._L.gymcuda_step_gather_device(self._h, C.c_void_p(d_actions), C.c_void_p(d_reward or 0),
+                                                   C.c_void_p(d_done or 0), C.byref(out)))
+        return out.value
+
+    def GatherWait(self):
+        N.check(self._L.gymcuda_gather_wait(self._h))
+
     # ---- source-compatible IVecEnv members -----------------------------------------------------------
     def Reset(self):
         """IVecEnv.Reset() -> NDArray[] (one observation array per env)."""

@@ -178,6 +178,18 @@ int gymcuda_comm_init(gymcuda_env* env, const uint8_t id[128], int rank, int wor
  * d_obs == NULL gathers the observations of the last step/reset. */
 int gymcuda_allgather_obs(gymcuda_env* env, const float* d_obs, float* d_out);
 
+/* ---- fused step + observation all-gather over NVLink peer memory (no NCCL on the step path) ------ */
+/* Every rank: gather_create (allocates its double-buffered [world][num_envs][obs_dim] gather buffer and
+ * arrival flags, returns a 64-byte cudaIpcMemHandle), exchange the handles out of band, gather_open.
+ * gymcuda_step_gather_device then runs the step kernel with the observation stores aimed at slot `rank`
+ * of EVERY rank's buffer (peer stores), and *d_gathered receives this rank's [world][num_envs][obs_dim]
+ * view of the step; gymcuda_gather_wait enqueues the arrival wait on the handle's stream. */
+int gymcuda_gather_create(gymcuda_env* env, int rank, int world_size, uint8_t handle_out[64]);
+int gymcuda_gather_open(gymcuda_env* env, const uint8_t* handles /* [world_size][64] */);
+int gymcuda_step_gather_device(gymcuda_env* env, const void* d_actions, float* d_reward, uint8_t* d_done,
+                               const float** d_gathered);
+int gymcuda_gather_wait(gymcuda_env* env);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,39 @@ def main():
         np.save(os.path.join(out_dir, "gathered.npy"), out.cpu().numpy())
     dist.barrier()
     env.Close()
+    # fused step + gather over peer memory (no NCCL on the step path) vs ncclAllGather of the same step
+    fz = G.CartPoleVecEnv(n, seed=33, device=local, env_id_offset=off, auto_reset=True)
+    fz.CommInit(_second_id(rank), rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, fz.GatherCreate(rank, world))
+    fz.GatherOpen(handles)
+    fz.ResetBatch()
+    f_rew = torch.empty((n,), dtype=torch.float32, device="cuda")
+    f_done = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    ref_out = torch.empty((world, n, 4), dtype=torch.float32, device="cuda")
+    gen = torch.Generator(device="cuda"); gen.manual_seed(100 + rank)
+    ok = True
+    for step in range(25):
+        a = torch.randint(0, 2, (n,), dtype=torch.int32, device="cuda", generator=gen)
+        torch.cuda.synchronize()
+        ptr = fz.StepGatherDevice(a.data_ptr(), f_rew.data_ptr(), f_done.data_ptr())
+        fz.GatherWait()
+        fz.AllGatherObs(ref_out.data_ptr())          # NCCL gather of the same observations (last_obs = own slot)
+        fz.Sync()
+        import ctypes
+        host = np.empty((world, n, 4), np.float32)
+        torch.cuda.synchronize()
+        import ctypes as C
+        libcudart = torch.cuda.cudart()
+        fused = torch.empty((world, n, 4), dtype=torch.float32, device="cuda")
+        libcudart.cudaMemcpy(fused.data_ptr(), ptr, fused.numel() * 4, 3)
+        ok = ok and bool(torch.equal(fused, ref_out))
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "fused_ok.npy"), flag.numpy())
+    dist.barrier()
+    fz.Close()
     # config 5 shape: LunarLander shards, one step, obs all-gather of the step's observations
     n2, off2 = G.shard_envs(2048, rank, world)
     ll = G.LunarLanderVecEnv(n2, seed=5, device=local, env_id_offset=off2, auto_reset=True)
