@@ -156,6 +156,51 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_gather(env, torch, dist, dev, rank, world, n, od, ad, t_act, steps=200):
+    import gymnet_b200 as G
+    ids = [G.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    env.CommInit(ids[0], rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, env.GatherCreate(rank, world))
+    env.GatherOpen(handles)
+    a1 = t_act[0].contiguous()
+    d_obs = torch.empty((n, od), dtype=torch.float32, device=dev)
+    d_rew = torch.empty((n,), dtype=torch.float32, device=dev)
+    d_done = torch.empty((n,), dtype=torch.uint8, device=dev)
+    out = torch.empty((world, n, od), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def timed(fn):
+        for _ in range(10):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) * 1e3   # us per step, max over ranks
+
+    def plain():
+        env.StepDevice(a1.data_ptr(), d_obs.data_ptr(), d_rew.data_ptr(), d_done.data_ptr())
+
+    def nccl():
+        env.StepDevice(a1.data_ptr(), d_obs.data_ptr(), d_rew.data_ptr(), d_done.data_ptr())
+        env.AllGatherObs(out.data_ptr(), d_obs.data_ptr())
+
+    def fused():
+        env.StepGatherDevice(a1.data_ptr(), d_rew.data_ptr(), d_done.data_ptr())
+        env.GatherWait()
+
+    return {"unit": "us per step of %d envs per GPU, max over ranks" % n, "step_only": timed(plain),
+            "step_then_ncclAllGather": timed(nccl), "step_fused_p2p_gather": timed(fused),
+            "gathered_bytes_per_rank": world * n * od * 4}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -278,6 +323,12 @@ def main():
            "h2d_bytes_per_step": n * ad * 4, "d2h_bytes_per_step": n * (od * 4 + 4 + 1),
            "api": "gymcuda_step (host buffers, pinned)", "steps": e2e_steps}
 
+    # ---- N > 1 only, outside the headline timing: what the optional observation all-gather costs per step,
+    # with NCCL after the step kernel and fused into it as NVLink peer stores (gymcuda_step_gather_device)
+    gather = None
+    if world > 1:
+        gather = measure_gather(env, torch, dist, dev, rank, world, n, od, ad, t_act)
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port of the reference's CPU path
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -294,7 +345,7 @@ def main():
                                    "fused rollout launch of %d env steps per env" % (args.env, n, K),
                        "num_envs_per_gpu": n, "inner_steps": K, "parallelism": "independent env shards, no collective",
                        "l2": "outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (launch_bytes / 1e6)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "obs_allgather": gather,
             "gpu_launches": args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -12,6 +12,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gymnet_b200 as G  # noqa: E402
 
 
+class _RawCuda:
+    """CUDA array interface over a raw device pointer returned by the C ABI."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 def _second_id(rank):
     ids = [G.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -57,13 +64,7 @@ def main():
         fz.GatherWait()
         fz.AllGatherObs(ref_out.data_ptr())          # NCCL gather of the same observations (last_obs = own slot)
         fz.Sync()
-        import ctypes
-        host = np.empty((world, n, 4), np.float32)
-        torch.cuda.synchronize()
-        import ctypes as C
-        libcudart = torch.cuda.cudart()
-        fused = torch.empty((world, n, 4), dtype=torch.float32, device="cuda")
-        libcudart.cudaMemcpy(fused.data_ptr(), ptr, fused.numel() * 4, 3)
+        fused = torch.as_tensor(_RawCuda(ptr, (world, n, 4)), device="cuda")   # zero-copy view of the gather buffer
         ok = ok and bool(torch.equal(fused, ref_out))
     flag = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
