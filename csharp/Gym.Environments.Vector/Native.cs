@@ -70,6 +70,9 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_step_broadcast(GymCudaHandle env, int action, float[] obs, float[] reward, byte[] done);
         [DllImport(Lib)] internal static extern int gymcuda_rollout_random_device(GymCudaHandle env, int kSteps, IntPtr dObs, IntPtr dReward, IntPtr dDone, IntPtr dActions);
         [DllImport(Lib)] internal static extern int gymcuda_rollout_random(GymCudaHandle env, int kSteps, float[] obs, float[] reward, byte[] done, int[] actions);
+        [DllImport(Lib)] internal static extern int gymcuda_sample_actions(GymCudaHandle env, byte[] mask, int[] actionsOut);
+        [DllImport(Lib)] internal static extern int gymcuda_sample_actions(GymCudaHandle env, byte[] mask, float[] actionsOut);
+        [DllImport(Lib)] internal static extern int gymcuda_sample_actions_device(GymCudaHandle env, IntPtr dMask, IntPtr dActionsOut);
         [DllImport(Lib)] internal static extern int gymcuda_done_indices(GymCudaHandle env, int[] idx, out int count);
         [DllImport(Lib)] internal static extern int gymcuda_done_indices_device(GymCudaHandle env, out IntPtr dIdx, out IntPtr dCount);
         [DllImport(Lib)] internal static extern int gymcuda_get_state(GymCudaHandle env, float[] state, int[] aux, out ulong t);

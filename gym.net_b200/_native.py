@@ -59,6 +59,8 @@ SYMBOLS = {
     "gymcuda_step_broadcast": (_I, [_VP, C.c_int32, _VP, _VP, _VP]),
     "gymcuda_rollout_random_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_rollout_random": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "gymcuda_sample_actions": (_I, [_VP, _VP, _VP]),
+    "gymcuda_sample_actions_device": (_I, [_VP, _VP, _VP]),
     "gymcuda_done_indices": (_I, [_VP, _VP, C.POINTER(C.c_int32)]),
     "gymcuda_done_indices_device": (_I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     "gymcuda_get_state": (_I, [_VP, _VP, _VP, C.POINTER(_U64)]),

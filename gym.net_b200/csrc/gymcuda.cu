@@ -125,6 +125,7 @@ struct gymcuda_env {
     void* d_state;
     int32_t *d_sbd, *d_ept, *d_episode, *d_seeds, *d_aux;
     EnvParams prm;
+    int32_t *d_perm, *d_block_free;   // LunarLander contact partition
     int auxw;   // int32 words per env in d_aux (LunarLander only)
     // I/O staging for the host-buffer entry points
     void* d_actions;
@@ -222,7 +223,13 @@ static cudaError_t launch_reset(gymcuda_env* e, const ResetArgs& a) {
 
 static cudaError_t dispatch_step(gymcuda_env* e, const StepArgs& a) { DISPATCH(step, a) }
 static cudaError_t dispatch_rollout(gymcuda_env* e, const RolloutArgs& a) { DISPATCH(rollout, a) }
+template <class E>
+static cudaError_t launch_sample(gymcuda_env* e, const SampleArgs& a) {
+    sample_kernel<E><<<(e->n + 127) / 128, 128, 0, e->stream>>>(a);
+    return cudaGetLastError();
+}
 static cudaError_t dispatch_reset(gymcuda_env* e, const ResetArgs& a) { DISPATCH(reset, a) }
+static cudaError_t dispatch_sample(gymcuda_env* e, const SampleArgs& a) { DISPATCH(sample, a) }
 
 // constructor draws (LunarLander only): at create and whenever the generator is replaced by Seed()
 static cudaError_t dispatch_ctor(gymcuda_env* e, const ResetArgs& a) {
@@ -233,6 +240,16 @@ static cudaError_t dispatch_ctor(gymcuda_env* e, const ResetArgs& a) {
 #endif
     (void)e; (void)a;
     return cudaGetLastError();
+}
+
+// LunarLander: stable partition of the env ids by "has a touching contact" (kernels.cuh); null otherwise
+static const int32_t* contact_partition(gymcuda_env* e) {
+    if (!e->d_perm) return nullptr;
+    const int nb = (e->n + PART_BLOCK - 1) / PART_BLOCK;
+    partition_count_kernel<<<nb, PART_BLOCK, 0, e->stream>>>(e->d_aux, e->n, e->d_block_free);
+    partition_scan_kernel<<<1, 1024, 0, e->stream>>>(e->d_block_free, nb);
+    partition_scatter_kernel<<<nb, PART_BLOCK, 0, e->stream>>>(e->d_aux, e->n, e->d_block_free, nb, e->d_perm);
+    return e->d_perm;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -273,7 +290,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     for (int r = 0; r < e->g_world; ++r) if (e->g_peer[r] && r != e->g_rank) cudaIpcCloseMemHandle(e->g_peer[r]);
     cudaFree(e->g_local);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
-    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux);
+    cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux); cudaFree(e->d_perm); cudaFree(e->d_block_free);
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats);
@@ -293,6 +310,10 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     if (e->auxw > 0) {
         CU_TRY(cudaMalloc(&e->d_aux, n * (size_t)e->auxw * 4));
         CU_TRY(cudaMemsetAsync(e->d_aux, 0, n * (size_t)e->auxw * 4, e->stream));
+        if (e->n >= 2048) {   // worth three tiny launches only for batches that fill the GPU
+            CU_TRY(cudaMalloc(&e->d_perm, n * 4));
+            CU_TRY(cudaMalloc(&e->d_block_free, ((n + PART_BLOCK - 1) / PART_BLOCK + 1) * 4));
+        }
     }
     CU_TRY(cudaMalloc(&e->d_sbd, n * 4));
     CU_TRY(cudaMalloc(&e->d_ept, n * 4));
@@ -480,6 +501,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
+    a.perm = contact_partition(e);
     if (gather) {
         e->g_seq += 1;
         a.world = e->g_world; a.rank = e->g_rank; a.gseq = e->g_seq;
@@ -585,6 +607,7 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats;
     a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
+    a.perm = contact_partition(e);
     CU_TRY(dispatch_rollout(e, a));
     e->t += (uint64_t)k_steps;
     e->env_steps += (unsigned long long)e->n * (unsigned long long)k_steps;
@@ -614,6 +637,40 @@ int gymcuda_rollout_random(gymcuda_env* e, int k_steps, float* obs, float* rewar
 #undef RB_TRY
     cleanup();
     return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ActionSpace.Sample on device
+// ------------------------------------------------------------------------------------------------
+int gymcuda_sample_actions_device(gymcuda_env* e, const uint8_t* d_mask, void* d_actions_out) {
+    ENTER(e);
+    if (!d_actions_out) return fail(GYMCUDA_EINVAL, "d_actions_out is null");
+    if (d_mask && e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "Box.sample cannot be provided a mask.");   // Box.cs:70-73
+    SampleArgs a{};
+    a.seeds = e->d_seeds; a.mask = d_mask; a.out = d_actions_out; a.n = e->n; a.env_off = e->cfg.env_id_offset;
+    a.seed = e->seed; a.t = e->t;
+    CU_TRY(dispatch_sample(e, a));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_sample_actions(gymcuda_env* e, const uint8_t* mask, void* actions_out) {
+    ENTER(e);
+    if (!actions_out) return fail(GYMCUDA_EINVAL, "actions_out is null");
+    if (mask && e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "Box.sample cannot be provided a mask.");
+    uint8_t* d_mask = nullptr;
+    if (mask) {
+        CU_TRY(cudaMalloc(&d_mask, (size_t)e->n * e->ki.actn));
+        cudaError_t ce = cudaMemcpyAsync(d_mask, mask, (size_t)e->n * e->ki.actn, cudaMemcpyHostToDevice, e->stream);
+        if (ce != cudaSuccess) { cudaFree(d_mask); return fail(GYMCUDA_ECUDA, "mask copy failed: %s", cudaGetErrorString(ce)); }
+    }
+    int rc = gymcuda_sample_actions_device(e, d_mask, e->d_actions);
+    if (rc == GYMCUDA_OK) {
+        cudaError_t ce = cudaMemcpyAsync(actions_out, e->d_actions, e->act_bytes(), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) rc = fail(GYMCUDA_ECUDA, "sample copy failed: %s", cudaGetErrorString(ce));
+    }
+    cudaFree(d_mask);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

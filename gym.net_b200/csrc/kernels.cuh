@@ -44,6 +44,7 @@ struct StepArgs {
     int32_t* ep_t;
     int32_t* episode;
     const int32_t* seeds;
+    const int32_t* perm;               // thread -> env map (LunarLander contact partition), null = identity
     const void* actions;
     float* obs;
     float* reward;
@@ -76,6 +77,7 @@ struct RolloutArgs {
     int32_t* ep_t;
     int32_t* episode;
     const int32_t* seeds;
+    const int32_t* perm;   // thread -> env map, null = identity
     float* obs;        // [k][n][OD]   may be null
     float* reward;     // [k][n]       may be null
     uint8_t* done;     // [k][n]       may be null
@@ -194,10 +196,12 @@ template <class E, bool AUTO_RESET, bool LIMIT>
 __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     using S = typename E::S;
     using Act = typename E::Act;
-    const int i = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    const int tix = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    int i = tix;
     bool done = false;
     bool invalid = false;
-    if (i < p.n) {
+    if (tix < p.n) {
+        if (p.perm) i = p.perm[tix];
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
         const Act a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
         int32_t sbd = -1;
@@ -309,9 +313,10 @@ __device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint
 template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT>
 __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
     using S = typename E::S;
-    const int i = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
+    const int tix = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
     unsigned episodes = 0;
-    if (i < p.n) {
+    if (tix < p.n) {
+        const int i = p.perm ? p.perm[tix] : tix;
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
         int32_t sbd = -1;
         if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
@@ -408,6 +413,105 @@ __global__ void __launch_bounds__(128) reset_kernel(const ResetArgs p) {
         E::obs(s, o);
         store_obs<E::OD, false>(p.obs, (size_t)i, o);
     }
+}
+
+// ---------------------------------------------------------------- contact partition (LunarLander)
+// A lander with a touching contact runs a several times longer solver path than one in free flight, and a
+// warp runs as long as its slowest lane.  A STABLE partition of the env ids by "has a touching contact"
+// (warp ballot + block counts + scan, the machinery of the done compaction) puts the expensive landers in
+// their own warps; stability keeps each class in ascending env order, so the field-major loads of a warp
+// still fall in a handful of neighbouring sectors.  Results are unaffected: which thread steps an env is
+// invisible to it.
+constexpr int PART_BLOCK = 256;
+
+__device__ __forceinline__ bool lander_in_contact(const int32_t* aux, int n, int i) {
+    return (aux[i] | aux[(size_t)n + i] | aux[2 * (size_t)n + i]) != 0;   // touch[0..2]: first three aux words
+}
+
+__global__ void __launch_bounds__(PART_BLOCK) partition_count_kernel(const int32_t* aux, int n, int32_t* block_free) {
+    const int i = blockIdx.x * PART_BLOCK + threadIdx.x;
+    const bool free_flight = i < n && !lander_in_contact(aux, n, i);
+    const int c = __syncthreads_count(free_flight);
+    if (threadIdx.x == 0) block_free[blockIdx.x] = c;
+}
+
+// single block: exclusive scan of the per-block counts, in place; block_free[nb] = total
+__global__ void __launch_bounds__(1024) partition_scan_kernel(int32_t* block_free, int nb) {
+    __shared__ int carry;
+    __shared__ int warp_sum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int j = base + (int)threadIdx.x;
+        const int v = j < nb ? block_free[j] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= (unsigned)o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_sum[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= (unsigned)o) w += y; }
+            warp_sum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int incl = x + ((threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0);
+        if (j < nb) block_free[j] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_free[nb] = carry;
+}
+
+__global__ void __launch_bounds__(PART_BLOCK) partition_scatter_kernel(const int32_t* aux, int n, const int32_t* block_free, int nb, int32_t* perm) {
+    __shared__ int warp_free[PART_BLOCK / 32];
+    const int i = blockIdx.x * PART_BLOCK + threadIdx.x;
+    const bool in = i < n;
+    const bool free_flight = in && !lander_in_contact(aux, n, i);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, free_flight);
+    if (lane == 0) warp_free[warp] = __popc(m);
+    __syncthreads();
+    int before = 0;   // free-flight envs of this block before this warp
+    for (int w = 0; w < (int)warp; ++w) before += warp_free[w];
+    const int free_rank = before + __popc(m & ((1u << lane) - 1u));
+    const int local = (int)threadIdx.x;
+    if (in) {
+        const int free_base = block_free[blockIdx.x], total_free = block_free[nb];
+        if (free_flight) perm[free_base + free_rank] = i;
+        else perm[total_free + (blockIdx.x * PART_BLOCK - free_base) + (local - free_rank)] = i;
+    }
+}
+
+// ActionSpace.Sample() for every env at step index t: the same draws the rollout kernel consumes, so
+// sample -> step loops reproduce gymcuda_rollout_random.  With a mask (Discrete only, Discrete.cs:19-25):
+// uniform over the entries equal to 1, `Start` (= 0) when none is.
+struct SampleArgs { const int32_t* seeds; const uint8_t* mask; void* out; int n; uint32_t env_off; uint64_t seed; uint64_t t; };
+
+template <class E>
+__global__ void __launch_bounds__(128) sample_kernel(const SampleArgs p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint64_t seed = seed_of(p.seeds, p.seed, i);
+    const uint32_t gid = p.env_off + (uint32_t)i;
+    ActionGen<E> gen;
+    typename E::Act a = gen.next(seed, gid, p.t, true);
+    if (E::ACTN > 0 && p.mask != nullptr) {
+        const uint8_t* m = p.mask + (size_t)i * (E::ACTN > 0 ? E::ACTN : 1);
+        int valid = 0;
+        for (int k = 0; k < E::ACTN; ++k) valid += (m[k] == 1);
+        int pick = 0;
+        if (valid > 0) {
+            // an independent full word of the ACTION stream (sub-block 1) picks the j-th valid entry
+            const Block b = draw(seed, gid, p.t, STREAM_ACTION, 1);
+            int j = (int)__umulhi(b.w0, (uint32_t)valid);
+            for (int k = 0; k < E::ACTN; ++k) if (m[k] == 1) { if (j == 0) { pick = k; break; } --j; }
+        }
+        a = ActCast<typename E::Act>::from_int(pick);
+    }
+    reinterpret_cast<typename E::Act*>(p.out)[i] = a;
 }
 
 template <class E>

@@ -151,6 +151,18 @@ class CudaVecEnv:
         N.check(self._L.gymcuda_rollout_random(self._h, k, _ptr(obs), _ptr(rew), _ptr(done), _ptr(act)))
         return obs, rew, done, act
 
+    def SampleActions(self, mask=None):
+        """ActionSpace.Sample() for every env on the device (Discrete.Sample(mask) / Box.Sample())."""
+        n = self.NumberOfEnvironments
+        out = np.empty(n, np.int32) if self.act_n > 0 else np.empty((n, self.act_dim), np.float32)
+        m = None
+        if mask is not None:
+            if self.act_n == 0:
+                raise NotImplementedError("Box.sample cannot be provided a mask.")
+            m = np.ascontiguousarray(mask, dtype=np.uint8).reshape(n, self.act_n)
+        N.check(self._L.gymcuda_sample_actions(self._h, _ptr(m), _ptr(out)))
+        return out
+
     def DoneIndices(self):
         cnt = C.c_int32()
         idx = np.empty(self.NumberOfEnvironments, np.int32)

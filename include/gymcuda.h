@@ -138,6 +138,14 @@ int gymcuda_rollout_random_device(gymcuda_env* env, int k_steps, float* d_obs, f
 int gymcuda_rollout_random(gymcuda_env* env, int k_steps, float* obs, float* reward, uint8_t* done,
                            void* actions);
 
+/* ---- ActionSpace.Sample() on device: Discrete.Sample(mask) / Box.Sample() ---------------------------- */
+/* One action per env from the engine's ACTION stream at the current step index -- the draws
+ * gymcuda_rollout_random consumes, so `sample; step` loops reproduce a rollout bit for bit.
+ * mask: Discrete spaces only, uint8 [num_envs][act_n], entries == 1 are valid (src/Gym/Spaces/Discrete.cs:17-28:
+ * uniform over the valid entries, Start when none); a mask on a Box space is GYMCUDA_EINVAL (Box.cs:70-73). */
+int gymcuda_sample_actions(gymcuda_env* env, const uint8_t* mask, void* actions_out);
+int gymcuda_sample_actions_device(gymcuda_env* env, const uint8_t* d_mask, void* d_actions_out);
+
 /* ---- done compaction (valid after a step) ------------------------------------------------------ */
 /* Indices (local env ids, ascending within a thread block, block order unspecified) of the envs
  * whose last step returned done, and their number.  idx may be NULL to fetch only the count. */

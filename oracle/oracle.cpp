@@ -341,6 +341,41 @@ void oracle_rollout_random(oracle_env* e, int K, float* obs, float* reward, uint
     }
 }
 
+// ActionSpace.Sample() at the current step index (Discrete.cs:17-28 with a mask, Box.cs:84): the ACTION-stream
+// draw of step t; with a mask, word 0 of sub-block 1 picks uniformly among the entries equal to 1.
+void oracle_sample_actions(oracle_env* e, const uint8_t* mask, void* out) {
+    const KindInfo ki = e->ki;
+    for (int i = 0; i < e->n; ++i) {
+        const uint32_t gid = e->off + (uint32_t)i;
+        const uint64_t seed = e->seed_of(i), t = e->t;
+        if (ki.actn > 0) {
+            int a = 0;
+            switch (ki.actn) {
+                case 2: a = action_discrete2(seed, gid, t); break;
+                case 3: a = action_discrete3(seed, gid, t); break;
+                default: a = action_discrete4(seed, gid, t); break;
+            }
+            if (mask) {
+                const uint8_t* m = mask + (size_t)i * ki.actn;
+                int valid = 0;
+                for (int k = 0; k < ki.actn; ++k) valid += m[k] == 1;
+                a = 0;
+                if (valid > 0) {
+                    Block b = draw(seed, gid, t, STREAM_ACTION, 1);
+                    int j = (int)(((uint64_t)b.w[0] * (uint32_t)valid) >> 32);
+                    for (int k = 0; k < ki.actn; ++k) if (m[k] == 1) { if (j == 0) { a = k; break; } --j; }
+                }
+            }
+            ((int32_t*)out)[i] = a;
+        } else if (ki.actd == 1) {
+            const float lo = e->kind == ORACLE_PENDULUM ? -2.0f : -1.0f;
+            ((float*)out)[i] = action_box1(seed, gid, t, lo, -lo);
+        } else {
+            action_box2(seed, gid, t, -1.0f, 1.0f, (float*)out + (size_t)i * 2);
+        }
+    }
+}
+
 void oracle_get_state(oracle_env* e, double* state, int32_t* aux, uint64_t* t) {
     const size_t m = (size_t)e->n * e->ki.sd;
 #ifdef ORACLE_WITH_LUNAR

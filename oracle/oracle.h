@@ -58,6 +58,8 @@ int oracle_step_many(oracle_env*, int k_steps, const void* actions);
 /* K steps of the random policy; any output pointer may be NULL.  Layouts [K][n][dim]. */
 void oracle_rollout_random(oracle_env*, int k_steps, float* obs, float* reward, uint8_t* done,
                            void* actions);
+/* ActionSpace.Sample() of every instance at the current step index; mask (Discrete only) may be NULL. */
+void oracle_sample_actions(oracle_env*, const uint8_t* mask, void* actions_out);
 /* state[n][state_dim] as doubles (float32 values are exactly representable), aux[n][aux_dim]. */
 void oracle_get_state(oracle_env*, double* state, int32_t* aux, uint64_t* t);
 void oracle_set_state(oracle_env*, const double* state, const int32_t* aux, uint64_t t);

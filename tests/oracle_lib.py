@@ -47,6 +47,7 @@ def lib():
         L.oracle_step.restype = C.c_int
         L.oracle_step_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_step_many.restype = C.c_int
+        L.oracle_sample_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_rollout_random.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.oracle_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -127,6 +128,12 @@ class OracleEnv:
         """actions [K][n](,act_dim): K steps, no outputs (timing loop)."""
         a = np.ascontiguousarray(actions, dtype=np.int32 if self.discrete else np.float32)
         return lib().oracle_step_many(self.h, a.shape[0], _p(a))
+
+    def sample_actions(self, mask=None):
+        out = np.empty(self.n, np.int32) if self.discrete else np.empty((self.n, self.d["act_dim"]), np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(self.n, self.d["act_n"])
+        lib().oracle_sample_actions(self.h, _p(m), _p(out))
+        return out
 
     def rollout_random(self, k, want_obs=True):
         obs = np.empty((k, self.n, self.d["obs_dim"]), np.float32) if want_obs else None

@@ -376,3 +376,34 @@ def test_zero_copy_pinned_buffers_match_staged_copies():
     del act, obs, rew, done, raw, buf
     N.check(L.gymcuda_host_free(ptr))
     a_env.Close(); b_env.Close()
+
+
+@pytest.mark.parametrize("name", ["CartPole-v1", "MountainCar-v0", "Pendulum-v1", "LunarLander-v2"])
+def test_device_action_sampling_matches_rollout_and_oracle(name):
+    """ActionSpace.Sample() on device: sample -> step reproduces the fused rollout; masked Discrete.Sample
+    (Discrete.cs:19-25) matches the oracle restatement."""
+    n, k = 512, 40
+    a_env = G.make(name, n, seed=12, auto_reset=True); a_env.ResetBatch()
+    b_env = G.make(name, n, seed=12, auto_reset=True); b_env.ResetBatch()
+    o = O.OracleEnv(KINDS[name], n, seed=12, auto_reset=True, mode=O.MODE_F32); o.reset()
+    obs, rew, done, act = a_env.RolloutRandom(k)
+    for t in range(k):
+        a = b_env.SampleActions()
+        assert np.array_equal(a.reshape(act[t].shape), act[t])
+        assert np.array_equal(a, o.sample_actions())
+        ob, r, d = b_env.StepBatch(a); o.step(a)
+        assert np.array_equal(ob, obs[t]) and np.array_equal(d, done[t])
+    if a_env.act_n > 0:
+        rng = np.random.default_rng(0)
+        mask = (rng.random((n, a_env.act_n)) < 0.5).astype(np.uint8)
+        mask[0] = 0                                   # nothing valid -> Start (= 0)
+        mask[1] = 0; mask[1, a_env.act_n - 1] = 1     # a single valid entry
+        got = b_env.SampleActions(mask)
+        assert np.array_equal(got, o.sample_actions(mask))
+        assert got[0] == 0 and got[1] == a_env.act_n - 1
+        rows = np.arange(n)
+        assert ((mask[rows, got] == 1) | (mask.sum(1) == 0)).all()
+    else:
+        with pytest.raises((NotImplementedError, ValueError)):
+            b_env.SampleActions(np.ones((n, 1), np.uint8))
+    a_env.Close(); b_env.Close()
