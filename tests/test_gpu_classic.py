@@ -407,3 +407,44 @@ def test_device_action_sampling_matches_rollout_and_oracle(name):
         with pytest.raises((NotImplementedError, ValueError)):
             b_env.SampleActions(np.ones((n, 1), np.uint8))
     a_env.Close(); b_env.Close()
+
+
+def test_config1_single_env_10k_steps_plumbing():
+    """BASELINE config 1: CartPole-v1, ONE env, 10 000 steps, random actions a_t = philox(seed 0, env 0, t) & 1,
+    reset on done by the caller (README.md:36-40 loop) -- replayed through the C ABI with N = 1 and compared
+    step for step with the CPU oracle (reference arithmetic for done/reward, engine twin bit for bit)."""
+    env = G.CartPoleVecEnv(1, seed=0)
+    twin = O.OracleEnv(O.CARTPOLE, 1, seed=0, mode=O.MODE_F32)
+    ref = O.OracleEnv(O.CARTPOLE, 1, seed=0, mode=O.MODE_F64_F32STORE)
+    obs = env.ResetBatch(); assert np.array_equal(obs, twin.reset()); ref.reset()
+    episodes = 0
+    for t in range(10000):
+        a = env.SampleActions()
+        assert np.array_equal(a, twin.sample_actions())
+        st, ax, tt = env.GetState() if t % 500 == 0 else (None, None, None)
+        if st is not None:
+            ref.set_state(st.astype(np.float64), ax, tt)
+            ro, rr, rd = ref.step(a)
+        obs, rew, done = env.StepBatch(a)
+        oo, orr, od = twin.step(a)
+        assert np.array_equal(obs, oo) and rew[0] == orr[0] and done[0] == od[0]
+        if st is not None:
+            assert done[0] == rd[0] and rew[0] == rr[0] and np.abs(obs - ro).max() <= 1e-5
+        if done[0]:
+            episodes += 1
+            assert np.array_equal(env.ResetBatch(), twin.reset())
+    assert 300 < episodes < 700        # ~22 steps per random-policy episode
+    env.Close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 4097])
+def test_ragged_batch_sizes(n):
+    env = G.CartPoleVecEnv(n, seed=3, auto_reset=True); env.ResetBatch()
+    o = O.OracleEnv(O.CARTPOLE, n, seed=3, auto_reset=True, mode=O.MODE_F32); o.reset()
+    tr = env.RolloutRandom(70); tw = o.rollout_random(70)
+    for x, y in zip(tr, tw):
+        assert np.array_equal(x, y)
+    a = np.ones(n, np.int32)
+    for x, y in zip(env.StepBatch(a), o.step(a)):
+        assert np.array_equal(x, y)
+    env.Close()
