@@ -12,7 +12,7 @@ namespace Gym.Environments.Vector {
         LunarLander = 5, LunarLanderContinuous = 6
     }
 
-    [Flags] public enum GymCudaFlags : uint { None = 0, AutoReset = 1 }
+    [Flags] public enum GymCudaFlags : uint { None = 0, AutoReset = 1, EpisodeStats = 2, DoneBits = 4 }
 
     [StructLayout(LayoutKind.Sequential)]
     public struct GymCudaConfig {
@@ -40,7 +40,7 @@ namespace Gym.Environments.Vector {
     }
 
     [StructLayout(LayoutKind.Sequential)]
-    public struct GymCudaStats { public ulong EnvSteps, Episodes, InvalidActions; }
+    public struct GymCudaStats { public ulong EnvSteps, Episodes, InvalidActions; public double ReturnSum; public ulong LengthSum; }
 
     /// <summary>Owns the native handle; released by gymcuda_destroy.</summary>
     public sealed class GymCudaHandle : SafeHandle {

@@ -14,7 +14,7 @@ OK, EINVAL, EACTION, ECUDA, ENCCL, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6
 STATUS_NAMES = {0: "OK", -1: "EINVAL", -2: "EACTION", -3: "ECUDA", -4: "ENCCL", -5: "ENOMEM", -6: "ESTATE"}
 
 CARTPOLE, PENDULUM, MOUNTAINCAR, MOUNTAINCAR_CONT, ACROBOT, LUNARLANDER, LUNARLANDER_CONT = range(7)
-FLAG_AUTO_RESET = 1
+FLAG_AUTO_RESET, FLAG_EPISODE_STATS, FLAG_DONE_BITS = 1, 2, 4
 
 
 class Config(C.Structure):
@@ -36,7 +36,8 @@ class SpaceInfo(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("env_steps", C.c_uint64), ("episodes", C.c_uint64), ("invalid_actions", C.c_uint64)]
+    _fields_ = [("env_steps", C.c_uint64), ("episodes", C.c_uint64), ("invalid_actions", C.c_uint64),
+                ("return_sum", C.c_double), ("length_sum", C.c_uint64)]
 
 
 # every symbol declared in include/gymcuda.h: name -> (restype, argtypes)

@@ -137,6 +137,9 @@ struct gymcuda_env {
     int* d_invalid_flag;
     int32_t *d_done_idx, *d_done_count;
     unsigned long long* d_stats;
+    float* d_ep_ret;          // GYMCUDA_FLAG_EPISODE_STATS
+    double* d_sums;
+    bool ep_stats, done_bits;
     const float* last_obs;   // device pointer of the most recent observations
     // pinned scratch: [0..1] stats, [2] done_count
     unsigned long long* h_small;
@@ -293,7 +296,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux); cudaFree(e->d_perm); cudaFree(e->d_block_free);
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
-    cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats);
+    cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -332,7 +335,13 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMalloc(&e->d_done_idx, n * 4));
     CU_TRY(cudaMalloc(&e->d_done_count, 2 * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&e->d_stats, 2 * sizeof(unsigned long long)));
-    CU_TRY(cudaHostAlloc((void**)&e->h_small, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc((void**)&e->h_small, 6 * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (e->ep_stats) {
+        CU_TRY(cudaMalloc(&e->d_ep_ret, n * 4));
+        CU_TRY(cudaMalloc(&e->d_sums, 2 * sizeof(double)));
+        CU_TRY(cudaMemsetAsync(e->d_ep_ret, 0, n * 4, e->stream));
+        CU_TRY(cudaMemsetAsync(e->d_sums, 0, 2 * sizeof(double), e->stream));
+    }
     CU_TRY(cudaMemsetAsync(e->d_state, 0, state_bytes, e->stream));
     CU_TRY(cudaMemsetAsync(e->d_sbd, 0xff, n * 4, e->stream));
     CU_TRY(cudaMemsetAsync(e->d_ept, 0, n * 4, e->stream));
@@ -381,6 +390,9 @@ int gymcuda_create(const gymcuda_config* cfg, gymcuda_env** out) {
     e->n = cfg->num_envs;
     e->limit = cfg->time_limit == 0 ? ki.default_limit : (cfg->time_limit < 0 ? 0 : cfg->time_limit);
     e->auto_reset = (cfg->flags & GYMCUDA_FLAG_AUTO_RESET) != 0;
+    e->ep_stats = (cfg->flags & GYMCUDA_FLAG_EPISODE_STATS) != 0;
+    e->done_bits = (cfg->flags & GYMCUDA_FLAG_DONE_BITS) != 0;
+    if (e->ep_stats && e->limit == 0) e->limit = 0x7fffffff;   // the episode-step counter doubles as the episode length
     e->seed = cfg->seed;
     e->last_obs = nullptr;
     e->prm = EnvParams{cfg->gravity, cfg->wind_power, cfg->turbulence_power, cfg->enable_wind ? 1 : 0};
@@ -399,7 +411,7 @@ int gymcuda_space(const gymcuda_env* e, gymcuda_space_info* o) {
     if (!e || !o) return fail(GYMCUDA_EINVAL, "null argument");
     std::memset(o, 0, sizeof(*o));
     o->obs_dim = e->ki.od; o->act_dim = e->ki.ad; o->act_n = e->ki.actn;
-    o->state_dim = e->ki.sd; o->aux_dim = e->ki.aux; o->time_limit = e->limit;
+    o->state_dim = e->ki.sd; o->aux_dim = e->ki.aux; o->time_limit = e->limit == 0x7fffffff ? 0 : e->limit;
     const float FMAX = std::numeric_limits<float>::max();
     const float PI_F = 3.1415927410125732f;
     auto set_obs = [&](std::initializer_list<float> hi) { int k = 0; for (float v : hi) { o->obs_high[k] = v; o->obs_low[k] = -v; ++k; } };
@@ -465,7 +477,7 @@ int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
 static int reset_impl(gymcuda_env* e, const uint8_t* d_mask, float* obs_host) {
     ResetArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
-    a.mask = d_mask; a.obs = e->d_obs; a.n = e->n; a.env_off = e->cfg.env_id_offset;
+    a.mask = d_mask; a.obs = e->d_obs; a.ep_ret = e->d_ep_ret; a.n = e->n; a.env_off = e->cfg.env_id_offset;
     a.seed = e->seed; a.t = e->t;
     CU_TRY(dispatch_reset(e, a));
     e->last_obs = e->d_obs;
@@ -498,7 +510,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     StepArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
-    a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag;
+    a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
     a.perm = contact_partition(e);
@@ -605,7 +617,7 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
     RolloutArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
-    a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats;
+    a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.perm = contact_partition(e);
     CU_TRY(dispatch_rollout(e, a));
@@ -793,12 +805,18 @@ int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
     ENTER(e);
     if (!out) return fail(GYMCUDA_EINVAL, "out is null");
     CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    double* hs = reinterpret_cast<double*>(e->h_small + 4);
+    hs[0] = hs[1] = 0.0;
+    if (e->d_sums) CU_TRY(cudaMemcpyAsync(hs, e->d_sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     out->env_steps = e->env_steps;
     out->episodes = e->h_small[0];
     out->invalid_actions = e->h_small[1];
+    out->return_sum = hs[0];
+    out->length_sum = (uint64_t)(hs[1] + 0.5);
     if (reset_counters) {
         CU_TRY(cudaMemsetAsync(e->d_stats, 0, 2 * sizeof(unsigned long long), e->stream));
+        if (e->d_sums) CU_TRY(cudaMemsetAsync(e->d_sums, 0, 2 * sizeof(double), e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
         e->env_steps = 0;
         e->invalid_seen = 0;

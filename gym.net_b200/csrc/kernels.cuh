@@ -52,6 +52,9 @@ struct StepArgs {
     int32_t* done_idx;                 // may be null
     int32_t* done_count;               // [2], indexed by the parity of `seq`
     unsigned long long* stats;         // [0] episodes finished, [1] invalid actions
+    float* ep_ret;                     // per-env running episode return (null: statistics off)
+    double* sums;                      // [0] sum of finished-episode returns, [1] sum of their lengths
+    int done_bits;                     // 1: done byte = 1 terminated, 2 truncated by the time limit only
     int* host_invalid;                 // mapped host flag raised when an action is rejected
     int n;
     uint32_t env_off;
@@ -83,6 +86,9 @@ struct RolloutArgs {
     uint8_t* done;     // [k][n]       may be null
     void* actions;     // [k][n][AD]   may be null
     unsigned long long* stats;
+    float* ep_ret;
+    double* sums;
+    int done_bits;
     int n;
     int k_steps;
     uint32_t env_off;
@@ -101,6 +107,7 @@ struct ResetArgs {
     const int32_t* seeds;
     const uint8_t* mask;   // may be null = all
     float* obs;            // may be null
+    float* ep_ret;         // may be null
     int n;
     uint32_t env_off;
     uint64_t seed;
@@ -200,6 +207,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     int i = tix;
     bool done = false;
     bool invalid = false;
+    bool trunc_only = false;
+    float fin_ret = 0.0f;
+    int32_t fin_len = 0;
     if (tix < p.n) {
         if (p.perm) i = p.perm[tix];
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
@@ -214,7 +224,12 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
             const uint64_t seed = seed_of(p.seeds, p.seed, i);
             const uint32_t gid = p.env_off + (uint32_t)i;
             r = E::step(s, a, sbd, seed, gid, p.t);
-            if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }   // truncation folded into done
+            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = true; trunc_only = true; } }   // truncation folded into done
+            if (p.ep_ret) {   // episode statistics (the caller-side bookkeeping of BasePlaySession.cs:58-69)
+                float ret = p.ep_ret[i] + r.reward;
+                if (r.done) { fin_ret = ret; fin_len = ept; ret = 0.0f; }
+                p.ep_ret[i] = ret;
+            }
             if (AUTO_RESET && r.done) {
                 const int32_t ep = p.episode[i];
                 E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         for (int r = 0; r < p.world; ++r)
             store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
         p.reward[i] = r.reward;
-        p.done[i] = (uint8_t)r.done;
+        p.done[i] = (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done;
         done = r.done;
     }
 
@@ -271,6 +286,12 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     if (p.done_idx != nullptr && total > 0) {
         __syncthreads();
         if (done) p.done_idx[block_base + warp_off + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+    if (p.sums != nullptr && m != 0) {   // finished episodes of this warp -> one atomic pair
+        double rs = done ? (double)fin_ret : 0.0, ls = done ? (double)fin_len : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); ls += __shfl_xor_sync(0xffffffffu, ls, o); }
+        if (lane == 0) { atomicAdd(&p.sums[0], rs); atomicAdd(&p.sums[1], ls); }
     }
     // ---- gather signal: once the LAST block's peer stores are fenced, publish gseq in every rank's flag word
     if (p.world > 0) {
@@ -315,6 +336,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
     using S = typename E::S;
     const int tix = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
     unsigned episodes = 0;
+    double fin_ret = 0.0, fin_len = 0.0;
     if (tix < p.n) {
         const int i = p.perm ? p.perm[tix] : tix;
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
@@ -334,6 +356,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         S next;
         if (PREGEN) next = s;
         bool have = false;
+        float ret = p.ep_ret ? p.ep_ret[i] : 0.0f;
         float* po = p.obs + (size_t)i * E::OD;
         float* pr = p.reward + i;
         uint8_t* pd = p.done + i;
@@ -346,9 +369,13 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             }
             const typename E::Act a = gen.next(seed, gid, t, k == 0);
             StepOut r = E::step(s, a, sbd, seed, gid, t);
-            if (LIMIT) { ept += 1; if (ept >= p.limit) r.done = true; }
+            bool trunc_only = false;
+            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = true; trunc_only = true; } }
+            ret += r.reward;
             if (r.done) {
                 episodes += 1;
+                if (p.sums) { fin_ret += (double)ret; fin_len += (double)ept; }
+                ret = 0.0f;
                 if (AUTO_RESET) {
                     if (PREGEN) {
                         if (!have) reset_cold<E>(next, seed, gid, ep, t + 1, p.prm);   // second done before the refill: rare
@@ -367,7 +394,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 E::obs(s, o);
                 store_obs<E::OD, true>(po, 0, o);
                 __stcs(pr, r.reward);
-                __stcs(pd, (uint8_t)r.done);
+                __stcs(pd, (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done);
                 __stcs(pa, a);
                 po += n * E::OD; pr += n; pd += n; pa += n;
             } else {
@@ -378,11 +405,12 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                     store_obs<E::OD, true>(p.obs, idx, o);
                 }
                 if (p.reward) __stcs(p.reward + idx, r.reward);
-                if (p.done) __stcs(p.done + idx, (uint8_t)r.done);
+                if (p.done) __stcs(p.done + idx, (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done);
                 if (p.actions) ActIO<E>::store(p.actions, idx, a);
             }
         }
         if (AUTO_RESET) p.episode[i] = ep;
+        if (p.ep_ret) p.ep_ret[i] = ret;
         E::store(p.state, p.aux, p.n, i, s);
         if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
         if (LIMIT) p.ep_t[i] = ept;
@@ -391,6 +419,11 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) episodes += __shfl_xor_sync(0xffffffffu, episodes, o);
     if ((threadIdx.x & 31) == 0 && episodes) atomicAdd(&p.stats[0], (unsigned long long)episodes);
+    if (p.sums != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { fin_ret += __shfl_xor_sync(0xffffffffu, fin_ret, o); fin_len += __shfl_xor_sync(0xffffffffu, fin_len, o); }
+        if ((threadIdx.x & 31) == 0 && episodes) { atomicAdd(&p.sums[0], fin_ret); atomicAdd(&p.sums[1], fin_len); }
+    }
 }
 
 // ---------------------------------------------------------------- reset / observe / ctor
@@ -407,6 +440,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const ResetArgs p) {
         p.episode[i] = ep + 1;
         p.sbd[i] = -1;     // CartPoleEnv.cs:64
         p.ep_t[i] = 0;
+        if (p.ep_ret) p.ep_ret[i] = 0.0f;
     }
     if (p.obs) {
         float o[E::OD];

@@ -46,14 +46,16 @@ class CudaVecEnv:
 
     ENV_KIND = None
 
-    def __init__(self, num_envs, seed=0, device=0, env_id_offset=0, auto_reset=False, time_limit=0, **params):
+    def __init__(self, num_envs, seed=0, device=0, env_id_offset=0, auto_reset=False, time_limit=0,
+                 episode_stats=False, done_bits=False, **params):
         if self.ENV_KIND is None:
             raise TypeError("use a concrete family: CartPoleVecEnv, PendulumVecEnv, ...")
         L = N.lib()
         cfg = N.Config()
         N.check(L.gymcuda_config_default(C.byref(cfg), self.ENV_KIND, int(num_envs)))
         cfg.device, cfg.seed, cfg.env_id_offset = int(device), int(seed) & (2**64 - 1), int(env_id_offset)
-        cfg.flags = N.FLAG_AUTO_RESET if auto_reset else 0
+        cfg.flags = ((N.FLAG_AUTO_RESET if auto_reset else 0) | (N.FLAG_EPISODE_STATS if episode_stats else 0)
+                     | (N.FLAG_DONE_BITS if done_bits else 0))
         cfg.time_limit = int(time_limit)
         for k, v in params.items():   # gravity, enable_wind, wind_power, turbulence_power (LunarLanderEnv ctor)
             if not hasattr(cfg, k):
@@ -191,7 +193,8 @@ class CudaVecEnv:
     def Stats(self, reset=False):
         s = N.Stats()
         N.check(self._L.gymcuda_get_stats(self._h, C.byref(s), 1 if reset else 0))
-        return {"env_steps": s.env_steps, "episodes": s.episodes, "invalid_actions": s.invalid_actions}
+        return {"env_steps": s.env_steps, "episodes": s.episodes, "invalid_actions": s.invalid_actions,
+                "return_sum": s.return_sum, "length_sum": s.length_sum}
 
     # ---- device-pointer API (torch tensors / raw pointers) ------------------------------------------
     def SetStream(self, cuda_stream):

@@ -63,7 +63,9 @@ typedef enum gymcuda_env_kind {
 } gymcuda_env_kind;
 
 enum {
-    GYMCUDA_FLAG_AUTO_RESET = 1u /* reset in-kernel at `done`; obs returned is the post-reset one */
+    GYMCUDA_FLAG_AUTO_RESET = 1u,    /* reset in-kernel at `done`; obs returned is the post-reset one */
+    GYMCUDA_FLAG_EPISODE_STATS = 2u, /* accumulate return / length of finished episodes on device     */
+    GYMCUDA_FLAG_DONE_BITS = 4u      /* done byte: 1 = terminated, 2 = truncated by the time limit only */
 };
 
 typedef struct gymcuda_config {
@@ -159,11 +161,14 @@ int gymcuda_set_state(gymcuda_env* env, const float* state, const int32_t* aux, 
 /* Current observations of all envs (no stepping). */
 int gymcuda_observe(gymcuda_env* env, float* obs);
 
-/* ---- episode statistics (accumulated on device by every step / rollout) ------------------------- */
+/* ---- episode statistics: what callers keep by hand (examples/.../BasePlaySession.cs:58-69) -- accumulated
+ * on device by every step / rollout ------------------------- */
 typedef struct gymcuda_stats {
     uint64_t env_steps;      /* env steps executed                */
     uint64_t episodes;       /* episodes finished (done returned) */
     uint64_t invalid_actions;
+    double return_sum;       /* GYMCUDA_FLAG_EPISODE_STATS: sum of the returns of finished episodes */
+    uint64_t length_sum;     /*                             sum of their lengths                    */
 } gymcuda_stats;
 int gymcuda_get_stats(gymcuda_env* env, gymcuda_stats* out, int reset_counters);
 

@@ -178,7 +178,8 @@ static int step_one_t(oracle_env* e, int i, const void* actions, float* obs, flo
             if (e->limit > 0) aux[1] += 1;   // the episode-step counter exists only under a time limit
         }
     }
-    if (!invalid && e->limit > 0 && aux[e->EPT()] >= e->limit) r.done = 1;   // truncation folded into done
+    if (!invalid && e->limit > 0 && aux[e->EPT()] >= e->limit && !r.done)   // truncation folded into done
+        r.done = (e->flags & ORACLE_FLAG_DONE_BITS) ? 2 : 1;
     if (!invalid && r.done && (e->flags & ORACLE_FLAG_AUTO_RESET)) reset_one(e, i, now + 1);
     write_obs(e, i, obs);
     if (reward) reward[i] = r.reward;

@@ -33,7 +33,7 @@ enum {
  *              kernels; used for bit-for-bit free-running regression at scale. */
 enum { ORACLE_MODE_F64 = 0, ORACLE_MODE_F64_F32STORE = 1, ORACLE_MODE_F32 = 2 };
 
-enum { ORACLE_FLAG_AUTO_RESET = 1u };
+enum { ORACLE_FLAG_AUTO_RESET = 1u, ORACLE_FLAG_DONE_BITS = 4u /* done: 1 terminated, 2 truncated only */ };
 
 typedef struct oracle_env oracle_env;
 

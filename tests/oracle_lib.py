@@ -72,11 +72,12 @@ def dims(kind):
 class OracleEnv:
     """Serial per-instance loop over `n` scalar envs: the reference's VecEnvWrapper shape."""
 
-    def __init__(self, kind, n, seed=0, env_id_offset=0, auto_reset=False, time_limit=0, mode=MODE_F64_F32STORE):
+    def __init__(self, kind, n, seed=0, env_id_offset=0, auto_reset=False, time_limit=0, mode=MODE_F64_F32STORE,
+                 done_bits=False):
         self.kind, self.n, self.mode = kind, n, mode
         self.d = dims(kind)
-        self.h = lib().oracle_create(kind, n, seed, env_id_offset, FLAG_AUTO_RESET if auto_reset else 0,
-                                     time_limit, mode)
+        self.h = lib().oracle_create(kind, n, seed, env_id_offset,
+                                     (FLAG_AUTO_RESET if auto_reset else 0) | (4 if done_bits else 0), time_limit, mode)
         if not self.h:
             raise ValueError("oracle_create failed")
         self.discrete = self.d["act_n"] > 0

@@ -448,3 +448,35 @@ def test_ragged_batch_sizes(n):
     for x, y in zip(env.StepBatch(a), o.step(a)):
         assert np.array_equal(x, y)
     env.Close()
+
+
+def test_episode_statistics_and_truncation_bits():
+    """episode return/length statistics and a truncation flag distinct from termination, fused
+    into the step / rollout kernels (what BasePlaySession.cs:58-69 keeps by hand)."""
+    n, k = 2048, 450
+    env = G.MountainCarVecEnv(n, seed=2, auto_reset=True, episode_stats=True, done_bits=True); env.ResetBatch()
+    o = O.OracleEnv(O.MOUNTAINCAR, n, seed=2, auto_reset=True, mode=O.MODE_F32, done_bits=True); o.reset()
+    obs, rew, done, act = env.RolloutRandom(k)
+    oo, orr, od, oa = o.rollout_random(k)
+    assert np.array_equal(done, od) and np.array_equal(obs, oo)
+    assert set(np.unique(done)) <= {0, 1, 2} and (done == 2).sum() >= n       # the 200-step limit truncates
+    st = env.Stats()
+    fin = done != 0
+    assert st["episodes"] == int(fin.sum())
+    # expected sums straight from the trajectory
+    ret = np.zeros(n); length = np.zeros(n, int); rs = 0.0; ls = 0
+    for t in range(k):
+        ret += rew[t]; length += 1
+        f = fin[t]
+        rs += ret[f].sum(); ls += int(length[f].sum()); ret[f] = 0; length[f] = 0
+    assert st["length_sum"] == ls and abs(st["return_sum"] - rs) <= 1e-6 * max(1.0, abs(rs))
+    # the per-launch step path accumulates the same way
+    env2 = G.CartPoleVecEnv(512, seed=3, auto_reset=True, episode_stats=True); env2.ResetBatch()
+    rng = np.random.default_rng(0); rs = 0.0; ls = 0; ret = np.zeros(512); length = np.zeros(512, int)
+    for _ in range(120):
+        _, r, d = env2.StepBatch(rng.integers(0, 2, 512).astype(np.int32))
+        ret += r; length += 1; f = d != 0
+        rs += ret[f].sum(); ls += int(length[f].sum()); ret[f] = 0; length[f] = 0
+    s2 = env2.Stats()
+    assert s2["length_sum"] == ls and abs(s2["return_sum"] - rs) < 1e-6 * max(1.0, rs) and env2.TimeLimit == 0
+    env.Close(); env2.Close()
