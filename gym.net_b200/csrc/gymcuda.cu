@@ -194,7 +194,7 @@ static void launch_rollout_variant(gymcuda_env* e, const RolloutArgs& a, int gri
 template <class E>
 static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
     const int grid = (e->n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
-    if (a.obs && a.reward && a.done && a.actions) launch_rollout_variant<E, true>(e, a, grid);
+    if (a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits) launch_rollout_variant<E, true>(e, a, grid);
     else launch_rollout_variant<E, false>(e, a, grid);
     return cudaGetLastError();
 }

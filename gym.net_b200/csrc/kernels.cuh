@@ -329,8 +329,9 @@ __device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint
     E::reset(next, seed, gid, (uint32_t)ep, t, prm);
 }
 
-// ALL_OUT: every trajectory pointer is non-null (the benchmark / learner case): the stores are
-// unconditional and addressed by four running pointers instead of per-step 64-bit index arithmetic.
+// ALL_OUT: every trajectory pointer is non-null and the optional statistics / truncation bits are off (the
+// benchmark / learner case): the stores are unconditional and addressed by four running pointers instead of
+// per-step 64-bit index arithmetic, and the statistics code is compiled out.
 template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT>
 __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
     using S = typename E::S;
@@ -356,7 +357,8 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         S next;
         if (PREGEN) next = s;
         bool have = false;
-        float ret = p.ep_ret ? p.ep_ret[i] : 0.0f;
+        constexpr bool STATS = !ALL_OUT;
+        float ret = (STATS && p.ep_ret) ? p.ep_ret[i] : 0.0f;
         float* po = p.obs + (size_t)i * E::OD;
         float* pr = p.reward + i;
         uint8_t* pd = p.done + i;
@@ -371,11 +373,11 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             StepOut r = E::step(s, a, sbd, seed, gid, t);
             bool trunc_only = false;
             if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = true; trunc_only = true; } }
-            ret += r.reward;
+            if (STATS) ret += r.reward;
             if (r.done) {
                 episodes += 1;
-                if (p.sums) { fin_ret += (double)ret; fin_len += (double)ept; }
-                ret = 0.0f;
+                if (STATS && p.sums) { fin_ret += (double)ret; fin_len += (double)ept; }
+                if (STATS) ret = 0.0f;
                 if (AUTO_RESET) {
                     if (PREGEN) {
                         if (!have) reset_cold<E>(next, seed, gid, ep, t + 1, p.prm);   // second done before the refill: rare
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 E::obs(s, o);
                 store_obs<E::OD, true>(po, 0, o);
                 __stcs(pr, r.reward);
-                __stcs(pd, (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done);
+                __stcs(pd, (uint8_t)r.done);
                 __stcs(pa, a);
                 po += n * E::OD; pr += n; pd += n; pa += n;
             } else {
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             }
         }
         if (AUTO_RESET) p.episode[i] = ep;
-        if (p.ep_ret) p.ep_ret[i] = ret;
+        if (STATS && p.ep_ret) p.ep_ret[i] = ret;
         E::store(p.state, p.aux, p.n, i, s);
         if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
         if (LIMIT) p.ep_t[i] = ept;
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) episodes += __shfl_xor_sync(0xffffffffu, episodes, o);
     if ((threadIdx.x & 31) == 0 && episodes) atomicAdd(&p.stats[0], (unsigned long long)episodes);
-    if (p.sums != nullptr) {
+    if (!ALL_OUT && p.sums != nullptr) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { fin_ret += __shfl_xor_sync(0xffffffffu, fin_ret, o); fin_len += __shfl_xor_sync(0xffffffffu, fin_len, o); }
         if ((threadIdx.x & 31) == 0 && episodes) { atomicAdd(&p.sums[0], fin_ret); atomicAdd(&p.sums[1], fin_len); }
