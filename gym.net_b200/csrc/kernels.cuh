@@ -156,17 +156,30 @@ template <class E, int ACTN = E::ACTN, int AD = E::AD> struct ActionGen;
 
 template <class E> struct ActionGen<E, 2, 1> {
     Block b;
+    uint32_t bits;   // current word, already shifted so that bit 0 is the draw of step t
     __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        if (first || (t & 127) == 0) b = draw(seed, gid, t >> 7, STREAM_ACTION);
-        return (int32_t)((word(b, (uint32_t)(t >> 5) & 3u) >> (t & 31)) & 1u);
+        const uint32_t tl = (uint32_t)t;
+        if (first || (tl & 31u) == 0) {
+            if (first || (tl & 127u) == 0) b = draw(seed, gid, t >> 7, STREAM_ACTION);
+            bits = word(b, (tl >> 5) & 3u) >> (tl & 31u);
+        }
+        const int32_t a = (int32_t)(bits & 1u);
+        bits >>= 1;
+        return a;
     }
 };
 template <class E> struct ActionGen<E, 4, 1> {
     Block b;
+    uint32_t bits;
     __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        if (first || (t & 63) == 0) b = draw(seed, gid, t >> 6, STREAM_ACTION);
-        const uint32_t i = (uint32_t)(t & 63);
-        return (int32_t)((word(b, i >> 4) >> (2 * (i & 15))) & 3u);
+        const uint32_t tl = (uint32_t)t;
+        if (first || (tl & 15u) == 0) {
+            if (first || (tl & 63u) == 0) b = draw(seed, gid, t >> 6, STREAM_ACTION);
+            bits = word(b, (tl >> 4) & 3u) >> (2u * (tl & 15u));
+        }
+        const int32_t a = (int32_t)(bits & 3u);
+        bits >>= 2;
+        return a;
     }
 };
 template <class E> struct ActionGen<E, 3, 1> {
@@ -359,13 +372,10 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         bool have = false;
         constexpr bool STATS = !ALL_OUT;
         float ret = (STATS && p.ep_ret) ? p.ep_ret[i] : 0.0f;
-        float* po = p.obs + (size_t)i * E::OD;
-        float* pr = p.reward + i;
-        uint8_t* pd = p.done + i;
-        typename E::Act* pa = reinterpret_cast<typename E::Act*>(p.actions) + i;
+        size_t row = (size_t)i;   // k * n + i: one running index addresses all four trajectory arrays
         for (int k = 0; k < p.k_steps; ++k) {
             const uint64_t t = p.t + (uint64_t)k;
-            if (PREGEN && (k & (ROLLOUT_REFILL - 1)) == 0 && !have) {
+            if (PREGEN && ((unsigned)k & (unsigned)(ROLLOUT_REFILL - 1)) == 0u && !have) {
                 E::reset(next, seed, gid, (uint32_t)ep, t, p.prm);
                 have = true;
             }
@@ -394,11 +404,11 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             if (ALL_OUT) {
                 float o[E::OD];
                 E::obs(s, o);
-                store_obs<E::OD, true>(po, 0, o);
-                __stcs(pr, r.reward);
-                __stcs(pd, (uint8_t)r.done);
-                __stcs(pa, a);
-                po += n * E::OD; pr += n; pd += n; pa += n;
+                store_obs<E::OD, true>(p.obs, row, o);
+                __stcs(p.reward + row, r.reward);
+                __stcs(p.done + row, (uint8_t)r.done);
+                __stcs(reinterpret_cast<typename E::Act*>(p.actions) + row, a);
+                row += n;
             } else {
                 const size_t idx = (size_t)k * n + (size_t)i;
                 if (p.obs) {
