@@ -157,10 +157,11 @@ template <class E, int ACTN = E::ACTN, int AD = E::AD> struct ActionGen;
 template <class E> struct ActionGen<E, 2, 1> {
     Block b;
     uint32_t bits;   // current word, already shifted so that bit 0 is the draw of step t
-    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        const uint32_t tl = (uint32_t)t;
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
+        const bool first = k == 0;
+        const uint32_t tl = (uint32_t)t0 + k;   // low word only on the hot path; the 64-bit step index is formed when a block is drawn
         if (first || (tl & 31u) == 0) {
-            if (first || (tl & 127u) == 0) b = draw(seed, gid, t >> 7, STREAM_ACTION);
+            if (first || (tl & 127u) == 0) b = draw(seed, gid, (t0 + k) >> 7, STREAM_ACTION);
             bits = word(b, (tl >> 5) & 3u) >> (tl & 31u);
         }
         const int32_t a = (int32_t)(bits & 1u);
@@ -171,10 +172,11 @@ template <class E> struct ActionGen<E, 2, 1> {
 template <class E> struct ActionGen<E, 4, 1> {
     Block b;
     uint32_t bits;
-    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        const uint32_t tl = (uint32_t)t;
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
+        const bool first = k == 0;
+        const uint32_t tl = (uint32_t)t0 + k;
         if (first || (tl & 15u) == 0) {
-            if (first || (tl & 63u) == 0) b = draw(seed, gid, t >> 6, STREAM_ACTION);
+            if (first || (tl & 63u) == 0) b = draw(seed, gid, (t0 + k) >> 6, STREAM_ACTION);
             bits = word(b, (tl >> 4) & 3u) >> (2u * (tl & 15u));
         }
         const int32_t a = (int32_t)(bits & 3u);
@@ -184,22 +186,25 @@ template <class E> struct ActionGen<E, 4, 1> {
 };
 template <class E> struct ActionGen<E, 3, 1> {
     Block b;
-    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        if (first || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
+        const uint64_t t = t0 + k;
+        if (k == 0 || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
         return (int32_t)__umulhi(word(b, (uint32_t)t & 3u), 3u);
     }
 };
 template <class E> struct ActionGen<E, 0, 1> {
     Block b;
-    __device__ __forceinline__ float next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        if (first || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
+    __device__ __forceinline__ float next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
+        const uint64_t t = t0 + k;
+        if (k == 0 || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
         return uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, (uint32_t)t & 3u));
     }
 };
 template <class E> struct ActionGen<E, 0, 2> {
     Block b;
-    __device__ __forceinline__ float2 next(uint64_t seed, uint32_t gid, uint64_t t, bool first) {
-        if (first || (t & 1) == 0) b = draw(seed, gid, t >> 1, STREAM_ACTION);
+    __device__ __forceinline__ float2 next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
+        const uint64_t t = t0 + k;
+        if (k == 0 || (t & 1) == 0) b = draw(seed, gid, t >> 1, STREAM_ACTION);
         const uint32_t j = 2u * ((uint32_t)t & 1u);
         return make_float2(uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, j)), uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, j + 1)));
     }
@@ -338,8 +343,10 @@ constexpr int ROLLOUT_BLOCK = 64;
 constexpr int ROLLOUT_REFILL = 8;   // steps between warp-wide refills of the pre-generated reset state
 
 template <class E>
-__device__ __noinline__ void reset_cold(typename E::S& next, uint64_t seed, uint32_t gid, int32_t ep, uint64_t t, const EnvParams& prm) {
+__device__ __noinline__ typename E::S reset_cold(uint64_t seed, uint32_t gid, int32_t ep, uint64_t t, EnvParams prm) {
+    typename E::S next;   // returned by value: taking the address of the caller's copy would pin it in local memory
     E::reset(next, seed, gid, (uint32_t)ep, t, prm);
+    return next;
 }
 
 // ALL_OUT: every trajectory pointer is non-null and the optional statistics / truncation bits are off (the
@@ -374,13 +381,12 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         float ret = (STATS && p.ep_ret) ? p.ep_ret[i] : 0.0f;
         size_t row = (size_t)i;   // k * n + i: one running index addresses all four trajectory arrays
         for (int k = 0; k < p.k_steps; ++k) {
-            const uint64_t t = p.t + (uint64_t)k;
             if (PREGEN && ((unsigned)k & (unsigned)(ROLLOUT_REFILL - 1)) == 0u && !have) {
-                E::reset(next, seed, gid, (uint32_t)ep, t, p.prm);
+                E::reset(next, seed, gid, (uint32_t)ep, p.t + (uint64_t)k, p.prm);
                 have = true;
             }
-            const typename E::Act a = gen.next(seed, gid, t, k == 0);
-            StepOut r = E::step(s, a, sbd, seed, gid, t);
+            const typename E::Act a = gen.next(seed, gid, p.t, (uint32_t)k);
+            StepOut r = E::step(s, a, sbd, seed, gid, p.t + (uint64_t)k);
             bool trunc_only = false;
             if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = true; trunc_only = true; } }
             if (STATS) ret += r.reward;
@@ -390,11 +396,11 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 if (STATS) ret = 0.0f;
                 if (AUTO_RESET) {
                     if (PREGEN) {
-                        if (!have) reset_cold<E>(next, seed, gid, ep, t + 1, p.prm);   // second done before the refill: rare
+                        if (!have) next = reset_cold<E>(seed, gid, ep, p.t + (uint64_t)k + 1, p.prm);   // second done before the refill: rare
                         s = next;
                         have = false;
                     } else {
-                        E::reset(s, seed, gid, (uint32_t)ep, t + 1, p.prm);
+                        E::reset(s, seed, gid, (uint32_t)ep, p.t + (uint64_t)k + 1, p.prm);
                     }
                     ep += 1;
                     sbd = -1;
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleArgs p) {
     const uint64_t seed = seed_of(p.seeds, p.seed, i);
     const uint32_t gid = p.env_off + (uint32_t)i;
     ActionGen<E> gen;
-    typename E::Act a = gen.next(seed, gid, p.t, true);
+    typename E::Act a = gen.next(seed, gid, p.t, 0u);
     if (E::ACTN > 0 && p.mask != nullptr) {
         const uint8_t* m = p.mask + (size_t)i * (E::ACTN > 0 ? E::ACTN : 1);
         int valid = 0;
