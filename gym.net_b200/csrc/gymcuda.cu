@@ -133,8 +133,8 @@ struct gymcuda_env {
     float *d_obs, *d_reward;
     uint8_t *d_done, *d_mask;
     const void* alias_host[4]; void* alias_dev[4];   // cache of mapped_alias()
-    volatile int* h_invalid; // mapped pinned flag: set by the step kernel when it rejects an action
-    int* d_invalid_flag;
+    volatile int* h_invalid; // mapped pinned flags: [0] set by the step kernel when it rejects an action,
+    int* d_invalid_flag;     //                      [1] set by gather_wait_kernel on a timeout (1 + missing rank)
     int32_t *d_done_idx, *d_done_count;
     unsigned long long* d_stats;
     float* d_ep_ret;          // GYMCUDA_FLAG_EPISODE_STATS
@@ -328,8 +328,8 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     e->d_obs = reinterpret_cast<float*>(e->d_out);
     e->d_reward = reinterpret_cast<float*>(e->d_out + e->obs_bytes());
     e->d_done = reinterpret_cast<uint8_t*>(e->d_out + e->obs_bytes() + n * 4);
-    CU_TRY(cudaHostAlloc((void**)&e->h_invalid, sizeof(int), cudaHostAllocMapped));
-    *e->h_invalid = 0;
+    CU_TRY(cudaHostAlloc((void**)&e->h_invalid, 2 * sizeof(int), cudaHostAllocMapped));
+    e->h_invalid[0] = 0; e->h_invalid[1] = 0;
     CU_TRY(cudaHostGetDevicePointer((void**)&e->d_invalid_flag, (void*)e->h_invalid, 0));
     CU_TRY(cudaMalloc(&e->d_mask, n));
     CU_TRY(cudaMalloc(&e->d_done_idx, n * 4));
@@ -837,6 +837,7 @@ int gymcuda_set_stream(gymcuda_env* e, void* cuda_stream) {
 int gymcuda_sync(gymcuda_env* e) {
     ENTER(e);
     CU_TRY(cudaStreamSynchronize(e->stream));
+    if (e->h_invalid[1]) { const int who = e->h_invalid[1] - 1; e->h_invalid[1] = 0; return fail(GYMCUDA_ENCCL, "gather wait timed out: rank %d never published its observations", who); }
     return GYMCUDA_OK;
 }
 
@@ -942,7 +943,8 @@ int gymcuda_step_gather_device(gymcuda_env* e, const void* d_actions, float* d_r
 int gymcuda_gather_wait(gymcuda_env* e) {
     ENTER(e);
     if (!e->g_local) return fail(GYMCUDA_EINVAL, "gather buffer not created");
-    gather_wait_kernel<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->g_local + e->g_flags_off), e->g_world, e->g_seq);
+    if (e->h_invalid[1]) { const int who = e->h_invalid[1] - 1; e->h_invalid[1] = 0; return fail(GYMCUDA_ENCCL, "an earlier gather wait timed out: rank %d never published its observations", who); }
+    gather_wait_kernel<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->g_local + e->g_flags_off), e->g_world, e->g_seq, e->d_invalid_flag + 1);
     CU_TRY(cudaGetLastError());
     return GYMCUDA_OK;
 }

@@ -328,12 +328,18 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
 }
 
 // Waits (on the consumer's stream) until every rank's observations of gather step `gseq` have landed in
-// this rank's buffer: one thread per peer spins on that peer's arrival flag.
-__global__ void gather_wait_kernel(const uint32_t* flags, int world, uint32_t gseq) {
+// this rank's buffer: one thread per peer spins on that peer's arrival flag.  Bounded: after ~2 s without
+// the flag (a peer died or never launched its step) it gives up and raises `timeout_flag` (mapped host
+// memory) instead of hanging the GPU.
+__global__ void gather_wait_kernel(const uint32_t* flags, int world, uint32_t gseq, int* timeout_flag) {
     const int r = threadIdx.x;
     if (r < world) {
         const volatile uint32_t* f = flags + r;
-        while ((int32_t)(*f - gseq) < 0) { __nanosleep(64); }
+        const long long start = clock64();
+        while ((int32_t)(*f - gseq) < 0) {
+            __nanosleep(64);
+            if (clock64() - start > 4000000000ll) { *reinterpret_cast<volatile int*>(timeout_flag) = 1 + r; break; }
+        }
     }
     __threadfence_system();
 }
