@@ -1,0 +1,30 @@
+"""Small pass over every kernel for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gymnet_b200 as G
+rng = np.random.default_rng(0)
+for name, n in (("CartPole-v1", 3001), ("Pendulum-v1", 1025), ("MountainCar-v0", 515), ("MountainCarContinuous-v0", 515),
+                ("Acrobot-v1", 777), ("LunarLander-v2", 2500)):
+    for auto in (False, True):
+        env = G.make(name, n, seed=1, auto_reset=auto, episode_stats=True, done_bits=True)
+        env.ResetBatch()
+        env.RolloutRandom(24)
+        env.RolloutRandom(5, want=("done",))
+        for _ in range(6):
+            a = env.SampleActions()
+            env.StepBatch(a)
+            env.DoneIndices()
+        if env.act_n > 0:
+            env.SampleActions(mask=(rng.random((n, env.act_n)) < 0.5).astype(np.uint8))
+            env.Step(1)
+        m = (rng.random(n) < 0.3).astype(np.uint8)
+        env.ResetBatch(mask=m)
+        st, ax, t = env.GetState(); env.SetState(st, ax, t); env.Observe(); env.Stats(reset=True)
+        env.Close()
+ll = G.LunarLanderVecEnv(2500, seed=2, auto_reset=True, time_limit=300); obs = ll.ResetBatch()
+for _ in range(120):      # long enough for contacts: exercises the contact partition + solver paths
+    obs, r, d = ll.StepBatch(np.full(2500, 0, np.int32))
+print("contacts", float((obs[:, 6:] > 0).any(1).mean()))
+ll.Close()
+print("sanitize probe done")
