@@ -120,10 +120,14 @@ struct Pendulum {
     static constexpr float ACT_LOW = -2.0f, ACT_HIGH = 2.0f;
     using Vec = float2;
     using Act = float;
-    struct S { float th, thdot; };
+    // sn, cs = sin/cos of th, carried in registers: the observation of step t and the dynamics of step t + 1
+    // need the same pair, so a fused rollout evaluates sincos once per step instead of twice
+    struct S { float th, thdot, sn, cs; };
     __device__ static __forceinline__ S load(const void* base, const int32_t*, int, int i, const EnvParams&) {
         const float2 v = reinterpret_cast<const float2*>(base)[i];
-        return S{v.x, v.y};
+        S s{v.x, v.y, 0.0f, 1.0f};
+        sincosf_det(s.th, &s.sn, &s.cs);
+        return s;
     }
     __device__ static __forceinline__ void store(void* base, int32_t*, int, int i, const S& s) {
         reinterpret_cast<float2*>(base)[i] = make_float2(s.th, s.thdot);
@@ -133,6 +137,7 @@ struct Pendulum {
         constexpr float PI_F = 3.1415927410125732f;
         s.th = uniformf(-PI_F, PI_F, b.w0);
         s.thdot = uniformf(-1.0f, 1.0f, b.w1);
+        sincosf_det(s.th, &s.sn, &s.cs);
     }
     __device__ static __forceinline__ bool valid(Act a) { return a == a; }
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
@@ -141,19 +146,14 @@ struct Pendulum {
         const float u = clampf(a, -2.0f, 2.0f);
         const float an = py_modf32(th + PI_F, TWO_PI_F) - PI_F;
         const float costs = (an * an + 0.1f * (thdot * thdot)) + 0.001f * (u * u);
-        float sn, cs;
-        sincosf_det(th, &sn, &cs);
-        float newthdot = thdot + (15.0f * sn + 3.0f * u) * 0.05f;
+        float newthdot = thdot + (15.0f * s.sn + 3.0f * u) * 0.05f;
         newthdot = clampf(newthdot, -8.0f, 8.0f);
         s.th = th + newthdot * 0.05f;
         s.thdot = newthdot;
+        sincosf_det(s.th, &s.sn, &s.cs);
         return StepOut{-costs, false};
     }
-    __device__ static __forceinline__ void obs(const S& s, float* o) {
-        float sn, cs;
-        sincosf_det(s.th, &sn, &cs);
-        o[0] = cs; o[1] = sn; o[2] = s.thdot;
-    }
+    __device__ static __forceinline__ void obs(const S& s, float* o) { o[0] = s.cs; o[1] = s.sn; o[2] = s.thdot; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -248,21 +248,29 @@ template <> struct AcroMath<float> {
     __device__ static __forceinline__ float cos_minus_half_pi(float x) { float s, c; sincosf_det(x, &s, &c); return s; }
 };
 
+// algebra of dsdt given sin/cos(theta2), cos(theta1 + theta2 - pi/2) and cos(theta1 - pi/2)
 template <class R>
-__device__ __forceinline__ void acrobot_dsdt(const R s[4], R a, R out[4]) {
+__device__ __forceinline__ void acrobot_dsdt_trig(const R s[4], R a, R s2, R c2, R cmh12, R cmh1, R out[4]) {
     const R m1 = 1, m2 = 1, l1 = 1, lc1 = R(0.5), lc2 = R(0.5), I1 = 1, I2 = 1, g = R(9.8);
-    const R theta1 = s[0], theta2 = s[1], dtheta1 = s[2], dtheta2 = s[3];
-    R s2, c2;
-    AcroMath<R>::sc(theta2, &s2, &c2);
+    const R dtheta1 = s[2], dtheta2 = s[3];
     const R d1 = m1 * lc1 * lc1 + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * c2) + I1 + I2;
     const R d2 = m2 * (lc2 * lc2 + l1 * lc2 * c2) + I2;
-    const R phi2 = m2 * lc2 * g * AcroMath<R>::cos_minus_half_pi(theta1 + theta2);
+    const R phi2 = m2 * lc2 * g * cmh12;
     const R phi1 = -m2 * l1 * lc2 * dtheta2 * dtheta2 * s2 - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * s2 +
-                   (m1 * lc1 + m2 * l1) * g * AcroMath<R>::cos_minus_half_pi(theta1) + phi2;
+                   (m1 * lc1 + m2 * l1) * g * cmh1 + phi2;
     const R ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * dtheta1 * dtheta1 * s2 - phi2) /
                        (m2 * lc2 * lc2 + I2 - d2 * d2 / d1);
     const R ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
     out[0] = dtheta1; out[1] = dtheta2; out[2] = ddtheta1; out[3] = ddtheta2;
+}
+
+template <class R>
+__device__ __forceinline__ void acrobot_dsdt(const R s[4], R a, R out[4]) {
+    R s2, c2;
+    AcroMath<R>::sc(s[1], &s2, &c2);
+    const R cmh12 = AcroMath<R>::cos_minus_half_pi(s[0] + s[1]);
+    const R cmh1 = AcroMath<R>::cos_minus_half_pi(s[0]);
+    acrobot_dsdt_trig<R>(s, a, s2, c2, cmh12, cmh1, out);
 }
 
 template <class R>
@@ -274,14 +282,26 @@ __device__ __forceinline__ R acro_wrap(R x, R m, R M) {
     return x;
 }
 
-// integrates s in place; returns -cos(th1) - cos(th2 + th1) of the new state
-template <class R>
-__device__ __forceinline__ R acrobot_integrate(R s[4], int action) {
+// sin/cos of the joint angles of one state: what the observation, the termination test and the first RK4
+// stage of the NEXT step all need -- carried in registers by the float32 path
+struct AcroTrig { float s1, c1, s2, c2, s12, c12; };
+
+__device__ __forceinline__ AcroTrig acrobot_trig(const float v[4]) {
+    AcroTrig t;
+    sincosf_det(v[0], &t.s1, &t.c1);
+    sincosf_det(v[1], &t.s2, &t.c2);
+    sincosf_det(v[1] + v[0], &t.s12, &t.c12);
+    return t;
+}
+
+// one classical RK4 step of dsdt over dt = 0.2, wrap and clamp (upstream acrobot.py); s updated in place
+template <class R, class Stage1>
+__device__ __forceinline__ void acrobot_rk4(R s[4], int action, Stage1 stage1) {
     const R PI = R(3.14159265358979323846);
     const R dt = R(0.2);
     const R a = (R)(action - 1);
     R k1[4], k2[4], k3[4], k4[4], y[4];
-    acrobot_dsdt<R>(s, a, k1);
+    stage1(s, a, k1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) y[i] = s[i] + dt / 2 * k1[i];
     acrobot_dsdt<R>(y, a, k2);
@@ -300,15 +320,17 @@ __device__ __forceinline__ R acrobot_integrate(R s[4], int action) {
     y[3] = y[3] < -MV2 ? -MV2 : (y[3] > MV2 ? MV2 : y[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[i] = y[i];
-    R s1, c1, s12, c12;
-    AcroMath<R>::sc(y[0], &s1, &c1);
-    AcroMath<R>::sc(y[1] + y[0], &s12, &c12);
-    return -c1 - c12;
+}
+
+// double-precision evaluation of the termination value  -cos(th1) - cos(th2 + th1)  of the new state
+__device__ __forceinline__ double acrobot_integrate_f64(double s[4], int action) {
+    acrobot_rk4<double>(s, action, [](const double* st, double a, double* out) { acrobot_dsdt<double>(st, a, out); });
+    return -cos(s[0]) - cos(s[1] + s[0]);
 }
 
 __device__ __noinline__ bool acrobot_done_f64(float s0, float s1, float s2, float s3, int action) {
     double sd[4] = {(double)s0, (double)s1, (double)s2, (double)s3};
-    return acrobot_integrate<double>(sd, action) > 1.0;
+    return acrobot_integrate_f64(sd, action) > 1.0;
 }
 
 struct Acrobot {
@@ -319,10 +341,13 @@ struct Acrobot {
     static constexpr bool REJECT_INVALID = true;
     using Vec = float4;
     using Act = int32_t;
-    struct S { float v[4]; };
+    struct S { float v[4]; AcroTrig t; };
     __device__ static __forceinline__ S load(const void* base, const int32_t*, int, int i, const EnvParams&) {
         const float4 v = reinterpret_cast<const float4*>(base)[i];
-        return S{{v.x, v.y, v.z, v.w}};
+        S s;
+        s.v[0] = v.x; s.v[1] = v.y; s.v[2] = v.z; s.v[3] = v.w;
+        s.t = acrobot_trig(s.v);
+        return s;
     }
     __device__ static __forceinline__ void store(void* base, int32_t*, int, int i, const S& s) {
         reinterpret_cast<float4*>(base)[i] = make_float4(s.v[0], s.v[1], s.v[2], s.v[3]);
@@ -333,20 +358,23 @@ struct Acrobot {
         s.v[1] = uniformf(-0.1f, 0.1f, b.w1);
         s.v[2] = uniformf(-0.1f, 0.1f, b.w2);
         s.v[3] = uniformf(-0.1f, 0.1f, b.w3);
+        s.t = acrobot_trig(s.v);
     }
     __device__ static __forceinline__ bool valid(Act a) { return a >= 0 && a < 3; }
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         const float o0 = s.v[0], o1 = s.v[1], o2 = s.v[2], o3 = s.v[3];
-        const float v = acrobot_integrate<float>(s.v, (int)a);
+        const AcroTrig t0 = s.t;   // the first RK4 stage reuses the trig of the current state (cos(x - pi/2) = sin x in float32)
+        acrobot_rk4<float>(s.v, (int)a, [t0](const float* st, float act, float* out) {
+            acrobot_dsdt_trig<float>(st, act, t0.s2, t0.c2, t0.s12, t0.s1, out);
+        });
+        s.t = acrobot_trig(s.v);
+        const float v = -s.t.c1 - s.t.c12;
         bool done = v > 1.0f;
         if (fabsf(v - 1.0f) <= 2e-5f) done = acrobot_done_f64(o0, o1, o2, o3, (int)a);
         return StepOut{done ? 0.0f : -1.0f, done};
     }
     __device__ static __forceinline__ void obs(const S& s, float* o) {
-        float s1, c1, s2, c2;
-        sincosf_det(s.v[0], &s1, &c1);
-        sincosf_det(s.v[1], &s2, &c2);
-        o[0] = c1; o[1] = s1; o[2] = c2; o[3] = s2; o[4] = s.v[2]; o[5] = s.v[3];
+        o[0] = s.t.c1; o[1] = s.t.s1; o[2] = s.t.c2; o[3] = s.t.s2; o[4] = s.v[2]; o[5] = s.v[3];
     }
 };
 
