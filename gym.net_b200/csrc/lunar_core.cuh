@@ -83,7 +83,7 @@ __device__ __forceinline__ float maxf(float a, float b) { return a > b ? a : b; 
 
 // ---------------------------------------------------------------- shapes (:189, :262-266), mass data
 // b2PolygonShape::Set order (gift-wrapped hull, CCW from the right-most lowest vertex) and
-// b2PolygonShape::ComputeMass evaluated once in float32 (tests/golden/make_golden.py documents how).
+// b2PolygonShape::ComputeMass evaluated once in float32 (tests/golden/lunar_mass_data.py re-derives the numbers).
 struct Shape { int count; V2 v[6]; V2 n[6]; V2 centroid; float mass, inv_mass, inertia, inv_inertia, friction; };
 __constant__ Shape SHAPES[3] = {
     {6,

@@ -171,3 +171,19 @@ def test_wind_phase_persists_across_episodes():
     assert (a1[:, 24] == a0[:, 24] + 1).all()
     e.reset()
     assert (e.get_state()[1][:, 24] == a1[:, 24] + 1).all()      # reset's zero step advances it; it is NOT re-drawn
+
+
+def test_mass_data_constants():
+    """The hard-coded polygon mass data (oracle/lunar.hpp and the CUDA twin) equal b2PolygonShape::ComputeMass in float32."""
+    import importlib.util, os, re
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("lunar_mass_data", os.path.join(here, "golden", "lunar_mass_data.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    c = mod.constants()
+    root = os.path.dirname(here)
+    for path in (os.path.join(root, "oracle", "lunar.hpp"), os.path.join(root, "gym.net_b200", "csrc", "lunar_core.cuh")):
+        text = open(path).read()
+        for part in ("fuselage", "leg"):
+            for key in ("mass", "inv_mass", "inertia", "inv_inertia"):
+                assert repr(c[part][key]) + "f" in text, "%s: %s.%s = %r not found" % (path, part, key, c[part][key])
+            assert repr(c[part]["centroid"][1]) + "f" in text
