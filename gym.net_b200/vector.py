@@ -251,7 +251,11 @@ class CudaVecEnv:
             raise NotImplementedError("IVecEnv.Step(int) needs a Discrete action space; use StepBatch")
         obs, rew, done = self._out()
         N.check(self._L.gymcuda_step_broadcast(self._h, int(action), _ptr(obs), _ptr(rew), _ptr(done)))
-        return [Step(obs[i], float(rew[i]), bool(done[i]), None) for i in range(self.NumberOfEnvironments)]
+        return [Step(obs[i], float(rew[i]), bool(done[i]), self._information(obs[i])) for i in range(self.NumberOfEnvironments)]
+
+    def _information(self, obs_row):
+        """Step.Information of one env (null for CartPole, CartPoleEnv.cs:185)."""
+        return None
 
 
 def shard_envs(total_envs, rank, world_size):
@@ -300,6 +304,11 @@ class LunarLanderVecEnv(CudaVecEnv):
         self.ENV_KIND = N.LUNARLANDER_CONT if continuous else N.LUNARLANDER
         self.ContinuousMode = bool(continuous)
         super().__init__(num_envs, **kw)
+
+    def _information(self, o):
+        """The Dict LunarLanderEnv.Step fills (LunarLanderEnv.cs:740-746); every entry is a view of the observation."""
+        return {"pos": (float(o[0]), float(o[1])), "velocity": (float(o[2]), float(o[3])), "angle": float(o[4]),
+                "omega": float(o[5]), "LeftContact": bool(o[6]), "RightContact": bool(o[7])}
 
 
 FAMILIES = {
