@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     bool trunc_only = false;
     float fin_ret = 0.0f;
     int32_t fin_len = 0;
+    uint8_t done_byte = 0;
     if (tix < p.n) {
         if (p.perm) i = p.perm[tix];
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
@@ -267,17 +268,23 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         for (int r = 0; r < p.world; ++r)
             store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
         p.reward[i] = r.reward;
-        p.done[i] = (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done;
+        done_byte = (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done;
         done = r.done;
     }
 
     // ---- done compaction: warp ballot + popc prefix -> block scan -> one atomicAdd per block
     __shared__ int warp_cnt[STEP_BLOCK / 32];
     __shared__ int block_base;
+    __shared__ __align__(16) uint8_t done_tile[STEP_BLOCK];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, done);
     const unsigned mi = __ballot_sync(0xffffffffu, invalid);
     if (lane == 0) warp_cnt[warp] = __popc(m);
+    // the done bytes of the CTA go out as one 128 B line (32 lanes x 4 B) instead of four 32 B pieces: over PCIe
+    // (zero-copy host buffers) every store instruction is a packet, and over HBM it is one full sector group
+    const bool packed = p.perm == nullptr && (reinterpret_cast<uintptr_t>(p.done) & 3u) == 0;
+    if (packed) done_tile[threadIdx.x] = done_byte;
+    else if (tix < p.n) p.done[i] = done_byte;
     if (mi != 0 && lane == 0) {
         atomicAdd(&p.stats[1], (unsigned long long)__popc(mi));
         *reinterpret_cast<volatile int*>(p.host_invalid) = 1;
@@ -290,6 +297,11 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         const int c = warp_cnt[w];
         if (w < (int)warp) warp_off += c;
         total += c;
+    }
+    if (packed && threadIdx.x < STEP_BLOCK / 4) {
+        const int first = blockIdx.x * STEP_BLOCK + 4 * (int)threadIdx.x;
+        if (first + 3 < p.n) *reinterpret_cast<uint32_t*>(p.done + first) = *reinterpret_cast<const uint32_t*>(done_tile + 4 * threadIdx.x);
+        else for (int k = first; k < p.n && k < first + 4; ++k) p.done[k] = done_tile[k - blockIdx.x * STEP_BLOCK];
     }
     int32_t* count = p.done_count + (p.seq & 1);
     if (threadIdx.x == 0) {
