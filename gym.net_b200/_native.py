@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgymcuda.so")
+# GYMCUDA_LIB: development aid -- load another build of the SAME library (kernel A/B experiments under tools/)
+LIB_PATH = os.environ.get("GYMCUDA_LIB") or os.path.join(HERE, "csrc", "libgymcuda.so")
 
 OK, EINVAL, EACTION, ECUDA, ENCCL, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6
 STATUS_NAMES = {0: "OK", -1: "EINVAL", -2: "EACTION", -3: "ECUDA", -4: "ENCCL", -5: "ENOMEM", -6: "ESTATE"}

@@ -22,7 +22,7 @@
 
 namespace gymcuda {
 
-struct StepOut { float reward; bool done; };
+struct StepOut { float reward; unsigned done; };   // done: 0 / 1 in a full register (a byte-sized bool costs PRMT packing around calls)
 
 // constructor arguments of the env (LunarLanderEnv.cs:381); unused by the classic-control family
 struct EnvParams { float gravity, wind_power, turbulence_power; int32_t use_wind; };
@@ -34,6 +34,7 @@ struct CartPole {
     static constexpr int SD = 4, OD = 4, AD = 1, ACTN = 2, DEFAULT_LIMIT = 0;
     static constexpr bool HAS_SBD = true;     // steps_beyond_done (CartPoleEnv.cs:41)
     static constexpr bool PREGEN_RESET = true;   // rollout kernel pre-generates the next initial state
+    static constexpr bool ROLLOUT_CHUNK = true;  // rollout kernel runs unrolled 8-step chunks
     static constexpr int AUXW = 0;               // extra int32 words per env in HBM
     static constexpr bool REJECT_INVALID = false;  // Debug.Assert only (CartPoleEnv.cs:139)
     using Vec = float4;
@@ -70,32 +71,62 @@ struct CartPole {
     }
     __device__ static __forceinline__ bool valid(Act a) { return a == 0 || a == 1; }
 
-    // CartPoleEnv.cs:137-186.  Accelerations (:146-151) in float32; the position updates (:154,:156)
-    // and the termination test (:167) with the reference's own double operations, so x, theta and
-    // `done` are exactly the reference's values from the same float32 state.
+    // The reference's own double-precision termination test (:154,:156,:167) from the float32 state; reached only
+    // when a float32 position lands exactly on a threshold (see step)
+    __device__ static __noinline__ unsigned done_f64(float x, float x_dot, float theta, float theta_dot) {
+        const double xd = (double)x + (double)TAU * (double)x_dot;                     // :154
+        const double thd = (double)theta + (double)TAU * (double)theta_dot;            // :156
+        return (unsigned)((fabs(xd) > (double)X_THRESHOLD) | (fabs(thd) > (double)THETA_THRESHOLD));  // :167
+    }
+
+    // CartPoleEnv.cs:137-186.  Accelerations (:146-151) in float32.  The position updates (:154,:156) are ONE
+    // float32 fma each: tau * x_dot is exact in double (24 x 24 bits), so fmaf(tau, x_dot, x) is the reference's
+    // double sum e = x + tau * x_dot rounded once to float32 (the reference rounds it to double first: the two
+    // differ only by double rounding, <= 1 ulp32, far inside 1e-5).  Termination (:167) compares against
+    // float32-representable thresholds T, and rounding is monotonic: fl32(e) > T implies fl64(e) > T and
+    // fl32(e) < T implies fl64(e) < T.  Only fl32(e) == T is undecided in float32 and goes to done_f64, so
+    // `done` is exactly the reference's double-precision flag from the same float32 state.
+    // SMALL: the caller guarantees small_ok(s): sincos is the bare polynomial, and the quotient :150 is the
+    // six-instruction core of the IEEE division without its exponent-range check (div_inrange): with
+    // |theta| <= pi/4 and |theta_dot| <= 70, den is in [0.62, 0.67] and num is 0 or in [2^-60, 2^8], where that
+    // core IS the correctly rounded quotient -- both variants return the same bits.
+    template <bool SMALL = false>
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t& sbd, uint64_t, uint32_t, uint64_t) {
         const float force = (a == 1) ? FORCE_MAG : -FORCE_MAG;                         // :146
         float sn, cs;
-        sincosf_det(s.theta, &sn, &cs);                                                // :147-148
+        if (SMALL) sincos_poly(s.theta, &sn, &cs);
+        else sincosf_det(s.theta, &sn, &cs);                                           // :147-148
         const float t1 = (POLEMASS_LENGTH * s.theta_dot) * s.theta_dot;
         const float temp = fmaf(t1, sn, force) * INV_TOTAL_MASS;                       // :149
         const float den = fmaf(-K1, cs * cs, K0);
         const float num = fmaf(GRAVITY, sn, -(cs * temp));
-        const float thetaacc = num / den;                                              // :150
+        const float thetaacc = SMALL ? div_inrange(num, den) : num / den;              // :150
         const float xacc = fmaf(-(PML_OVER_M * thetaacc), cs, temp);                   // :151
-        const double xd = (double)s.x + (double)TAU * (double)s.x_dot;                 // :154
-        const double thd = (double)s.theta + (double)TAU * (double)s.theta_dot;        // :156
+        const float nx = fmaf(TAU, s.x_dot, s.x);                                      // :154
+        const float nth = fmaf(TAU, s.theta_dot, s.theta);                             // :156
+        unsigned done = 0;
+        if ((fabsf(nx) >= X_THRESHOLD) | (fabsf(nth) >= THETA_THRESHOLD)) {             // :167
+            done = (unsigned)((fabsf(nx) > X_THRESHOLD) | (fabsf(nth) > THETA_THRESHOLD));
+            if (!done) done = done_f64(s.x, s.x_dot, s.theta, s.theta_dot);            // exactly on a threshold
+        }
         s.x_dot = fmaf(TAU, xacc, s.x_dot);                                            // :155
         s.theta_dot = fmaf(TAU, thetaacc, s.theta_dot);                                // :157
-        s.x = (float)xd;
-        s.theta = (float)thd;
-        const bool done = (fabs(xd) > (double)X_THRESHOLD) | (fabs(thd) > (double)THETA_THRESHOLD);  // :167
+        s.x = nx;
+        s.theta = nth;
         float reward = 1.0f;                                                           // :170,:174
         if (done) {
             if (sbd == -1) sbd = 0;                                                    // :173
             else { sbd += 1; reward = 0.0f; }                                          // :181-182
         }
         return StepOut{reward, done};
+    }
+    // rollout fast path: true when step<true> is valid for this state and, with auto-reset, for every later one.
+    // A non-terminal state has |theta| <= 0.2095 and a reset state |theta|, |theta_dot| <= 0.05; a step changes
+    // theta_dot by < 6 while |theta_dot| <= 70, and a state entered with |theta_dot| > 21 and |theta| <= 0.2095
+    // terminates at once (theta moves by 0.02 * theta_dot), so from |theta_dot| <= 64 no later entry exceeds 70.
+    static constexpr bool HAS_SMALL = true;
+    __device__ static __forceinline__ bool small_ok(const S& s) {
+        return (fabsf(s.theta) <= 0.7853981852531433f) & (fabsf(s.theta_dot) <= 64.0f);
     }
     __device__ static __forceinline__ void obs(const S& s, float* o) {
         o[0] = s.x; o[1] = s.x_dot; o[2] = s.theta; o[3] = s.theta_dot;                // :166,:185
@@ -105,8 +136,27 @@ struct CartPole {
 // ------------------------------------------------------------------------------------------------
 // Pendulum-v1 (not in the reference, README.md:76; spec = upstream gym 0.26 pendulum.py)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float py_modf32(float a, float b) {   // Python float %, b > 0 (fmodf is exact)
-    float m = fmodf(a, b);
+__device__ __noinline__ float fmodf_cold(float a, float b) { return fmodf(a, b); }
+
+// Python float `a % b` for b > 0 (upstream angle_normalize): fmod is exact, so the result is defined by IEEE
+// alone.  For |a| <= 2^21 (every angle a pendulum reaches) fmod is computed without branches or conversions:
+// the quotient is rounded to the nearest integer with the 1.5 * 2^23 magic number (it is floor(|a| / b) or one
+// more), the remainder |a| - q * b is ONE fma -- exact whenever q is the true quotient, because the true
+// remainder is representable -- and a negative remainder steps q down and recomputes.  Beyond: CUDA's fmodf.
+__device__ __forceinline__ float py_mod_2pi(float a) {
+    constexpr float b = 6.2831854820251465f;          // fl32(2 pi)
+    constexpr float INV_B = 0.15915493667125702f;     // fl32(1 / b): only steers the quotient estimate
+    constexpr float MAGIC = 12582912.0f;
+    const float ax = fabsf(a);
+    float r;
+    if (ax <= 2097152.0f) {
+        float q = fmaf(ax, INV_B, MAGIC) - MAGIC;
+        r = fmaf(-q, b, ax);
+        if (r < 0.0f) { q = q - 1.0f; r = fmaf(-q, b, ax); }
+    } else {
+        r = fmodf_cold(ax, b);
+    }
+    float m = (a < 0.0f) ? -r : r;               // fmod carries the sign of a
     if (m != 0.0f) { if (m < 0.0f) m += b; } else m = 0.0f;
     return m;
 }
@@ -117,6 +167,8 @@ struct Pendulum {
     static constexpr bool PREGEN_RESET = true;
     static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
+    static constexpr bool HAS_SMALL = false;        // no reduced-range variant of step
+    static constexpr bool ROLLOUT_CHUNK = true;     // rollout kernel runs unrolled 8-step chunks
     static constexpr float ACT_LOW = -2.0f, ACT_HIGH = 2.0f;
     using Vec = float2;
     using Act = float;
@@ -141,17 +193,17 @@ struct Pendulum {
     }
     __device__ static __forceinline__ bool valid(Act a) { return a == a; }
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
-        constexpr float PI_F = 3.1415927410125732f, TWO_PI_F = 6.2831854820251465f;
+        constexpr float PI_F = 3.1415927410125732f;
         const float th = s.th, thdot = s.thdot;
         const float u = clampf(a, -2.0f, 2.0f);
-        const float an = py_modf32(th + PI_F, TWO_PI_F) - PI_F;
+        const float an = py_mod_2pi(th + PI_F) - PI_F;
         const float costs = (an * an + 0.1f * (thdot * thdot)) + 0.001f * (u * u);
         float newthdot = thdot + (15.0f * s.sn + 3.0f * u) * 0.05f;
         newthdot = clampf(newthdot, -8.0f, 8.0f);
         s.th = th + newthdot * 0.05f;
         s.thdot = newthdot;
         sincosf_det(s.th, &s.sn, &s.cs);
-        return StepOut{-costs, false};
+        return StepOut{-costs, 0u};
     }
     __device__ static __forceinline__ void obs(const S& s, float* o) { o[0] = s.cs; o[1] = s.sn; o[2] = s.thdot; }
 };
@@ -167,6 +219,8 @@ struct MountainCarT {
     static constexpr bool PREGEN_RESET = true;
     static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
+    static constexpr bool HAS_SMALL = false;        // no reduced-range variant of step
+    static constexpr bool ROLLOUT_CHUNK = true;     // rollout kernel runs unrolled 8-step chunks
     static constexpr float ACT_LOW = -1.0f, ACT_HIGH = 1.0f;
     using Vec = float2;
     using Act = typename std::conditional<CONTINUOUS, float, int32_t>::type;
@@ -188,7 +242,7 @@ struct MountainCarT {
         return a >= 0 && a < 3;
     }
     // upstream double-precision step, used only to refine `done` next to a threshold
-    __device__ static bool done_f64(float position0, float velocity0, Act a) {
+    __device__ static __noinline__ unsigned done_f64(float position0, float velocity0, Act a) {
         double position = (double)position0, velocity = (double)velocity0;
         if (CONTINUOUS) {
             double force = (double)a;
@@ -201,7 +255,7 @@ struct MountainCarT {
         position += velocity;
         position = position < -1.2 ? -1.2 : (position > 0.6 ? 0.6 : position);
         if (position == -1.2 && velocity < 0) velocity = 0;
-        return position >= (CONTINUOUS ? 0.45 : 0.5) && velocity >= 0.0;
+        return (unsigned)(position >= (CONTINUOUS ? 0.45 : 0.5) && velocity >= 0.0);
     }
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         constexpr float MIN_POS = -1.2f, MAX_POS = 0.6f, MAX_SPEED = 0.07f;
@@ -217,7 +271,7 @@ struct MountainCarT {
         float np = position + nv;
         np = clampf(np, MIN_POS, MAX_POS);
         if (np == MIN_POS && nv < 0.0f) nv = 0.0f;
-        bool done = np >= GOAL && nv >= 0.0f;
+        unsigned done = (unsigned)((np >= GOAL) & (nv >= 0.0f));
         if (fabsf(np - GOAL) <= 1e-6f || fabsf(nv) <= 1e-7f) done = done_f64(position, velocity, a);
         s.position = np;
         s.velocity = nv;
@@ -328,9 +382,9 @@ __device__ __forceinline__ double acrobot_integrate_f64(double s[4], int action)
     return -cos(s[0]) - cos(s[1] + s[0]);
 }
 
-__device__ __noinline__ bool acrobot_done_f64(float s0, float s1, float s2, float s3, int action) {
+__device__ __noinline__ unsigned acrobot_done_f64(float s0, float s1, float s2, float s3, int action) {
     double sd[4] = {(double)s0, (double)s1, (double)s2, (double)s3};
-    return acrobot_integrate_f64(sd, action) > 1.0;
+    return (unsigned)(acrobot_integrate_f64(sd, action) > 1.0);
 }
 
 struct Acrobot {
@@ -339,6 +393,8 @@ struct Acrobot {
     static constexpr bool PREGEN_RESET = true;
     static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
+    static constexpr bool HAS_SMALL = false;        // no reduced-range variant of step
+    static constexpr bool ROLLOUT_CHUNK = false;    // one RK4 step is ~900 instructions: 8 unrolled copies thrash the instruction cache (measured 1.5x slower)
     using Vec = float4;
     using Act = int32_t;
     struct S { float v[4]; AcroTrig t; };
@@ -369,7 +425,7 @@ struct Acrobot {
         });
         s.t = acrobot_trig(s.v);
         const float v = -s.t.c1 - s.t.c12;
-        bool done = v > 1.0f;
+        unsigned done = (unsigned)(v > 1.0f);
         if (fabsf(v - 1.0f) <= 2e-5f) done = acrobot_done_f64(o0, o1, o2, o3, (int)a);
         return StepOut{done ? 0.0f : -1.0f, done};
     }

@@ -194,7 +194,9 @@ static void launch_rollout_variant(gymcuda_env* e, const RolloutArgs& a, int gri
 template <class E>
 static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
     const int grid = (e->n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
-    if (a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits) launch_rollout_variant<E, true>(e, a, grid);
+    // ALL_OUT addresses the trajectory with one 32-bit row index: every row * envs + env must fit
+    const bool idx32 = (unsigned long long)a.k_steps * (unsigned long long)a.n <= 0xffffffffull;
+    if (a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits && idx32) launch_rollout_variant<E, true>(e, a, grid);
     else launch_rollout_variant<E, false>(e, a, grid);
     return cudaGetLastError();
 }

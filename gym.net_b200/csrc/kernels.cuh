@@ -28,6 +28,7 @@
 // initial state and refill it for the whole warp at once instead of diverging at every `done`.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "env_classic.cuh"
@@ -152,62 +153,100 @@ template <class E> struct ActIO {
 // Random policy: Discrete.Sample = randint(0, N) (Discrete.cs:27), Box.Sample = uniform(low, high) (Box.cs:84).
 // Draw t of env e comes from block (t >> SHIFT) of the ACTION stream; the block is regenerated only
 // when t crosses a block boundary (CartPole: once per 128 steps).
+//   init(t)     makes the generator valid for step index t (one Philox evaluation)
+//   next(t)     the draw of step t; calls must be consecutive in t after init
+//   at<J>(tc)   the same draw for step tc + J of an 8-step chunk (tc % 8 == 0, J = 0..7 in order): block and
+//               word boundaries can only fall on J == 0 (or J == 4), so the unrolled chunk carries no per-step tests
 template <class E, int ACTN = E::ACTN, int AD = E::AD> struct ActionGen;
 
 template <class E> struct ActionGen<E, 2, 1> {
     Block b;
-    uint32_t bits;   // current word, already shifted so that bit 0 is the draw of step t
-    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
-        const bool first = k == 0;
-        const uint32_t tl = (uint32_t)t0 + k;   // low word only on the hot path; the 64-bit step index is formed when a block is drawn
-        if (first || (tl & 31u) == 0) {
-            if (first || (tl & 127u) == 0) b = draw(seed, gid, (t0 + k) >> 7, STREAM_ACTION);
-            bits = word(b, (tl >> 5) & 3u) >> (tl & 31u);
-        }
+    uint32_t bits;   // current word, already shifted so that bit 0 is the draw of the next step
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t gid, uint64_t t) {
+        b = draw(seed, gid, t >> 7, STREAM_ACTION);
+        bits = word(b, ((uint32_t)t >> 5) & 3u) >> ((uint32_t)t & 31u);
+    }
+    __device__ __forceinline__ void refill(uint64_t seed, uint32_t gid, uint64_t t) {   // t % 32 == 0
+        if (((uint32_t)t & 127u) == 0) b = draw(seed, gid, t >> 7, STREAM_ACTION);
+        bits = word(b, ((uint32_t)t >> 5) & 3u);
+    }
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t) {
+        if (((uint32_t)t & 31u) == 0) refill(seed, gid, t);
         const int32_t a = (int32_t)(bits & 1u);
         bits >>= 1;
+        return a;
+    }
+    template <int J> __device__ __forceinline__ int32_t at(uint64_t seed, uint32_t gid, uint64_t tc) {
+        if (J == 0 && ((uint32_t)tc & 31u) == 0) refill(seed, gid, tc);
+        const int32_t a = (bits & (1u << J)) ? 1 : 0;   // one predicate-setting LOP3 feeds both the force select and the stored action
+        if (J == 7) bits >>= 8;
         return a;
     }
 };
 template <class E> struct ActionGen<E, 4, 1> {
     Block b;
     uint32_t bits;
-    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
-        const bool first = k == 0;
-        const uint32_t tl = (uint32_t)t0 + k;
-        if (first || (tl & 15u) == 0) {
-            if (first || (tl & 63u) == 0) b = draw(seed, gid, (t0 + k) >> 6, STREAM_ACTION);
-            bits = word(b, (tl >> 4) & 3u) >> (2u * (tl & 15u));
-        }
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t gid, uint64_t t) {
+        b = draw(seed, gid, t >> 6, STREAM_ACTION);
+        bits = word(b, ((uint32_t)t >> 4) & 3u) >> (2u * ((uint32_t)t & 15u));
+    }
+    __device__ __forceinline__ void refill(uint64_t seed, uint32_t gid, uint64_t t) {   // t % 16 == 0
+        if (((uint32_t)t & 63u) == 0) b = draw(seed, gid, t >> 6, STREAM_ACTION);
+        bits = word(b, ((uint32_t)t >> 4) & 3u);
+    }
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t) {
+        if (((uint32_t)t & 15u) == 0) refill(seed, gid, t);
         const int32_t a = (int32_t)(bits & 3u);
         bits >>= 2;
         return a;
     }
-};
-template <class E> struct ActionGen<E, 3, 1> {
-    Block b;
-    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
-        const uint64_t t = t0 + k;
-        if (k == 0 || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
-        return (int32_t)__umulhi(word(b, (uint32_t)t & 3u), 3u);
+    template <int J> __device__ __forceinline__ int32_t at(uint64_t seed, uint32_t gid, uint64_t tc) {
+        if (J == 0 && ((uint32_t)tc & 15u) == 0) refill(seed, gid, tc);
+        const int32_t a = (int32_t)((bits >> (2 * J)) & 3u);
+        if (J == 7) bits >>= 16;
+        return a;
     }
 };
-template <class E> struct ActionGen<E, 0, 1> {
+// one 32-bit word per draw, four draws per block (Discrete(3), Box 1-D)
+template <class E> struct WordGen {
     Block b;
-    __device__ __forceinline__ float next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
-        const uint64_t t = t0 + k;
-        if (k == 0 || (t & 3) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
-        return uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, (uint32_t)t & 3u));
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t gid, uint64_t t) { b = draw(seed, gid, t >> 2, STREAM_ACTION); }
+    __device__ __forceinline__ uint32_t next_word(uint64_t seed, uint32_t gid, uint64_t t) {
+        if (((uint32_t)t & 3u) == 0) b = draw(seed, gid, t >> 2, STREAM_ACTION);
+        return word(b, (uint32_t)t & 3u);
+    }
+    template <int J> __device__ __forceinline__ uint32_t word_at(uint64_t seed, uint32_t gid, uint64_t tc) {
+        if ((J & 3) == 0) b = draw(seed, gid, (tc + J) >> 2, STREAM_ACTION);
+        return (J & 3) == 0 ? b.w0 : ((J & 3) == 1 ? b.w1 : ((J & 3) == 2 ? b.w2 : b.w3));
+    }
+};
+template <class E> struct ActionGen<E, 3, 1> : WordGen<E> {
+    __device__ __forceinline__ int32_t next(uint64_t seed, uint32_t gid, uint64_t t) { return (int32_t)__umulhi(this->next_word(seed, gid, t), 3u); }
+    template <int J> __device__ __forceinline__ int32_t at(uint64_t seed, uint32_t gid, uint64_t tc) {
+        return (int32_t)__umulhi(this->template word_at<J>(seed, gid, tc), 3u);
+    }
+};
+// Box.Sample = uniform(low, high) for the spans used here (2 and 4: powers of two, see uniformf_pow2)
+template <class E> __device__ __forceinline__ float box_uniform(uint32_t w) {
+    constexpr float span = E::ACT_HIGH - E::ACT_LOW;
+    static_assert(span == 2.0f || span == 4.0f, "Box action span must be 2 or 4 (else use uniformf)");
+    return uniformf_pow2<span == 2.0f ? 1 : 2>(E::ACT_LOW, w);
+}
+template <class E> struct ActionGen<E, 0, 1> : WordGen<E> {
+    __device__ __forceinline__ float next(uint64_t seed, uint32_t gid, uint64_t t) { return box_uniform<E>(this->next_word(seed, gid, t)); }
+    template <int J> __device__ __forceinline__ float at(uint64_t seed, uint32_t gid, uint64_t tc) {
+        return box_uniform<E>(this->template word_at<J>(seed, gid, tc));
     }
 };
 template <class E> struct ActionGen<E, 0, 2> {
     Block b;
-    __device__ __forceinline__ float2 next(uint64_t seed, uint32_t gid, uint64_t t0, uint32_t k) {
-        const uint64_t t = t0 + k;
-        if (k == 0 || (t & 1) == 0) b = draw(seed, gid, t >> 1, STREAM_ACTION);
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t gid, uint64_t t) { b = draw(seed, gid, t >> 1, STREAM_ACTION); }
+    __device__ __forceinline__ float2 next(uint64_t seed, uint32_t gid, uint64_t t) {
+        if (((uint32_t)t & 1u) == 0) b = draw(seed, gid, t >> 1, STREAM_ACTION);
         const uint32_t j = 2u * ((uint32_t)t & 1u);
-        return make_float2(uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, j)), uniformf(E::ACT_LOW, E::ACT_HIGH, word(b, j + 1)));
+        return make_float2(box_uniform<E>(word(b, j)), box_uniform<E>(word(b, j + 1)));
     }
+    template <int J> __device__ __forceinline__ float2 at(uint64_t seed, uint32_t gid, uint64_t tc) { return next(seed, gid, tc + J); }
 };
 
 __device__ __forceinline__ uint64_t seed_of(const int32_t* seeds, uint64_t seed, int i) {
@@ -237,13 +276,13 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
         int32_t ept = 0;
         if (LIMIT) ept = p.ep_t[i];
-        StepOut r{0.0f, false};
+        StepOut r{0.0f, 0u};
         invalid = E::REJECT_INVALID && !E::valid(a);
         if (!invalid) {
             const uint64_t seed = seed_of(p.seeds, p.seed, i);
             const uint32_t gid = p.env_off + (uint32_t)i;
             r = E::step(s, a, sbd, seed, gid, p.t);
-            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = true; trunc_only = true; } }   // truncation folded into done
+            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }   // truncation folded into done
             if (p.ep_ret) {   // episode statistics (the caller-side bookkeeping of BasePlaySession.cs:58-69)
                 float ret = p.ep_ret[i] + r.reward;
                 if (r.done) { fin_ret = ret; fin_len = ept; ret = 0.0f; }
@@ -269,7 +308,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
             store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
         p.reward[i] = r.reward;
         done_byte = (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done;
-        done = r.done;
+        done = r.done != 0;
     }
 
     // ---- done compaction: warp ballot + popc prefix -> block scan -> one atomicAdd per block
@@ -367,15 +406,47 @@ __device__ __noinline__ typename E::S reset_cold(uint64_t seed, uint32_t gid, in
     return next;
 }
 
-// ALL_OUT: every trajectory pointer is non-null and the optional statistics / truncation bits are off (the
-// benchmark / learner case): the stores are unconditional and addressed by four running pointers instead of
-// per-step 64-bit index arithmetic, and the statistics code is compiled out.
+// E::step, or its reduced-range variant E::step<true> for envs that have one (HAS_SMALL)
+template <class E, bool SMALL> struct StepSel {
+    __device__ static __forceinline__ StepOut go(typename E::S& s, typename E::Act a, int32_t& sbd, uint64_t seed, uint32_t gid, uint64_t t) {
+        return E::step(s, a, sbd, seed, gid, t);
+    }
+};
+template <class E> struct StepSel<E, true> {
+    __device__ static __forceinline__ StepOut go(typename E::S& s, typename E::Act a, int32_t& sbd, uint64_t seed, uint32_t gid, uint64_t t) {
+        return E::template step<true>(s, a, sbd, seed, gid, t);
+    }
+};
+
+// compile-time unrolled 8-step chunk: f(integral_constant<int, J>) for J = 0..7
+template <int J, class F>
+__device__ __forceinline__ void unroll8(F& f) {
+    f(std::integral_constant<int, J>{});
+    if constexpr (J < 7) unroll8<J + 1>(f);
+}
+
+// ALL_OUT: every trajectory pointer is non-null, the optional statistics / truncation bits are off and the whole
+// trajectory has fewer than 2^32 rows x envs (the benchmark / learner case, checked by the host): the stores are
+// unconditional, all four trajectory arrays are addressed from ONE running 32-bit row index (one IMAD.WIDE per
+// address instead of 64-bit shift/add chains), and the statistics code is compiled out.
+// Envs with ROLLOUT_CHUNK run the bulk of the launch as 8-step chunks aligned to the absolute step index,
+// fully unrolled: action-word and reset-refill boundaries fall only on chunk starts, so the per-step loop tests,
+// shifts and branches of the generic loop disappear; with HAS_SMALL (CartPole) a warp whose angles are all in
+// the polynomial range runs the chunk on step<true> (no range reduction, no branches around sincos).
 template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT>
 __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
     using S = typename E::S;
+    using Act = typename E::Act;
     const int tix = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
     unsigned episodes = 0;
     double fin_ret = 0.0, fin_len = 0.0;
+    // Observations of 3 or 6 floats per env (Pendulum, Acrobot): a warp's 32 rows are one contiguous 384 / 768 B
+    // run, but per-lane stores of 4 / 8 B pieces at a 12 / 24 B stride touch every 32 B sector 2-3 times.  A full
+    // warp stages its rows in shared memory and writes the run as 16 B vectors: each sector is written once.
+    constexpr bool STAGE_OBS = ALL_OUT && (E::OD == 3 || E::OD == 6);
+    __shared__ __align__(16) float obs_tile[STAGE_OBS ? ROLLOUT_BLOCK * E::OD : 4];
+    const unsigned lane = threadIdx.x & 31u;
+    const bool staged = STAGE_OBS && p.perm == nullptr && (p.n & 3) == 0 && (tix - (int)lane + 32 <= p.n);   // warp-uniform
     if (tix < p.n) {
         const int i = p.perm ? p.perm[tix] : tix;
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
@@ -386,6 +457,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         const uint64_t seed = seed_of(p.seeds, p.seed, i);
         const uint32_t gid = p.env_off + (uint32_t)i;
         ActionGen<E> gen;
+        gen.init(seed, gid, p.t);
         const size_t n = (size_t)p.n;
         // next initial state, pre-generated: consumed at `done`, refilled for all lanes of the warp that
         // need it every REFILL steps (one Philox evaluation per warp per refill instead of per done)
@@ -394,19 +466,20 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         constexpr bool PREGEN = AUTO_RESET && E::PREGEN_RESET;
         S next;
         if (PREGEN) next = s;
-        bool have = false;
+        unsigned have = 0;   // (word-sized flags: a bool that lives across the cold calls gets byte-packed with PRMTs)
         constexpr bool STATS = !ALL_OUT;
         float ret = (STATS && p.ep_ret) ? p.ep_ret[i] : 0.0f;
-        size_t row = (size_t)i;   // k * n + i: one running index addresses all four trajectory arrays
-        for (int k = 0; k < p.k_steps; ++k) {
-            if (PREGEN && ((unsigned)k & (unsigned)(ROLLOUT_REFILL - 1)) == 0u && !have) {
-                E::reset(next, seed, gid, (uint32_t)ep, p.t + (uint64_t)k, p.prm);
-                have = true;
-            }
-            const typename E::Act a = gen.next(seed, gid, p.t, (uint32_t)k);
-            StepOut r = E::step(s, a, sbd, seed, gid, p.t + (uint64_t)k);
+        uint32_t row = (uint32_t)i;   // ALL_OUT: k * n + i, addresses all four trajectory arrays
+        float* const obs_base = p.obs; float* const reward_base = p.reward; uint8_t* const done_base = p.done;
+        Act* const act_base = reinterpret_cast<Act*>(p.actions);
+
+        // one env step of this lane: transition, time limit, statistics, auto-reset, trajectory stores
+        auto body = [&](int k, const Act a, auto small_tag) {
+            constexpr bool SMALL = decltype(small_tag)::value;
+            const uint64_t t = p.t + (uint64_t)k;
+            StepOut r = StepSel<E, SMALL>::go(s, a, sbd, seed, gid, t);
             bool trunc_only = false;
-            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = true; trunc_only = true; } }
+            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }
             if (STATS) ret += r.reward;
             if (r.done) {
                 episodes += 1;
@@ -414,11 +487,11 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 if (STATS) ret = 0.0f;
                 if (AUTO_RESET) {
                     if (PREGEN) {
-                        if (!have) next = reset_cold<E>(seed, gid, ep, p.t + (uint64_t)k + 1, p.prm);   // second done before the refill: rare
+                        if (!have) next = reset_cold<E>(seed, gid, ep, t + 1, p.prm);   // second done before the refill: rare
                         s = next;
-                        have = false;
+                        have = 0;
                     } else {
-                        E::reset(s, seed, gid, (uint32_t)ep, p.t + (uint64_t)k + 1, p.prm);
+                        E::reset(s, seed, gid, (uint32_t)ep, t + 1, p.prm);
                     }
                     ep += 1;
                     sbd = -1;
@@ -428,11 +501,22 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             if (ALL_OUT) {
                 float o[E::OD];
                 E::obs(s, o);
-                store_obs<E::OD, true>(p.obs, row, o);
-                __stcs(p.reward + row, r.reward);
-                __stcs(p.done + row, (uint8_t)r.done);
-                __stcs(reinterpret_cast<typename E::Act*>(p.actions) + row, a);
-                row += n;
+                if (STAGE_OBS && staged) {
+                    float* tile = obs_tile + (threadIdx.x - lane) * E::OD;
+#pragma unroll
+                    for (int j = 0; j < E::OD; ++j) tile[lane * E::OD + j] = o[j];
+                    __syncwarp();
+                    float4* dst = reinterpret_cast<float4*>(obs_base + (size_t)(row - lane) * E::OD);
+#pragma unroll
+                    for (int v = (int)lane; v < 8 * E::OD; v += 32) __stcs(dst + v, reinterpret_cast<const float4*>(tile)[v]);
+                    __syncwarp();
+                } else {
+                    store_obs<E::OD, true>(obs_base, (size_t)row, o);
+                }
+                __stcs(reward_base + row, r.reward);
+                __stcs(done_base + row, (uint8_t)r.done);
+                __stcs(act_base + row, a);
+                row += (uint32_t)p.n;
             } else {
                 const size_t idx = (size_t)k * n + (size_t)i;
                 if (p.obs) {
@@ -444,6 +528,39 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 if (p.done) __stcs(p.done + idx, (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done);
                 if (p.actions) ActIO<E>::store(p.actions, idx, a);
             }
+        };
+
+        int k = 0;
+        if constexpr (ALL_OUT && E::ROLLOUT_CHUNK) {
+            // head: single steps until the absolute step index is a multiple of 8
+            int head = (int)((8u - ((uint32_t)p.t & 7u)) & 7u);
+            if (head > p.k_steps) head = p.k_steps;
+            for (; k < head; ++k) body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{});
+#pragma unroll 1
+            for (; k + 8 <= p.k_steps; k += 8) {
+                const uint64_t tc = p.t + (uint64_t)k;
+                if (PREGEN && !have) {
+                    E::reset(next, seed, gid, (uint32_t)ep, tc, p.prm);
+                    have = 1;
+                }
+                if constexpr (E::HAS_SMALL && AUTO_RESET) {
+                    if (__all_sync(__activemask(), E::small_ok(s))) {
+                        auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::true_type{}); };
+                        unroll8<0>(f);
+                        continue;
+                    }
+                }
+                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::false_type{}); };
+                unroll8<0>(f);
+            }
+        }
+        // generic loop: everything for the other variants, the tail (< 8 steps) of a chunked launch
+        for (int k0 = k; k < p.k_steps; ++k) {
+            if (PREGEN && ((unsigned)(k - k0) & (unsigned)(ROLLOUT_REFILL - 1)) == 0u && !have) {
+                E::reset(next, seed, gid, (uint32_t)ep, p.t + (uint64_t)k, p.prm);
+                have = 1;
+            }
+            body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{});
         }
         if (AUTO_RESET) p.episode[i] = ep;
         if (STATS && p.ep_ret) p.ep_ret[i] = ret;
@@ -567,7 +684,8 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleArgs p) {
     const uint64_t seed = seed_of(p.seeds, p.seed, i);
     const uint32_t gid = p.env_off + (uint32_t)i;
     ActionGen<E> gen;
-    typename E::Act a = gen.next(seed, gid, p.t, 0u);
+    gen.init(seed, gid, p.t);
+    typename E::Act a = gen.next(seed, gid, p.t);
     if (E::ACTN > 0 && p.mask != nullptr) {
         const uint8_t* m = p.mask + (size_t)i * (E::ACTN > 0 ? E::ACTN : 1);
         int valid = 0;

@@ -59,6 +59,8 @@ struct LunarLanderT {
     static constexpr int OD = 8, AD = CONTINUOUS ? 2 : 1, ACTN = CONTINUOUS ? 0 : 4, DEFAULT_LIMIT = 0;
     static constexpr bool HAS_SBD = false;
     static constexpr bool REJECT_INVALID = true;    // InvalidActionError (LunarLanderEnv.cs:604-607)
+    static constexpr bool HAS_SMALL = false;
+    static constexpr bool ROLLOUT_CHUNK = false;    // one step is thousands of instructions: no unrolling
     static constexpr bool PREGEN_RESET = false;     // resets are rare and a full zero step: done in place
     static constexpr float ACT_LOW = -1.0f, ACT_HIGH = 1.0f;
     using Act = typename std::conditional<CONTINUOUS, float2, int32_t>::type;
@@ -81,12 +83,12 @@ struct LunarLanderT {
     __device__ static __forceinline__ StepOut step(S& L, int32_t a, int32_t&, uint64_t seed, uint32_t gid, uint64_t t) {
         const float none[2] = {0.0f, 0.0f};
         const lunar::StepResult r = lunar::step(L, seed, gid, t, (int)a, none);
-        return StepOut{r.reward, r.done != 0};
+        return StepOut{r.reward, (unsigned)(r.done != 0)};
     }
     __device__ static __forceinline__ StepOut step(S& L, float2 a, int32_t&, uint64_t seed, uint32_t gid, uint64_t t) {
         const float act[2] = {a.x, a.y};
         const lunar::StepResult r = lunar::step(L, seed, gid, t, 0, act);
-        return StepOut{r.reward, r.done != 0};
+        return StepOut{r.reward, (unsigned)(r.done != 0)};
     }
     __device__ static __forceinline__ void obs(const S& L, float* o) { lunar::observe(L, o); }
     // LunarLanderEnv ctor (:409-410): _wind_idx / _torque_idx = randint(-9999, 9999), once per generator

@@ -55,4 +55,12 @@ __device__ __forceinline__ float uniformf(float lo, float hi, uint32_t w) {
     return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u01(w)));
 }
 
+// The same value when high - low is a power of two (every Box action space here: 2 and 4): scaling by a power
+// of two is exact, so float(w >> 8) * ((high - low) * 2^-24) has the bits of (high - low) * u01(w) with one
+// multiply instead of two.
+template <int SPAN_LOG2>
+__device__ __forceinline__ float uniformf_pow2(float lo, uint32_t w) {
+    return __fadd_rn(lo, __fmul_rn((float)(w >> 8), __int_as_float((127 - 24 + SPAN_LOG2) << 23)));
+}
+
 }  // namespace gymcuda

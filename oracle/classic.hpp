@@ -67,9 +67,12 @@ inline StepOut cartpole_step_f64(double s[4], int action, int32_t* steps_beyond_
 }
 
 // Engine arithmetic v1 (restated from DESIGN.md, not from the reference): accelerations in fp32 with
-// the divisions by total_mass folded into float32-rounded reciprocals and explicit fma; positions
-// and the termination test in double with the reference's own operations (:154,:156,:167), so x,
-// theta and `done` are exactly what cartpole_step_f64 gives from the same float32 state.
+// the divisions by total_mass folded into float32-rounded reciprocals and explicit fma.  Positions
+// (:154,:156) are one float32 fma each = the reference's double sum rounded once to float32 (tau * x_dot
+// is exact in double).  `done` (:167) is the reference's own double-precision test from the same
+// float32 state, evaluated here unconditionally; the kernel decides it in float32 and only falls back
+// to double when a new position equals a threshold exactly -- the same flag, since the thresholds are
+// float32 values and rounding is monotonic.
 inline StepOut cartpole_step_f32(float s[4], int action, int32_t* steps_beyond_done) {
     using namespace cp;
     const float INV_TOTAL_MASS = 0.9090908765792847f;   // fl32(1 / total_mass)
@@ -90,8 +93,8 @@ inline StepOut cartpole_step_f32(float s[4], int action, int32_t* steps_beyond_d
     double thd = (double)theta + (double)TAU * (double)theta_dot;
     s[1] = std::fma(TAU, xacc, x_dot);
     s[3] = std::fma(TAU, thetaacc, theta_dot);
-    s[0] = (float)xd;
-    s[2] = (float)thd;
+    s[0] = std::fma(TAU, x_dot, x);
+    s[2] = std::fma(TAU, theta_dot, theta);
     bool done = std::fabs(xd) > (double)X_THRESHOLD || std::fabs(thd) > (double)THETA_THRESHOLD;
     float reward = 1.0f;
     if (done) {

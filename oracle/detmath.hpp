@@ -2,7 +2,7 @@
 //
 // "detmath v1": the fp32 elementary functions of the engine's storage-precision arithmetic,
 // written so that every operation is a single IEEE-754 binary32 (or binary64) operation with
-// round-to-nearest-even: +, -, *, /, sqrt, fma, rint.  The same sequence of operations on the
+// round-to-nearest-even: +, -, *, /, sqrt, fma, rint (binary64 only).  The same sequence of operations on the
 // GPU (compiled with -fmad=false, explicit fmaf) gives the same bits, which is what lets the
 // F32 mode of this oracle be compared BIT-FOR-BIT with the CUDA kernels on free-running rollouts.
 // Compile this file with -ffp-contract=off.
@@ -35,7 +35,10 @@ inline void sincosf_det(float x, float* s, float* c) {
     if (ax <= PIO4_F) {
         r = x; q = 0;
     } else if (ax <= 32768.0f) {
-        float fq = std::rint(x * TWO_OVER_PI);
+        // quadrant = x * 2/pi rounded ONCE to an integer (ties to even) by adding 1.5 * 2^23 inside the fma
+        const float MAGIC = 12582912.0f;
+        float t = std::fma(x, TWO_OVER_PI, MAGIC);
+        float fq = t - MAGIC;
         r = std::fma(fq, -PIO2_1, x);
         r = std::fma(fq, -PIO2_2, r);
         r = std::fma(fq, -PIO2_3, r);

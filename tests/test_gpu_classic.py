@@ -130,6 +130,39 @@ def test_t1_teacher_forced_single_step(name, adversarial):
     assert np.array_equal(rew, orr)
 
 
+def test_cartpole_done_on_exact_float32_threshold_ties():
+    """The kernel decides `done` from the float32 position fmaf(tau, x_dot, x) and recomputes the reference's
+    double-precision test (CartPoleEnv.cs:154,156,167) only when that float32 value EQUALS a threshold: a
+    velocity too small to move the float32 sum still makes the reference's double sum exceed (or not) the
+    threshold.  Every sign combination, against numpy float64 and both oracle modes."""
+    xthr, tthr = np.float32(2.4), np.float32(12 * 2 * np.pi / 360)
+    tau = np.float64(np.float32(0.02))
+    rows = []
+    for comp, thr in ((0, xthr), (2, tthr)):
+        for side in (1.0, -1.0):
+            for vel in (0.0, 1e-12, -1e-12, 1e-9, -1e-9, 3e-8, -3e-8, 1e-6, -1e-6):
+                st = np.zeros(4, np.float32)
+                st[comp] = np.float32(side) * thr
+                st[comp + 1] = np.float32(vel)
+                rows.append(st)
+    states = np.stack(rows)
+    n = len(states)
+    actions = (np.arange(n) % 2).astype(np.int32)
+    s64 = states.astype(np.float64)
+    nx = s64[:, 0] + tau * s64[:, 1]
+    nth = s64[:, 2] + tau * s64[:, 3]
+    expect = ((np.abs(nx) > np.float64(xthr)) | (np.abs(nth) > np.float64(tthr))).astype(np.uint8)
+    assert 0 < expect.sum() < n
+    # the float32 sums of the tiny-velocity rows really are ties
+    f32sum = (s64[:, 2] + tau * s64[:, 3]).astype(np.float32)
+    assert (np.abs(f32sum[n // 2:]) == tthr).sum() >= 10
+    r = teacher_forced("CartPole-v1", states, actions)
+    assert np.array_equal(r["gpu"][2], expect)
+    assert np.array_equal(r[O.MODE_F64_F32STORE][2], expect)
+    assert np.array_equal(r[O.MODE_F32][2], expect)
+    assert np.array_equal(r["gpu"][3], r[O.MODE_F32][3].astype(np.float32))
+
+
 @pytest.mark.parametrize("name", CLASSIC)
 def test_t2_free_running_rollout_bit_exact_vs_twin(name):
     n, k = 4096, 600
@@ -275,18 +308,26 @@ def test_t4_sharding_invariance(name):
     full.Close()
 
 
-def test_t4_rollout_equals_repeated_step_and_k_split():
-    n = 1024
-    a_env = G.CartPoleVecEnv(n, seed=8, auto_reset=True); a_env.ResetBatch()
-    b_env = G.CartPoleVecEnv(n, seed=8, auto_reset=True); b_env.ResetBatch()
-    c_env = G.CartPoleVecEnv(n, seed=8, auto_reset=True); c_env.ResetBatch()
+@pytest.mark.parametrize("name", CLASSIC)
+def test_t4_rollout_equals_repeated_step_and_k_split(name):
+    """One 130-step rollout == the same steps split over launches that start at unaligned step indices (the
+    kernel's 8-step chunks are aligned to the absolute step index: heads and tails run the generic loop)
+    == 130 single steps fed the recorded actions."""
+    n = 1024 if name == "CartPole-v1" else 256
+    a_env = G.make(name, n, seed=8, auto_reset=True); a_env.ResetBatch()
+    b_env = G.make(name, n, seed=8, auto_reset=True); b_env.ResetBatch()
+    c_env = G.make(name, n, seed=8, auto_reset=True); c_env.ResetBatch()
     obs, rew, done, act = a_env.RolloutRandom(130)
-    parts = [b_env.RolloutRandom(k) for k in (1, 64, 65)]
-    assert np.array_equal(np.concatenate([p[0] for p in parts]), obs)
-    assert np.array_equal(np.concatenate([p[2] for p in parts]), done)
+    parts = [b_env.RolloutRandom(k) for k in (1, 3, 61, 8, 57)]
+    for j in range(4):
+        assert np.array_equal(np.concatenate([p[j] for p in parts]), (obs, rew, done, act)[j])
     for t in range(130):
         o, r, d = c_env.StepBatch(act[t])
         assert np.array_equal(o, obs[t]) and np.array_equal(d, done[t]) and np.array_equal(r, rew[t])
+    sa, _, ta = a_env.GetState()
+    for e in (b_env, c_env):
+        se, _, te = e.GetState()
+        assert te == ta == 130 and np.array_equal(se, sa)
     for e in (a_env, b_env, c_env):
         e.Close()
 

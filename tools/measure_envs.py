@@ -25,6 +25,8 @@ CONFIGS = [   # (name, envs per GPU, rollout inner steps, kwargs)
 
 
 def main():
+    only = os.environ.get("MEASURE_MODE", "")          # "rollout" / "step" / "" = both
+    names = [x for x in os.environ.get("MEASURE_ENVS", "").split(",") if x]
     peak = 6650.0
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -34,6 +36,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     for name, n, K, kw in CONFIGS:
+        if names and name not in names:
+            continue
         env = G.make(name, n, seed=0, auto_reset=True, **kw)
         env.SetStream(stream.cuda_stream)
         env.ResetBatch()
@@ -43,8 +47,8 @@ def main():
         rew = torch.empty((K, n), dtype=torch.float32, device=dev)
         done = torch.empty((K, n), dtype=torch.uint8, device=dev)
         act = torch.empty((K, n, ad), dtype=adt, device=dev)
-        reps = 5
-        for _ in range(2):
+        reps = 10
+        for _ in range(3):
             env.RolloutRandomDevice(K, obs.data_ptr(), rew.data_ptr(), done.data_ptr(), act.data_ptr())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record(stream)
@@ -58,6 +62,10 @@ def main():
                           "env_steps_per_s": rate, "algo_bytes_per_env_step": bytes_step,
                           "achieved_gbs": rate * bytes_step / 1e9, "frac_of_measured_hbm": rate * bytes_step / 1e9 / peak,
                           "episodes_per_env": float(done.sum().item()) / n}), flush=True)
+        if only == "rollout":
+            env.Close()
+            del obs, rew, done, act
+            continue
         # per-launch step with device-resident actions
         a1 = act[0].contiguous()
         steps = 200
