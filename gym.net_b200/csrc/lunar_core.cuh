@@ -306,12 +306,26 @@ struct ActiveContact {
     float k11, k12, k22, nm11, nm12, nm21, nm22;   // K and its inverse (block solver)
 };
 
-struct JointWork { V2 ra, rb; float m_exx, m_eyx, m_ezx, m_eyy, m_ezy, m_ezz, motor_mass; };
+// effective-mass matrix of a revolute joint plus everything b2Mat33::Solve33 / Solve22 compute from the matrix
+// alone -- cross(ey, ez) and the two reciprocal determinants -- evaluated once per step instead of in each of the
+// 180 velocity iterations (same operations on the same operands: same bits)
+struct JointWork {
+    V2 ra, rb;
+    float m_exx, m_eyx, m_ezx, m_eyy, m_ezy, m_ezz, motor_mass;
+    float c1x, c1y, c1z, inv_det33, inv_det22;
+};
 
-__device__ __forceinline__ V2 solve22(float a11, float a12, float a21, float a22, V2 b) {   // b2Mat22::Solve / b2Mat33::Solve22
+__device__ __forceinline__ float inv_det22(float a11, float a12, float a21, float a22) {
     float det = a11 * a22 - a12 * a21;
     if (det != 0.0f) det = 1.0f / det;
+    return det;
+}
+// b2Mat22::Solve / b2Mat33::Solve22 with the reciprocal determinant given
+__device__ __forceinline__ V2 solve22_pre(float a11, float a12, float a21, float a22, float det, V2 b) {
     return mk(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+__device__ __forceinline__ V2 solve22(float a11, float a12, float a21, float a22, V2 b) {
+    return solve22_pre(a11, a12, a21, a22, inv_det22(a11, a12, a21, a22), b);
 }
 
 // Body-indexed access with a run-time body index, written as selects over compile-time indices so that
@@ -403,7 +417,7 @@ __device__ __noinline__ void world_step(Lander& L) {
         for (int k = 0; k < nc; ++k) {
             ActiveContact& cc = ac[k];
             const int B = cc.body;
-            V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
+            V2 cB = GETB(c, B); float aB = GETB(a, B);
             const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
             const Rot qB = rot(aB);
             const V2 pB = cB - rmul(qB, SHAPES[B].centroid);
@@ -464,14 +478,14 @@ __device__ __noinline__ void world_step(Lander& L) {
         for (int k = 0; k < nc; ++k) {
             ActiveContact& cc = ac[k];
             const int B = cc.body;
-            V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
+            V2 vB = GETB(v, B); float wB = GETB(w, B);
             const V2 tangent = cross_vs(cc.normal, 1.0f);
             for (int j = 0; j < cc.count; ++j) {
                 const V2 P = cc.p[j].normal_impulse * cc.normal + cc.p[j].tangent_impulse * tangent;
                 wB = wB + SHAPES[B].inv_inertia * cross(cc.p[j].rb, P);
                 vB = vB + SHAPES[B].inv_mass * P;
             }
-            SETB(v, B, vB); SETB(w, B, wB); SETB(c, B, cB); SETB(a, B, aB);
+            SETB(v, B, vB); SETB(w, B, wB);
         }
         // joints: InitVelocityConstraints, island order leg1's joint, then leg0's
         JointWork jw[2];
@@ -493,6 +507,16 @@ __device__ __noinline__ void world_step(Lander& L) {
             W.m_ezz = iA + iB;
             W.motor_mass = iA + iB;
             if (W.motor_mass > 0.0f) W.motor_mass = 1.0f / W.motor_mass;
+            {   // the matrix-only part of Solve33 (cross(ey, ez), det) and of Solve22
+                const float exx = W.m_exx, exy = W.m_eyx, exz = W.m_ezx;
+                const float eyx = W.m_eyx, eyy = W.m_eyy, eyz = W.m_ezy;
+                const float ezx = W.m_ezx, ezy = W.m_ezy, ezz = W.m_ezz;
+                W.c1x = eyy * ezz - eyz * ezy; W.c1y = eyz * ezx - eyx * ezz; W.c1z = eyx * ezy - eyy * ezx;
+                float det = exx * W.c1x + exy * W.c1y + exz * W.c1z;
+                if (det != 0.0f) det = 1.0f / det;
+                W.inv_det33 = det;
+                W.inv_det22 = inv_det22(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy);
+            }
             const float angle = a[B] - a[A] - JOINTS[ji].ref_angle;
             if (fabsf(JOINTS[ji].upper - JOINTS[ji].lower) < 2.0f * ANGULAR_SLOP) {
                 J.limit_state = LIMIT_EQUAL;
@@ -543,10 +567,8 @@ __device__ __noinline__ void world_step(Lander& L) {
                     const float eyx = W.m_eyx, eyy = W.m_eyy, eyz = W.m_ezy;
                     const float ezx = W.m_ezx, ezy = W.m_ezy, ezz = W.m_ezz;
                     const float bx = Cdot1.x, by = Cdot1.y, bz = Cdot2;
-                    // cross(ey, ez)
-                    const float c1x = eyy * ezz - eyz * ezy, c1y = eyz * ezx - eyx * ezz, c1z = eyx * ezy - eyy * ezx;
-                    float det = exx * c1x + exy * c1y + exz * c1z;
-                    if (det != 0.0f) det = 1.0f / det;
+                    // cross(ey, ez) and 1 / det: from JointWork
+                    const float c1x = W.c1x, c1y = W.c1y, c1z = W.c1z, det = W.inv_det33;
                     const float sx = det * (bx * c1x + by * c1y + bz * c1z);
                     // cross(b, ez)
                     const float c2x = by * ezz - bz * ezy, c2y = bz * ezx - bx * ezz, c2z = bx * ezy - by * ezx;
@@ -562,7 +584,7 @@ __device__ __noinline__ void world_step(Lander& L) {
                         const bool release = J.limit_state == LIMIT_AT_LOWER ? new_impulse < 0.0f : new_impulse > 0.0f;
                         if (release) {
                             const V2 rhs = -Cdot1 + J.iz * mk(W.m_ezx, W.m_ezy);
-                            const V2 reduced = solve22(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, rhs);
+                            const V2 reduced = solve22_pre(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, W.inv_det22, rhs);
                             imx = reduced.x; imy = reduced.y; imz = -J.iz;
                             J.ix += reduced.x; J.iy += reduced.y; J.iz = 0.0f;
                         } else {
@@ -576,7 +598,7 @@ __device__ __noinline__ void world_step(Lander& L) {
                     w[B] = w[B] + iB * (cross(W.rb, P) + imz);
                 } else {
                     const V2 Cdot = v[B] + cross_sv(w[B], W.rb) - v[A] - cross_sv(w[A], W.ra);
-                    const V2 impulse = solve22(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, -Cdot);
+                    const V2 impulse = solve22_pre(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, W.inv_det22, -Cdot);
                     J.ix += impulse.x; J.iy += impulse.y;
                     v[A] = v[A] - mA * impulse;
                     w[A] = w[A] - iA * cross(W.ra, impulse);
@@ -587,7 +609,7 @@ __device__ __noinline__ void world_step(Lander& L) {
             for (int k = 0; k < nc; ++k) {
                 ActiveContact& cc = ac[k];
                 const int B = cc.body;
-                V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
+                V2 vB = GETB(v, B); float wB = GETB(w, B);   // only velocities change in a velocity iteration
                 const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 const V2 normal = cc.normal;
                 const V2 tangent = cross_vs(normal, 1.0f);
@@ -653,7 +675,7 @@ __device__ __noinline__ void world_step(Lander& L) {
                         cp2.normal_impulse = x.y;
                     }
                 }
-                SETB(v, B, vB); SETB(w, B, wB); SETB(c, B, cB); SETB(a, B, aB);
+                SETB(v, B, vB); SETB(w, B, wB);
             }
         }
 
@@ -675,13 +697,20 @@ __device__ __noinline__ void world_step(Lander& L) {
         }
 
         // position iterations
+        // A position iteration is a pure function of the nine coordinates (c, a) of the three bodies.  Box2D's exit
+        // test never fires while a leg rests on its joint limit (the limit is corrected down to angular_error ~
+        // ANGULAR_SLOP + 1 ulp, just above what joints_okay accepts), but after two or three iterations the
+        // corrections round to nothing: once an iteration returns bit-identical coordinates, the remaining ones
+        // would too, so the loop stops there -- same result as all 60, position_solved stays false.
         bool position_solved = false;
         for (int it = 0; it < POSITION_ITERATIONS; ++it) {
+            const V2 c_in[3] = {c[0], c[1], c[2]};
+            const float a_in[3] = {a[0], a[1], a[2]};
             float min_separation = 0.0f;
             for (int k = 0; k < nc; ++k) {
                 const ActiveContact& cc = ac[k];
                 const int B = cc.body;
-                V2 vB = GETB(v, B); float wB = GETB(w, B); V2 cB = GETB(c, B); float aB = GETB(a, B);
+                V2 cB = GETB(c, B); float aB = GETB(a, B);   // only positions change in a position iteration
                 const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 for (int j = 0; j < cc.m.count; ++j) {
                     const Rot qB = rot(aB);
@@ -712,7 +741,7 @@ __device__ __noinline__ void world_step(Lander& L) {
                     cB = cB + mB * P;
                     aB = aB + iB * cross(rB, P);
                 }
-                SETB(v, B, vB); SETB(w, B, wB); SETB(c, B, cB); SETB(a, B, aB);
+                SETB(c, B, cB); SETB(a, B, aB);
             }
             const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
             bool joints_okay = true;
@@ -761,6 +790,12 @@ __device__ __noinline__ void world_step(Lander& L) {
                 joints_okay = joints_okay && (position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP);
             }
             if (contacts_okay && joints_okay) { position_solved = true; break; }
+            int moved = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                moved |= (__float_as_int(c[i].x) ^ __float_as_int(c_in[i].x)) | (__float_as_int(c[i].y) ^ __float_as_int(c_in[i].y)) |
+                         (__float_as_int(a[i]) ^ __float_as_int(a_in[i]));
+            if (moved == 0) break;   // fixed point
         }
 
         // copy back, store impulses (b2ContactSolver::StoreImpulses)
