@@ -491,6 +491,79 @@ def test_ragged_batch_sizes(n):
     env.Close()
 
 
+@pytest.mark.parametrize("name", ["Pendulum-v1", "Acrobot-v1"])
+@pytest.mark.parametrize("n", [20, 96, 116, 1030, 4100])
+def test_staged_obs_store_ragged_sizes(name, n):
+    """Pendulum (3 floats) and Acrobot (6 floats) observations leave a full warp through a shared-memory tile as
+    16 B vectors; a partial last warp, or n not a multiple of 4 (the row base is then not 16 B aligned), falls
+    back to per-lane stores.  All shapes must give the oracle's trajectory bit for bit."""
+    env = G.make(name, n, seed=4, auto_reset=True); env.ResetBatch()
+    o = O.OracleEnv(KINDS[name], n, seed=4, auto_reset=True, mode=O.MODE_F32); o.reset()
+    for k in (3, 37):   # unaligned start for the second launch: head + chunks + tail
+        tr = env.RolloutRandom(k); tw = o.rollout_random(k)
+        for x, y in zip(tr, tw):
+            assert np.array_equal(x, y)
+    env.Close()
+
+
+def _rollout_from_states(name, states, k=40, seed=6):
+    n = len(states)
+    env = G.make(name, n, seed=seed, auto_reset=True); env.ResetBatch()
+    o = O.OracleEnv(KINDS[name], n, seed=seed, auto_reset=True, mode=O.MODE_F32); o.reset()
+    st, ax, t = env.GetState()
+    env.SetState(states, ax, t)
+    o.set_state(states.astype(np.float64), ax, t)
+    tr = env.RolloutRandom(k); tw = o.rollout_random(k)
+    for x, y in zip(tr, tw):
+        assert np.array_equal(x, y, equal_nan=True)
+    sg, _, _ = env.GetState(); so, _, _ = o.get_state()
+    assert np.array_equal(sg, so.astype(np.float32), equal_nan=True)
+    env.Close()
+    return tr
+
+
+def test_cartpole_rollout_from_out_of_range_states():
+    """The unrolled chunk runs the reduced-range step (bare sincos polynomial, division without the range check)
+    only for warps whose lanes all have |theta| <= pi/4 and |theta_dot| <= 64; anything else -- set through
+    SetState here -- takes the generic chunk until auto-reset brings the warp back in range."""
+    rng = np.random.default_rng(2)
+    n = 512
+    st = rng.uniform([-2, -3, -0.2, -3], [2, 3, 0.2, 3], size=(n, 4)).astype(np.float32)
+    st[0:40, 2] = rng.uniform(0.8, 3.0, 40)          # beyond pi/4: Cody-Waite sincos
+    st[40:80, 3] = rng.uniform(65, 500, 40)           # fast poles: generic division
+    st[80:90, 2] = [1e3, -1e3, 4e4, -4e4, 1e6, 3e9, 2e14, -2e14, 0.7853982, -0.7853982]   # incl. the double reduction and NaN
+    st[90:96, 3] = [64.0, -64.0, 64.00001, 1e8, 1e20, -1e30]
+    st[96:100, 0] = [1e10, -1e30, 2.4, -2.4]
+    tr = _rollout_from_states("CartPole-v1", st)
+    assert tr[2][0, :100].sum() > 50                  # most of them terminate at once and are reset
+
+
+def test_pendulum_rollout_from_huge_angles():
+    """angle_normalize beyond 2^21 rad takes CUDA's fmodf, sincos beyond 32768 rad the double-precision reduction:
+    both off the branch-free fast paths, both defined by IEEE alone -- same bits as the oracle's libm fmod."""
+    n = 256
+    rng = np.random.default_rng(3)
+    st = rng.uniform([-10, -8], [10, 8], size=(n, 2)).astype(np.float32)
+    st[:16, 0] = [3e4, -3e4, 32768.0, -32769.0, 1e5, -1e6, 2097152.0, 2097153.0, -2.1e6, 5e7, -6e7, 1e9, 1e12, -9e13, 3.1415927, -3.1415927]
+    st[16:32, 0] = rng.uniform(-2e6, 2e6, 16)
+    st[32:48, 0] = np.float32(2 * np.pi) * np.arange(-8, 8, dtype=np.float32)      # exact multiples: remainder 0
+    _rollout_from_states("Pendulum-v1", st, k=24)
+
+
+@pytest.mark.parametrize("name", ["MountainCar-v0", "MountainCarContinuous-v0", "Acrobot-v1"])
+def test_rollout_from_edge_states(name):
+    rng = np.random.default_rng(5)
+    n = 256
+    st = random_states(name, rng, n)
+    if name == "Acrobot-v1":
+        st[:8, 0] = [3.1415927, -3.1415927, 0.0, 1e4, -4e4, 2.0, 2.1, -2.1]
+        st[8:12, 2] = [12.566371, -12.566371, 20.0, -20.0]
+    else:
+        st[:8, 0] = [-1.2, 0.6, 0.5, 0.45, 0.4999999, 0.45000002, -1.1999999, 0.0]
+        st[8:12, 1] = [0.07, -0.07, 0.0, 1e-8]
+    _rollout_from_states(name, st, k=24)
+
+
 def test_episode_statistics_and_truncation_bits():
     """episode return/length statistics and a truncation flag distinct from termination, fused
     into the step / rollout kernels (what BasePlaySession.cs:58-69 keeps by hand)."""

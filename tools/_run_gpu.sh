@@ -1,3 +1,4 @@
 set -x
-(time python -m pytest tests/test_gpu_lunar.py -x -q) > gpurun_out/pytest_gpu_s2f.log 2>&1; tail -4 gpurun_out/pytest_gpu_s2f.log
-MEASURE_ENVS=LunarLander-v2 python tools/measure_envs.py > gpurun_out/envs_s2f.jsonl 2>&1; cat gpurun_out/envs_s2f.jsonl | cut -c1-330
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_s2i.log 2>&1; tail -3 gpurun_out/pytest_gpu_s2i.log
+(timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_probe.py 2>&1 | tail -4) > gpurun_out/sanitizer_mem_s2i.log 2>&1; cat gpurun_out/sanitizer_mem_s2i.log
+(timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_probe.py 2>&1 | tail -4) > gpurun_out/sanitizer_race_s2i.log 2>&1; cat gpurun_out/sanitizer_race_s2i.log

@@ -22,6 +22,14 @@ for name, n in (("CartPole-v1", 3001), ("Pendulum-v1", 1025), ("MountainCar-v0",
         env.ResetBatch(mask=m)
         st, ax, t = env.GetState(); env.SetState(st, ax, t); env.Observe(); env.Stats(reset=True)
         env.Close()
+# the ALL_OUT rollout variant (no statistics): 8-step chunks, 32-bit row index, staged 3/6-float observation stores
+for name, n in (("CartPole-v1", 3000), ("Pendulum-v1", 1028), ("Pendulum-v1", 1030), ("MountainCar-v0", 516),
+                ("MountainCarContinuous-v0", 516), ("Acrobot-v1", 772), ("Acrobot-v1", 70), ("LunarLander-v2", 512)):
+    env = G.make(name, n, seed=1, auto_reset=True)
+    env.ResetBatch()
+    env.RolloutRandom(3)
+    env.RolloutRandom(29)
+    env.Close()
 ll = G.LunarLanderVecEnv(2500, seed=2, auto_reset=True, time_limit=300); obs = ll.ResetBatch()
 for _ in range(120):      # long enough for contacts: exercises the contact partition + solver paths
     obs, r, d = ll.StepBatch(np.full(2500, 0, np.int32))
