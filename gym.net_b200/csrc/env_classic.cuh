@@ -344,8 +344,59 @@ __device__ __forceinline__ AcroTrig acrobot_trig(const float v[4]) {
     AcroTrig t;
     sincosf_det(v[0], &t.s1, &t.c1);
     sincosf_det(v[1], &t.s2, &t.c2);
-    sincosf_det(v[1] + v[0], &t.s12, &t.c12);
+    // theta1 + theta2: angle-addition formulas (one fma + one multiply each) instead of a third sincos
+    t.s12 = fmaf(t.s1, t.c2, t.c1 * t.s2);
+    t.c12 = fmaf(t.c1, t.c2, -(t.s1 * t.s2));
     return t;
+}
+
+// Engine arithmetic of Acrobot (float32): the same book dynamics with the constants folded (m1 = m2 = l1 = 1,
+// lc = 0.5, I = 1, g = 9.8: d1 = 3.5 + cos t2, d2 = 1.25 + cos t2 / 2, m2 lc2 g = 4.9, (m1 lc1 + m2 l1) g = 14.7),
+// explicit fma, ONE reciprocal of d1 instead of three divisions by it, cos(x - pi/2) taken as sin x.  The two
+// quotients have d1 in [2.5, 4.5] and 1.25 - d2^2/d1 in [0.56, 1.03]: div_inrange is the IEEE quotient for every
+// state whose velocities are finite and below ~1e15 (every state the clamps of the previous step can produce).
+__device__ __forceinline__ void acrobot_dsdt_f32(const float s[4], float a, float s2, float c2, float sh12, float sh1, float out[4]) {
+    const float dth1 = s[2], dth2 = s[3];
+    const float d1 = c2 + 3.5f;
+    const float d2 = fmaf(0.5f, c2, 1.25f);
+    const float phi2 = 4.9f * sh12;
+    const float phi1 = fmaf(14.7f, sh1, phi2) - (s2 * dth2) * fmaf(0.5f, dth2, dth1);
+    const float r1 = div_inrange(1.0f, d1);
+    const float e = d2 * r1;
+    const float num = (a - phi2) + fmaf(e, phi1, -((0.5f * s2) * (dth1 * dth1)));
+    const float den = fmaf(-d2, e, 1.25f);
+    const float ddth2 = div_inrange(num, den);
+    const float ddth1 = -(fmaf(d2, ddth2, phi1) * r1);
+    out[0] = dth1; out[1] = dth2; out[2] = ddth1; out[3] = ddth2;
+}
+
+// one classical RK4 step over dt = 0.2 in engine arithmetic, wrap and clamp; t0 = trig of the current state
+__device__ __forceinline__ void acrobot_rk4_f32(float s[4], int action, const AcroTrig& t0) {
+    constexpr float PI = 3.14159265358979323846f;
+    const float a = (float)(action - 1);
+    float k1[4], k2[4], k3[4], k4[4], y[4];
+    acrobot_dsdt_f32(s, a, t0.s2, t0.c2, t0.s12, t0.s1, k1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fmaf(0.1f, k1[i], s[i]);
+    AcroTrig t = acrobot_trig(y);
+    acrobot_dsdt_f32(y, a, t.s2, t.c2, t.s12, t.s1, k2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fmaf(0.1f, k2[i], s[i]);
+    t = acrobot_trig(y);
+    acrobot_dsdt_f32(y, a, t.s2, t.c2, t.s12, t.s1, k3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fmaf(0.2f, k3[i], s[i]);
+    t = acrobot_trig(y);
+    acrobot_dsdt_f32(y, a, t.s2, t.c2, t.s12, t.s1, k4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fmaf(0.2f / 6.0f, fmaf(2.0f, k2[i] + k3[i], k1[i] + k4[i]), s[i]);
+    y[0] = acro_wrap<float>(y[0], -PI, PI);
+    y[1] = acro_wrap<float>(y[1], -PI, PI);
+    constexpr float MV1 = 4 * PI, MV2 = 9 * PI;
+    y[2] = y[2] < -MV1 ? -MV1 : (y[2] > MV1 ? MV1 : y[2]);
+    y[3] = y[3] < -MV2 ? -MV2 : (y[3] > MV2 ? MV2 : y[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = y[i];
 }
 
 // one classical RK4 step of dsdt over dt = 0.2, wrap and clamp (upstream acrobot.py); s updated in place
@@ -419,10 +470,8 @@ struct Acrobot {
     __device__ static __forceinline__ bool valid(Act a) { return a >= 0 && a < 3; }
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         const float o0 = s.v[0], o1 = s.v[1], o2 = s.v[2], o3 = s.v[3];
-        const AcroTrig t0 = s.t;   // the first RK4 stage reuses the trig of the current state (cos(x - pi/2) = sin x in float32)
-        acrobot_rk4<float>(s.v, (int)a, [t0](const float* st, float act, float* out) {
-            acrobot_dsdt_trig<float>(st, act, t0.s2, t0.c2, t0.s12, t0.s1, out);
-        });
+        const AcroTrig t0 = s.t;   // the first RK4 stage reuses the trig of the current state
+        acrobot_rk4_f32(s.v, (int)a, t0);
         s.t = acrobot_trig(s.v);
         const float v = -s.t.c1 - s.t.c12;
         unsigned done = (unsigned)(v > 1.0f);

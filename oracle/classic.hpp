@@ -294,9 +294,68 @@ inline StepOut acrobot_step_f64(double s[4], int action) {
     return StepOut{done ? 0.0f : -1.0f, (uint8_t)done};
 }
 
+// Engine arithmetic of Acrobot (float32; restated from DESIGN.md, not from upstream): the same book dynamics
+// with the constants folded (m1 = m2 = l1 = 1, lc = 0.5, I = 1, g = 9.8: d1 = 3.5 + cos t2, d2 = 1.25 + cos t2 / 2,
+// m2 lc2 g = 4.9, (m1 lc1 + m2 l1) g = 14.7), explicit fma, ONE reciprocal of d1 instead of three divisions by it,
+// cos(x - pi/2) taken as sin x, and sin/cos(theta1 + theta2) from the angle-addition formulas.
+// s2, c2 = sin/cos(theta2), sh12 = sin(theta1 + theta2), sh1 = sin(theta1).
+inline void acrobot_dsdt_f32(const float s[4], float a, float s2, float c2, float sh12, float sh1, float out[4]) {
+    const float dth1 = s[2], dth2 = s[3];
+    const float d1 = c2 + 3.5f;
+    const float d2 = std::fma(0.5f, c2, 1.25f);
+    const float phi2 = 4.9f * sh12;
+    const float phi1 = std::fma(14.7f, sh1, phi2) - (s2 * dth2) * std::fma(0.5f, dth2, dth1);
+    const float r1 = 1.0f / d1;
+    const float e = d2 * r1;
+    const float num = (a - phi2) + std::fma(e, phi1, -((0.5f * s2) * (dth1 * dth1)));
+    const float den = std::fma(-d2, e, 1.25f);
+    const float ddth2 = num / den;
+    const float ddth1 = -(std::fma(d2, ddth2, phi1) * r1);
+    out[0] = dth1; out[1] = dth2; out[2] = ddth1; out[3] = ddth2;
+}
+
+// sin / cos of theta1 + theta2 from the two angles' own sin / cos (angle-addition formulas, one fma + one
+// multiply each) instead of a third sincos evaluation
+inline void acrobot_trig_f32(const float y[4], float* s1, float* c1, float* s2, float* c2, float* s12, float* c12) {
+    det::sincosf_det(y[0], s1, c1);
+    det::sincosf_det(y[1], s2, c2);
+    *s12 = std::fma(*s1, *c2, *c1 * *s2);
+    *c12 = std::fma(*c1, *c2, -(*s1 * *s2));
+}
+
+inline void acrobot_dsdt_f32(const float y[4], float a, float out[4]) {
+    float s2, c2, s12, c12, s1, c1;
+    acrobot_trig_f32(y, &s1, &c1, &s2, &c2, &s12, &c12);
+    acrobot_dsdt_f32(y, a, s2, c2, s12, s1, out);
+}
+
+// one classical RK4 step over dt = 0.2 in engine arithmetic, wrap and clamp; returns -cos(th1) - cos(th2 + th1)
+inline float acrobot_integrate_f32(float s[4], int action) {
+    const float PI = 3.14159265358979323846f;
+    const float a = (float)(action - 1);
+    float k1[4], k2[4], k3[4], k4[4], y[4];
+    acrobot_dsdt_f32(s, a, k1);
+    for (int i = 0; i < 4; ++i) y[i] = std::fma(0.1f, k1[i], s[i]);
+    acrobot_dsdt_f32(y, a, k2);
+    for (int i = 0; i < 4; ++i) y[i] = std::fma(0.1f, k2[i], s[i]);
+    acrobot_dsdt_f32(y, a, k3);
+    for (int i = 0; i < 4; ++i) y[i] = std::fma(0.2f, k3[i], s[i]);
+    acrobot_dsdt_f32(y, a, k4);
+    for (int i = 0; i < 4; ++i) y[i] = std::fma(0.2f / 6.0f, std::fma(2.0f, k2[i] + k3[i], k1[i] + k4[i]), s[i]);
+    y[0] = acro_wrap<float>(y[0], -PI, PI);
+    y[1] = acro_wrap<float>(y[1], -PI, PI);
+    const float MV1 = 4 * PI, MV2 = 9 * PI;
+    y[2] = y[2] < -MV1 ? -MV1 : (y[2] > MV1 ? MV1 : y[2]);
+    y[3] = y[3] < -MV2 ? -MV2 : (y[3] > MV2 ? MV2 : y[3]);
+    for (int i = 0; i < 4; ++i) s[i] = y[i];
+    float s1, c1, s2, c2, s12, c12;
+    acrobot_trig_f32(y, &s1, &c1, &s2, &c2, &s12, &c12);
+    return -c1 - c12;
+}
+
 inline StepOut acrobot_step_f32(float s[4], int action) {
     double sd[4] = {s[0], s[1], s[2], s[3]};
-    float v = acrobot_integrate<float>(s, action);
+    float v = acrobot_integrate_f32(s, action);
     bool done = v > 1.0f;
     if (std::fabs(v - 1.0f) <= 2e-5f) done = acrobot_integrate<double>(sd, action) > 1.0;
     return StepOut{done ? 0.0f : -1.0f, (uint8_t)done};
