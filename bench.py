@@ -312,10 +312,14 @@ def main():
         h_act.numpy()[:] = rng.uniform(-1, 1, (n, ad))
     L = G._native.lib()
 
+    # the four buffer arguments are marshalled once: a C# caller pins its arrays once too, and the per-call cost of
+    # building ctypes objects would otherwise be timed as part of the library
+    e2e_args = (env._h, C.c_void_p(h_act.data_ptr()), C.c_void_p(h_obs.data_ptr()),
+                C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr()))
+    step_fn = L.gymcuda_step
+
     def e2e_step():
-        rc = L.gymcuda_step(env._h, C.c_void_p(h_act.data_ptr()), C.c_void_p(h_obs.data_ptr()),
-                            C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr()))
-        if rc != 0:
+        if step_fn(*e2e_args) != 0:
             raise RuntimeError(L.gymcuda_last_error())
 
     for _ in range(5):

@@ -83,6 +83,8 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_sync(GymCudaHandle env);
         [DllImport(Lib)] internal static extern int gymcuda_host_alloc(out IntPtr ptr, UIntPtr bytes);
         [DllImport(Lib)] internal static extern int gymcuda_host_free(IntPtr ptr);
+        [DllImport(Lib)] internal static extern int gymcuda_host_register(IntPtr ptr, UIntPtr bytes);
+        [DllImport(Lib)] internal static extern int gymcuda_host_unregister(IntPtr ptr);
         [DllImport(Lib)] internal static extern int gymcuda_nccl_load([MarshalAs(UnmanagedType.LPStr)] string path);
         [DllImport(Lib)] internal static extern int gymcuda_nccl_unique_id(byte[] id128);
         [DllImport(Lib)] internal static extern int gymcuda_comm_init(GymCudaHandle env, byte[] id128, int rank, int worldSize);

@@ -73,6 +73,8 @@ SYMBOLS = {
     "gymcuda_sync": (_I, [_VP]),
     "gymcuda_host_alloc": (_I, [C.POINTER(_VP), C.c_size_t]),
     "gymcuda_host_free": (_I, [_VP]),
+    "gymcuda_host_register": (_I, [_VP, C.c_size_t]),
+    "gymcuda_host_unregister": (_I, [_VP]),
     "gymcuda_nccl_load": (_I, [C.c_char_p]),
     "gymcuda_nccl_unique_id": (_I, [_VP]),
     "gymcuda_comm_init": (_I, [_VP, _VP, _I, _I]),

@@ -445,7 +445,7 @@ struct Acrobot {
     static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
     static constexpr bool HAS_SMALL = false;        // no reduced-range variant of step
-    static constexpr bool ROLLOUT_CHUNK = false;    // one RK4 step is ~900 instructions: 8 unrolled copies thrash the instruction cache (measured 1.5x slower)
+    static constexpr bool ROLLOUT_CHUNK = false;    // one RK4 step is ~450 instructions: 8 unrolled copies run 1.4x slower (measured; instruction cache)
     using Vec = float4;
     using Act = int32_t;
     struct S { float v[4]; AcroTrig t; };

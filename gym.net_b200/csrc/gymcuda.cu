@@ -133,6 +133,7 @@ struct gymcuda_env {
     float *d_obs, *d_reward;
     uint8_t *d_done, *d_mask;
     const void* alias_host[4]; void* alias_dev[4];   // cache of mapped_alias()
+    unsigned alias_epoch;
     volatile int* h_invalid; // mapped pinned flags: [0] set by the step kernel when it rejects an action,
     int* d_invalid_flag;     //                      [1] set by gather_wait_kernel on a timeout (1 + missing rank)
     int32_t *d_done_idx, *d_done_count;
@@ -535,8 +536,14 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
 
 // Device-visible alias of a host pointer if (and only if) it is page-locked memory mapped into the
 // device address space (cudaHostAlloc / cudaHostRegister / gymcuda_host_alloc), else null.
+static unsigned g_host_epoch = 1;   // bumped by every (un)registration / pinned (de)allocation made through this library
+
 static void* mapped_alias(gymcuda_env* e, const void* host, int slot) {
     if (!host) return nullptr;
+    if (e->alias_epoch != g_host_epoch) {   // a buffer may have been registered or released since the answers were cached
+        for (int k = 0; k < 4; ++k) e->alias_host[k] = nullptr;
+        e->alias_epoch = g_host_epoch;
+    }
     if (e->alias_host[slot] == host) return e->alias_dev[slot];
     cudaPointerAttributes at;
     void* dev = nullptr;
@@ -589,10 +596,15 @@ int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward,
         if (*e->h_invalid) return step_finish_host(e, nullptr, nullptr, nullptr);
         return GYMCUDA_OK;
     }
-    CU_TRY(cudaMemcpyAsync(e->d_actions, actions, e->act_bytes(), cudaMemcpyHostToDevice, e->stream));
-    int rc = step_launch(e, e->d_actions, 0, 0, e->d_obs, e->d_reward, e->d_done);
+    // mixed / pageable buffers: every page-locked one is still accessed in place, the others are staged
+    if (!za) CU_TRY(cudaMemcpyAsync(e->d_actions, actions, e->act_bytes(), cudaMemcpyHostToDevice, e->stream));
+    const bool any_mapped_out = zo || zr || zd;
+    int rc = step_launch(e, za ? za : e->d_actions, 0, 0, zo ? (float*)zo : e->d_obs, zr ? (float*)zr : e->d_reward,
+                         zd ? (uint8_t*)zd : e->d_done);
     if (rc) return rc;
-    return step_finish_host(e, obs, reward, done);
+    if (zo) e->last_obs = nullptr;
+    if (!any_mapped_out) return step_finish_host(e, obs, reward, done);   // one DMA when the three are adjacent
+    return step_finish_host(e, zo ? nullptr : obs, zr ? nullptr : reward, zd ? nullptr : done);
 }
 
 int gymcuda_step_broadcast(gymcuda_env* e, int32_t action, float* obs, float* reward, uint8_t* done) {
@@ -846,11 +858,27 @@ int gymcuda_sync(gymcuda_env* e) {
 int gymcuda_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(GYMCUDA_EINVAL, "ptr is null");
     CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    g_host_epoch += 1;
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_free(void* ptr) {
     if (ptr) CU_TRY(cudaFreeHost(ptr));
+    g_host_epoch += 1;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(GYMCUDA_EINVAL, "gymcuda_host_register: null pointer or empty range");
+    CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    g_host_epoch += 1;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_host_unregister(void* ptr) {
+    if (!ptr) return GYMCUDA_OK;
+    CU_TRY(cudaHostUnregister(ptr));
+    g_host_epoch += 1;
     return GYMCUDA_OK;
 }
 

@@ -120,8 +120,9 @@ int gymcuda_reset_masked(gymcuda_env* env, const uint8_t* mask, float* obs_out);
 /* ---- Env.Step / IVecEnv.Step ------------------------------------------------------------------ */
 /* Host buffers; H2D(actions) -> kernel -> D2H(obs, reward, done); synchronous.
  * Pageable buffers are staged with cudaMemcpyAsync (one DMA for obs|reward|done when they are adjacent);
- * page-locked buffers (gymcuda_host_alloc, cudaHostAlloc, cudaHostRegister, GCHandle-pinned + registered)
- * are read and written by the kernel directly over PCIe (zero-copy), which is the fast path.
+ * page-locked buffers (gymcuda_host_alloc, cudaHostAlloc, gymcuda_host_register / cudaHostRegister)
+ * are read and written by the kernel directly over PCIe (zero-copy), which is the fast path; the two
+ * kinds can be mixed freely among the four buffers.
  * Returns GYMCUDA_EACTION if any action was outside the action space of an env kind that rejects
  * it (all but CartPole, whose reference only Debug.Asserts, CartPoleEnv.cs:139); those envs are
  * left unstepped, the others step normally. */
@@ -179,6 +180,13 @@ int gymcuda_set_stream(gymcuda_env* env, void* cuda_stream);
 int gymcuda_sync(gymcuda_env* env);
 int gymcuda_host_alloc(void** ptr, size_t bytes); /* pinned (page-locked) host memory */
 int gymcuda_host_free(void* ptr);
+/* Page-lock and map memory the CALLER owns (cudaHostRegister) so that gymcuda_step reads / writes it in place:
+ * what the C# shim does once with the GCHandle-pinned result arrays it hands back from Step (managed arrays are
+ * pageable for CUDA even while pinned for the GC).  The range must stay allocated and pinned until
+ * gymcuda_host_unregister.  Each of the four buffers of gymcuda_step is treated on its own: registered ones are
+ * accessed directly, the others are staged with a copy. */
+int gymcuda_host_register(void* ptr, size_t bytes);
+int gymcuda_host_unregister(void* ptr);
 
 /* ---- multi-GPU: optional all-gather of observations over NVLink (one process per GPU) ------- */
 /* Rank 0 calls gymcuda_nccl_unique_id and distributes the 128 bytes out of band; every rank then

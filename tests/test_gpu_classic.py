@@ -419,6 +419,52 @@ def test_zero_copy_pinned_buffers_match_staged_copies():
     a_env.Close(); b_env.Close()
 
 
+@pytest.mark.parametrize("registered", ["out", "act", "obs_only", "all"])
+def test_registered_and_mixed_host_buffers(registered):
+    """gymcuda_host_register page-locks memory the caller owns (the C# shim's GCHandle-pinned result arrays): the
+    step kernel then accesses it in place.  Every mix of registered and pageable buffers gives the same results,
+    registrations are picked up (and dropped) between calls, and an invalid action is still reported."""
+    import ctypes as C
+    from gymnet_b200 import _native as N
+    n = 2500
+    L = N.lib()
+    a_env = G.MountainCarVecEnv(n, seed=7, auto_reset=True); a_env.ResetBatch()
+    b_env = G.MountainCarVecEnv(n, seed=7, auto_reset=True); b_env.ResetBatch()
+    # page-aligned numpy arrays (cudaHostRegister works on any range; alignment keeps the pinned pages private)
+    def arr(shape, dtype):
+        count = int(np.prod(shape)); item = np.dtype(dtype).itemsize
+        raw = np.empty(count * item + 8192, np.uint8)
+        off = (-raw.ctypes.data) % 4096
+        return raw[off: off + count * item].view(dtype).reshape(shape), raw
+    act, k0 = arr((n,), np.int32); obs, k1 = arr((n, 2), np.float32); rew, k2 = arr((n,), np.float32); done, k3 = arr((n,), np.uint8)
+    which = {"out": [obs, rew, done], "act": [act], "obs_only": [obs], "all": [act, obs, rew, done]}[registered]
+    def step(a):
+        act[:] = a
+        return L.gymcuda_step(a_env._h, C.c_void_p(act.ctypes.data), C.c_void_p(obs.ctypes.data),
+                              C.c_void_p(rew.ctypes.data), C.c_void_p(done.ctypes.data))
+    rng = np.random.default_rng(5)
+    for phase in range(3):   # pageable -> registered -> pageable again
+        if phase == 1:
+            for x in which:
+                N.check(L.gymcuda_host_register(C.c_void_p(x.ctypes.data), x.nbytes))
+        if phase == 2:
+            for x in which:
+                N.check(L.gymcuda_host_unregister(C.c_void_p(x.ctypes.data)))
+        for _ in range(25):
+            a = rng.integers(0, 3, n).astype(np.int32)
+            N.check(step(a))
+            o, r, d = b_env.StepBatch(a)
+            assert np.array_equal(obs, o) and np.array_equal(rew, r) and np.array_equal(done, d)
+        if phase == 1:
+            bad = rng.integers(0, 3, n).astype(np.int32); bad[17] = 9
+            assert step(bad) == N.EACTION
+            with pytest.raises(N.InvalidActionError):
+                b_env.StepBatch(bad)
+            assert np.array_equal(obs, b_env.Observe())
+    assert np.array_equal(a_env.Observe(), b_env.Observe())
+    a_env.Close(); b_env.Close()
+
+
 @pytest.mark.parametrize("name", ["CartPole-v1", "MountainCar-v0", "Pendulum-v1", "LunarLander-v2"])
 def test_device_action_sampling_matches_rollout_and_oracle(name):
     """ActionSpace.Sample() on device: sample -> step reproduces the fused rollout; masked Discrete.Sample
