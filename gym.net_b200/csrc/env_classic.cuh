@@ -9,7 +9,7 @@
 //   step(S&, Act, sbd)        transition + reward + termination
 //   obs(S, float*)            observation (OD floats)
 //
-// Arithmetic ("engine arithmetic v1"): float32 state and float32 math built from single IEEE
+// Arithmetic ("engine arithmetic"): float32 state and float32 math built from single IEEE
 // operations (detmath.cuh), with the termination test refined in double wherever float32 rounding
 // could flip it, so that `done` equals the reference's double-precision evaluation from the same
 // stored state.  Compiled with -fmad=false; fused operations are explicit.

@@ -134,6 +134,7 @@ struct gymcuda_env {
     uint8_t *d_done, *d_mask;
     const void* alias_host[4]; void* alias_dev[4];   // cache of mapped_alias()
     unsigned alias_epoch;
+    void* scratch[4]; size_t scratch_cap[4];   // device scratch of gymcuda_rollout_random (host buffers)
     volatile int* h_invalid; // mapped pinned flags: [0] set by the step kernel when it rejects an action,
     int* d_invalid_flag;     //                      [1] set by gather_wait_kernel on a timeout (1 + missing rank)
     int32_t *d_done_idx, *d_done_count;
@@ -299,6 +300,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux); cudaFree(e->d_perm); cudaFree(e->d_block_free);
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
+    for (int k = 0; k < 4; ++k) cudaFree(e->scratch[k]);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -641,27 +643,40 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     return GYMCUDA_OK;
 }
 
+// grow-only device scratch for the host-buffer rollout (a cudaMalloc + cudaFree pair per call costs more than a
+// short rollout itself)
+static cudaError_t scratch_reserve(gymcuda_env* e, int slot, size_t bytes, void** out) {
+    *out = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    if (e->scratch_cap[slot] < bytes) {
+        cudaFree(e->scratch[slot]);
+        e->scratch[slot] = nullptr; e->scratch_cap[slot] = 0;
+        cudaError_t ce = cudaMalloc(&e->scratch[slot], bytes);
+        if (ce != cudaSuccess) return ce;
+        e->scratch_cap[slot] = bytes;
+    }
+    *out = e->scratch[slot];
+    return cudaSuccess;
+}
+
 int gymcuda_rollout_random(gymcuda_env* e, int k_steps, float* obs, float* reward, uint8_t* done, void* actions) {
     ENTER(e);
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     const size_t kn = (size_t)k_steps * (size_t)e->n;
-    float *d_obs = nullptr, *d_reward = nullptr; uint8_t* d_done = nullptr; void* d_act = nullptr;
-    int rc = GYMCUDA_OK;
-    auto cleanup = [&]() { cudaFree(d_obs); cudaFree(d_reward); cudaFree(d_done); cudaFree(d_act); };
-#define RB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
-    if (obs) RB_TRY(cudaMalloc(&d_obs, kn * e->ki.od * 4));
-    if (reward) RB_TRY(cudaMalloc(&d_reward, kn * 4));
-    if (done) RB_TRY(cudaMalloc(&d_done, kn));
-    if (actions) RB_TRY(cudaMalloc(&d_act, kn * e->ki.ad * 4));
-    rc = gymcuda_rollout_random_device(e, k_steps, d_obs, d_reward, d_done, d_act);
-    if (rc) { cleanup(); return rc; }
+    void *d_obs = nullptr, *d_reward = nullptr, *d_done = nullptr, *d_act = nullptr;
+#define RB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    RB_TRY(scratch_reserve(e, 0, obs ? kn * e->ki.od * 4 : 0, &d_obs));
+    RB_TRY(scratch_reserve(e, 1, reward ? kn * 4 : 0, &d_reward));
+    RB_TRY(scratch_reserve(e, 2, done ? kn : 0, &d_done));
+    RB_TRY(scratch_reserve(e, 3, actions ? kn * e->ki.ad * 4 : 0, &d_act));
+    int rc = gymcuda_rollout_random_device(e, k_steps, (float*)d_obs, (float*)d_reward, (uint8_t*)d_done, d_act);
+    if (rc) return rc;
     if (obs) RB_TRY(cudaMemcpyAsync(obs, d_obs, kn * e->ki.od * 4, cudaMemcpyDeviceToHost, e->stream));
     if (reward) RB_TRY(cudaMemcpyAsync(reward, d_reward, kn * 4, cudaMemcpyDeviceToHost, e->stream));
     if (done) RB_TRY(cudaMemcpyAsync(done, d_done, kn, cudaMemcpyDeviceToHost, e->stream));
     if (actions) RB_TRY(cudaMemcpyAsync(actions, d_act, kn * e->ki.ad * 4, cudaMemcpyDeviceToHost, e->stream));
     RB_TRY(cudaStreamSynchronize(e->stream));
 #undef RB_TRY
-    cleanup();
     return GYMCUDA_OK;
 }
 

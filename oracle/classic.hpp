@@ -66,7 +66,7 @@ inline StepOut cartpole_step_f64(double s[4], int action, int32_t* steps_beyond_
     return StepOut{reward, (uint8_t)done};
 }
 
-// Engine arithmetic v1 (restated from DESIGN.md, not from the reference): accelerations in fp32 with
+// Engine arithmetic (restated from DESIGN.md section 5, not from the reference): accelerations in fp32 with
 // the divisions by total_mass folded into float32-rounded reciprocals and explicit fma.  Positions
 // (:154,:156) are one float32 fma each = the reference's double sum rounded once to float32 (tau * x_dot
 // is exact in double).  `done` (:167) is the reference's own double-precision test from the same
