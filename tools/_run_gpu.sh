@@ -1,7 +1,3 @@
-export MEASURE_MODE=step MEASURE_ENVS=CartPole-v1,Pendulum-v1
-for lib in libgymcuda exp_old exp_older; do for i in 1 2; do
-GYMCUDA_LIB=$PWD/gym.net_b200/csrc/$lib.so python tools/measure_envs.py 2>&1 | python -c "import sys,json
-for l in sys.stdin:
-    d=json.loads(l)
-    if d['mode']=='step_device': print('$lib', d['env'], '%.2f us' % (d['ms_per_launch']*1e3))"
-done; done
+set -x
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err; tail -1 gpurun_out/bench_8gpu.json; tail -3 gpurun_out/bench_8gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/bench_4gpu.json 2> gpurun_out/bench_4gpu.err; tail -1 gpurun_out/bench_4gpu.json | cut -c1-200
