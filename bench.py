@@ -222,6 +222,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # one process per GPU: run on the cores of that GPU's NUMA node, so that the page-locked host buffers of the
+    # e2e leg (first-touched below) sit next to the GPU that writes them
+    host_cpus = G.bind_host_to_device(local_rank) if world > 1 else None
     n, K = args.num_envs, args.inner
     env = G.make(args.env, n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True)
     od, ad = env.obs_dim, env.act_dim
@@ -336,7 +339,8 @@ def main():
         e2e_s = float(tt.item())
     e2e = {"value": world * n * e2e_steps / e2e_s, "unit": "env-steps/s",
            "h2d_bytes_per_step": n * ad * 4, "d2h_bytes_per_step": n * (od * 4 + 4 + 1),
-           "api": "gymcuda_step (host buffers, pinned)", "steps": e2e_steps}
+           "api": "gymcuda_step (host buffers, pinned)", "steps": e2e_steps,
+           "host_affinity": ("%d cores of the GPU's NUMA node" % len(host_cpus)) if host_cpus else "unchanged"}
 
     # ---- N > 1 only, outside the headline timing: what the optional observation all-gather costs per step,
     # with NCCL after the step kernel and fused into it as NVLink peer stores (gymcuda_step_gather_device)

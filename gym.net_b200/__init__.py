@@ -9,8 +9,8 @@ from ._native import GymCudaError, InvalidActionError
 from .spaces import Box, Discrete, Space
 from .vector import (AcrobotVecEnv, CartPoleVecEnv, CudaVecEnv, LunarLanderVecEnv,
                      MountainCarContinuousVecEnv, MountainCarVecEnv, PendulumVecEnv, Step, make,
-                     nccl_unique_id, shard_envs)
+                     bind_host_to_device, nccl_unique_id, shard_envs)
 
 __all__ = ["GymCudaError", "InvalidActionError", "Box", "Discrete", "Space", "CudaVecEnv", "Step", "make",
            "CartPoleVecEnv", "PendulumVecEnv", "MountainCarVecEnv", "MountainCarContinuousVecEnv",
-           "AcrobotVecEnv", "LunarLanderVecEnv", "nccl_unique_id", "shard_envs"]
+           "AcrobotVecEnv", "LunarLanderVecEnv", "nccl_unique_id", "shard_envs", "bind_host_to_device"]

@@ -269,6 +269,35 @@ def shard_envs(total_envs, rank, world_size):
     return n, off
 
 
+def bind_host_to_device(device):
+    """Pin the calling process to the CPU cores next to GPU `device` (its PCIe root's NUMA node) and return them.
+
+    The host-buffer step writes ~21 B per env-step into page-locked host memory; with one process per GPU, a
+    process that runs (and therefore first-touches its pinned buffers) on the other socket pushes every one of
+    those bytes across the socket interconnect.  Call this BEFORE allocating host buffers.  Returns None when
+    the topology cannot be read (no sysfs entry, single node): the affinity is then left alone."""
+    import os
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(int(device)), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:], rest)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def nccl_unique_id():
     buf = (C.c_uint8 * 128)()
     N.check(N.lib().gymcuda_nccl_unique_id(buf))
