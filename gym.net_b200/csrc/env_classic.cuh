@@ -143,13 +143,14 @@ __device__ __noinline__ float fmodf_cold(float a, float b) { return fmodf(a, b);
 // the quotient is rounded to the nearest integer with the 1.5 * 2^23 magic number (it is floor(|a| / b) or one
 // more), the remainder |a| - q * b is ONE fma -- exact whenever q is the true quotient, because the true
 // remainder is representable -- and a negative remainder steps q down and recomputes.  Beyond: CUDA's fmodf.
+template <bool IN_RANGE = false>   // IN_RANGE: the caller guarantees |a| <= 2^21
 __device__ __forceinline__ float py_mod_2pi(float a) {
     constexpr float b = 6.2831854820251465f;          // fl32(2 pi)
     constexpr float INV_B = 0.15915493667125702f;     // fl32(1 / b): only steers the quotient estimate
     constexpr float MAGIC = 12582912.0f;
     const float ax = fabsf(a);
     float r;
-    if (ax <= 2097152.0f) {
+    if (IN_RANGE || ax <= 2097152.0f) {
         float q = fmaf(ax, INV_B, MAGIC) - MAGIC;
         r = fmaf(-q, b, ax);
         if (r < 0.0f) { q = q - 1.0f; r = fmaf(-q, b, ax); }
@@ -167,7 +168,7 @@ struct Pendulum {
     static constexpr bool PREGEN_RESET = true;
     static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
-    static constexpr bool HAS_SMALL = false;        // no reduced-range variant of step
+    static constexpr bool HAS_SMALL = true;         // step<true>: |theta| known to be far inside the branch-free ranges
     static constexpr bool ROLLOUT_CHUNK = true;     // rollout kernel runs unrolled 8-step chunks
     static constexpr float ACT_LOW = -2.0f, ACT_HIGH = 2.0f;
     using Vec = float2;
@@ -192,17 +193,21 @@ struct Pendulum {
         sincosf_det(s.th, &s.sn, &s.cs);
     }
     __device__ static __forceinline__ bool valid(Act a) { return a == a; }
+    // rollout fast path: theta moves by at most 8 * 0.05 per step, so from |theta| <= 30000 the eight steps of a
+    // chunk stay inside the branch-free ranges of sincos (32768) and fmod (2^21); a reset lands in [-pi, pi]
+    __device__ static __forceinline__ bool small_ok(const S& s) { return fabsf(s.th) <= 30000.0f; }
+    template <bool SMALL = false>
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         constexpr float PI_F = 3.1415927410125732f;
         const float th = s.th, thdot = s.thdot;
         const float u = clampf(a, -2.0f, 2.0f);
-        const float an = py_mod_2pi(th + PI_F) - PI_F;
+        const float an = py_mod_2pi<SMALL>(th + PI_F) - PI_F;
         const float costs = (an * an + 0.1f * (thdot * thdot)) + 0.001f * (u * u);
         float newthdot = thdot + (15.0f * s.sn + 3.0f * u) * 0.05f;
         newthdot = clampf(newthdot, -8.0f, 8.0f);
         s.th = th + newthdot * 0.05f;
         s.thdot = newthdot;
-        sincosf_det(s.th, &s.sn, &s.cs);
+        sincosf_det<SMALL>(s.th, &s.sn, &s.cs);
         return StepOut{-costs, 0u};
     }
     __device__ static __forceinline__ void obs(const S& s, float* o) { o[0] = s.cs; o[1] = s.sn; o[2] = s.thdot; }
@@ -219,7 +224,7 @@ struct MountainCarT {
     static constexpr bool PREGEN_RESET = true;
     static constexpr int AUXW = 0;
     static constexpr bool REJECT_INVALID = true;
-    static constexpr bool HAS_SMALL = false;        // no reduced-range variant of step
+    static constexpr bool HAS_SMALL = true;         // step<true>: position known to be in range for the branch-free sincos
     static constexpr bool ROLLOUT_CHUNK = true;     // rollout kernel runs unrolled 8-step chunks
     static constexpr float ACT_LOW = -1.0f, ACT_HIGH = 1.0f;
     using Vec = float2;
@@ -257,12 +262,15 @@ struct MountainCarT {
         if (position == -1.2 && velocity < 0) velocity = 0;
         return (unsigned)(position >= (CONTINUOUS ? 0.45 : 0.5) && velocity >= 0.0);
     }
+    // rollout fast path: every step clamps the position to [-1.2, 0.6] and a reset draws it from [-0.6, -0.4]
+    __device__ static __forceinline__ bool small_ok(const S& s) { return fabsf(s.position) <= 10000.0f; }
+    template <bool SMALL = false>
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         constexpr float MIN_POS = -1.2f, MAX_POS = 0.6f, MAX_SPEED = 0.07f;
         constexpr float GOAL = CONTINUOUS ? 0.45f : 0.5f;
         const float position = s.position, velocity = s.velocity;
         float sn, cs;
-        sincosf_det(3.0f * position, &sn, &cs);
+        sincosf_det<SMALL>(3.0f * position, &sn, &cs);
         float push;
         if (CONTINUOUS) push = clampf((float)a, -1.0f, 1.0f) * 0.0015f;
         else push = (float)((int)a - 1) * 0.001f;
@@ -271,8 +279,13 @@ struct MountainCarT {
         float np = position + nv;
         np = clampf(np, MIN_POS, MAX_POS);
         if (np == MIN_POS && nv < 0.0f) nv = 0.0f;
-        unsigned done = (unsigned)((np >= GOAL) & (nv >= 0.0f));
-        if (fabsf(np - GOAL) <= 1e-6f || fabsf(nv) <= 1e-7f) done = done_f64(position, velocity, a);
+        // everything about termination sits behind ONE rarely taken test: below goal - 1e-6 the float32 flag is 0
+        // and the double evaluation (which differs from float32 by < 1e-7 in position) agrees
+        unsigned done = 0;
+        if (np >= GOAL - 1e-6f) {
+            done = (unsigned)((np >= GOAL) & (nv >= 0.0f));
+            if (fabsf(np - GOAL) <= 1e-6f || fabsf(nv) <= 1e-7f) done = done_f64(position, velocity, a);
+        }
         s.position = np;
         s.velocity = nv;
         float reward;

@@ -208,11 +208,14 @@ inline StepOut mountaincar_any_step_f32(float s[2], bool continuous, int iaction
     float np = position + nv;
     np = det::clampf(np, MIN_POS, MAX_POS);
     if (np == MIN_POS && nv < 0.0f) nv = 0.0f;
-    bool done = np >= goal && nv >= 0.0f;
-    if (std::fabs(np - goal) <= 1e-6f || std::fabs(nv) <= 1e-7f) {
-        double sd[2] = {(double)position, (double)velocity};
-        StepOut r = continuous ? mountaincar_cont_step_f64(sd, faction) : mountaincar_step_f64(sd, iaction);
-        done = r.done != 0;
+    bool done = false;
+    if (np >= goal - 1e-6f) {   // below: not done in float32, and the double evaluation (< 1e-7 away) agrees
+        done = np >= goal && nv >= 0.0f;
+        if (std::fabs(np - goal) <= 1e-6f || std::fabs(nv) <= 1e-7f) {
+            double sd[2] = {(double)position, (double)velocity};
+            StepOut r = continuous ? mountaincar_cont_step_f64(sd, faction) : mountaincar_step_f64(sd, iaction);
+            done = r.done != 0;
+        }
     }
     s[0] = np; s[1] = nv;
     float reward;
