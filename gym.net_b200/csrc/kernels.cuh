@@ -474,12 +474,17 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
         Act* const act_base = reinterpret_cast<Act*>(p.actions);
 
         // one env step of this lane: transition, time limit, statistics, auto-reset, trajectory stores
-        auto body = [&](int k, const Act a, auto small_tag) {
+        // limit_tag false: the caller has established that no lane can reach the time limit in this step (the
+        // episode counter still runs); for an env that never terminates by itself (Pendulum) `done` is then a
+        // compile-time 0 and the whole reset path drops out of the chunk
+        auto body = [&](int k, const Act a, auto small_tag, auto limit_tag) {
             constexpr bool SMALL = decltype(small_tag)::value;
+            constexpr bool CHECK_LIMIT = LIMIT && decltype(limit_tag)::value;
             const uint64_t t = p.t + (uint64_t)k;
             StepOut r = StepSel<E, SMALL>::go(s, a, sbd, seed, gid, t);
             bool trunc_only = false;
-            if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }
+            if (LIMIT) ept += 1;
+            if (CHECK_LIMIT) { if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }
             if (STATS) ret += r.reward;
             if (r.done) {
                 episodes += 1;
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
             // head: single steps until the absolute step index is a multiple of 8
             int head = (int)((8u - ((uint32_t)p.t & 7u)) & 7u);
             if (head > p.k_steps) head = p.k_steps;
-            for (; k < head; ++k) body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{});
+            for (; k < head; ++k) body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{}, std::true_type{});
 #pragma unroll 1
             for (; k + 8 <= p.k_steps; k += 8) {
                 const uint64_t tc = p.t + (uint64_t)k;
@@ -545,12 +550,21 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 }
                 if constexpr (E::HAS_SMALL && AUTO_RESET) {
                     if (__all_sync(__activemask(), E::small_ok(s))) {
-                        auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::true_type{}); };
+                        if constexpr (LIMIT) {
+                            // no lane within 8 steps of the time limit (a reset only lowers the counter): the chunk
+                            // runs without the per-step limit test
+                            if (__all_sync(__activemask(), ept + 8 < p.limit)) {
+                                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::true_type{}, std::false_type{}); };
+                                unroll8<0>(f);
+                                continue;
+                            }
+                        }
+                        auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::true_type{}, std::true_type{}); };
                         unroll8<0>(f);
                         continue;
                     }
                 }
-                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::false_type{}); };
+                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::false_type{}, std::true_type{}); };
                 unroll8<0>(f);
             }
         }
@@ -560,7 +574,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 E::reset(next, seed, gid, (uint32_t)ep, p.t + (uint64_t)k, p.prm);
                 have = 1;
             }
-            body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{});
+            body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{}, std::true_type{});
         }
         if (AUTO_RESET) p.episode[i] = ep;
         if (STATS && p.ep_ret) p.ep_ret[i] = ret;
