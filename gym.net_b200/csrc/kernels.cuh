@@ -574,7 +574,12 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArg
                 E::reset(next, seed, gid, (uint32_t)ep, p.t + (uint64_t)k, p.prm);
                 have = 1;
             }
-            body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{}, std::true_type{});
+            const Act a = gen.next(seed, gid, p.t + (uint64_t)k);
+            if constexpr (ALL_OUT && E::HAS_SMALL && !E::ROLLOUT_CHUNK) {
+                // envs too large to unroll (Acrobot): the same warp vote, per step, picks the reduced-range step
+                if (__all_sync(__activemask(), E::small_ok(s))) { body(k, a, std::true_type{}, std::true_type{}); continue; }
+            }
+            body(k, a, std::false_type{}, std::true_type{});
         }
         if (AUTO_RESET) p.episode[i] = ep;
         if (STATS && p.ep_ret) p.ep_ret[i] = ret;
