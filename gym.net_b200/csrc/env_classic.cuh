@@ -305,16 +305,13 @@ using MountainCarCont = MountainCarT<true>;
 // ------------------------------------------------------------------------------------------------
 // Acrobot-v1 (not in the reference, README.md:73; upstream acrobot.py, "book" dynamics, RK4, dt 0.2)
 // ------------------------------------------------------------------------------------------------
+// upstream double-precision dynamics (used to refine `done` next to its threshold); the float32 engine arithmetic is
+// acrobot_dsdt_f32 / acrobot_rk4_f32 below
 template <class R> struct AcroMath;
 template <> struct AcroMath<double> {
     __device__ static __forceinline__ void sc(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
     __device__ static __forceinline__ double cos_minus_half_pi(double x) { return cos(x - 3.14159265358979323846 / 2.0); }
 };
-template <> struct AcroMath<float> {
-    __device__ static __forceinline__ void sc(float x, float* s, float* c) { sincosf_det(x, s, c); }
-    __device__ static __forceinline__ float cos_minus_half_pi(float x) { float s, c; sincosf_det(x, &s, &c); return s; }
-};
-
 // algebra of dsdt given sin/cos(theta2), cos(theta1 + theta2 - pi/2) and cos(theta1 - pi/2)
 template <class R>
 __device__ __forceinline__ void acrobot_dsdt_trig(const R s[4], R a, R s2, R c2, R cmh12, R cmh1, R out[4]) {

@@ -226,12 +226,7 @@ template <class E> struct ActionGen<E, 3, 1> : WordGen<E> {
         return (int32_t)__umulhi(this->template word_at<J>(seed, gid, tc), 3u);
     }
 };
-// Box.Sample = uniform(low, high) for the spans used here (2 and 4: powers of two, see uniformf_pow2)
-template <class E> __device__ __forceinline__ float box_uniform(uint32_t w) {
-    constexpr float span = E::ACT_HIGH - E::ACT_LOW;
-    static_assert(span == 2.0f || span == 4.0f, "Box action span must be 2 or 4 (else use uniformf)");
-    return uniformf_pow2<span == 2.0f ? 1 : 2>(E::ACT_LOW, w);
-}
+template <class E> __device__ __forceinline__ float box_uniform(uint32_t w) { return uniformf(E::ACT_LOW, E::ACT_HIGH, w); }
 template <class E> struct ActionGen<E, 0, 1> : WordGen<E> {
     __device__ __forceinline__ float next(uint64_t seed, uint32_t gid, uint64_t t) { return box_uniform<E>(this->next_word(seed, gid, t)); }
     template <int J> __device__ __forceinline__ float at(uint64_t seed, uint32_t gid, uint64_t tc) {

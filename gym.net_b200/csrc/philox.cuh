@@ -50,17 +50,12 @@ __device__ __forceinline__ uint32_t word(const Block& b, uint32_t i) {
 // [0,1) on 24 bits: exact in fp32
 __device__ __forceinline__ float u01(uint32_t w) { return __fmul_rn((float)(w >> 8), 0x1p-24f); }
 
-// low + (high - low) * u : separate multiply and add, never fused
+// low + (high - low) * u01(w), the multiply and the add never fused.  Evaluated as float(w >> 8) * ((high - low) * 2^-24):
+// the integer converts exactly, scaling the float32 span by 2^-24 is exact, so the single multiply rounds the same
+// real number as (high - low) * u01(w) would -- the same bits with one multiply (the scaled span folds at compile
+// time for constant bounds).
 __device__ __forceinline__ float uniformf(float lo, float hi, uint32_t w) {
-    return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u01(w)));
-}
-
-// The same value when high - low is a power of two (every Box action space here: 2 and 4): scaling by a power
-// of two is exact, so float(w >> 8) * ((high - low) * 2^-24) has the bits of (high - low) * u01(w) with one
-// multiply instead of two.
-template <int SPAN_LOG2>
-__device__ __forceinline__ float uniformf_pow2(float lo, uint32_t w) {
-    return __fadd_rn(lo, __fmul_rn((float)(w >> 8), __int_as_float((127 - 24 + SPAN_LOG2) << 23)));
+    return __fadd_rn(lo, __fmul_rn((float)(w >> 8), __fmul_rn(__fsub_rn(hi, lo), 0x1p-24f)));
 }
 
 }  // namespace gymcuda

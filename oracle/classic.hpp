@@ -233,10 +233,6 @@ template <> struct AcroMath<double> {
     // upstream evaluates cos(theta - pi/2) literally
     static double cos_minus_half_pi(double x) { return std::cos(x - 3.14159265358979323846 / 2.0); }
 };
-template <> struct AcroMath<float> {
-    static void sincos(float x, float* s, float* c) { det::sincosf_det(x, s, c); }
-    static float cos_minus_half_pi(float x) { float s, c; det::sincosf_det(x, &s, &c); return s; }
-};
 
 template <class R>
 inline void acrobot_dsdt(const R s[4], R a, R out[4]) {
