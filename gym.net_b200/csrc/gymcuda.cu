@@ -126,6 +126,7 @@ struct gymcuda_env {
     int32_t *d_sbd, *d_ept, *d_episode, *d_seeds, *d_aux;
     EnvParams prm;
     int32_t *d_perm, *d_block_free;   // LunarLander contact partition
+    int sm_count;                     // multiprocessors of the device (launch heuristics)
     int auxw;   // int32 words per env in d_aux (LunarLander only)
     // I/O staging for the host-buffer entry points
     void* d_actions;
@@ -184,22 +185,30 @@ static cudaError_t launch_step(gymcuda_env* e, const StepArgs& a) {
     return cudaGetLastError();
 }
 
-template <class E, bool ALL_OUT>
-static void launch_rollout_variant(gymcuda_env* e, const RolloutArgs& a, int grid) {
+template <class E, bool ALL_OUT, int BLOCK>
+static void launch_rollout_variant(gymcuda_env* e, const RolloutArgs& a) {
+    const int grid = (e->n + BLOCK - 1) / BLOCK;
     const bool ar = e->auto_reset, lim = e->limit > 0;
-    if (ar && lim) rollout_kernel<E, true, true, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
-    else if (ar) rollout_kernel<E, true, false, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
-    else if (lim) rollout_kernel<E, false, true, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
-    else rollout_kernel<E, false, false, ALL_OUT><<<grid, ROLLOUT_BLOCK, 0, e->stream>>>(a);
+    if (ar && lim) rollout_kernel<E, true, true, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
+    else if (ar) rollout_kernel<E, true, false, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
+    else if (lim) rollout_kernel<E, false, true, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
+    else rollout_kernel<E, false, false, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
 }
 
 template <class E>
 static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
-    const int grid = (e->n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
     // ALL_OUT addresses the trajectory with one 32-bit row index: every row * envs + env must fit
     const bool idx32 = (unsigned long long)a.k_steps * (unsigned long long)a.n <= 0xffffffffull;
-    if (a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits && idx32) launch_rollout_variant<E, true>(e, a, grid);
-    else launch_rollout_variant<E, false>(e, a, grid);
+    if (a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits && idx32) {
+        // one wave of 16-warp CTAs, one per SM, when the batch fits and fills at least 3/4 of the SMs (kernels.cuh)
+        const long long wave = (long long)e->sm_count * ROLLOUT_BLOCK_WAVE;
+        bool one_wave = false;
+        if constexpr (E::ROLLOUT_CHUNK) one_wave = (long long)e->n <= wave && 4ll * e->n >= 3ll * wave;
+        if constexpr (E::ROLLOUT_CHUNK) { if (one_wave) { launch_rollout_variant<E, true, ROLLOUT_BLOCK_WAVE>(e, a); return cudaGetLastError(); } }
+        launch_rollout_variant<E, true, ROLLOUT_BLOCK>(e, a);
+    } else {
+        launch_rollout_variant<E, false, ROLLOUT_BLOCK>(e, a);
+    }
     return cudaGetLastError();
 }
 
@@ -311,6 +320,7 @@ int gymcuda_destroy(gymcuda_env* e) {
 static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaSetDevice(cfg->device));
     CU_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     e->stream = e->own_stream;
     const size_t n = (size_t)e->n;
     const size_t state_bytes = n * (size_t)e->ki.sd * 4;

@@ -391,7 +391,14 @@ __global__ void gather_wait_kernel(const uint32_t* flags, int world, uint32_t gs
 }
 
 // ---------------------------------------------------------------- fused random-policy rollout
+// Threads per CTA of the rollout kernel.  64 by default (many small CTAs spread a large batch evenly).  When the whole
+// batch fits in ONE wave of 16-warp CTAs and is large enough to use most SMs (CartPole's 65 536 envs: 128 CTAs on 148
+// SMs), ROLLOUT_BLOCK_WAVE gives every SM that works exactly 4 warps per sub-partition and makes each SM stream one
+// contiguous 512-env slice of every trajectory row: measured 147 -> 130 us per launch, the DRAM time of the launch
+// (block 32 / 128 / 192 / 256 / 1024: 155 / 149 / 175 / 138 / 231 us).  At 262 144 envs the same CTAs need several
+// waves at one CTA per SM and lose (Pendulum 138 -> 154 us), hence the one-wave rule in launch_rollout.
 constexpr int ROLLOUT_BLOCK = 64;
+constexpr int ROLLOUT_BLOCK_WAVE = 512;
 constexpr int ROLLOUT_REFILL = 8;   // steps between warp-wide refills of the pre-generated reset state
 
 template <class E>
@@ -428,18 +435,18 @@ __device__ __forceinline__ void unroll8(F& f) {
 // fully unrolled: action-word and reset-refill boundaries fall only on chunk starts, so the per-step loop tests,
 // shifts and branches of the generic loop disappear; with HAS_SMALL (CartPole) a warp whose angles are all in
 // the polynomial range runs the chunk on step<true> (no range reduction, no branches around sincos).
-template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const RolloutArgs p) {
+template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT, int BLOCK = ROLLOUT_BLOCK>
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
     using S = typename E::S;
     using Act = typename E::Act;
-    const int tix = blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
+    const int tix = blockIdx.x * BLOCK + threadIdx.x;
     unsigned episodes = 0;
     double fin_ret = 0.0, fin_len = 0.0;
     // Observations of 3 or 6 floats per env (Pendulum, Acrobot): a warp's 32 rows are one contiguous 384 / 768 B
     // run, but per-lane stores of 4 / 8 B pieces at a 12 / 24 B stride touch every 32 B sector 2-3 times.  A full
     // warp stages its rows in shared memory and writes the run as 16 B vectors: each sector is written once.
     constexpr bool STAGE_OBS = ALL_OUT && (E::OD == 3 || E::OD == 6);
-    __shared__ __align__(16) float obs_tile[STAGE_OBS ? ROLLOUT_BLOCK * E::OD : 4];
+    __shared__ __align__(16) float obs_tile[STAGE_OBS ? BLOCK * E::OD : 4];
     const unsigned lane = threadIdx.x & 31u;
     const bool staged = STAGE_OBS && p.perm == nullptr && (p.n & 3) == 0 && (tix - (int)lane + 32 <= p.n);   // warp-uniform
     if (tix < p.n) {
