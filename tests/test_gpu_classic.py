@@ -552,6 +552,20 @@ def test_staged_obs_store_ragged_sizes(name, n):
     env.Close()
 
 
+@pytest.mark.parametrize("name,n", [("CartPole-v1", 65536), ("CartPole-v1", 60001), ("Pendulum-v1", 65536),
+                                    ("MountainCar-v0", 75776), ("MountainCarContinuous-v0", 57000)])
+def test_one_wave_cta_shape_matches_oracle(name, n):
+    """Batches that fit one wave of 512-thread CTAs (3/4 .. 1 x 148 x 512 envs) run the rollout kernel in that
+    shape (launch_rollout): same trajectory as the oracle, ragged last CTA and last warp included."""
+    env = G.make(name, n, seed=12, auto_reset=True); env.ResetBatch()
+    o = O.OracleEnv(KINDS[name], n, seed=12, auto_reset=True, mode=O.MODE_F32); o.set_threads(8); o.reset()
+    for k in (5, 27):
+        tr = env.RolloutRandom(k); tw = o.rollout_random(k)
+        for x, y in zip(tr, tw):
+            assert np.array_equal(x, y)
+    env.Close()
+
+
 def _rollout_from_states(name, states, k=40, seed=6):
     n = len(states)
     env = G.make(name, n, seed=seed, auto_reset=True); env.ResetBatch()
