@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -548,13 +549,15 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
 
 // Device-visible alias of a host pointer if (and only if) it is page-locked memory mapped into the
 // device address space (cudaHostAlloc / cudaHostRegister / gymcuda_host_alloc), else null.
-static unsigned g_host_epoch = 1;   // bumped by every (un)registration / pinned (de)allocation made through this library
+static std::atomic<unsigned> g_host_epoch{1};   // bumped by every (un)registration / pinned (de)allocation made through this library
+                                                // (handles may live on different host threads)
 
 static void* mapped_alias(gymcuda_env* e, const void* host, int slot) {
     if (!host) return nullptr;
-    if (e->alias_epoch != g_host_epoch) {   // a buffer may have been registered or released since the answers were cached
+    const unsigned epoch = g_host_epoch.load(std::memory_order_acquire);
+    if (e->alias_epoch != epoch) {   // a buffer may have been registered or released since the answers were cached
         for (int k = 0; k < 4; ++k) e->alias_host[k] = nullptr;
-        e->alias_epoch = g_host_epoch;
+        e->alias_epoch = epoch;
     }
     if (e->alias_host[slot] == host) return e->alias_dev[slot];
     cudaPointerAttributes at;
@@ -883,27 +886,27 @@ int gymcuda_sync(gymcuda_env* e) {
 int gymcuda_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(GYMCUDA_EINVAL, "ptr is null");
     CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-    g_host_epoch += 1;
+    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_free(void* ptr) {
     if (ptr) CU_TRY(cudaFreeHost(ptr));
-    g_host_epoch += 1;
+    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_register(void* ptr, size_t bytes) {
     if (!ptr || bytes == 0) return fail(GYMCUDA_EINVAL, "gymcuda_host_register: null pointer or empty range");
     CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
-    g_host_epoch += 1;
+    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_unregister(void* ptr) {
     if (!ptr) return GYMCUDA_OK;
     CU_TRY(cudaHostUnregister(ptr));
-    g_host_epoch += 1;
+    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
