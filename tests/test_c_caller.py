@@ -4,6 +4,8 @@ GYMCUDA_ECUDA (exit code 3) -- there is no CPU path to fall back to."""
 import os
 import subprocess
 
+import pytest
+
 from conftest import HAS_GPU
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,3 +22,14 @@ def test_c_program_compiles_links_and_runs():
     else:
         assert r.returncode == 3, (r.returncode, r.stderr)
         assert "no CPU path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_program_steps_on_the_gpu():
+    ex = os.path.join(ROOT, "examples")
+    subprocess.run(["make", "-C", ex, "-s"], check=True)
+    r = subprocess.run([os.path.join(ex, "c_driver"), "4096", "50"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "env-steps/s" in r.stdout and "rollout_random" in r.stdout
+    episodes = int(r.stdout.split("steps,")[1].split("episodes")[0])
+    assert episodes > 0      # alternating actions: an episode ends every ~40 steps
