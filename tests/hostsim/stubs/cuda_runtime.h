@@ -1,0 +1,26 @@
+// TEST INFRASTRUCTURE: a stand-in for <cuda_runtime.h> that lets g++ compile the DEVICE headers of the engine
+// (gym.net_b200/csrc/{detmath,philox,env_classic,lunar,lunar_core}.cuh) as plain host C++ -- see hostsim.cpp.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define GYMCUDA_HOSTSIM 1
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__ static const
+#define __restrict__
+
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 v; v.x = x; v.y = y; return v; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+static inline float __fmul_rn(float a, float b) { return a * b; }   // compiled with -ffp-contract=off: never fused
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }

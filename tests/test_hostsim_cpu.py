@@ -1,0 +1,150 @@
+"""CPU: the engine's DEVICE source, compiled for the host, against the oracle -- bit for bit.
+
+tests/hostsim/hostsim.cpp includes gym.net_b200/csrc/{detmath,philox,env_classic,lunar,lunar_core}.cuh through a stub
+<cuda_runtime.h> (every __device__ function becomes plain C++, -ffp-contract=off like nvcc -fmad=false) and replays
+the per-thread body of step_kernel / reset_kernel.  What the GPU tests establish through the C ABI on a B200 --
+kernel == oracle F32 on free-running trajectories with auto-reset -- is established here for the same source lines
+on any machine: reset draws, action validation, transitions, rewards, termination, time limits, the LunarLander
+solver through landings and crashes."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HS_DIR = os.path.join(ROOT, "tests", "hostsim")
+CSRC = os.path.join(ROOT, "gym.net_b200", "csrc")
+LIB = os.path.join(HS_DIR, "_hostsim.so")
+
+
+def _build():
+    srcs = [os.path.join(HS_DIR, "hostsim.cpp"), os.path.join(HS_DIR, "stubs", "cuda_runtime.h")] + [
+        os.path.join(CSRC, f) for f in ("detmath.cuh", "philox.cuh", "env_classic.cuh", "lunar.cuh", "lunar_core.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + os.path.join(HS_DIR, "stubs"),
+                        "-I" + CSRC, "-shared", "-fPIC", "-o", LIB, srcs[0]], check=True)
+    L = C.CDLL(LIB)
+    V, I, U32, U64, F = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_float
+    L.hostsim_step.argtypes = [I, V, V, V, V, V, V, V, V, V, I, U32, U64, U64, I, I, F, F, F, I]
+    L.hostsim_reset.argtypes = [I, V, V, V, V, V, V, I, U32, U64, U64, F, F, F, I]
+    L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
+    L.hostsim_div_inrange.argtypes = [V, V, V, C.c_size_t]
+    L.hostsim_sincos.argtypes = [V, V, V, C.c_size_t]
+    return L
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return _build()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+DEFAULT_LIMIT = {O.CARTPOLE: 0, O.PENDULUM: 200, O.MOUNTAINCAR: 200, O.MOUNTAINCAR_CONT: 999, O.ACROBOT: 500,
+                 O.LUNARLANDER: 0, O.LUNARLANDER_CONT: 0}
+PRM = (-10.0, 15.0, 1.5, 0)   # gravity, wind_power, turbulence_power, enable_wind (LunarLanderEnv.cs:351-354)
+
+
+class HostSim:
+    """Device-layout buffers + the replayed kernel bodies."""
+
+    def __init__(self, L, kind, n, seed, env_off=0, auto_reset=True):
+        self.L, self.kind, self.n, self.seed, self.off, self.auto = L, kind, n, seed, env_off, auto_reset
+        d = O.dims(kind)
+        self.sd, self.od, self.ad, self.actn = d["state_dim"], d["obs_dim"], d["act_dim"], d["act_n"]
+        self.lunar = kind >= O.LUNARLANDER
+        self.auxw = d["aux_dim"] - 2 if self.lunar else 0
+        self.state = np.zeros((self.sd, n) if self.lunar else (n, self.sd), np.float32)
+        self.aux = np.zeros((max(self.auxw, 1), n), np.int32)
+        self.sbd = np.full(n, -1, np.int32); self.ept = np.zeros(n, np.int32); self.episode = np.zeros(n, np.int32)
+        self.limit = DEFAULT_LIMIT[kind]
+        self.t = 0
+        L.hostsim_ctor(kind, _p(self.state), _p(self.aux), n, env_off, seed)
+
+    def reset(self):
+        obs = np.empty((self.n, self.od), np.float32)
+        self.L.hostsim_reset(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
+                             self.n, self.off, self.seed, self.t, *PRM)
+        return obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions)
+        obs = np.empty((self.n, self.od), np.float32); rew = np.empty(self.n, np.float32); done = np.empty(self.n, np.uint8)
+        bad = self.L.hostsim_step(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(a),
+                                  _p(obs), _p(rew), _p(done), self.n, self.off, self.seed, self.t, self.limit, int(self.auto), *PRM)
+        self.t += 1
+        return obs, rew, done, bad
+
+    def abi_state(self):
+        """[n][state_dim] like gymcuda_get_state."""
+        return self.state.T.copy() if self.lunar else self.state.copy()
+
+
+CASES = [("CartPole-v1", O.CARTPOLE, 256, 300), ("Pendulum-v1", O.PENDULUM, 128, 450), ("MountainCar-v0", O.MOUNTAINCAR, 128, 450),
+         ("MountainCarContinuous-v0", O.MOUNTAINCAR_CONT, 64, 1020), ("Acrobot-v1", O.ACROBOT, 128, 600),
+         ("LunarLander-v2", O.LUNARLANDER, 96, 400), ("LunarLanderContinuous-v2", O.LUNARLANDER_CONT, 48, 300)]
+
+
+@pytest.mark.parametrize("name,kind,n,k", CASES, ids=[c[0] for c in CASES])
+def test_device_source_on_host_equals_oracle(hs, name, kind, n, k):
+    seed, off = 21, 1000
+    o = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=True, mode=O.MODE_F32)
+    sim = HostSim(hs, kind, n, seed, off)
+    assert np.array_equal(sim.reset(), o.reset())
+    episodes = 0
+    for t in range(k):
+        a = o.sample_actions()                       # the random policy of the rollout kernel, from the oracle
+        oo, orr, od = o.step(a)
+        so, sr, sdn, bad = sim.step(a)
+        assert bad == 0
+        assert np.array_equal(sdn, od), "done differs at step %d" % t
+        assert np.array_equal(sr, orr), "reward differs at step %d" % t
+        assert np.array_equal(so, oo), "observation differs at step %d" % t
+        episodes += int(od.sum())
+        if t % 97 == 0 or t == k - 1:
+            st, aux, ot = o.get_state()
+            assert ot == sim.t
+            assert np.array_equal(sim.abi_state(), st.astype(np.float32)), "state differs at step %d" % t
+    assert episodes > 0
+
+
+def test_invalid_actions_leave_the_env_unstepped(hs):
+    n = 8
+    sim = HostSim(hs, O.MOUNTAINCAR, n, 3); sim.reset()
+    before = sim.abi_state()
+    a = np.array([0, 1, 2, 3, -1, 2, 1, 0], np.int32)
+    obs, rew, done, bad = sim.step(a)
+    assert bad == 2
+    after = sim.abi_state()
+    assert np.array_equal(after[[3, 4]], before[[3, 4]]) and not np.array_equal(after[[0, 1, 2]], before[[0, 1, 2]])
+
+
+def test_div_inrange_is_the_ieee_quotient_on_its_stated_ranges(hs):
+    """detmath.cuh div_inrange against numpy's float32 division on the operand ranges its callers state
+    (CartPole: den in [0.62, 0.67], |num| up to 2^8; Acrobot: den in [0.56, 4.5], |num| up to ~1e5), zero included.
+    (The host build seeds the Newton step with 1.0f / y instead of MUFU.RCP; the GPU tests cover the real one.)"""
+    rng = np.random.default_rng(0)
+    m = 1 << 20
+    y = np.concatenate([rng.uniform(0.62, 0.67, m), rng.uniform(0.56, 4.5, m)]).astype(np.float32)
+    x = np.concatenate([rng.uniform(-256, 256, m), rng.standard_normal(m) * 1e4]).astype(np.float32)
+    x[:1000] = 0.0
+    x[1000:2000] = np.float32(2.0) ** rng.integers(-60, 8, 1000).astype(np.float32)
+    q = np.empty_like(x)
+    hs.hostsim_div_inrange(_p(x), _p(y), _p(q), x.size)
+    assert np.array_equal(q, x / y)
+
+
+def test_sincos_det_host_build_equals_oracle(hs):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-40000, 40000, 200000), rng.uniform(-1, 1, 100000), rng.standard_normal(1000) * 1e9,
+                        [0.0, 0.7853981852531433, -0.7853981852531433, 0.78539824, 32768.0, -32768.0, 32769.0, 1e14, 2e14]]).astype(np.float32)
+    s = np.empty_like(x); c = np.empty_like(x); so = np.empty_like(x); co = np.empty_like(x)
+    hs.hostsim_sincos(_p(x), _p(s), _p(c), x.size)
+    O.lib().oracle_sincosf(_p(x), _p(so), _p(co), x.size)
+    assert np.array_equal(s, so, equal_nan=True) and np.array_equal(c, co, equal_nan=True)
