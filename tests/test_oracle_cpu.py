@@ -181,3 +181,18 @@ def test_partition_invariance_cpu():
         sh = O.OracleEnv(O.CARTPOLE, 16, seed=9, env_id_offset=16 * part, auto_reset=True, mode=O.MODE_F32); sh.reset()
         so, _, sd, sa = sh.rollout_random(100)
         assert np.array_equal(so, fo[:, 16 * part:16 * part + 16]) and np.array_equal(sa, fa[:, 16 * part:16 * part + 16])
+
+
+def test_free_running_drift_report_runs():
+    """SURVEY 8(c) T2, free-running half (tools/f32_vs_f64_drift.py): the float32 engine arithmetic against the float64
+    reference arithmetic with NO teacher forcing.  CartPole's episodes are short and its termination test is evaluated
+    exactly, so the two agree on (almost) every `done` for hundreds of steps; chaotic Pendulum / Acrobot trajectories
+    separate by construction -- which is why the parity criterion is per-step (teacher-forced), not per-trajectory."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("drift", os.path.join(root, "tools", "f32_vs_f64_drift.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = mod.drift("CartPole-v1", 512, 300)
+    assert r["frac_diverged"] <= 0.01 and r["max_rel_state_err_while_in_step"] < 0.05
+    r = mod.drift("MountainCar-v0", 256, 300)
+    assert r["diverged"] == 0 and r["max_rel_state_err_while_in_step"] < 1e-4
