@@ -106,8 +106,8 @@ __constant__ Shape SHAPES[3] = {
 // referenceAngle = leg.Rotation - fuselage.Rotation at creation = -+0.05 (:259)
 struct JointDef { V2 anchor_b; float ref_angle, motor_speed, lower, upper; };
 __constant__ JointDef JOINTS[2] = {
-    {{-0.6666666865348816f, 0.6000000238418579f}, -0.05f, -0.3f, 0.4f, 0.9f},      // leg 0: (1*0.9 - 0.5, 1*0.9 + 0)
-    {{0.6666666865348816f, 0.6000000238418579f}, 0.05f, 0.3f, -0.9f, -0.4f},       // leg 1: (-0.9 + 0, -0.9 + 0.5)
+    {{-0.6666666865348816f, 0.6000000238418579f}, -0.05f, -0.3f, 0.3999999761581421f, 0.9f},      // leg 0: (0.9f - 0.5f, 0.9f) evaluated in float32 like the C# (:276-277): NOT 0.4f
+    {{0.6666666865348816f, 0.6000000238418579f}, 0.05f, 0.3f, -0.9f, -0.3999999761581421f},       // leg 1: (-0.9f, -0.9f + 0.5f)
 };
 constexpr float MAX_MOTOR_TORQUE = 40.0f;   // LEG_SPRING_TORQUE (:188, :274)
 enum { LIMIT_INACTIVE = 0, LIMIT_AT_LOWER = 1, LIMIT_AT_UPPER = 2, LIMIT_EQUAL = 3 };
