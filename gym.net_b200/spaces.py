@@ -100,7 +100,11 @@ class Discrete(Space):
 
     def Sample(self, mask=None):
         if mask is not None:
-            valid = np.nonzero(np.asarray(mask) == 1)[0]      # Discrete.cs:19-25
+            # Discrete.cs:19-25.  The reference casts the ARRAY of valid indices to one int and draws
+            # `choice(int)` = randint(0, that int), which can return a masked-out action; implemented here (and in
+            # the device sampler, kernels.cuh sample_kernel) is what its comment and upstream gym say: uniform over
+            # the entries equal to 1, `Start` when there is none.
+            valid = np.nonzero(np.asarray(mask) == 1)[0]
             if valid.size:
                 return self.Start + int(self.RandomState.choice(valid))
             return self.Start
