@@ -9,6 +9,7 @@
 
 #include "env_classic.cuh"
 #include "lunar.cuh"
+#include "kernels.cuh"
 
 using namespace gymcuda;
 
@@ -72,6 +73,33 @@ void sim_reset(const Bufs& b, float* obs, int n, uint32_t env_off, uint64_t seed
 
 }  // namespace
 
+// The rollout kernel itself (kernels.cuh), executed one thread at a time: a "warp" here has one lane, so warp votes are
+// per-thread and the staged observation store (which needs the 32 lanes of a warp side by side) must be off: callers
+// pass n % 4 != 0 for 3- and 6-float observations.  Everything else is the kernel's own code: action generator, head /
+// unrolled chunks / tail, reduced-range and limit-free chunk variants, pre-generated resets, 32-bit row index.
+template <class E, bool AR, bool LIM, bool ALL_OUT, int BLOCK>
+static void run_rollout(const RolloutArgs& a) {
+    const int grid = (a.n + BLOCK - 1) / BLOCK;
+    gridDim.x = (unsigned)grid; blockDim.x = (unsigned)BLOCK;
+    for (int b = 0; b < grid; ++b)
+        for (int tid = 0; tid < BLOCK; ++tid) {
+            blockIdx.x = (unsigned)b; threadIdx.x = (unsigned)tid;
+            rollout_kernel<E, AR, LIM, ALL_OUT, BLOCK>(a);
+        }
+}
+
+template <class E>
+static int rollout_dispatch(const RolloutArgs& a, int auto_reset, int all_out, int block) {
+    const bool lim = a.limit > 0;
+#define HS_CASE(AR, LIM, AO, BL) if (auto_reset == AR && lim == LIM && all_out == AO && block == BL) { run_rollout<E, AR, LIM, AO, BL>(a); return 0; }
+    HS_CASE(1, 0, 1, 64) HS_CASE(1, 1, 1, 64) HS_CASE(1, 0, 0, 64) HS_CASE(1, 1, 0, 64) HS_CASE(0, 0, 0, 64) HS_CASE(0, 1, 0, 64)
+    HS_CASE(0, 0, 1, 64) HS_CASE(0, 1, 1, 64)
+    if constexpr (E::ROLLOUT_CHUNK) { HS_CASE(1, 0, 1, 512) HS_CASE(1, 1, 1, 512) }
+#undef HS_CASE
+    return -2;
+}
+
+
 extern "C" {
 
 // kinds as in include/gymcuda.h: 0 CartPole, 1 Pendulum, 2 MountainCar, 3 MountainCarContinuous, 4 Acrobot,
@@ -126,6 +154,27 @@ void hostsim_div_inrange(const float* x, const float* y, float* q, size_t n) {
 
 void hostsim_sincos(const float* x, float* s, float* c, size_t n) {
     for (size_t i = 0; i < n; ++i) sincosf_det(x[i], &s[i], &c[i]);
+}
+
+int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* ep_t, int32_t* episode, float* obs, float* reward,
+                    uint8_t* done, void* actions, unsigned long long* stats, int n, int k_steps, uint32_t env_off, uint64_t seed,
+                    uint64_t t, int limit, int auto_reset, int all_out, int block, float gravity, float wind_power,
+                    float turbulence_power, int use_wind) {
+    RolloutArgs a{};
+    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.perm = nullptr;
+    a.obs = obs; a.reward = reward; a.done = done; a.actions = actions; a.stats = stats; a.ep_ret = nullptr; a.sums = nullptr;
+    a.done_bits = 0; a.n = n; a.k_steps = k_steps; a.env_off = env_off; a.seed = seed; a.t = t; a.limit = limit;
+    a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
+    switch (kind) {
+        case 0: return rollout_dispatch<CartPole>(a, auto_reset, all_out, block);
+        case 1: return rollout_dispatch<Pendulum>(a, auto_reset, all_out, block);
+        case 2: return rollout_dispatch<MountainCar>(a, auto_reset, all_out, block);
+        case 3: return rollout_dispatch<MountainCarCont>(a, auto_reset, all_out, block);
+        case 4: return rollout_dispatch<Acrobot>(a, auto_reset, all_out, block);
+        case 5: return rollout_dispatch<LunarLander>(a, auto_reset, all_out, block);
+        case 6: return rollout_dispatch<LunarLanderCont>(a, auto_reset, all_out, block);
+    }
+    return -1;
 }
 
 }  // extern "C"

@@ -24,3 +24,26 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+// ---- what kernels.cuh needs on top: a warp of ONE lane, executed one thread at a time (hostsim.cpp) --------------
+#include <cstddef>
+struct hostsim_dim3 { unsigned x, y, z; };
+static thread_local hostsim_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+#define __global__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+static inline void __syncthreads() {}
+static inline void __syncwarp() {}
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) {}
+static inline long long clock64() { return 0; }
+static inline unsigned __activemask() { return 1u; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline int __all_sync(unsigned, int p) { return p; }
+static inline int __syncthreads_count(int p) { return p; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(0); }   // lanes that do not exist contribute nothing
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T, class U> static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }

@@ -32,6 +32,7 @@ def _build():
     L.hostsim_step.argtypes = [I, V, V, V, V, V, V, V, V, V, I, U32, U64, U64, I, I, F, F, F, I]
     L.hostsim_reset.argtypes = [I, V, V, V, V, V, V, I, U32, U64, U64, F, F, F, I]
     L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
+    L.hostsim_rollout.argtypes = [I, V, V, V, V, V, V, V, V, V, V, I, I, U32, U64, U64, I, I, I, I, F, F, F, I]
     L.hostsim_div_inrange.argtypes = [V, V, V, C.c_size_t]
     L.hostsim_sincos.argtypes = [V, V, V, C.c_size_t]
     return L
@@ -80,6 +81,18 @@ class HostSim:
                                   _p(obs), _p(rew), _p(done), self.n, self.off, self.seed, self.t, self.limit, int(self.auto), *PRM)
         self.t += 1
         return obs, rew, done, bad
+
+    def rollout(self, k, all_out=True, block=64):
+        n = self.n
+        obs = np.empty((k, n, self.od), np.float32); rew = np.empty((k, n), np.float32); done = np.empty((k, n), np.uint8)
+        act = np.empty((k, n), np.int32) if self.actn > 0 else np.empty((k, n, self.ad), np.float32)
+        stats = np.zeros(2, np.uint64)
+        rc = self.L.hostsim_rollout(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
+                                    _p(rew), _p(done), _p(act), _p(stats), n, k, self.off, self.seed, self.t, self.limit,
+                                    int(self.auto), int(all_out), block, *PRM)
+        assert rc == 0, rc
+        self.t += k
+        return obs, rew, done, act, int(stats[0])
 
     def abi_state(self):
         """[n][state_dim] like gymcuda_get_state."""
@@ -148,3 +161,35 @@ def test_sincos_det_host_build_equals_oracle(hs):
     hs.hostsim_sincos(_p(x), _p(s), _p(c), x.size)
     O.lib().oracle_sincosf(_p(x), _p(so), _p(co), x.size)
     assert np.array_equal(s, so, equal_nan=True) and np.array_equal(c, co, equal_nan=True)
+
+
+ROLLOUT_CASES = [("CartPole-v1", O.CARTPOLE, 200), ("Pendulum-v1", O.PENDULUM, 201), ("MountainCar-v0", O.MOUNTAINCAR, 200),
+                 ("MountainCarContinuous-v0", O.MOUNTAINCAR_CONT, 200), ("Acrobot-v1", O.ACROBOT, 201), ("LunarLander-v2", O.LUNARLANDER, 40)]
+
+
+@pytest.mark.parametrize("name,kind,n", ROLLOUT_CASES, ids=[c[0] for c in ROLLOUT_CASES])
+@pytest.mark.parametrize("shape", ["all_out_64", "all_out_512", "generic_64"])
+def test_rollout_kernel_source_on_host_equals_oracle(hs, name, kind, n, shape):
+    """kernels.cuh's rollout_kernel compiled for the host and run one thread at a time (one-lane warps; the staged
+    observation store, which needs a real warp, is kept off by n % 4 != 0 for 3- and 6-float observations): the action
+    generator, head / unrolled chunks / tail for launches that start at unaligned step indices, the reduced-range and
+    limit-free chunk variants, the pre-generated resets and the 32-bit row index -- against the oracle's rollout."""
+    all_out = shape != "generic_64"
+    block = 512 if shape == "all_out_512" else 64
+    if block == 512 and kind in (O.ACROBOT, O.LUNARLANDER):
+        pytest.skip("no one-wave shape for envs whose step is not unrolled")
+    seed, off = 5, 77
+    o = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=True, mode=O.MODE_F32)
+    sim = HostSim(hs, kind, n, seed, off)
+    assert np.array_equal(sim.reset(), o.reset())
+    episodes = 0
+    launches = {O.LUNARLANDER: (3, 37, 120), O.ACROBOT: (3, 37, 8, 210, 260)}.get(kind, (3, 37, 8, 210))   # Acrobot: past its 500-step limit
+    for k in launches:
+        tr = sim.rollout(k, all_out, block)
+        tw = o.rollout_random(k)
+        for j, what in enumerate(("obs", "reward", "done", "actions")):
+            assert np.array_equal(tr[j], tw[j]), "%s differs in the launch of %d steps" % (what, k)
+        episodes += int(tw[2].sum())   # (the kernel's own episode counter is a warp reduction: meaningless with one-lane warps)
+        st, _, ot = o.get_state()
+        assert ot == sim.t and np.array_equal(sim.abi_state(), st.astype(np.float32))
+    assert episodes > 0 or kind == O.MOUNTAINCAR_CONT
