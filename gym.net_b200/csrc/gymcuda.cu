@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -62,8 +63,10 @@ struct NcclApi {
 };
 }  // namespace
 static NcclApi g_nccl;
+static std::mutex g_nccl_mutex;   // handles may initialise their communicators from different host threads
 
 static int nccl_load(const char* path) {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.lib) return GYMCUDA_OK;
     const char* candidates[] = {path, getenv("GYMCUDA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     void* h = nullptr;
