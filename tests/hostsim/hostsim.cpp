@@ -1,11 +1,15 @@
 // TEST INFRASTRUCTURE ONLY.  The engine's device headers compiled for the HOST: every __device__ function of
 // gym.net_b200/csrc (detmath, Philox, the five classic envs, the LunarLander solver) becomes plain C++ through
 // stubs/cuda_runtime.h, and the per-thread body of step_kernel / reset_kernel (kernels.cuh) is replayed here
-// one env at a time.  tests/test_hostsim_cpu.py compares it bit for bit with the CPU oracle: the kernel SOURCE
-// is then checked on machines without a GPU.  It proves nothing about speed and is never part of the product.
+// one env at a time; the kernels of kernels.cuh themselves are launched either one thread at a time or, through
+// simt.hpp, as CTAs of fibers with real warp / block primitives.  tests/test_hostsim_cpu.py and
+// tests/test_hostsim_simt_cpu.py compare all of it bit for bit with the CPU oracle: the kernel SOURCE is then checked
+// on machines without a GPU.  It proves nothing about speed and is never part of the product.
 //
 //   g++ -O2 -std=c++17 -ffp-contract=off -Itests/hostsim/stubs -Igym.net_b200/csrc -shared -fPIC ...
 #include <cuda_runtime.h>   // the stub
+
+#include <functional>
 
 #include "env_classic.cuh"
 #include "lunar.cuh"
@@ -73,19 +77,26 @@ void sim_reset(const Bufs& b, float* obs, int n, uint32_t env_off, uint64_t seed
 
 }  // namespace
 
-// The rollout kernel itself (kernels.cuh), executed one thread at a time: a "warp" here has one lane, so warp votes are
-// per-thread and the staged observation store (which needs the 32 lanes of a warp side by side) must be off: callers
-// pass n % 4 != 0 for 3- and 6-float observations.  Everything else is the kernel's own code: action generator, head /
-// unrolled chunks / tail, reduced-range and limit-free chunk variants, pre-generated resets, 32-bit row index.
+// Kernel launches on the host, two ways (g_simt, set by hostsim_set_simt):
+//   0  one thread at a time: a "warp" has one lane, so warp votes are per-thread and the staged observation store of
+//      the rollout kernel (which needs the 32 lanes of a warp side by side) must be off -- callers pass n % 4 != 0 for
+//      3- and 6-float observations.  Fast; everything per-thread is the kernel's own code.
+//   1  simt.hpp: the threads of a CTA are fibers, ballots / votes / shuffles / barriers are real rendezvous, `static`
+//      stands in for __shared__.  The kernels run as written, warp-cooperative parts included.
+static int g_simt = 0;
+static void set_block(unsigned b, unsigned grid, unsigned block) { blockIdx.x = b; gridDim.x = grid; blockDim.x = block; }
+static void set_thread(unsigned t) { threadIdx.x = t; }
+
+template <class F>
+static void launch(int grid, int block, F&& kernel_call) {
+    if (g_simt) { simt::launch(grid, block, set_block, set_thread, std::function<void()>(kernel_call)); return; }
+    for (int b = 0; b < grid; ++b)
+        for (int tid = 0; tid < block; ++tid) { set_block((unsigned)b, (unsigned)grid, (unsigned)block); set_thread((unsigned)tid); kernel_call(); }
+}
+
 template <class E, bool AR, bool LIM, bool ALL_OUT, int BLOCK>
 static void run_rollout(const RolloutArgs& a) {
-    const int grid = (a.n + BLOCK - 1) / BLOCK;
-    gridDim.x = (unsigned)grid; blockDim.x = (unsigned)BLOCK;
-    for (int b = 0; b < grid; ++b)
-        for (int tid = 0; tid < BLOCK; ++tid) {
-            blockIdx.x = (unsigned)b; threadIdx.x = (unsigned)tid;
-            rollout_kernel<E, AR, LIM, ALL_OUT, BLOCK>(a);
-        }
+    launch((a.n + BLOCK - 1) / BLOCK, BLOCK, [&] { rollout_kernel<E, AR, LIM, ALL_OUT, BLOCK>(a); });
 }
 
 template <class E>
@@ -97,6 +108,18 @@ static int rollout_dispatch(const RolloutArgs& a, int auto_reset, int all_out, i
     if constexpr (E::ROLLOUT_CHUNK) { HS_CASE(1, 0, 1, 512) HS_CASE(1, 1, 1, 512) }
 #undef HS_CASE
     return -2;
+}
+
+
+template <class E>
+static int k_step(const StepArgs& a, int auto_reset) {
+    const int grid = (a.n + STEP_BLOCK - 1) / STEP_BLOCK;
+    const bool lim = a.limit > 0;
+    if (auto_reset && lim) launch(grid, STEP_BLOCK, [&] { step_kernel<E, true, true>(a); });
+    else if (auto_reset) launch(grid, STEP_BLOCK, [&] { step_kernel<E, true, false>(a); });
+    else if (lim) launch(grid, STEP_BLOCK, [&] { step_kernel<E, false, true>(a); });
+    else launch(grid, STEP_BLOCK, [&] { step_kernel<E, false, false>(a); });
+    return 0;
 }
 
 
@@ -157,13 +180,13 @@ void hostsim_sincos(const float* x, float* s, float* c, size_t n) {
 }
 
 int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* ep_t, int32_t* episode, float* obs, float* reward,
-                    uint8_t* done, void* actions, unsigned long long* stats, int n, int k_steps, uint32_t env_off, uint64_t seed,
-                    uint64_t t, int limit, int auto_reset, int all_out, int block, float gravity, float wind_power,
-                    float turbulence_power, int use_wind) {
+                    uint8_t* done, void* actions, unsigned long long* stats, float* ep_ret, double* sums, int done_bits, int n,
+                    int k_steps, uint32_t env_off, uint64_t seed, uint64_t t, int limit, int auto_reset, int all_out, int block,
+                    float gravity, float wind_power, float turbulence_power, int use_wind) {
     RolloutArgs a{};
     a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.perm = nullptr;
-    a.obs = obs; a.reward = reward; a.done = done; a.actions = actions; a.stats = stats; a.ep_ret = nullptr; a.sums = nullptr;
-    a.done_bits = 0; a.n = n; a.k_steps = k_steps; a.env_off = env_off; a.seed = seed; a.t = t; a.limit = limit;
+    a.obs = obs; a.reward = reward; a.done = done; a.actions = actions; a.stats = stats; a.ep_ret = ep_ret; a.sums = sums;
+    a.done_bits = done_bits; a.n = n; a.k_steps = k_steps; a.env_off = env_off; a.seed = seed; a.t = t; a.limit = limit;
     a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
     switch (kind) {
         case 0: return rollout_dispatch<CartPole>(a, auto_reset, all_out, block);
@@ -175,6 +198,97 @@ int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* 
         case 6: return rollout_dispatch<LunarLanderCont>(a, auto_reset, all_out, block);
     }
     return -1;
+}
+
+
+// ---- the kernels themselves (not their per-thread bodies): meant for hostsim_set_simt(1) --------------------------
+void hostsim_set_simt(int on) { g_simt = on ? 1 : 0; }
+
+// The NEXT hostsim_step_kernel call runs as rank `rank` of a fused step + observation gather (gymcuda_step_gather_device):
+// peer_obs[r] / peer_flags[r] stand for the cudaIpc-mapped gather buffer and arrival flags of rank r.
+static struct { int world, rank; uint32_t gseq; float* peer_obs[MAX_PEERS]; uint32_t* peer_flags[MAX_PEERS]; unsigned* block_counter; } g_gather;
+void hostsim_set_gather(int world, int rank, uint32_t gseq, float** peer_obs, uint32_t** peer_flags, unsigned* block_counter) {
+    g_gather.world = world; g_gather.rank = rank; g_gather.gseq = gseq; g_gather.block_counter = block_counter;
+    for (int r = 0; r < world; ++r) { g_gather.peer_obs[r] = peer_obs[r]; g_gather.peer_flags[r] = peer_flags[r]; }
+}
+
+// gather_wait_kernel: returns the timeout flag (0, or 1 + the rank that never published)
+int hostsim_gather_wait(const uint32_t* flags, int world, uint32_t gseq) {
+    int timeout_flag = 0;
+    launch(1, 32, [&] { gather_wait_kernel(flags, world, gseq, &timeout_flag); });
+    return timeout_flag;
+}
+
+// step_kernel as launched by gymcuda_step_device: done compaction, statistics, packed done bytes, optional perm
+int hostsim_step_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* ep_t, int32_t* episode, const int32_t* perm,
+                        const void* actions, float* obs, float* reward, uint8_t* done, int32_t* done_idx, int32_t* done_count,
+                        unsigned long long* stats, float* ep_ret, double* sums, int done_bits, int* host_invalid, int n,
+                        uint32_t env_off, uint64_t seed, uint64_t t, int limit, int auto_reset, int use_bcast, int32_t bcast_action,
+                        uint32_t seq, float gravity, float wind_power, float turbulence_power, int use_wind) {
+    StepArgs a{};
+    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.perm = perm; a.actions = actions;
+    a.obs = obs; a.reward = reward; a.done = done; a.done_idx = done_idx; a.done_count = done_count; a.stats = stats; a.ep_ret = ep_ret;
+    a.sums = sums; a.done_bits = done_bits; a.host_invalid = host_invalid; a.n = n; a.env_off = env_off; a.seed = seed; a.t = t;
+    a.limit = limit; a.use_bcast = use_bcast; a.bcast_action = bcast_action; a.seq = seq;
+    a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
+    a.world = g_gather.world; a.rank = g_gather.rank; a.gseq = g_gather.gseq; a.block_counter = g_gather.block_counter;
+    for (int r = 0; r < g_gather.world; ++r) { a.peer_obs[r] = g_gather.peer_obs[r]; a.peer_flags[r] = g_gather.peer_flags[r]; }
+    g_gather.world = 0;   // one launch
+    switch (kind) {
+        case 0: return k_step<CartPole>(a, auto_reset);
+        case 1: return k_step<Pendulum>(a, auto_reset);
+        case 2: return k_step<MountainCar>(a, auto_reset);
+        case 3: return k_step<MountainCarCont>(a, auto_reset);
+        case 4: return k_step<Acrobot>(a, auto_reset);
+        case 5: return k_step<LunarLander>(a, auto_reset);
+        case 6: return k_step<LunarLanderCont>(a, auto_reset);
+    }
+    return -1;
+}
+
+// reset_kernel (mask may be null = all)
+int hostsim_reset_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* ep_t, int32_t* episode, const uint8_t* mask,
+                         float* obs, float* ep_ret, int n, uint32_t env_off, uint64_t seed, uint64_t t, float gravity,
+                         float wind_power, float turbulence_power, int use_wind) {
+    ResetArgs a{};
+    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.mask = mask; a.obs = obs;
+    a.ep_ret = ep_ret; a.n = n; a.env_off = env_off; a.seed = seed; a.t = t; a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
+    const int grid = (n + 127) / 128;
+    switch (kind) {
+        case 0: launch(grid, 128, [&] { reset_kernel<CartPole>(a); }); return 0;
+        case 1: launch(grid, 128, [&] { reset_kernel<Pendulum>(a); }); return 0;
+        case 2: launch(grid, 128, [&] { reset_kernel<MountainCar>(a); }); return 0;
+        case 3: launch(grid, 128, [&] { reset_kernel<MountainCarCont>(a); }); return 0;
+        case 4: launch(grid, 128, [&] { reset_kernel<Acrobot>(a); }); return 0;
+        case 5: launch(grid, 128, [&] { reset_kernel<LunarLander>(a); }); return 0;
+        case 6: launch(grid, 128, [&] { reset_kernel<LunarLanderCont>(a); }); return 0;
+    }
+    return -1;
+}
+
+// sample_kernel: ActionSpace.Sample per env (mask: Discrete only, [n][ACTN] bytes, may be null)
+int hostsim_sample_kernel(int kind, const uint8_t* mask, void* out, int n, uint32_t env_off, uint64_t seed, uint64_t t) {
+    SampleArgs a{nullptr, mask, out, n, env_off, seed, t};
+    const int grid = (n + 127) / 128;
+    switch (kind) {
+        case 0: launch(grid, 128, [&] { sample_kernel<CartPole>(a); }); return 0;
+        case 1: launch(grid, 128, [&] { sample_kernel<Pendulum>(a); }); return 0;
+        case 2: launch(grid, 128, [&] { sample_kernel<MountainCar>(a); }); return 0;
+        case 3: launch(grid, 128, [&] { sample_kernel<MountainCarCont>(a); }); return 0;
+        case 4: launch(grid, 128, [&] { sample_kernel<Acrobot>(a); }); return 0;
+        case 5: launch(grid, 128, [&] { sample_kernel<LunarLander>(a); }); return 0;
+        case 6: launch(grid, 128, [&] { sample_kernel<LunarLanderCont>(a); }); return 0;
+    }
+    return -1;
+}
+
+// the three launches of contact_partition() (gymcuda.cu): aux field-major, block_free [nb + 1] scratch, perm [n] out
+int hostsim_partition(const int32_t* aux, int n, int32_t* block_free, int32_t* perm) {
+    const int nb = (n + PART_BLOCK - 1) / PART_BLOCK;
+    launch(nb, PART_BLOCK, [&] { partition_count_kernel(aux, n, block_free); });
+    launch(1, 1024, [&] { partition_scan_kernel(block_free, nb); });
+    launch(nb, PART_BLOCK, [&] { partition_scatter_kernel(aux, n, block_free, nb, perm); });
+    return nb;
 }
 
 }  // extern "C"

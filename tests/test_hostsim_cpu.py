@@ -6,97 +6,17 @@ the per-thread body of step_kernel / reset_kernel.  What the GPU tests establish
 kernel == oracle F32 on free-running trajectories with auto-reset -- is established here for the same source lines
 on any machine: reset draws, action validation, transitions, rewards, termination, time limits, the LunarLander
 solver through landings and crashes."""
-import ctypes as C
-import os
-import subprocess
-
 import numpy as np
 import pytest
 
 import oracle_lib as O
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HS_DIR = os.path.join(ROOT, "tests", "hostsim")
-CSRC = os.path.join(ROOT, "gym.net_b200", "csrc")
-LIB = os.path.join(HS_DIR, "_hostsim.so")
-
-
-def _build():
-    srcs = [os.path.join(HS_DIR, "hostsim.cpp"), os.path.join(HS_DIR, "stubs", "cuda_runtime.h")] + [
-        os.path.join(CSRC, f) for f in ("detmath.cuh", "philox.cuh", "env_classic.cuh", "lunar.cuh", "lunar_core.cuh")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + os.path.join(HS_DIR, "stubs"),
-                        "-I" + CSRC, "-shared", "-fPIC", "-o", LIB, srcs[0]], check=True)
-    L = C.CDLL(LIB)
-    V, I, U32, U64, F = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_float
-    L.hostsim_step.argtypes = [I, V, V, V, V, V, V, V, V, V, I, U32, U64, U64, I, I, F, F, F, I]
-    L.hostsim_reset.argtypes = [I, V, V, V, V, V, V, I, U32, U64, U64, F, F, F, I]
-    L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
-    L.hostsim_rollout.argtypes = [I, V, V, V, V, V, V, V, V, V, V, I, I, U32, U64, U64, I, I, I, I, F, F, F, I]
-    L.hostsim_div_inrange.argtypes = [V, V, V, C.c_size_t]
-    L.hostsim_sincos.argtypes = [V, V, V, C.c_size_t]
-    return L
+from hostsim_lib import DEFAULT_LIMIT, PRM, HostSim, _p, build
 
 
 @pytest.fixture(scope="module")
 def hs():
-    return _build()
-
-
-def _p(a):
-    return a.ctypes.data_as(C.c_void_p)
-
-
-DEFAULT_LIMIT = {O.CARTPOLE: 0, O.PENDULUM: 200, O.MOUNTAINCAR: 200, O.MOUNTAINCAR_CONT: 999, O.ACROBOT: 500,
-                 O.LUNARLANDER: 0, O.LUNARLANDER_CONT: 0}
-PRM = (-10.0, 15.0, 1.5, 0)   # gravity, wind_power, turbulence_power, enable_wind (LunarLanderEnv.cs:351-354)
-
-
-class HostSim:
-    """Device-layout buffers + the replayed kernel bodies."""
-
-    def __init__(self, L, kind, n, seed, env_off=0, auto_reset=True):
-        self.L, self.kind, self.n, self.seed, self.off, self.auto = L, kind, n, seed, env_off, auto_reset
-        d = O.dims(kind)
-        self.sd, self.od, self.ad, self.actn = d["state_dim"], d["obs_dim"], d["act_dim"], d["act_n"]
-        self.lunar = kind >= O.LUNARLANDER
-        self.auxw = d["aux_dim"] - 2 if self.lunar else 0
-        self.state = np.zeros((self.sd, n) if self.lunar else (n, self.sd), np.float32)
-        self.aux = np.zeros((max(self.auxw, 1), n), np.int32)
-        self.sbd = np.full(n, -1, np.int32); self.ept = np.zeros(n, np.int32); self.episode = np.zeros(n, np.int32)
-        self.limit = DEFAULT_LIMIT[kind]
-        self.t = 0
-        L.hostsim_ctor(kind, _p(self.state), _p(self.aux), n, env_off, seed)
-
-    def reset(self):
-        obs = np.empty((self.n, self.od), np.float32)
-        self.L.hostsim_reset(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
-                             self.n, self.off, self.seed, self.t, *PRM)
-        return obs
-
-    def step(self, actions):
-        a = np.ascontiguousarray(actions)
-        obs = np.empty((self.n, self.od), np.float32); rew = np.empty(self.n, np.float32); done = np.empty(self.n, np.uint8)
-        bad = self.L.hostsim_step(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(a),
-                                  _p(obs), _p(rew), _p(done), self.n, self.off, self.seed, self.t, self.limit, int(self.auto), *PRM)
-        self.t += 1
-        return obs, rew, done, bad
-
-    def rollout(self, k, all_out=True, block=64):
-        n = self.n
-        obs = np.empty((k, n, self.od), np.float32); rew = np.empty((k, n), np.float32); done = np.empty((k, n), np.uint8)
-        act = np.empty((k, n), np.int32) if self.actn > 0 else np.empty((k, n, self.ad), np.float32)
-        stats = np.zeros(2, np.uint64)
-        rc = self.L.hostsim_rollout(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
-                                    _p(rew), _p(done), _p(act), _p(stats), n, k, self.off, self.seed, self.t, self.limit,
-                                    int(self.auto), int(all_out), block, *PRM)
-        assert rc == 0, rc
-        self.t += k
-        return obs, rew, done, act, int(stats[0])
-
-    def abi_state(self):
-        """[n][state_dim] like gymcuda_get_state."""
-        return self.state.T.copy() if self.lunar else self.state.copy()
+    return build()
 
 
 CASES = [("CartPole-v1", O.CARTPOLE, 256, 300), ("Pendulum-v1", O.PENDULUM, 128, 450), ("MountainCar-v0", O.MOUNTAINCAR, 128, 450),

@@ -1,0 +1,228 @@
+"""CPU: the engine's KERNELS (kernels.cuh), compiled for the host and run as CTAs of cooperating fibers, against the
+oracle -- bit for bit.
+
+tests/hostsim/simt.hpp executes the threads of a CTA as ucontext fibers and makes __ballot_sync / __all_sync /
+__shfl_*_sync / __syncwarp / __activemask / __syncthreads real rendezvous between them, so the warp-cooperative parts
+of the kernels run as written on a machine without a GPU: the done compaction and the packed done bytes of
+step_kernel, the statistics reductions, the staged observation stores and the warp votes of rollout_kernel in its 64-
+and 512-thread shapes, ragged last warps, and the three kernels of the LunarLander contact partition.  (Test
+infrastructure: nothing here is part of the product, and the GPU tests remain the parity tests proper.)"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+from hostsim_lib import HostSim, build
+
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return build()
+
+
+@pytest.fixture(autouse=True)
+def hs(lib):
+    lib.hostsim_set_simt(1)
+    yield lib
+    lib.hostsim_set_simt(0)
+
+
+def pair(hs, kind, n, seed=5, off=77, done_bits=False, time_limit=0):
+    o = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=True, mode=O.MODE_F32, done_bits=done_bits, time_limit=time_limit)
+    sim = HostSim(hs, kind, n, seed, off)
+    if time_limit:
+        sim.limit = time_limit
+    assert np.array_equal(sim.reset_kernel(), o.reset())
+    return o, sim
+
+
+def same_state(o, sim):
+    st, _, ot = o.get_state()
+    return ot == sim.t and np.array_equal(sim.abi_state(), st.astype(F32))
+
+
+# n chosen so that 3- and 6-float observations take the staged path (n % 4 == 0) in the full warps and the per-lane
+# path in a ragged last warp (Acrobot 100 = 3 full warps + 4 lanes), and so that the 512-thread shape has idle warps
+ROLLOUT_CASES = [("CartPole-v1", O.CARTPOLE, 200), ("Pendulum-v1", O.PENDULUM, 128), ("Pendulum-v1 ragged", O.PENDULUM, 76),
+                 ("MountainCar-v0", O.MOUNTAINCAR, 77), ("MountainCarContinuous-v0", O.MOUNTAINCAR_CONT, 64),
+                 ("Acrobot-v1", O.ACROBOT, 100), ("LunarLander-v2", O.LUNARLANDER, 70)]
+
+
+@pytest.mark.parametrize("name,kind,n", ROLLOUT_CASES, ids=[c[0] for c in ROLLOUT_CASES])
+@pytest.mark.parametrize("block", [64, 512])
+def test_rollout_kernel_all_outputs_with_real_warps(hs, name, kind, n, block):
+    if block == 512 and kind in (O.ACROBOT, O.LUNARLANDER):
+        pytest.skip("no one-wave shape for envs whose step is not unrolled")
+    o, sim = pair(hs, kind, n)
+    launches = (3, 37, 100) if kind == O.LUNARLANDER else (3, 37, 8, 210, 260)
+    for k in launches:
+        tr = sim.rollout(k, True, block)
+        tw = o.rollout_random(k)
+        for j, what in enumerate(("obs", "reward", "done", "actions")):
+            assert np.array_equal(tr[j], tw[j]), "%s differs in the launch of %d steps" % (what, k)
+        assert tr[4] == int(tw[2].sum())          # the warp-reduced episode counter
+        assert same_state(o, sim)
+
+
+@pytest.mark.parametrize("name,kind,n", [("CartPole-v1", O.CARTPOLE, 100), ("Pendulum-v1", O.PENDULUM, 96), ("MountainCar-v0", O.MOUNTAINCAR, 70),
+                                         ("Acrobot-v1", O.ACROBOT, 64)], ids=["CartPole-v1", "Pendulum-v1", "MountainCar-v0", "Acrobot-v1"])
+def test_rollout_kernel_generic_shape_statistics_and_truncation_bits(hs, name, kind, n):
+    """The generic variant: episode return / length sums (per-thread double accumulators, warp shuffles, one atomic pair
+    per warp), the running return carried in ep_ret across launches, and done bytes that tell truncation (2) from
+    termination (1)."""
+    o, sim = pair(hs, kind, n, done_bits=True)
+    if sim.limit == 0:
+        sim.limit = 0x7fffffff            # what gymcuda_create does for episode statistics without a time limit
+    ep_ret = np.zeros(n, F32); sums = np.zeros(2, np.float64)
+    ret = np.zeros(n, F32); length = np.zeros(n, np.int64); want_ret = 0.0; want_len = 0; episodes = 0
+    for k in (5, 130, 260, 300):
+        tr = sim.rollout(k, False, 64, ep_ret=ep_ret, sums=sums, done_bits=1)
+        tw = o.rollout_random(k)
+        for j, what in enumerate(("obs", "reward", "done", "actions")):
+            assert np.array_equal(tr[j], tw[j]), "%s differs in the launch of %d steps" % (what, k)
+        for t in range(k):
+            ret = (ret + tw[1][t]).astype(F32); length += 1
+            d = tw[2][t] != 0
+            want_ret += float(ret[d].astype(np.float64).sum()); want_len += int(length[d].sum()); episodes += int(d.sum())
+            ret[d] = 0; length[d] = 0
+        assert np.array_equal(ep_ret, ret)
+        assert np.isclose(sums[0], want_ret, rtol=1e-12, atol=1e-9) and sums[1] == want_len
+    assert episodes > 0
+    if kind == O.PENDULUM:
+        assert set(np.unique(tw[2])) == {0, 2}        # Pendulum never terminates by itself
+
+
+STEP_CASES = [("CartPole-v1", O.CARTPOLE, 333, 120), ("Pendulum-v1", O.PENDULUM, 130, 210), ("MountainCar-v0", O.MOUNTAINCAR, 260, 210),
+              ("Acrobot-v1 limit 25", O.ACROBOT, 129, 60), ("LunarLander-v2", O.LUNARLANDER, 70, 150), ("LunarLanderContinuous-v2", O.LUNARLANDER_CONT, 40, 120)]
+
+
+@pytest.mark.parametrize("name,kind,n,k", STEP_CASES, ids=[c[0] for c in STEP_CASES])
+def test_step_kernel_compaction_statistics_and_packed_done(hs, name, kind, n, k):
+    """step_kernel as gymcuda_step_device launches it, ragged last CTA included: outputs against the oracle, the compacted
+    list of finished envs (ballot + block scan + one atomic per CTA) against nonzero(done), the double-buffered counter,
+    the statistics, done bytes through the packed 4-byte stores and (misaligned buffer) the per-lane stores, and for
+    LunarLander the thread -> env permutation of the contact partition."""
+    o, sim = pair(hs, kind, n, done_bits=True, time_limit=25 if kind == O.ACROBOT else 0)
+    if sim.limit == 0:
+        sim.limit = 0x7fffffff
+    ep_ret = np.zeros(n, F32); sums = np.zeros(2, np.float64)
+    ret = np.zeros(n, F32); length = np.zeros(n, np.int64); want_ret = 0.0; want_len = 0; episodes = 0
+    for t in range(k):
+        a = o.sample_actions()
+        assert np.array_equal(sim.sample_kernel(), a)
+        oo, orr, od = o.step(a)
+        perm = sim.partition()[0] if (sim.lunar and t % 2 == 0) else None
+        so, sr, sd, idx, flag = sim.step_kernel(a, perm=perm, ep_ret=ep_ret, sums=sums, done_bits=1, done_offset=(t % 3 == 2) * 1)
+        assert flag == 0
+        assert np.array_equal(sd, od), "done differs at step %d" % t
+        assert np.array_equal(sr, orr), "reward differs at step %d" % t
+        assert np.array_equal(so, oo), "observation differs at step %d" % t
+        assert np.array_equal(np.sort(idx), np.nonzero(od)[0]), "compacted done list differs at step %d" % t
+        ret = (ret + orr).astype(F32); length += 1
+        d = od != 0
+        want_ret += float(ret[d].astype(np.float64).sum()); want_len += int(length[d].sum()); episodes += int(d.sum())
+        ret[d] = 0; length[d] = 0
+        assert int(sim.stats[0]) == episodes and int(sim.stats[1]) == 0
+        assert np.array_equal(ep_ret, ret)
+        assert np.isclose(sums[0], want_ret, rtol=1e-12, atol=1e-9) and sums[1] == want_len
+    assert same_state(o, sim)
+    assert episodes > 0
+
+
+def test_step_kernel_rejects_invalid_actions_and_broadcasts(hs):
+    n = 200
+    o, sim = pair(hs, O.MOUNTAINCAR, n)
+    before = sim.abi_state()
+    a = o.sample_actions()
+    bad = np.array([3, 64, 65, 199])
+    a[bad] = [3, -1, 7, 1 << 20]
+    obs, rew, done, idx, flag = sim.step_kernel(a)
+    assert flag == 1 and int(sim.stats[1]) == len(bad)           # mapped host flag raised, invalid actions counted per warp
+    after = sim.abi_state()
+    assert np.array_equal(after[bad], before[bad])               # those envs were not stepped
+    ok = np.setdiff1d(np.arange(n), bad)
+    assert not np.array_equal(after[ok], before[ok]) and not done.any() and (rew[bad] == 0).all()
+    # IVecEnv.Step(int action): one action for every env (VecEnvWrapper.cs:22-24)
+    o2, sim2 = pair(hs, O.CARTPOLE, 150)
+    for t in range(40):
+        oo, orr, od = o2.step(np.full(150, t % 2, np.int32))       # the reference test's i % 2 loop (CartpoleEnvironment.cs:19-26)
+        so, sr, sd, idx, flag = sim2.step_kernel(None, bcast=t % 2)
+        assert np.array_equal(so, oo) and np.array_equal(sr, orr) and np.array_equal(sd, od)
+        assert np.array_equal(np.sort(idx), np.nonzero(od)[0])
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 5000, 270000])
+def test_contact_partition_is_a_stable_partition(hs, n):
+    """partition_count / partition_scan / partition_scatter (gymcuda.cu: contact_partition): free-flight landers first,
+    landers with a touching contact after them, each class in ascending env order; 270 000 envs make the single-CTA scan
+    walk more than one 1024-wide tile of block counts."""
+    rng = np.random.default_rng(n)
+    sim = HostSim(hs, O.LUNARLANDER, n, 1)
+    sim.aux[:] = 0
+    touching = rng.random(n) < (0.3 if n < 100000 else 0.02)
+    which = rng.integers(0, 3, n)
+    sim.aux[which[touching], np.nonzero(touching)[0]] = rng.integers(1, 64, int(touching.sum()))
+    perm, block_free = sim.partition()
+    want = np.concatenate([np.nonzero(~touching)[0], np.nonzero(touching)[0]]).astype(np.int32)
+    assert np.array_equal(perm, want)
+    assert block_free[-1] == int((~touching).sum())
+
+
+@pytest.mark.parametrize("kind", [O.CARTPOLE, O.MOUNTAINCAR, O.ACROBOT, O.LUNARLANDER, O.PENDULUM, O.MOUNTAINCAR_CONT, O.LUNARLANDER_CONT])
+def test_sample_and_masked_reset_kernels(hs, kind):
+    n = 150
+    o, sim = pair(hs, kind, n)
+    rng = np.random.default_rng(kind)
+    for t in range(6):
+        a = o.sample_actions()
+        assert np.array_equal(sim.sample_kernel(), a)
+        if sim.actn > 0:        # Discrete.Sample(mask): uniform over the entries equal to 1, Start when there is none (Discrete.cs:19-25)
+            mask = (rng.random((n, sim.actn)) < 0.5).astype(np.uint8)
+            mask[:5] = 0; mask[5:10] = 1; mask[10:15, 1:] = 2
+            assert np.array_equal(sim.sample_kernel(mask), o.sample_actions(mask))
+        oo, orr, od = o.step(a)
+        so, sr, sd, idx, flag = sim.step_kernel(a)
+        assert np.array_equal(so, oo) and np.array_equal(sd, od)
+        m = (rng.random(n) < 0.3).astype(np.uint8)
+        assert np.array_equal(sim.reset_kernel(m), o.reset(m))          # reset_masked: obs of every env, new episode for the masked ones
+        assert same_state(o, sim)
+
+
+def test_fused_step_gather_and_wait_kernels(hs):
+    """gymcuda_step_gather_device on the host: four "ranks" (shards of one batch) run step_kernel one after the other with
+    every rank's gather buffer standing in for the cudaIpc mapping; each rank's buffer must end up holding the
+    observations of the whole batch in the slot of this step's parity, its arrival flags must carry the gather sequence
+    number (published by the LAST CTA, which also re-arms the block counter), and gather_wait_kernel must accept exactly
+    that -- and name the missing rank when one never publishes."""
+    import ctypes as C
+    world, n, kind = 4, 300, O.ACROBOT
+    od = O.dims(kind)["obs_dim"]
+    full = O.OracleEnv(kind, world * n, seed=9, env_id_offset=0, auto_reset=True, mode=O.MODE_F32)
+    full.reset()
+    sims = [HostSim(hs, kind, n, 9, r * n) for r in range(world)]
+    for s in sims:
+        s.reset_kernel()
+    bufs = [np.full((2, world, n, od), np.nan, F32) for _ in range(world)]
+    flags = [np.zeros(world, np.uint32) for _ in range(world)]
+    counters = [np.zeros(1, np.uint32) for _ in range(world)]
+    PF = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    PG = (C.c_void_p * world)(*[f.ctypes.data for f in flags])
+    for gseq in range(1, 6):
+        a = full.sample_actions()
+        oo, orr, od_ = full.step(a)
+        for r, s in enumerate(sims):
+            if gseq == 5 and r == 2:
+                continue                                  # rank 2 "dies" before its fifth step
+            hs.hostsim_set_gather(world, r, gseq, PF, PG, counters[r].ctypes.data_as(C.c_void_p))
+            so, sr, sd, idx, flag = s.step_kernel(a[r * n:(r + 1) * n])
+            assert np.array_equal(sr, orr[r * n:(r + 1) * n]) and np.array_equal(sd, od_[r * n:(r + 1) * n])
+            assert counters[r][0] == 0                    # re-armed by the last CTA
+        for r in range(world):
+            if gseq < 5:
+                assert hs.hostsim_gather_wait(flags[r].ctypes.data_as(C.c_void_p), world, gseq) == 0
+                assert np.array_equal(bufs[r][gseq & 1].reshape(world * n, od), oo), "rank %d, gather %d" % (r, gseq)
+                assert (flags[r] == gseq).all()
+            else:
+                assert hs.hostsim_gather_wait(flags[r].ctypes.data_as(C.c_void_p), world, gseq) == 1 + 2
