@@ -22,6 +22,8 @@ namespace Gym.Environments.Vector {
         // CUDA (gymcuda_host_register): the step kernel then writes them in place over PCIe (42 us per 65 536-env
         // CartPole step) instead of the library staging pageable memory (160 us).  A caller that steps with the
         // same action array every time can give it the same treatment with PinActions().
+        // (The data of a managed array is 8-byte aligned; when _obs lands on 8 mod 16 the library stages that one
+        // buffer instead of writing it in place -- same results, see INTEGRATION.md "Host buffers".)
         private readonly List<GCHandle> _pins = new List<GCHandle>();
 
         public int ObsDim => _info.ObsDim;

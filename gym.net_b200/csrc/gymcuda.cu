@@ -555,8 +555,23 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
 static std::atomic<unsigned> g_host_epoch{1};   // bumped by every (un)registration / pinned (de)allocation made through this library
                                                 // (handles may live on different host threads)
 
-static void* mapped_alias(gymcuda_env* e, const void* host, int slot) {
-    if (!host) return nullptr;
+static bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// What the kernels' vector accesses need: observations leave as 16 B (float4) or 8 B (float2) vectors, a 2-D Box action
+// is read as one float2.  (A GCHandle-pinned managed float[] is only 8-byte aligned.)
+constexpr size_t OBS_ALIGN = 16;
+static size_t act_align(const gymcuda_env* e) { return (size_t)e->ki.ad * 4; }
+
+static int check_device_buffers(const gymcuda_env* e, const void* actions, const float* obs, const float* reward) {
+    if (actions && !is_aligned(actions, act_align(e))) return fail(GYMCUDA_EINVAL, "device action buffer must be %zu-byte aligned", act_align(e));
+    if (obs && !is_aligned(obs, OBS_ALIGN)) return fail(GYMCUDA_EINVAL, "device observation buffer must be 16-byte aligned (it is written with vector stores)");
+    if (reward && !is_aligned(reward, 4)) return fail(GYMCUDA_EINVAL, "device reward buffer must be 4-byte aligned");
+    return GYMCUDA_OK;
+}
+
+// `align`: a mapped buffer the kernel could not address with its vector accesses counts as not mapped (it is staged)
+static void* mapped_alias(gymcuda_env* e, const void* host, int slot, size_t align) {
+    if (!host || !is_aligned(host, align)) return nullptr;
     const unsigned epoch = g_host_epoch.load(std::memory_order_acquire);
     if (e->alias_epoch != epoch) {   // a buffer may have been registered or released since the answers were cached
         for (int k = 0; k < 4; ++k) e->alias_host[k] = nullptr;
@@ -567,6 +582,7 @@ static void* mapped_alias(gymcuda_env* e, const void* host, int slot) {
     void* dev = nullptr;
     if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) dev = at.devicePointer;
     else cudaGetLastError();   // pageable memory reports an error on old drivers: clear it
+    if (dev && !is_aligned(dev, align)) dev = nullptr;
     e->alias_host[slot] = host;
     e->alias_dev[slot] = dev;
     return dev;
@@ -602,10 +618,10 @@ int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward,
     // Zero-copy path: when all four host buffers are page-locked, the kernel reads the actions and
     // writes obs / reward / done straight through their device aliases -- the H2D and D2H traffic
     // crosses PCIe inside the step kernel, overlapped with the math, with no DMA set-up per buffer.
-    void* za = mapped_alias(e, actions, 0);
-    void* zo = mapped_alias(e, obs, 1);
-    void* zr = mapped_alias(e, reward, 2);
-    void* zd = mapped_alias(e, done, 3);
+    void* za = mapped_alias(e, actions, 0, act_align(e));
+    void* zo = mapped_alias(e, obs, 1, OBS_ALIGN);
+    void* zr = mapped_alias(e, reward, 2, 4);
+    void* zd = mapped_alias(e, done, 3, 1);
     if (za && zo && zr && zd) {
         int rc = step_launch(e, za, 0, 0, (float*)zo, (float*)zr, (uint8_t*)zd);
         if (rc) return rc;
@@ -636,6 +652,7 @@ int gymcuda_step_broadcast(gymcuda_env* e, int32_t action, float* obs, float* re
 int gymcuda_step_device(gymcuda_env* e, const void* d_actions, float* d_obs, float* d_reward, uint8_t* d_done) {
     ENTER(e);
     if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
+    if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
     return step_launch(e, d_actions, 0, 0, d_obs ? d_obs : e->d_obs, d_reward ? d_reward : e->d_reward,
                        d_done ? d_done : e->d_done);
 }
@@ -647,6 +664,7 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     ENTER(e);
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
+    if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
     RolloutArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
@@ -702,6 +720,7 @@ int gymcuda_rollout_random(gymcuda_env* e, int k_steps, float* obs, float* rewar
 int gymcuda_sample_actions_device(gymcuda_env* e, const uint8_t* d_mask, void* d_actions_out) {
     ENTER(e);
     if (!d_actions_out) return fail(GYMCUDA_EINVAL, "d_actions_out is null");
+    if (int rc = check_device_buffers(e, d_actions_out, nullptr, nullptr)) return rc;
     if (d_mask && e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "Box.sample cannot be provided a mask.");   // Box.cs:70-73
     SampleArgs a{};
     a.seeds = e->d_seeds; a.mask = d_mask; a.out = d_actions_out; a.n = e->n; a.env_off = e->cfg.env_id_offset;
@@ -992,6 +1011,7 @@ int gymcuda_step_gather_device(gymcuda_env* e, const void* d_actions, float* d_r
     ENTER(e);
     if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
     if (!e->g_local) return fail(GYMCUDA_EINVAL, "gather buffer not created");
+    if (int rc = check_device_buffers(e, d_actions, nullptr, d_reward)) return rc;
     for (int r = 0; r < e->g_world; ++r) if (!e->g_peer[r]) return fail(GYMCUDA_EINVAL, "gymcuda_gather_open has not mapped rank %d", r);
     int rc = step_launch(e, d_actions, 0, 0, nullptr, d_reward ? d_reward : e->d_reward, d_done ? d_done : e->d_done, true);
     if (rc) return rc;

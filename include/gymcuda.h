@@ -122,12 +122,16 @@ int gymcuda_reset_masked(gymcuda_env* env, const uint8_t* mask, float* obs_out);
  * Pageable buffers are staged with cudaMemcpyAsync (one DMA for obs|reward|done when they are adjacent);
  * page-locked buffers (gymcuda_host_alloc, cudaHostAlloc, gymcuda_host_register / cudaHostRegister)
  * are read and written by the kernel directly over PCIe (zero-copy), which is the fast path; the two
- * kinds can be mixed freely among the four buffers.
+ * kinds can be mixed freely among the four buffers.  A page-locked buffer the kernel's vector accesses
+ * cannot address in place -- observations not 16-byte aligned, a 2-D Box action array not 8-byte aligned,
+ * e.g. a pinned managed float[] whose data starts at 8 mod 16 -- is simply staged like a pageable one.
  * Returns GYMCUDA_EACTION if any action was outside the action space of an env kind that rejects
  * it (all but CartPole, whose reference only Debug.Asserts, CartPoleEnv.cs:139); those envs are
  * left unstepped, the others step normally. */
 int gymcuda_step(gymcuda_env* env, const void* actions, float* obs, float* reward, uint8_t* done);
-/* Same, all pointers in device memory, asynchronous on the handle's stream; no copies. */
+/* Same, all pointers in device memory, asynchronous on the handle's stream; no copies.
+ * Alignment (every *_device entry point; cudaMalloc'd and torch-allocated buffers satisfy it): observations
+ * 16 bytes, actions 4 bytes (8 for a 2-D Box), rewards 4; anything else is GYMCUDA_EINVAL. */
 int gymcuda_step_device(gymcuda_env* env, const void* d_actions, float* d_obs, float* d_reward,
                         uint8_t* d_done);
 /* Broadcast of one action to every env: the shipped IVecEnv.Step(int action) (IVecEnv.cs:14). */

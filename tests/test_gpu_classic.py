@@ -465,6 +465,42 @@ def test_registered_and_mixed_host_buffers(registered):
     a_env.Close(); b_env.Close()
 
 
+def test_registered_buffers_aligned_like_managed_arrays():
+    """A GCHandle-pinned managed float[] starts 8 mod 16: the kernel's float4 observation stores cannot address it in
+    place, so that one buffer is staged while the others stay zero-copy -- same results either way."""
+    import ctypes as C
+    from gymnet_b200 import _native as N
+    n = 2500
+    L = N.lib()
+    a_env = G.CartPoleVecEnv(n, seed=11, auto_reset=True); a_env.ResetBatch()
+    b_env = G.CartPoleVecEnv(n, seed=11, auto_reset=True); b_env.ResetBatch()
+    def arr(shape, dtype, rem):          # data pointer == rem mod 16, on pages no other buffer shares
+        count = int(np.prod(shape)); item = np.dtype(dtype).itemsize
+        raw = np.empty(count * item + 3 * 4096, np.uint8)
+        off = (-raw.ctypes.data) % 4096 + rem
+        view = raw[off: off + count * item].view(dtype).reshape(shape)
+        assert view.ctypes.data % 16 == rem
+        return view, raw
+    act, k0 = arr((n,), np.int32, 4); obs, k1 = arr((n, 4), np.float32, 8); rew, k2 = arr((n,), np.float32, 12); done, k3 = arr((n,), np.uint8, 1)
+    bufs = [act, obs, rew, done]
+    rng = np.random.default_rng(6)
+    for phase in range(2):               # pageable, then registered
+        if phase == 1:
+            for x in bufs:
+                N.check(L.gymcuda_host_register(C.c_void_p(x.ctypes.data), x.nbytes))
+        for _ in range(25):
+            a = rng.integers(0, 2, n).astype(np.int32)
+            act[:] = a
+            N.check(L.gymcuda_step(a_env._h, C.c_void_p(act.ctypes.data), C.c_void_p(obs.ctypes.data),
+                                   C.c_void_p(rew.ctypes.data), C.c_void_p(done.ctypes.data)))
+            o, r, d = b_env.StepBatch(a)
+            assert np.array_equal(obs, o) and np.array_equal(rew, r) and np.array_equal(done, d)
+    for x in bufs:
+        N.check(L.gymcuda_host_unregister(C.c_void_p(x.ctypes.data)))
+    assert np.array_equal(a_env.Observe(), b_env.Observe())
+    a_env.Close(); b_env.Close()
+
+
 @pytest.mark.parametrize("name", ["CartPole-v1", "MountainCar-v0", "Pendulum-v1", "LunarLander-v2"])
 def test_device_action_sampling_matches_rollout_and_oracle(name):
     """ActionSpace.Sample() on device: sample -> step reproduces the fused rollout; masked Discrete.Sample
