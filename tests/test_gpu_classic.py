@@ -474,20 +474,22 @@ def test_registered_buffers_aligned_like_managed_arrays():
     L = N.lib()
     a_env = G.CartPoleVecEnv(n, seed=11, auto_reset=True); a_env.ResetBatch()
     b_env = G.CartPoleVecEnv(n, seed=11, auto_reset=True); b_env.ResetBatch()
-    def arr(shape, dtype, rem):          # data pointer == rem mod 16, on pages no other buffer shares
+    def arr(shape, dtype, rem):          # data pointer == rem mod 16, inside whole pages no other buffer shares
         count = int(np.prod(shape)); item = np.dtype(dtype).itemsize
         raw = np.empty(count * item + 3 * 4096, np.uint8)
-        off = (-raw.ctypes.data) % 4096 + rem
-        view = raw[off: off + count * item].view(dtype).reshape(shape)
+        page = (-raw.ctypes.data) % 4096
+        view = raw[page + rem: page + rem + count * item].view(dtype).reshape(shape)
         assert view.ctypes.data % 16 == rem
-        return view, raw
-    act, k0 = arr((n,), np.int32, 4); obs, k1 = arr((n, 4), np.float32, 8); rew, k2 = arr((n,), np.float32, 12); done, k3 = arr((n,), np.uint8, 1)
-    bufs = [act, obs, rew, done]
+        span = (rem + count * item + 4095) // 4096 * 4096          # the pages the view lives in: what gets page-locked
+        return view, (raw.ctypes.data + page, span), raw
+    act, r0, k0 = arr((n,), np.int32, 4); obs, r1, k1 = arr((n, 4), np.float32, 8)
+    rew, r2, k2 = arr((n,), np.float32, 12); done, r3, k3 = arr((n,), np.uint8, 1)
+    regions = [r0, r1, r2, r3]
     rng = np.random.default_rng(6)
     for phase in range(2):               # pageable, then registered
         if phase == 1:
-            for x in bufs:
-                N.check(L.gymcuda_host_register(C.c_void_p(x.ctypes.data), x.nbytes))
+            for base, span in regions:
+                N.check(L.gymcuda_host_register(C.c_void_p(base), span))
         for _ in range(25):
             a = rng.integers(0, 2, n).astype(np.int32)
             act[:] = a
@@ -495,8 +497,8 @@ def test_registered_buffers_aligned_like_managed_arrays():
                                    C.c_void_p(rew.ctypes.data), C.c_void_p(done.ctypes.data)))
             o, r, d = b_env.StepBatch(a)
             assert np.array_equal(obs, o) and np.array_equal(rew, r) and np.array_equal(done, d)
-    for x in bufs:
-        N.check(L.gymcuda_host_unregister(C.c_void_p(x.ctypes.data)))
+    for base, span in regions:
+        N.check(L.gymcuda_host_unregister(C.c_void_p(base)))
     assert np.array_equal(a_env.Observe(), b_env.Observe())
     a_env.Close(); b_env.Close()
 
