@@ -203,6 +203,8 @@ int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* 
 
 // ---- the kernels themselves (not their per-thread bodies): meant for hostsim_set_simt(1) --------------------------
 void hostsim_set_simt(int on) { g_simt = on ? 1 : 0; }
+// thread scheduling order of the SIMT executor: 0 ascending, 1 descending, 2 pseudo-random (seeded)
+void hostsim_set_schedule(int policy, uint64_t seed) { simt::g_policy = policy; simt::g_rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull; }
 
 // The NEXT hostsim_step_kernel call runs as rank `rank` of a fused step + observation gather (gymcuda_step_gather_device):
 // peer_obs[r] / peer_flags[r] stand for the cudaIpc-mapped gather buffer and arrival flags of rank r.

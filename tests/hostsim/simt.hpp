@@ -46,6 +46,13 @@ struct Cta {
     const std::function<void()>* body = nullptr;
 };
 
+// Which runnable thread goes next: 0 = oldest first (lanes proceed in ascending order), 1 = newest first (descending),
+// 2 = pseudo-random.  A kernel that is correct under CUDA's rules gives the same results under every order; one that
+// leans on an ordering between lanes that only a missing __syncwarp / __syncthreads would provide does not.
+static int g_policy = 0;
+static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+static inline uint64_t next_random() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17; return g_rng; }
+
 static Cta* g_cta = nullptr;                    // non-null while a launch is running
 static void (*g_set_thread)(unsigned) = nullptr;   // installs threadIdx.x before a fiber resumes
 
@@ -151,10 +158,8 @@ static void run_cta(int nthreads, const std::function<void()>& body, char* stack
         c.runq.push_back(i);
     }
     g_cta = &c;
-    size_t head = 0;
     for (;;) {
-        if (head == c.runq.size()) {
-            c.runq.clear(); head = 0;
+        if (c.runq.empty()) {
             for (int w = 0; w * 32 < nthreads; ++w) resolve_warp(c, w);
             resolve_block(c);
             if (c.runq.empty()) {
@@ -164,7 +169,11 @@ static void run_cta(int nthreads, const std::function<void()>& body, char* stack
                 deadlock(c);
             }
         }
-        const int id = c.runq[head++];
+        size_t pick = 0;
+        if (g_policy == 1) pick = c.runq.size() - 1;
+        else if (g_policy == 2) pick = (size_t)(next_random() % c.runq.size());
+        const int id = c.runq[pick];
+        c.runq.erase(c.runq.begin() + (long)pick);
         c.cur = id;
         g_set_thread((unsigned)id);
         swapcontext(&c.sched, &c.f[id].ctx);

@@ -27,6 +27,7 @@ def build():
     L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
     L.hostsim_rollout.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, I, I, I, U32, U64, U64, I, I, I, I, F, F, F, I]
     L.hostsim_set_simt.argtypes = [I]
+    L.hostsim_set_schedule.argtypes = [I, U64]
     L.hostsim_step_kernel.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, V, V, V, I, V, I, U32, U64, U64, I, I, I, C.c_int32, U32, F, F, F, I]
     L.hostsim_reset_kernel.argtypes = [I, V, V, V, V, V, V, V, V, I, U32, U64, U64, F, F, F, I]
     L.hostsim_sample_kernel.argtypes = [I, V, V, I, U32, U64, U64]

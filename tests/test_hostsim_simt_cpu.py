@@ -22,10 +22,15 @@ def lib():
     return build()
 
 
-@pytest.fixture(autouse=True)
-def hs(lib):
+# Every test runs under three thread schedules of the executor: runnable lanes proceed in ascending order, in descending
+# order, and in a seeded pseudo-random order.  Correct kernels give identical results under all of them; a kernel that
+# relies on an ordering only a missing __syncwarp / __syncthreads would provide breaks under at least one.
+@pytest.fixture(autouse=True, params=["ascending", "descending", "random"])
+def hs(lib, request):
     lib.hostsim_set_simt(1)
+    lib.hostsim_set_schedule(["ascending", "descending", "random"].index(request.param), 12345)
     yield lib
+    lib.hostsim_set_schedule(0, 0)
     lib.hostsim_set_simt(0)
 
 
