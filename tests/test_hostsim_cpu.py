@@ -113,3 +113,96 @@ def test_rollout_kernel_source_on_host_equals_oracle(hs, name, kind, n, shape):
         st, _, ot = o.get_state()
         assert ot == sim.t and np.array_equal(sim.abi_state(), st.astype(np.float32))
     assert episodes > 0 or kind == O.MOUNTAINCAR_CONT
+
+
+def test_cartpole_teacher_forced_ten_million_states(hs):
+    """SURVEY section 7 step 3 at its stated size, on the CPU: 10^7 teacher-forced CartPole states -- uniform over and
+    beyond the episode range, plus states constructed so that the successor's x or theta lands within a few float32
+    ulps of +-x_threshold / +-theta_threshold -- through (1) the reference arithmetic (oracle F64: the C# doubles of
+    CartPoleEnv.cs:137-186), (2) the engine arithmetic (oracle F32) and (3) the DEVICE source compiled for the host.
+    done: identical in all three.  State: (3) == (2) bit for bit, and within 1e-5 of (1)."""
+    rng = np.random.default_rng(7)
+    chunk, chunks = 1_000_000, 10
+    tau = np.float64(np.float32(0.02)); xthr = np.float64(np.float32(2.4)); ththr = np.float64(np.float32(12 * 2 * np.pi / 360))
+    n_done = 0
+    for c in range(chunks):
+        s = rng.uniform([-2.6, -3, -0.25, -3.5], [2.6, 3, 0.25, 3.5], size=(chunk, 4)).astype(np.float32)
+        k = chunk // 4                                  # a quarter each: successor x / theta at a threshold (+- a few ulps)
+        sign = rng.choice([-1.0, 1.0], 2 * k)
+        jit = rng.integers(-3, 4, 2 * k)
+        x0 = (sign[:k] * xthr - tau * s[:k, 1].astype(np.float64)).astype(np.float32)
+        s[:k, 0] = np.nextafter(x0, np.where(jit[:k] > 0, np.float32(np.inf), np.float32(-np.inf))) if c % 2 else x0
+        t0 = (sign[k:] * ththr - tau * s[k:2 * k, 3].astype(np.float64)).astype(np.float32)
+        s[k:2 * k, 2] = np.nextafter(t0, np.where(jit[k:] > 0, np.float32(np.inf), np.float32(-np.inf))) if c % 2 else t0
+        a = rng.integers(0, 2, chunk).astype(np.int32)
+        ax = np.zeros((chunk, 3), np.int32); ax[:, 0] = -1
+        out = {}
+        for mode in (O.MODE_F64, O.MODE_F32):
+            e = O.OracleEnv(O.CARTPOLE, chunk, seed=0, time_limit=-1, mode=mode)
+            e.set_threads(8)
+            e.reset(); e.set_state(s.astype(np.float64), ax, 0)
+            obs, rew, done = e.step(a)
+            out[mode] = (done, e.get_state()[0], rew)
+            e.close()
+        d64, s64, r64 = out[O.MODE_F64]; d32, s32, r32 = out[O.MODE_F32]
+        assert np.array_equal(d64, d32), "engine arithmetic disagrees with the reference arithmetic on done (chunk %d)" % c
+        assert np.array_equal(r64, r32)
+        den = np.maximum(np.maximum(np.abs(s32), np.abs(s64)), [2.4, 1, 0.21, 1])
+        assert (np.abs(s32 - s64) / den).max() <= 1e-5
+        sim = HostSim(hs, O.CARTPOLE, chunk, 0, auto_reset=False)
+        sim.state[:] = s
+        so, sr, sd, bad = sim.step(a)
+        assert bad == 0 and np.array_equal(sd, d32) and np.array_equal(sr, r32)
+        assert np.array_equal(sim.abi_state(), s32.astype(np.float32))
+        n_done += int(d32.sum())
+    assert 0.2 < n_done / (chunk * chunks) < 0.8
+
+
+@pytest.mark.parametrize("name,kind,lo,hi,scale,rtol", [
+    ("Pendulum-v1", O.PENDULUM, [-40, -8], [40, 8], [3.14, 8], 1e-5),
+    ("MountainCar-v0 near the goal", O.MOUNTAINCAR, [0.40, -0.01], [0.56, 0.07], [1.2, 0.07], 1e-5),
+    ("MountainCarContinuous-v0 near the goal", O.MOUNTAINCAR_CONT, [0.36, -0.01], [0.52, 0.07], [1.2, 0.07], 1e-5),
+    ("MountainCar-v0 at the left wall", O.MOUNTAINCAR, [-1.2, -0.07], [-1.1, 0.02], [1.2, 0.07], 1e-5),
+    ("Acrobot-v1 around the terminal height", O.ACROBOT, [1.6, -2.2, -3, -5], [3.14, 2.2, 3, 5], [3.14, 3.14, 12, 28], 1e-5),
+    ("Acrobot-v1 fast", O.ACROBOT, [-3.14, -3.14, -9, -18], [3.14, 3.14, 9, 18], [3.14, 3.14, 12, 28], 1e-5),
+    # the corners of the velocity clamp box (|dtheta1| -> 4 pi, |dtheta2| -> 9 pi): one RK4 step of 0.2 s changes the
+    # velocities by tens of rad/s there and amplifies ANY rounding difference about a hundredfold (DESIGN.md section 5);
+    # random-policy episodes stay below about (6, 12) rad/s
+    ("Acrobot-v1 clamp-box corners", O.ACROBOT, [-3.14, -3.14, -12.5, -28], [3.14, 3.14, 12.5, 28], [3.14, 3.14, 12, 28], 1e-3),
+], ids=lambda v: v if isinstance(v, str) else None)
+def test_upstream_envs_teacher_forced_two_million_states(hs, name, kind, lo, hi, scale, rtol):
+    """2 x 10^6 teacher-forced states per case, concentrated where `done`, the clamps and the wall rule decide: reference
+    arithmetic (oracle F64) vs engine arithmetic (oracle F32) vs the device source on the host -- done identical in all
+    three, device source == engine arithmetic bit for bit, state within `rtol` (1e-5) of the reference arithmetic."""
+    rng = np.random.default_rng(11)
+    chunk = 500_000
+    d = O.dims(kind)
+    seen_done = 0
+    for c in range(4):
+        s = rng.uniform(lo, hi, size=(chunk, len(lo))).astype(np.float32)
+        a = (rng.integers(0, d["act_n"], chunk).astype(np.int32) if d["act_n"] else rng.uniform(-2.5, 2.5, (chunk, 1)).astype(np.float32))
+        ax = np.zeros((chunk, 3), np.int32); ax[:, 0] = -1
+        out = {}
+        for mode in (O.MODE_F64_F32STORE, O.MODE_F32):
+            e = O.OracleEnv(kind, chunk, seed=0, time_limit=-1, mode=mode)
+            e.set_threads(8)
+            e.reset(); e.set_state(s.astype(np.float64), ax, 0)
+            obs, rew, done = e.step(a)
+            out[mode] = (done, e.get_state()[0], rew, obs)
+            e.close()
+        d64, s64, r64, o64 = out[O.MODE_F64_F32STORE]; d32, s32, r32, o32 = out[O.MODE_F32]
+        assert np.array_equal(d64, d32), "done differs between the two arithmetics (chunk %d)" % c
+        diff = s32 - s64
+        if kind == O.ACROBOT:
+            diff[:, :2] = (diff[:, :2] + np.pi) % (2 * np.pi) - np.pi
+        den = np.maximum(np.maximum(np.abs(s32), np.abs(s64)), np.array(scale))
+        assert (np.abs(diff) / den).max() <= rtol
+        sim = HostSim(hs, kind, chunk, 0, auto_reset=False)
+        sim.limit = 0
+        sim.state[:] = s
+        so, sr, sd, bad = sim.step(a)
+        assert bad == 0 and np.array_equal(sd, d32) and np.array_equal(sr, r32) and np.array_equal(so, o32)
+        assert np.array_equal(sim.abi_state(), s32.astype(np.float32))
+        seen_done += int(d32.sum())
+    if kind != O.PENDULUM and "wall" not in name:
+        assert 0.02 < seen_done / (4 * chunk) < 0.98
