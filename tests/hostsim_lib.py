@@ -51,8 +51,9 @@ PRM = (-10.0, 15.0, 1.5, 0)   # gravity, wind_power, turbulence_power, enable_wi
 class HostSim:
     """Device-layout buffers + the replayed kernel bodies."""
 
-    def __init__(self, L, kind, n, seed, env_off=0, auto_reset=True):
+    def __init__(self, L, kind, n, seed, env_off=0, auto_reset=True, prm=PRM):
         self.L, self.kind, self.n, self.seed, self.off, self.auto = L, kind, n, seed, env_off, auto_reset
+        self.prm = tuple(prm)          # gravity, wind_power, turbulence_power, enable_wind
         d = O.dims(kind)
         self.sd, self.od, self.ad, self.actn = d["state_dim"], d["obs_dim"], d["act_dim"], d["act_n"]
         self.lunar = kind >= O.LUNARLANDER
@@ -67,14 +68,14 @@ class HostSim:
     def reset(self):
         obs = np.empty((self.n, self.od), np.float32)
         self.L.hostsim_reset(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
-                             self.n, self.off, self.seed, self.t, *PRM)
+                             self.n, self.off, self.seed, self.t, *self.prm)
         return obs
 
     def step(self, actions):
         a = np.ascontiguousarray(actions)
         obs = np.empty((self.n, self.od), np.float32); rew = np.empty(self.n, np.float32); done = np.empty(self.n, np.uint8)
         bad = self.L.hostsim_step(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(a),
-                                  _p(obs), _p(rew), _p(done), self.n, self.off, self.seed, self.t, self.limit, int(self.auto), *PRM)
+                                  _p(obs), _p(rew), _p(done), self.n, self.off, self.seed, self.t, self.limit, int(self.auto), *self.prm)
         self.t += 1
         return obs, rew, done, bad
 
@@ -86,7 +87,7 @@ class HostSim:
         rc = self.L.hostsim_rollout(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
                                     _p(rew), _p(done), _p(act), _p(stats), None if ep_ret is None else _p(ep_ret),
                                     None if sums is None else _p(sums), done_bits, n, k, self.off, self.seed, self.t, self.limit,
-                                    int(self.auto), int(all_out), block, *PRM)
+                                    int(self.auto), int(all_out), block, *self.prm)
         assert rc == 0, rc
         self.t += k
         return obs, rew, done, act, int(stats[0])
@@ -107,7 +108,7 @@ class HostSim:
                                         C.c_void_p(done_buf.ctypes.data + done_offset), _p(idx), _p(self.done_count), _p(self.stats),
                                         None if ep_ret is None else _p(ep_ret), None if sums is None else _p(sums), done_bits, _p(flag),
                                         n, self.off, self.seed, self.t, self.limit, int(self.auto), int(bcast is not None),
-                                        0 if bcast is None else int(bcast), self.seq, *PRM)
+                                        0 if bcast is None else int(bcast), self.seq, *self.prm)
         assert rc == 0, rc
         count = int(self.done_count[self.seq & 1])
         assert self.done_count[(self.seq + 1) & 1] == 0          # the kernel zeroes the next launch's counter
@@ -120,7 +121,7 @@ class HostSim:
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         rc = self.L.hostsim_reset_kernel(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode),
                                          None if m is None else _p(m), _p(obs), None if ep_ret is None else _p(ep_ret), self.n,
-                                         self.off, self.seed, self.t, *PRM)
+                                         self.off, self.seed, self.t, *self.prm)
         assert rc == 0, rc
         return obs
 

@@ -206,3 +206,33 @@ def test_upstream_envs_teacher_forced_two_million_states(hs, name, kind, lo, hi,
         seen_done += int(d32.sum())
     if kind != O.PENDULUM and "wall" not in name:
         assert 0.02 < seen_done / (4 * chunk) < 0.98
+
+
+@pytest.mark.parametrize("kind", [O.LUNARLANDER, O.LUNARLANDER_CONT], ids=["discrete", "continuous"])
+def test_lunarlander_wind_and_gravity_parameters_on_host(hs, kind):
+    """The constructor parameters of LunarLanderEnv (LunarLanderEnv.cs:383-410): wind and turbulence on (the double
+    tanh(sin(..) + sin(..)) of :588-596 with its two phases drawn once per env, kept across episodes) and a weaker gravity,
+    device source on the host vs oracle, bit for bit (both call the host libm here; on the GPU the wind terms may differ
+    from libm in an ulp, which tests/test_gpu_lunar.py allows for)."""
+    n, seed, off = 64, 9, 300
+    prm = (-6.5, 18.0, 1.9, 1)
+    o = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=True, time_limit=120, mode=O.MODE_F32)
+    O.lib().oracle_set_lunar_params(o.h, prm[0], prm[3], prm[1], prm[2])
+    sim = HostSim(hs, kind, n, seed, off, prm=prm)
+    sim.limit = 120
+    assert np.array_equal(sim.reset(), o.reset())
+    for k in (5, 120, 150):
+        tr = sim.rollout(k, True, 64)
+        tw = o.rollout_random(k)
+        for j, what in enumerate(("obs", "reward", "done", "actions")):
+            assert np.array_equal(tr[j], tw[j]), "%s differs in the launch of %d steps" % (what, k)
+    st, _, ot = o.get_state()
+    assert ot == sim.t and np.array_equal(sim.abi_state(), st.astype(np.float32))
+    # the wind really blew: the same envs without it fly differently
+    first = {}
+    for use_wind in (0, 1):
+        e = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=True, time_limit=120, mode=O.MODE_F32)
+        O.lib().oracle_set_lunar_params(e.h, prm[0], use_wind, prm[1], prm[2])
+        e.reset()
+        first[use_wind] = e.rollout_random(60)[0]
+    assert not np.array_equal(first[0], first[1])
