@@ -84,6 +84,7 @@ void sim_reset(const Bufs& b, float* obs, int n, uint32_t env_off, uint64_t seed
 //   1  simt.hpp: the threads of a CTA are fibers, ballots / votes / shuffles / barriers are real rendezvous, `static`
 //      stands in for __shared__.  The kernels run as written, warp-cooperative parts included.
 static int g_simt = 0;
+static const int32_t* g_seeds = nullptr;
 static void set_block(unsigned b, unsigned grid, unsigned block) { blockIdx.x = b; gridDim.x = grid; blockDim.x = block; }
 static void set_thread(unsigned t) { threadIdx.x = t; }
 
@@ -164,8 +165,9 @@ int hostsim_reset(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* ep
 int hostsim_ctor(int kind, void* state, int32_t* aux, int n, uint32_t env_off, uint64_t seed) {
     if (kind != 5 && kind != 6) return 0;
     for (int i = 0; i < n; ++i) {
-        if (kind == 5) LunarLander::ctor(state, aux, n, i, seed, env_off + (uint32_t)i);
-        else LunarLanderCont::ctor(state, aux, n, i, seed, env_off + (uint32_t)i);
+        const uint64_t sd = seed_of(g_seeds, seed, i);
+        if (kind == 5) LunarLander::ctor(state, aux, n, i, sd, env_off + (uint32_t)i);
+        else LunarLanderCont::ctor(state, aux, n, i, sd, env_off + (uint32_t)i);
     }
     return 0;
 }
@@ -184,7 +186,7 @@ int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* 
                     int k_steps, uint32_t env_off, uint64_t seed, uint64_t t, int limit, int auto_reset, int all_out, int block,
                     float gravity, float wind_power, float turbulence_power, int use_wind) {
     RolloutArgs a{};
-    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.perm = nullptr;
+    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = g_seeds; a.perm = nullptr;
     a.obs = obs; a.reward = reward; a.done = done; a.actions = actions; a.stats = stats; a.ep_ret = ep_ret; a.sums = sums;
     a.done_bits = done_bits; a.n = n; a.k_steps = k_steps; a.env_off = env_off; a.seed = seed; a.t = t; a.limit = limit;
     a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
@@ -202,6 +204,8 @@ int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* 
 
 
 // ---- the kernels themselves (not their per-thread bodies): meant for hostsim_set_simt(1) --------------------------
+// per-env seeds of VecEnv.Seed(int[]) (VecEnv.cs:48-53) for every kernel launched from now on; null = the handle's one seed
+void hostsim_set_seeds(const int32_t* seeds) { g_seeds = seeds; }
 void hostsim_set_simt(int on) { g_simt = on ? 1 : 0; }
 // thread scheduling order of the SIMT executor: 0 ascending, 1 descending, 2 pseudo-random (seeded)
 void hostsim_set_schedule(int policy, uint64_t seed) { simt::g_policy = policy; simt::g_rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull; }
@@ -228,7 +232,7 @@ int hostsim_step_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32
                         uint32_t env_off, uint64_t seed, uint64_t t, int limit, int auto_reset, int use_bcast, int32_t bcast_action,
                         uint32_t seq, float gravity, float wind_power, float turbulence_power, int use_wind) {
     StepArgs a{};
-    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.perm = perm; a.actions = actions;
+    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = g_seeds; a.perm = perm; a.actions = actions;
     a.obs = obs; a.reward = reward; a.done = done; a.done_idx = done_idx; a.done_count = done_count; a.stats = stats; a.ep_ret = ep_ret;
     a.sums = sums; a.done_bits = done_bits; a.host_invalid = host_invalid; a.n = n; a.env_off = env_off; a.seed = seed; a.t = t;
     a.limit = limit; a.use_bcast = use_bcast; a.bcast_action = bcast_action; a.seq = seq;
@@ -253,7 +257,7 @@ int hostsim_reset_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int3
                          float* obs, float* ep_ret, int n, uint32_t env_off, uint64_t seed, uint64_t t, float gravity,
                          float wind_power, float turbulence_power, int use_wind) {
     ResetArgs a{};
-    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = nullptr; a.mask = mask; a.obs = obs;
+    a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = g_seeds; a.mask = mask; a.obs = obs;
     a.ep_ret = ep_ret; a.n = n; a.env_off = env_off; a.seed = seed; a.t = t; a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
     const int grid = (n + 127) / 128;
     switch (kind) {
@@ -270,7 +274,7 @@ int hostsim_reset_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int3
 
 // sample_kernel: ActionSpace.Sample per env (mask: Discrete only, [n][ACTN] bytes, may be null)
 int hostsim_sample_kernel(int kind, const uint8_t* mask, void* out, int n, uint32_t env_off, uint64_t seed, uint64_t t) {
-    SampleArgs a{nullptr, mask, out, n, env_off, seed, t};
+    SampleArgs a{g_seeds, mask, out, n, env_off, seed, t};
     const int grid = (n + 127) / 128;
     switch (kind) {
         case 0: launch(grid, 128, [&] { sample_kernel<CartPole>(a); }); return 0;

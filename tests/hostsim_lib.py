@@ -27,6 +27,7 @@ def build():
     L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
     L.hostsim_rollout.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, I, I, I, U32, U64, U64, I, I, I, I, F, F, F, I]
     L.hostsim_set_simt.argtypes = [I]
+    L.hostsim_set_seeds.argtypes = [V]
     L.hostsim_set_schedule.argtypes = [I, U64]
     L.hostsim_step_kernel.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, V, V, V, I, V, I, U32, U64, U64, I, I, I, C.c_int32, U32, F, F, F, I]
     L.hostsim_reset_kernel.argtypes = [I, V, V, V, V, V, V, V, V, I, U32, U64, U64, F, F, F, I]
@@ -138,6 +139,18 @@ class HostSim:
         block_free = np.zeros(nb + 1, np.int32); perm = np.full(self.n, -1, np.int32)
         assert self.L.hostsim_partition(_p(self.aux), self.n, _p(block_free), _p(perm)) == nb
         return perm, block_free
+
+    def seed_each(self, seeds):
+        """gymcuda_seed_each: per-env seeds, generators restarted (episode ordinals and t back to 0, constructor draws redone)."""
+        self._seeds = np.ascontiguousarray(seeds, np.int32)
+        assert self._seeds.shape == (self.n,)
+        self.L.hostsim_set_seeds(_p(self._seeds))
+        self.episode[:] = 0
+        self.t = 0
+        self.L.hostsim_ctor(self.kind, _p(self.state), _p(self.aux), self.n, self.off, self.seed)
+
+    def unseed(self):
+        self.L.hostsim_set_seeds(None)
 
     def abi_state(self):
         """[n][state_dim] like gymcuda_get_state."""

@@ -231,3 +231,32 @@ def test_fused_step_gather_and_wait_kernels(hs):
                 assert (flags[r] == gseq).all()
             else:
                 assert hs.hostsim_gather_wait(flags[r].ctypes.data_as(C.c_void_p), world, gseq) == 1 + 2
+
+
+@pytest.mark.parametrize("kind", [O.CARTPOLE, O.ACROBOT, O.LUNARLANDER], ids=["CartPole-v1", "Acrobot-v1", "LunarLander-v2"])
+def test_per_env_seeds(hs, kind):
+    """VecEnv.Seed(int[]) (VecEnv.cs:48-53): every env draws from the stream of ITS seed -- reset, random policy,
+    LunarLander's constructor and per-step dispersion draws -- in every kernel."""
+    n = 130
+    o, sim = pair(hs, kind, n)
+    seeds = np.random.default_rng(3).integers(-2**31, 2**31, n).astype(np.int32)
+    seeds[:4] = [0, 5, 5, -1]
+    o.seed_each(seeds)
+    sim.seed_each(seeds)
+    try:
+        obs = sim.reset_kernel()
+        assert np.array_equal(obs, o.reset())
+        assert not np.array_equal(obs[1], obs[2])                    # same seed, different env id: different streams
+        for t in range(12):
+            a = o.sample_actions()
+            assert np.array_equal(sim.sample_kernel(), a)
+            oo, orr, od = o.step(a)
+            so, sr, sd, idx, flag = sim.step_kernel(a)
+            assert np.array_equal(so, oo) and np.array_equal(sr, orr) and np.array_equal(sd, od)
+        tr = sim.rollout(70, True, 64)
+        tw = o.rollout_random(70)
+        for j, what in enumerate(("obs", "reward", "done", "actions")):
+            assert np.array_equal(tr[j], tw[j]), what
+        assert same_state(o, sim)
+    finally:
+        sim.unseed()
