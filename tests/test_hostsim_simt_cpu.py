@@ -260,3 +260,32 @@ def test_per_env_seeds(hs, kind):
         assert same_state(o, sim)
     finally:
         sim.unseed()
+
+
+@pytest.mark.parametrize("kind,n", [(O.CARTPOLE, 150), (O.MOUNTAINCAR, 97), (O.PENDULUM, 64)], ids=["CartPole-v1", "MountainCar-v0", "Pendulum-v1"])
+def test_reference_semantics_without_auto_reset(hs, kind, n):
+    """Auto-reset off = the reference's semantics: a finished env keeps stepping until the caller resets it; CartPole
+    then counts steps_beyond_done and pays 1, 0, 0, ... (CartPoleEnv.cs:168-183), and `done` stays up."""
+    o = O.OracleEnv(kind, n, seed=8, env_id_offset=3, auto_reset=False, mode=O.MODE_F32)
+    sim = HostSim(hs, kind, n, 8, 3, auto_reset=False)
+    assert np.array_equal(sim.reset_kernel(), o.reset())
+    for t in range(60):
+        a = o.sample_actions()
+        oo, orr, od = o.step(a)
+        so, sr, sd, idx, flag = sim.step_kernel(a)
+        assert np.array_equal(so, oo) and np.array_equal(sr, orr) and np.array_equal(sd, od), "step %d" % t
+        assert np.array_equal(np.sort(idx), np.nonzero(od)[0])
+    for k, all_out in ((21, True), (40, False), (160, True)):
+        tr = sim.rollout(k, all_out, 64)
+        tw = o.rollout_random(k)
+        for j, what in enumerate(("obs", "reward", "done", "actions")):
+            assert np.array_equal(tr[j], tw[j]), "%s differs in the launch of %d steps" % (what, k)
+    st, aux, ot = o.get_state()
+    assert ot == sim.t and np.array_equal(sim.abi_state(), st.astype(F32))
+    if kind == O.CARTPOLE:
+        assert np.array_equal(sim.sbd, aux[:, 0]) and (sim.sbd > 0).any()      # poles fell and kept being stepped
+        assert (tw[1][-1][sim.sbd > 0] == 0).all()                             # ... for a reward of 0
+    # the caller's reset of the finished envs (README.md:36-40), as a masked reset
+    mask = (tw[2][-1] != 0).astype(np.uint8)
+    assert np.array_equal(sim.reset_kernel(mask), o.reset(mask))
+    assert same_state(o, sim)
