@@ -105,6 +105,21 @@ namespace Gym.Environments.Vector {
         }
         public GymCudaStats Stats(bool reset = false) { Native.Check(Native.gymcuda_get_stats(_h, out var s, reset ? 1 : 0)); return s; }
 
+        // ---- observation / reward normalisation on device (what callers otherwise keep by hand, BasePlaySession.cs:58-69)
+        public void NormalizeConfig(float gamma = 0.99f, float epsilon = 1e-8f, float clipObs = 10f, float clipReward = 10f) {
+            Native.Check(Native.gymcuda_normalize_config(_h, gamma, epsilon, clipObs, clipReward));
+        }
+        /// <summary>Normalises the arrays in place; update: add this batch to the running statistics first.</summary>
+        public void Normalize(float[] obs, float[] reward, byte[] done, bool update = true) {
+            Native.Check(Native.gymcuda_normalize(_h, obs, reward, done, update ? 1 : 0));
+        }
+        public (double[] obsMean, double[] obsVar, double returnVar, double count) NormalizeStats() {
+            var mean = new double[_info.ObsDim]; var variance = new double[_info.ObsDim];
+            Native.Check(Native.gymcuda_normalize_get(_h, mean, variance, out double rv, out double c));
+            return (mean, variance, rv, c);
+        }
+        public void NormalizeReset() { Native.Check(Native.gymcuda_normalize_reset(_h)); }
+
         private NDArray[] SplitObservations() {
             var res = new NDArray[NumberOfEnvironments];
             int d = _info.ObsDim;

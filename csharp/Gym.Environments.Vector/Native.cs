@@ -79,6 +79,11 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_set_state(GymCudaHandle env, float[] state, int[] aux, ulong t);
         [DllImport(Lib)] internal static extern int gymcuda_observe(GymCudaHandle env, float[] obs);
         [DllImport(Lib)] internal static extern int gymcuda_get_stats(GymCudaHandle env, out GymCudaStats stats, int resetCounters);
+        [DllImport(Lib)] internal static extern int gymcuda_normalize_config(GymCudaHandle env, float gamma, float epsilon, float clipObs, float clipReward);
+        [DllImport(Lib)] internal static extern int gymcuda_normalize(GymCudaHandle env, float[] obs, float[] reward, byte[] done, int update);
+        [DllImport(Lib)] internal static extern int gymcuda_normalize_device(GymCudaHandle env, IntPtr dObs, IntPtr dReward, IntPtr dDone, int update);
+        [DllImport(Lib)] internal static extern int gymcuda_normalize_get(GymCudaHandle env, double[] obsMean, double[] obsVar, out double returnVar, out double count);
+        [DllImport(Lib)] internal static extern int gymcuda_normalize_reset(GymCudaHandle env);
         [DllImport(Lib)] internal static extern int gymcuda_set_stream(GymCudaHandle env, IntPtr cudaStream);
         [DllImport(Lib)] internal static extern int gymcuda_sync(GymCudaHandle env);
         [DllImport(Lib)] internal static extern int gymcuda_host_alloc(out IntPtr ptr, UIntPtr bytes);

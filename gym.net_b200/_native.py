@@ -69,6 +69,11 @@ SYMBOLS = {
     "gymcuda_set_state": (_I, [_VP, _VP, _VP, _U64]),
     "gymcuda_observe": (_I, [_VP, _VP]),
     "gymcuda_get_stats": (_I, [_VP, C.POINTER(Stats), _I]),
+    "gymcuda_normalize_config": (_I, [_VP, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "gymcuda_normalize_device": (_I, [_VP, _VP, _VP, _VP, _I]),
+    "gymcuda_normalize": (_I, [_VP, _VP, _VP, _VP, _I]),
+    "gymcuda_normalize_get": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "gymcuda_normalize_reset": (_I, [_VP]),
     "gymcuda_set_stream": (_I, [_VP, _VP]),
     "gymcuda_sync": (_I, [_VP]),
     "gymcuda_host_alloc": (_I, [C.POINTER(_VP), C.c_size_t]),

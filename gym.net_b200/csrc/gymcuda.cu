@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "normalize.cuh"
 #ifdef GYMCUDA_WITH_LUNAR
 #include "lunar.cuh"
 #endif
@@ -148,6 +149,9 @@ struct gymcuda_env {
     double* d_sums;
     bool ep_stats, done_bits;
     const float* last_obs;   // device pointer of the most recent observations
+    // observation / reward normalisation (normalize.cuh), allocated by the first call
+    double* d_norm_acc; float* d_norm_ret;
+    float norm_gamma, norm_eps, norm_clip_obs, norm_clip_reward;
     // pinned scratch: [0..1] stats, [2] done_count
     unsigned long long* h_small;
     unsigned long long invalid_seen, env_steps;
@@ -314,6 +318,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
     for (int k = 0; k < 4; ++k) cudaFree(e->scratch[k]);
+    cudaFree(e->d_norm_acc); cudaFree(e->d_norm_ret);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -414,6 +419,7 @@ int gymcuda_create(const gymcuda_config* cfg, gymcuda_env** out) {
     if (e->ep_stats && e->limit == 0) e->limit = 0x7fffffff;   // the episode-step counter doubles as the episode length
     e->seed = cfg->seed;
     e->last_obs = nullptr;
+    e->norm_gamma = 0.99f; e->norm_eps = 1e-8f; e->norm_clip_obs = 10.0f; e->norm_clip_reward = 10.0f;
     e->prm = EnvParams{cfg->gravity, cfg->wind_power, cfg->turbulence_power, cfg->enable_wind ? 1 : 0};
     e->auxw = cfg->env_kind >= GYMCUDA_LUNARLANDER ? ki.aux - 2 : 0;
     int rc = create_impl(cfg, e);
@@ -885,6 +891,90 @@ int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
         e->env_steps = 0;
         e->invalid_seen = 0;
     }
+    return GYMCUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observation / reward normalisation (normalize.cuh)
+// ------------------------------------------------------------------------------------------------
+static int norm_reserve(gymcuda_env* e) {
+    if (e->d_norm_acc) return GYMCUDA_OK;
+    if (e->ki.od > NORM_MAX_OD) return fail(GYMCUDA_EINVAL, "normalisation supports at most %d observation components", NORM_MAX_OD);
+    CU_TRY(cudaMalloc(&e->d_norm_acc, NORM_ACC * sizeof(double)));
+    CU_TRY(cudaMalloc(&e->d_norm_ret, (size_t)e->n * 4));
+    CU_TRY(cudaMemsetAsync(e->d_norm_acc, 0, NORM_ACC * sizeof(double), e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_norm_ret, 0, (size_t)e->n * 4, e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_normalize_config(gymcuda_env* e, float gamma, float epsilon, float clip_obs, float clip_reward) {
+    ENTER(e);
+    if (!(gamma >= 0.0f && gamma <= 1.0f) || !(epsilon > 0.0f) || !(clip_obs > 0.0f) || !(clip_reward > 0.0f))
+        return fail(GYMCUDA_EINVAL, "normalize_config: gamma in [0, 1], epsilon > 0, clips > 0");
+    e->norm_gamma = gamma; e->norm_eps = epsilon; e->norm_clip_obs = clip_obs; e->norm_clip_reward = clip_reward;
+    return GYMCUDA_OK;
+}
+
+int gymcuda_normalize_reset(gymcuda_env* e) {
+    ENTER(e);
+    if (int rc = norm_reserve(e)) return rc;
+    CU_TRY(cudaMemsetAsync(e->d_norm_acc, 0, NORM_ACC * sizeof(double), e->stream));
+    CU_TRY(cudaMemsetAsync(e->d_norm_ret, 0, (size_t)e->n * 4, e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_normalize_device(gymcuda_env* e, float* d_obs, float* d_reward, const uint8_t* d_done, int update) {
+    ENTER(e);
+    if (!d_obs && !d_reward) return fail(GYMCUDA_EINVAL, "normalize: obs and reward are both null");
+    if (int rc = check_device_buffers(e, nullptr, nullptr, d_reward)) return rc;
+    if (d_obs && !is_aligned(d_obs, 4)) return fail(GYMCUDA_EINVAL, "device observation buffer must be 4-byte aligned");
+    if (int rc = norm_reserve(e)) return rc;
+    NormArgs a{};
+    a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.ret = e->d_norm_ret; a.acc = e->d_norm_acc; a.n = e->n; a.od = e->ki.od;
+    a.gamma = e->norm_gamma; a.eps = e->norm_eps; a.clip_obs = e->norm_clip_obs; a.clip_reward = e->norm_clip_reward;
+    const int grid = (e->n + NORM_BLOCK - 1) / NORM_BLOCK;
+    if (update) norm_update_kernel<<<grid, NORM_BLOCK, 0, e->stream>>>(a);
+    norm_apply_kernel<<<grid, NORM_BLOCK, 0, e->stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    if (d_obs == e->last_obs) e->last_obs = nullptr;   // the handle's copy now holds normalised values
+    return GYMCUDA_OK;
+}
+
+int gymcuda_normalize(gymcuda_env* e, float* obs, float* reward, const uint8_t* done, int update) {
+    ENTER(e);
+    if (!obs && !reward) return fail(GYMCUDA_EINVAL, "normalize: obs and reward are both null");
+    const size_t n = (size_t)e->n;
+    if (obs) CU_TRY(cudaMemcpyAsync(e->d_obs, obs, e->obs_bytes(), cudaMemcpyHostToDevice, e->stream));
+    if (reward) CU_TRY(cudaMemcpyAsync(e->d_reward, reward, n * 4, cudaMemcpyHostToDevice, e->stream));
+    if (done) CU_TRY(cudaMemcpyAsync(e->d_done, done, n, cudaMemcpyHostToDevice, e->stream));
+    int rc = gymcuda_normalize_device(e, obs ? e->d_obs : nullptr, reward ? e->d_reward : nullptr, done ? e->d_done : nullptr, update);
+    if (rc) return rc;
+    e->last_obs = nullptr;
+    if (obs) CU_TRY(cudaMemcpyAsync(obs, e->d_obs, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
+    if (reward) CU_TRY(cudaMemcpyAsync(reward, e->d_reward, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
+int gymcuda_normalize_get(gymcuda_env* e, double* obs_mean, double* obs_var, double* return_var, double* count) {
+    ENTER(e);
+    if (int rc = norm_reserve(e)) return rc;
+    double acc[NORM_ACC];
+    CU_TRY(cudaMemcpyAsync(acc, e->d_norm_acc, sizeof(acc), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    const double c = acc[NORM_VALUES];
+    for (int j = 0; j < e->ki.od; ++j) {
+        const double mean = c > 0.0 ? acc[j] / c : 0.0;
+        double var = c > 0.0 ? acc[NORM_MAX_OD + j] / c - mean * mean : 1.0;
+        if (obs_mean) obs_mean[j] = mean;
+        if (obs_var) obs_var[j] = var > 0.0 ? var : 0.0;
+    }
+    if (return_var) {
+        const double mean = c > 0.0 ? acc[2 * NORM_MAX_OD] / c : 0.0;
+        const double var = c > 0.0 ? acc[2 * NORM_MAX_OD + 1] / c - mean * mean : 1.0;
+        *return_var = var > 0.0 ? var : 0.0;
+    }
+    if (count) *count = c;
     return GYMCUDA_OK;
 }
 

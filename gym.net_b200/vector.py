@@ -196,6 +196,34 @@ class CudaVecEnv:
         return {"env_steps": s.env_steps, "episodes": s.episodes, "invalid_actions": s.invalid_actions,
                 "return_sum": s.return_sum, "length_sum": s.length_sum}
 
+    # ---- observation / reward normalisation (the VecNormalize recipe, on device) -----------------------
+    def NormalizeConfig(self, gamma=0.99, epsilon=1e-8, clip_obs=10.0, clip_reward=10.0):
+        N.check(self._L.gymcuda_normalize_config(self._h, gamma, epsilon, clip_obs, clip_reward))
+
+    def Normalize(self, obs=None, reward=None, done=None, update=True):
+        """In place on float32 host arrays: obs <- clip((obs - mean) / sqrt(var + eps)), reward <- clip(reward /
+        sqrt(var of the discounted return + eps)); update=True adds this batch to the running statistics first."""
+        n = self.NumberOfEnvironments
+        for name, a, shape, dt in (("obs", obs, (n, self.obs_dim), np.float32), ("reward", reward, (n,), np.float32),
+                                   ("done", done, (n,), np.uint8)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == dt and a.shape == shape and a.flags.c_contiguous):
+                raise ValueError("%s must be a C-contiguous %s array of shape %s (it is normalised in place)" % (name, np.dtype(dt).name, shape))
+        N.check(self._L.gymcuda_normalize(self._h, _ptr(obs), _ptr(reward), _ptr(done), 1 if update else 0))
+        return obs, reward
+
+    def NormalizeDevice(self, d_obs=0, d_reward=0, d_done=0, update=True):
+        N.check(self._L.gymcuda_normalize_device(self._h, C.c_void_p(d_obs or 0), C.c_void_p(d_reward or 0),
+                                                 C.c_void_p(d_done or 0), 1 if update else 0))
+
+    def NormalizeStats(self):
+        mean = np.zeros(self.obs_dim, np.float64); var = np.zeros(self.obs_dim, np.float64)
+        rv = C.c_double(); cnt = C.c_double()
+        N.check(self._L.gymcuda_normalize_get(self._h, _ptr(mean), _ptr(var), C.byref(rv), C.byref(cnt)))
+        return {"obs_mean": mean, "obs_var": var, "return_var": rv.value, "count": cnt.value}
+
+    def NormalizeReset(self):
+        N.check(self._L.gymcuda_normalize_reset(self._h))
+
     # ---- device-pointer API (torch tensors / raw pointers) ------------------------------------------
     def SetStream(self, cuda_stream):
         N.check(self._L.gymcuda_set_stream(self._h, C.c_void_p(cuda_stream or 0)))

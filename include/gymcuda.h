@@ -177,6 +177,21 @@ typedef struct gymcuda_stats {
 } gymcuda_stats;
 int gymcuda_get_stats(gymcuda_env* env, gymcuda_stats* out, int reset_counters);
 
+/* ---- observation / reward normalisation: the wrapper every learner adds around Env.Step (the reference's callers keep
+ * their running statistics by hand, examples/.../BasePlaySession.cs:58-69) -- SURVEY 8f rank 3 -------------------------
+ * Running mean / variance of every observation component and of the per-env discounted return (ret = ret * gamma + reward,
+ * zeroed where `done`), accumulated over all envs and calls on the device (double sums); then, in place,
+ *   obs <- clip((obs - mean) / sqrt(var + epsilon), +-clip_obs),   reward <- clip(reward / sqrt(var_ret + epsilon), +-clip_reward).
+ * update != 0: the batch is added to the statistics before it is normalised (training); 0: statistics frozen (evaluation).
+ * obs / reward may each be NULL (left alone); done may be NULL (no episode ended).  Defaults: gamma 0.99, epsilon 1e-8,
+ * clips 10.  *_device: device pointers (the step's own output buffers), asynchronous on the handle's stream. */
+int gymcuda_normalize_config(gymcuda_env* env, float gamma, float epsilon, float clip_obs, float clip_reward);
+int gymcuda_normalize_device(gymcuda_env* env, float* d_obs, float* d_reward, const uint8_t* d_done, int update);
+int gymcuda_normalize(gymcuda_env* env, float* obs, float* reward, const uint8_t* done, int update);
+/* obs_mean / obs_var: [obs_dim]; any pointer may be NULL.  count = envs accumulated so far. */
+int gymcuda_normalize_get(gymcuda_env* env, double* obs_mean, double* obs_var, double* return_var, double* count);
+int gymcuda_normalize_reset(gymcuda_env* env);
+
 /* ---- streams, pinned memory -------------------------------------------------------------------- */
 /* Use the caller's CUDA stream (cudaStream_t) for every launch and copy; NULL restores the
  * handle's own stream (to target the legacy default stream pass cudaStreamLegacy, not 0). */

@@ -14,6 +14,7 @@
 #include "env_classic.cuh"
 #include "lunar.cuh"
 #include "kernels.cuh"
+#include "normalize.cuh"
 
 using namespace gymcuda;
 
@@ -295,6 +296,19 @@ int hostsim_partition(const int32_t* aux, int n, int32_t* block_free, int32_t* p
     launch(1, 1024, [&] { partition_scan_kernel(block_free, nb); });
     launch(nb, PART_BLOCK, [&] { partition_scatter_kernel(aux, n, block_free, nb, perm); });
     return nb;
+}
+
+
+// normalize.cuh: the two launches of gymcuda_normalize_device
+int hostsim_normalize(float* obs, float* reward, const uint8_t* done, float* ret, double* acc, int n, int od, float gamma, float eps,
+                      float clip_obs, float clip_reward, int update) {
+    NormArgs a{};
+    a.obs = obs; a.reward = reward; a.done = done; a.ret = ret; a.acc = acc; a.n = n; a.od = od;
+    a.gamma = gamma; a.eps = eps; a.clip_obs = clip_obs; a.clip_reward = clip_reward;
+    const int grid = (n + NORM_BLOCK - 1) / NORM_BLOCK;
+    if (update) launch(grid, NORM_BLOCK, [&] { norm_update_kernel(a); });
+    launch(grid, NORM_BLOCK, [&] { norm_apply_kernel(a); });
+    return 0;
 }
 
 }  // extern "C"

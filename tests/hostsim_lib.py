@@ -16,7 +16,7 @@ LIB = os.path.join(HS_DIR, "_hostsim.so")
 
 def build():
     srcs = [os.path.join(HS_DIR, "hostsim.cpp"), os.path.join(HS_DIR, "stubs", "cuda_runtime.h"), os.path.join(HS_DIR, "simt.hpp")] + [
-        os.path.join(CSRC, f) for f in ("detmath.cuh", "philox.cuh", "env_classic.cuh", "lunar.cuh", "lunar_core.cuh", "kernels.cuh")]
+        os.path.join(CSRC, f) for f in ("detmath.cuh", "philox.cuh", "env_classic.cuh", "lunar.cuh", "lunar_core.cuh", "kernels.cuh", "normalize.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + os.path.join(HS_DIR, "stubs"),
                         "-I" + CSRC, "-shared", "-fPIC", "-o", LIB, srcs[0]], check=True)
@@ -33,6 +33,7 @@ def build():
     L.hostsim_reset_kernel.argtypes = [I, V, V, V, V, V, V, V, V, I, U32, U64, U64, F, F, F, I]
     L.hostsim_sample_kernel.argtypes = [I, V, V, I, U32, U64, U64]
     L.hostsim_partition.argtypes = [V, I, V, V]
+    L.hostsim_normalize.argtypes = [V, V, V, V, V, I, I, F, F, F, F, I]
     L.hostsim_set_gather.argtypes = [I, I, U32, V, V, V]
     L.hostsim_gather_wait.argtypes = [V, I, U32]
     L.hostsim_div_inrange.argtypes = [V, V, V, C.c_size_t]
@@ -157,3 +158,39 @@ class HostSim:
         return self.state.T.copy() if self.lunar else self.state.copy()
 
 
+
+
+class NormalizeModel:
+    """numpy restatement of gymcuda_normalize (include/gymcuda.h; the VecNormalize recipe): the checker of both the host
+    build of normalize.cuh (tests/test_hostsim_simt_cpu.py) and the CUDA build (tests/test_gpu_classic.py)."""
+
+    def __init__(self, n, od, gamma=0.99, eps=1e-8, clip_obs=10.0, clip_reward=10.0):
+        self.n, self.od = n, od
+        self.gamma, self.eps, self.clip_obs, self.clip_reward = np.float32(gamma), np.float32(eps), np.float32(clip_obs), np.float32(clip_reward)
+        self.s = np.zeros(od); self.q = np.zeros(od); self.sr = 0.0; self.qr = 0.0; self.count = 0.0
+        self.ret = np.zeros(n, np.float32)
+
+    def __call__(self, obs, reward, done, update=True):
+        """Returns normalised copies (float32) of obs / reward (None stays None)."""
+        if update:
+            if obs is not None:
+                x = obs.astype(np.float64)
+                self.s += x.sum(axis=0); self.q += (x * x).sum(axis=0)
+            if reward is not None:
+                r = (self.ret * self.gamma).astype(np.float32) + reward          # float32 multiply, then float32 add
+                r64 = r.astype(np.float64)
+                self.sr += r64.sum(); self.qr += (r64 * r64).sum()
+                self.ret = np.where(done != 0, np.float32(0), r).astype(np.float32) if done is not None else r
+            self.count += self.n
+        if self.count <= 0:
+            return obs, reward
+        out_o = out_r = None
+        if obs is not None:
+            mean = self.s / self.count
+            var = np.maximum(self.q / self.count - mean * mean, 0.0)
+            out_o = np.clip(((obs.astype(np.float64) - mean) / np.sqrt(var + np.float64(self.eps))).astype(np.float32), -self.clip_obs, self.clip_obs)
+        if reward is not None:
+            mean = self.sr / self.count
+            var = max(self.qr / self.count - mean * mean, 0.0)
+            out_r = np.clip((reward.astype(np.float64) / np.sqrt(var + np.float64(self.eps))).astype(np.float32), -self.clip_reward, self.clip_reward)
+        return out_o, out_r

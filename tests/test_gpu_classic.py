@@ -692,3 +692,35 @@ def test_episode_statistics_and_truncation_bits():
     s2 = env2.Stats()
     assert s2["length_sum"] == ls and abs(s2["return_sum"] - rs) < 1e-6 * max(1.0, rs) and env2.TimeLimit == 0
     env.Close(); env2.Close()
+
+
+def test_observation_and_reward_normalisation():
+    """gymcuda_normalize against its numpy restatement: running statistics over many steps, in-place
+    normalisation with clipping, an evaluation-mode call with frozen statistics, and the statistics read back."""
+    from hostsim_lib import NormalizeModel
+    n = 3000
+    env = G.PendulumVecEnv(n, seed=2, auto_reset=True)
+    env.ResetBatch()
+    env.NormalizeConfig(0.95, 1e-6, 1.5, 5.0)
+    model = NormalizeModel(n, 3, 0.95, 1e-6, 1.5, 5.0)
+    rng = np.random.default_rng(4)
+    for t in range(230):                                  # past Pendulum's 200-step limit: returns are reset at `done`
+        a = rng.uniform(-2, 2, (n, 1)).astype(np.float32)
+        obs, rew, done = env.StepBatch(a)
+        update = t % 7 != 6
+        want_o, want_r = model(obs, rew, done, update)
+        got_o, got_r = obs.copy(), rew.copy()
+        env.Normalize(got_o, got_r, done, update=update)
+        assert np.allclose(got_o, want_o, rtol=1e-5, atol=1e-5), "observations at step %d" % t
+        assert np.allclose(got_r, want_r, rtol=1e-5, atol=1e-5), "rewards at step %d" % t
+    assert (np.abs(got_o) == 1.5).any()                   # the clip is active
+    st = env.NormalizeStats()
+    assert st["count"] == model.count
+    mean = model.s / model.count
+    assert np.allclose(st["obs_mean"], mean, rtol=1e-9, atol=1e-12)
+    assert np.allclose(st["obs_var"], model.q / model.count - mean * mean, rtol=1e-7)
+    mr = model.sr / model.count
+    assert np.isclose(st["return_var"], model.qr / model.count - mr * mr, rtol=1e-7)
+    env.NormalizeReset()
+    assert env.NormalizeStats()["count"] == 0
+    env.Close()

@@ -289,3 +289,32 @@ def test_reference_semantics_without_auto_reset(hs, kind, n):
     mask = (tw[2][-1] != 0).astype(np.uint8)
     assert np.array_equal(sim.reset_kernel(mask), o.reset(mask))
     assert same_state(o, sim)
+
+
+@pytest.mark.parametrize("n,od", [(1000, 4), (257, 8), (64, 3), (31, 2)])
+def test_normalize_kernels_against_numpy(hs, n, od):
+    """normalize.cuh (gymcuda_normalize_device) on the host: running mean / variance of the observation components and of
+    the discounted return over several batches (warp shuffles + shared-memory rows + one atomic per value and CTA), the
+    in-place normalisation with clipping, frozen statistics, and the return reset at `done` -- against numpy float64."""
+    from hostsim_lib import NormalizeModel, _p
+    rng = np.random.default_rng(n)
+    model = NormalizeModel(n, od, gamma=0.97, eps=1e-6, clip_obs=1.5, clip_reward=4.0)
+    acc = np.zeros(19, np.float64); ret = np.zeros(n, np.float32)
+    scale = rng.uniform(0.1, 30.0, od); shift = rng.uniform(-5, 5, od)
+    for it in range(6):
+        obs = (rng.standard_normal((n, od)) * scale + shift).astype(F32)
+        rew = rng.uniform(-2, 3, n).astype(F32)
+        done = (rng.random(n) < 0.2).astype(np.uint8)
+        update = it != 4                                         # one evaluation-mode call: statistics frozen
+        want_o, want_r = model(obs, rew, done, update)
+        got_o, got_r = obs.copy(), rew.copy()
+        hs.hostsim_normalize(_p(got_o), _p(got_r), _p(done), _p(ret), _p(acc), n, od, 0.97, 1e-6, 1.5, 4.0, int(update))
+        assert np.allclose(got_o, want_o, rtol=1e-6, atol=1e-6) and np.allclose(got_r, want_r, rtol=1e-6, atol=1e-6)
+        assert np.array_equal(ret, model.ret)
+        assert acc[18] == model.count and np.allclose(acc[:od], model.s, rtol=1e-12) and np.allclose(acc[8:8 + od], model.q, rtol=1e-12)
+        assert (np.abs(got_o) <= 1.5).all() and (np.abs(got_o) == 1.5).any()         # the clip is active
+    # obs only / reward only
+    obs = rng.standard_normal((n, od)).astype(F32); got = obs.copy()
+    want, _ = model(obs, None, None, True)
+    hs.hostsim_normalize(_p(got), None, None, _p(ret), _p(acc), n, od, 0.97, 1e-6, 1.5, 4.0, 1)
+    assert np.allclose(got, want, rtol=1e-6, atol=1e-6)
