@@ -465,6 +465,13 @@ def test_registered_and_mixed_host_buffers(registered):
     a_env.Close(); b_env.Close()
 
 
+# Added after this round's last GPU session (the GPU budget was spent): verified on the host SIMT executor / by construction,
+# never yet run on a B200.  Non-strict xfail keeps an unexpected failure from hiding the rest of the suite behind `-x`;
+# a pass shows up as XPASS -- drop the marker then.
+NOT_YET_RUN_ON_GPU = pytest.mark.xfail(reason="added after the round's last GPU session; not yet run on a B200", strict=False)
+
+
+@NOT_YET_RUN_ON_GPU
 def test_registered_buffers_aligned_like_managed_arrays():
     """A GCHandle-pinned managed float[] starts 8 mod 16: the kernel's float4 observation stores cannot address it in
     place, so that one buffer is staged while the others stay zero-copy -- same results either way."""
@@ -694,6 +701,7 @@ def test_episode_statistics_and_truncation_bits():
     env.Close(); env2.Close()
 
 
+@NOT_YET_RUN_ON_GPU
 def test_observation_and_reward_normalisation():
     """gymcuda_normalize against its numpy restatement: running statistics over many steps, in-place
     normalisation with clipping, an evaluation-mode call with frozen statistics, and the statistics read back."""
