@@ -46,17 +46,17 @@ constexpr int BASE_EDGE = 10;
 
 // Box2D-2.3 / Farseer-3.5 lineage settings
 constexpr float LINEAR_SLOP = 0.005f;
-constexpr float ANGULAR_SLOP = 0.03490658476948738f;          // 2/180*pi
+constexpr float ANGULAR_SLOP = 0.03490658849477768f;          // (2.0f / 180.0f * Pi) folded in float32 like the C# / C++ constant expression (NOT the double product rounded once: 0.034906584769…)
 constexpr float POLYGON_RADIUS = 0.01f;                      // 2 * linearSlop
 constexpr float BAUMGARTE = 0.2f;
 constexpr float MAX_LINEAR_CORRECTION = 0.2f;
-constexpr float MAX_ANGULAR_CORRECTION = 0.13962633907794952f;  // 8/180*pi
+constexpr float MAX_ANGULAR_CORRECTION = 0.13962635397911072f;  // (8.0f / 180.0f * Pi), float32 folding
 constexpr float MAX_TRANSLATION = 2.0f;
 constexpr float MAX_ROTATION = 1.5707963705062866f;          // 0.5*pi
 constexpr float VELOCITY_THRESHOLD = 1.0f;
 constexpr float TIME_TO_SLEEP = 0.5f;
 constexpr float LINEAR_SLEEP_TOL = 0.01f;
-constexpr float ANGULAR_SLEEP_TOL = 0.03490658476948738f;
+constexpr float ANGULAR_SLEEP_TOL = 0.03490658849477768f;
 constexpr int VELOCITY_ITERATIONS = 180, POSITION_ITERATIONS = 60;   // :723-724
 constexpr float DEFAULT_FRICTION = 0.2f;
 
@@ -383,7 +383,7 @@ __device__ __noinline__ void world_step(Lander& L) {
                     for (int s = 0; s < MAXC; ++s) {
                         if (L.c[s].pair != pair) continue;
                         for (int k = 0; k < m.count; ++k)
-                            for (int o = 0; o < 2; ++o)
+                            for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
                                 if (L.c[s].key[o] != NO_KEY && L.c[s].key[o] == m.key[k]) {
                                     c.p[k].normal_impulse = L.c[s].ni[o]; c.p[k].tangent_impulse = L.c[s].ti[o];
                                 }

@@ -50,17 +50,17 @@ static const int BASE_EDGE = 10;
 
 // Box2D-2.3 / Farseer-3.5 lineage settings
 static const float LINEAR_SLOP = 0.005f;
-static const float ANGULAR_SLOP = 0.03490658476948738f;          // 2/180*pi
+static const float ANGULAR_SLOP = 0.03490658849477768f;          // (2.0f / 180.0f * Pi) folded in float32 like the C# / C++ constant expression (NOT the double product rounded once: 0.034906584769…)
 static const float POLYGON_RADIUS = 0.01f;                      // 2 * linearSlop
 static const float BAUMGARTE = 0.2f;
 static const float MAX_LINEAR_CORRECTION = 0.2f;
-static const float MAX_ANGULAR_CORRECTION = 0.13962633907794952f;  // 8/180*pi
+static const float MAX_ANGULAR_CORRECTION = 0.13962635397911072f;  // (8.0f / 180.0f * Pi), float32 folding
 static const float MAX_TRANSLATION = 2.0f;
 static const float MAX_ROTATION = 1.5707963705062866f;          // 0.5*pi
 static const float VELOCITY_THRESHOLD = 1.0f;
 static const float TIME_TO_SLEEP = 0.5f;
 static const float LINEAR_SLEEP_TOL = 0.01f;
-static const float ANGULAR_SLEEP_TOL = 0.03490658476948738f;
+static const float ANGULAR_SLEEP_TOL = 0.03490658849477768f;
 static const int VELOCITY_ITERATIONS = 180, POSITION_ITERATIONS = 60;   // :723-724
 static const float DEFAULT_FRICTION = 0.2f;
 
@@ -391,7 +391,7 @@ inline void world_step(Lander& L) {
                     for (int s = 0; s < MAXC; ++s) {
                         if (L.c[s].pair != pair) continue;
                         for (int k = 0; k < m.count; ++k)
-                            for (int o = 0; o < 2; ++o)
+                            for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
                                 if (L.c[s].key[o] != NO_KEY && L.c[s].key[o] == m.key[k]) {
                                     c.p[k].normal_impulse = L.c[s].ni[o]; c.p[k].tangent_impulse = L.c[s].ti[o];
                                 }
