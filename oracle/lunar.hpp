@@ -65,6 +65,8 @@ static const int VELOCITY_ITERATIONS = 180, POSITION_ITERATIONS = 60;   // :723-
 static const float DEFAULT_FRICTION = 0.2f;
 
 static const int MAXC = 6;   // touching manifolds kept per lander
+static const int MAXP = 12;  // broad-phase pairs (contacts that exist, touching or not) kept per lander, in creation order
+static const float AABB_EXTENSION = 0.1f, AABB_MULTIPLIER = 2.0f;   // Settings.AABBExtension / AABBMultiplier
 
 // ---------------------------------------------------------------- small vector algebra (b2Math)
 struct V2 { float x, y; };
@@ -135,6 +137,8 @@ struct Lander {
     V2 force;                  // force accumulator of the fuselage (ApplyForce in Reset, :496)
     float torque;
     uint32_t touch[3];         // bit e of touch[body]: polygon `body` was touching edge e after the last Collide
+    float fat[3][4];           // broad-phase proxy box of each polygon (lo.x, lo.y, hi.x, hi.y): replaced only when the swept tight box leaves it
+    uint32_t pairs[3];         // the contacts that exist (fat boxes overlap), in creation order: byte k = body * 16 + edge, 0xff = none
     int32_t flags;
     int32_t wind_idx, torque_idx;
     float gravity, wind_power, turbulence_power;
@@ -142,8 +146,8 @@ struct Lander {
     float obs[8];
 };
 
-static const int STATE_DIM = 21 + 8 + 4 * MAXC + CHUNKS + 1 + 3;        // 68
-static const int AUX_DIM = 3 + 1 + 2 + 3 * MAXC + 2 + 2;                  // touch[3], flags, limit[2], slots, wind idx, ep_t, episode
+static const int STATE_DIM = 21 + 8 + 4 * MAXC + CHUNKS + 1 + 3 + 12;   // 80
+static const int AUX_DIM = 3 + 1 + 2 + 3 * MAXC + 2 + 3 + 2;              // touch[3], flags, limit[2], slots, wind idx, pairs[3], ep_t, episode
 
 inline void get_state(const Lander& L, double* s, int32_t* a) {
     if (s) {
@@ -153,6 +157,7 @@ inline void get_state(const Lander& L, double* s, int32_t* a) {
         for (int i = 0; i < MAXC; ++i) { s[k++] = L.c[i].ni[0]; s[k++] = L.c[i].ti[0]; s[k++] = L.c[i].ni[1]; s[k++] = L.c[i].ti[1]; }
         for (int i = 0; i < CHUNKS; ++i) s[k++] = L.terrain[i];
         s[k++] = L.prev_shaping; s[k++] = L.force.x; s[k++] = L.force.y; s[k++] = L.torque;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) s[k++] = L.fat[i][j];
     }
     if (a) {
         int k = 0;
@@ -160,6 +165,7 @@ inline void get_state(const Lander& L, double* s, int32_t* a) {
         a[k++] = L.flags; a[k++] = L.j[0].limit_state; a[k++] = L.j[1].limit_state;
         for (int i = 0; i < MAXC; ++i) { a[k++] = L.c[i].pair; a[k++] = (int32_t)L.c[i].key[0]; a[k++] = (int32_t)L.c[i].key[1]; }
         a[k++] = L.wind_idx; a[k++] = L.torque_idx;
+        for (int i = 0; i < 3; ++i) a[k++] = (int32_t)L.pairs[i];
         // a[k], a[k+1] = episode step / episode ordinal: owned by the container (oracle.cpp)
     }
 }
@@ -171,11 +177,13 @@ inline void set_state(Lander& L, const double* s, const int32_t* a) {
     for (int i = 0; i < MAXC; ++i) { L.c[i].ni[0] = (float)s[k++]; L.c[i].ti[0] = (float)s[k++]; L.c[i].ni[1] = (float)s[k++]; L.c[i].ti[1] = (float)s[k++]; }
     for (int i = 0; i < CHUNKS; ++i) L.terrain[i] = (float)s[k++];
     L.prev_shaping = (float)s[k++]; L.force.x = (float)s[k++]; L.force.y = (float)s[k++]; L.torque = (float)s[k++];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) L.fat[i][j] = (float)s[k++];
     k = 0;
     for (int i = 0; i < 3; ++i) L.touch[i] = (uint32_t)a[k++];
     L.flags = a[k++]; L.j[0].limit_state = a[k++]; L.j[1].limit_state = a[k++];
     for (int i = 0; i < MAXC; ++i) { L.c[i].pair = a[k++]; L.c[i].key[0] = (uint32_t)a[k++]; L.c[i].key[1] = (uint32_t)a[k++]; }
     L.wind_idx = a[k++]; L.torque_idx = a[k++];
+    for (int i = 0; i < 3; ++i) L.pairs[i] = (uint32_t)a[k++];
 }
 
 // ---------------------------------------------------------------- geometry helpers
@@ -352,56 +360,92 @@ inline void set_awake(Lander& L, bool awake) {
     }
 }
 
+// ---------------------------------------------------------------- broad phase (b2BroadPhase / b2Fixture::Synchronize)
+// A contact EXISTS while the fat boxes of its two fixtures overlap -- created by FindNewContacts (appended to the world's
+// contact list, pushed on the FRONT of the body's contact list), destroyed by Collide when they stop overlapping -- and is
+// TOUCHING while its manifold has points.  The order of creation is state: Collide fires BeginContact / EndContact in
+// creation order ("last BeginContact wins", LunarLanderEnv.cs:316-329) and the island takes a body's contacts newest first.
+struct Box { float lx, ly, hx, hy; };
+inline Box body_box(const Shape& sh, V2 p, Rot q) {   // b2PolygonShape::ComputeAABB
+    V2 lo = rmul(q, sh.v[0]) + p, hi = lo;
+    for (int i = 1; i < sh.count; ++i) {
+        const V2 w = rmul(q, sh.v[i]) + p;
+        lo = mk(minf(lo.x, w.x), minf(lo.y, w.y)); hi = mk(maxf(hi.x, w.x), maxf(hi.y, w.y));
+    }
+    return Box{lo.x - POLYGON_RADIUS, lo.y - POLYGON_RADIUS, hi.x + POLYGON_RADIUS, hi.y + POLYGON_RADIUS};
+}
+inline Box edge_fat_box(const Lander& L, int e) {     // b2EdgeShape::ComputeAABB grown once by aabbExtension (static: never moves)
+    V2 v1, v2;
+    edge_points(L, e, &v1, &v2);
+    const float lx = minf(v1.x, v2.x) - POLYGON_RADIUS, ly = minf(v1.y, v2.y) - POLYGON_RADIUS;
+    const float hx = maxf(v1.x, v2.x) + POLYGON_RADIUS, hy = maxf(v1.y, v2.y) + POLYGON_RADIUS;
+    return Box{lx - AABB_EXTENSION, ly - AABB_EXTENSION, hx + AABB_EXTENSION, hy + AABB_EXTENSION};
+}
+inline bool boxes_overlap(const Box& a, const Box& b) {
+    if (b.lx - a.hx > 0.0f || b.ly - a.hy > 0.0f) return false;
+    if (a.lx - b.hx > 0.0f || a.ly - b.hy > 0.0f) return false;
+    return true;
+}
+inline Box fat_of(const Lander& L, int body) { return Box{L.fat[body][0], L.fat[body][1], L.fat[body][2], L.fat[body][3]}; }
+inline uint32_t pair_at(const Lander& L, int k) { return (L.pairs[k >> 2] >> (8 * (k & 3))) & 0xffu; }
+inline void pair_put(Lander& L, int k, uint32_t v) { L.pairs[k >> 2] = (L.pairs[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (v << (8 * (k & 3))); }
+inline int pair_count(const Lander& L) { int n = 0; while (n < MAXP && pair_at(L, n) != 0xffu) ++n; return n; }
+
 inline void world_step(Lander& L) {
     const float h = DT;
     const float dt_ratio = (L.flags & F_FIRST_STEP) ? 0.0f : 1.0f;   // inv_dt0 * dt: 0 on a new World, then 50 * 0.02f = 1
     ActiveContact ac[MAXC];
     int nc = 0;
 
-    // ---- ContactManager.Collide: update every (polygon, edge) pair whose AABBs can overlap
+    // ---- ContactManager.Collide: every existing contact, in creation order
     if (L.flags & F_AWAKE) {
-        for (int body = 0; body < 3; ++body) {
-            const Shape& sh = SHAPES[body];
-            const Rot q = rot(L.b[body].a);
-            const V2 p = L.b[body].c - rmul(q, sh.centroid);
-            float xmin = 3.4028234663852886e38f, xmax = -3.4028234663852886e38f, ymin = 3.4028234663852886e38f;
-            for (int i = 0; i < sh.count; ++i) {
-                const V2 w = rmul(q, sh.v[i]) + p;
-                xmin = minf(xmin, w.x); xmax = maxf(xmax, w.x); ymin = minf(ymin, w.y);
+        Rot q[3]; V2 p[3];
+        for (int body = 0; body < 3; ++body) { q[body] = rot(L.b[body].a); p[body] = L.b[body].c - rmul(q[body], SHAPES[body].centroid); }
+        const int np = pair_count(L);
+        int kept = 0;
+        for (int k = 0; k < np; ++k) {
+            const uint32_t pr = pair_at(L, k);
+            const int body = (int)(pr >> 4), e = (int)(pr & 15u);
+            const bool was = (L.touch[body] >> e) & 1u;
+            if (!boxes_overlap(edge_fat_box(L, e), fat_of(L, body))) {   // the fat boxes parted: the contact is destroyed
+                if (was) { end_contact(L, body); L.touch[body] &= ~(1u << e); }
+                continue;
             }
-            const float margin = 0.1f;   // aabbExtension: a pair farther than this cannot be touching
-            uint32_t now = 0;
-            for (int e = 0; e < NUM_EDGES; ++e) {
-                V2 v1, v2;
-                edge_points(L, e, &v1, &v2);
-                const bool overlap = xmax + margin >= v1.x && xmin - margin <= v2.x &&
-                                     ymin - margin <= maxf(v1.y, v2.y);
-                Manifold m;
-                m.count = 0;
-                if (overlap) collide_edge_polygon(&m, v1, v2, sh, p, q);
-                const bool touching = m.count > 0 && nc < MAXC;
-                const bool was = (L.touch[body] >> e) & 1u;
-                if (touching) {
-                    now |= 1u << e;
-                    ActiveContact& c = ac[nc++];
-                    c.body = body; c.edge = e; c.count = m.count; c.m = m;
-                    for (int k = 0; k < 2; ++k) { c.p[k].normal_impulse = 0.0f; c.p[k].tangent_impulse = 0.0f; }
-                    // b2Contact::Update: match old manifold points by id, copy their impulses (warm start)
-                    const int32_t pair = body * 16 + e;
-                    for (int s = 0; s < MAXC; ++s) {
-                        if (L.c[s].pair != pair) continue;
-                        for (int k = 0; k < m.count; ++k)
-                            for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
-                                if (L.c[s].key[o] != NO_KEY && L.c[s].key[o] == m.key[k]) {
-                                    c.p[k].normal_impulse = L.c[s].ni[o]; c.p[k].tangent_impulse = L.c[s].ti[o];
-                                }
-                    }
+            pair_put(L, kept++, pr);
+            V2 v1, v2;
+            edge_points(L, e, &v1, &v2);
+            Manifold m;
+            collide_edge_polygon(&m, v1, v2, SHAPES[body], p[body], q[body]);
+            const bool touching = m.count > 0 && nc < MAXC;
+            if (touching) {
+                L.touch[body] |= 1u << e;
+                ActiveContact& c = ac[nc++];
+                c.body = body; c.edge = e; c.count = m.count; c.m = m;
+                for (int j = 0; j < 2; ++j) { c.p[j].normal_impulse = 0.0f; c.p[j].tangent_impulse = 0.0f; }
+                // b2Contact::Update: match old manifold points by id, copy their impulses (warm start)
+                const int32_t pair = body * 16 + e;
+                for (int sl = 0; sl < MAXC; ++sl) {
+                    if (L.c[sl].pair != pair) continue;
+                    for (int j = 0; j < m.count; ++j)
+                        for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
+                            if (L.c[sl].key[o] != NO_KEY && L.c[sl].key[o] == m.key[j]) {
+                                c.p[j].normal_impulse = L.c[sl].ni[o]; c.p[j].tangent_impulse = L.c[sl].ti[o];
+                            }
                 }
-                if (touching && !was) begin_contact(L, body);
-                if (!touching && was) end_contact(L, body);
+            } else {
+                L.touch[body] &= ~(1u << e);
             }
-            L.touch[body] = now;
+            if (touching && !was) begin_contact(L, body);
+            if (!touching && was) end_contact(L, body);
         }
+        for (int k = kept; k < np; ++k) pair_put(L, k, 0xffu);
+    }
+    // island order of the touching contacts: bodies in DFS order (fuselage, leg 0, leg 1), each body's contacts newest first
+    int order[MAXC];
+    {
+        int no = 0;
+        for (int body = 0; body < 3; ++body)
+            for (int k = nc - 1; k >= 0; --k) if (ac[k].body == body) order[no++] = k;
     }
 
     // ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1}
@@ -421,7 +465,7 @@ inline void world_step(Lander& L) {
 
         // contact solver: InitializeVelocityConstraints
         for (int k = 0; k < nc; ++k) {
-            ActiveContact& cc = ac[k];
+            ActiveContact& cc = ac[order[k]];
             const int B = cc.body;
             const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
             const Rot qB = rot(a[B]);
@@ -481,7 +525,7 @@ inline void world_step(Lander& L) {
         }
         // contact solver: WarmStart
         for (int k = 0; k < nc; ++k) {
-            ActiveContact& cc = ac[k];
+            ActiveContact& cc = ac[order[k]];
             const int B = cc.body;
             const V2 tangent = cross_vs(cc.normal, 1.0f);
             for (int j = 0; j < cc.count; ++j) {
@@ -600,7 +644,7 @@ inline void world_step(Lander& L) {
                 }
             }
             for (int k = 0; k < nc; ++k) {
-                ActiveContact& cc = ac[k];
+                ActiveContact& cc = ac[order[k]];
                 const int B = cc.body;
                 const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 const V2 normal = cc.normal;
@@ -691,7 +735,7 @@ inline void world_step(Lander& L) {
         for (int it = 0; it < POSITION_ITERATIONS; ++it) {
             float min_separation = 0.0f;
             for (int k = 0; k < nc; ++k) {
-                const ActiveContact& cc = ac[k];
+                const ActiveContact& cc = ac[order[k]];
                 const int B = cc.body;
                 const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
                 for (int j = 0; j < cc.m.count; ++j) {
@@ -773,6 +817,8 @@ inline void world_step(Lander& L) {
         }
 
         // copy back, store impulses (b2ContactSolver::StoreImpulses)
+        V2 c0[3]; float a0[3];   // the sweep's c0 / a0: the pose this step started from
+        for (int i = 0; i < 3; ++i) { c0[i] = L.b[i].c; a0[i] = L.b[i].a; }
         for (int i = 0; i < 3; ++i) { L.b[i].c = c[i]; L.b[i].a = a[i]; L.b[i].v = v[i]; L.b[i].w = w[i]; }
         for (int s = 0; s < MAXC; ++s) {
             ContactSlot& cs = L.c[s];
@@ -802,6 +848,41 @@ inline void world_step(Lander& L) {
             }
         }
         if (min_sleep >= TIME_TO_SLEEP && position_solved) set_awake(L, false);
+
+        // b2Body::SynchronizeFixtures: the proxy box must hold the tight boxes of the start and end pose of the step; when it
+        // does not, it is replaced by their union grown by aabbExtension and stretched along twice the displacement
+        uint32_t moved = 0u;
+        for (int i = 0; i < 3; ++i) {
+            const Rot q1 = rot(a0[i]), q2 = rot(L.b[i].a);
+            const V2 p1 = c0[i] - rmul(q1, SHAPES[i].centroid), p2 = L.b[i].c - rmul(q2, SHAPES[i].centroid);
+            const Box b1 = body_box(SHAPES[i], p1, q1), b2 = body_box(SHAPES[i], p2, q2);
+            const Box u = Box{minf(b1.lx, b2.lx), minf(b1.ly, b2.ly), maxf(b1.hx, b2.hx), maxf(b1.hy, b2.hy)};
+            const Box f = fat_of(L, i);
+            if (f.lx <= u.lx && f.ly <= u.ly && u.hx <= f.hx && u.hy <= f.hy) continue;
+            Box n = Box{u.lx - AABB_EXTENSION, u.ly - AABB_EXTENSION, u.hx + AABB_EXTENSION, u.hy + AABB_EXTENSION};
+            const V2 d = AABB_MULTIPLIER * (p2 - p1);
+            if (d.x < 0.0f) n.lx = n.lx + d.x; else n.hx = n.hx + d.x;
+            if (d.y < 0.0f) n.ly = n.ly + d.y; else n.hy = n.hy + d.y;
+            L.fat[i][0] = n.lx; L.fat[i][1] = n.ly; L.fat[i][2] = n.hx; L.fat[i][3] = n.hy;
+            moved |= 1u << i;
+        }
+        // ContactManager.FindNewContacts: pairs of a moved proxy, sorted by proxy id (body, then edge in creation order: the
+        // base edge was created first, :541, then the ten terrain edges), appended unless they exist already
+        if (moved) {
+            int np = pair_count(L);
+            for (int i = 0; i < 3; ++i) {
+                if (!((moved >> i) & 1u)) continue;
+                const Box f = fat_of(L, i);
+                for (int ee = 0; ee < NUM_EDGES; ++ee) {
+                    const int e = ee == 0 ? BASE_EDGE : ee - 1;
+                    if (!boxes_overlap(f, edge_fat_box(L, e))) continue;
+                    const uint32_t pr = (uint32_t)(i * 16 + e);
+                    bool exists = false;
+                    for (int k = 0; k < np; ++k) if (pair_at(L, k) == pr) exists = true;
+                    if (!exists && np < MAXP) pair_put(L, np++, pr);
+                }
+            }
+        }
     }
     // ClearForces
     L.force = mk(0.0f, 0.0f);
@@ -843,7 +924,12 @@ inline StepResult step(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i
         const float wind_mag = (float)(std::tanh(std::sin(0.02 * L.wind_idx) + std::sin(3.14159265358979323846 * 0.01 * L.wind_idx))) * L.wind_power;
         L.wind_idx += 1;
         set_awake(L, true);
-        L.force = L.force + mk(wind_mag, 0.0f);
+        {   // Body.ApplyForce(Vector2) applies the force at the body ORIGIN (Farseer lineage: ApplyForce(ref force, ref _xf.p)), so it also makes a torque about the centre
+            const Rot qw = rot(L.b[0].a);
+            const V2 origin = L.b[0].c - rmul(qw, SHAPES[0].centroid);
+            L.force = L.force + mk(wind_mag, 0.0f);
+            L.torque = L.torque + ((origin.x - L.b[0].c.x) * 0.0f - (origin.y - L.b[0].c.y) * wind_mag);
+        }
         const float torque_mag = (float)(std::tanh(std::sin(0.02 * L.torque_idx) + std::sin(3.14159265358979323846 * 0.01 * L.torque_idx))) * L.turbulence_power;
         L.torque_idx += 1;
         L.torque = L.torque + torque_mag;
@@ -917,6 +1003,11 @@ inline void reset(Lander& L, uint64_t seed, uint32_t gid, uint64_t index, bool c
     const Block b0 = draw(seed, gid, index, STREAM_RESET, 0), b1 = draw(seed, gid, index, STREAM_RESET, 1),
                 b2 = draw(seed, gid, index, STREAM_RESET, 2), b3 = draw(seed, gid, index, STREAM_RESET, 3);
     L.force = mk(uniformf(-INITIAL_RANDOM, INITIAL_RANDOM, b0.w[0]), uniformf(-INITIAL_RANDOM, INITIAL_RANDOM, b0.w[1]));   // :496
+    {   // ... applied at the body origin while the fuselage still sits at (0, 0), rotation 0 (:496 precedes :561): torque about the centre of mass
+        const V2 c_at_creation = rmul(rot(0.0f), SHAPES[0].centroid) + mk(0.0f, 0.0f);
+        L.torque = (0.0f - c_at_creation.x) * L.force.y - (0.0f - c_at_creation.y) * L.force.x;
+    }
+    L.pairs[0] = L.pairs[1] = L.pairs[2] = 0xffffffffu;
     L.prev_shaping = -3.4028234663852886e38f;                                                  // :498
     float height[CHUNKS + 1];
     const uint32_t hw[12] = {b0.w[2], b0.w[3], b1.w[0], b1.w[1], b1.w[2], b1.w[3], b2.w[0], b2.w[1], b2.w[2], b2.w[3], b3.w[0], b3.w[1]};
@@ -939,6 +1030,8 @@ inline void reset(Lander& L, uint64_t seed, uint32_t gid, uint64_t index, bool c
         L.b[i].a = ang;
         L.b[i].c = rmul(rot(ang), SHAPES[i].centroid) + pos;
         L.b[i].v = mk(0.0f, 0.0f); L.b[i].w = 0.0f; L.b[i].sleep_time = 0.0f;
+        const Box bx = body_box(SHAPES[i], pos, rot(ang));   // Body.Position setter -> MoveProxy with no displacement
+        L.fat[i][0] = bx.lx - AABB_EXTENSION; L.fat[i][1] = bx.ly - AABB_EXTENSION; L.fat[i][2] = bx.hx + AABB_EXTENSION; L.fat[i][3] = bx.hy + AABB_EXTENSION;
     }
     const float zero[2] = {0.0f, 0.0f};
     step(L, seed, gid, t, 0, zero);                                                            // :567-571

@@ -11,7 +11,7 @@
 // 14 uniforms, step its two dispersion uniforms, so the caller can feed the engine's Philox stream.
 //
 // export_state / import_state translate between the generic world and the kernel's per-lander state layout
-// (gym.net_b200/csrc/lunar.cuh: 68 float + 26 int32 words) -- the only place that knows that layout.
+// (gym.net_b200/csrc/lunar.cuh: 80 float + 29 int32 words) -- the only place that knows that layout.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -30,7 +30,8 @@ constexpr float MAIN_ENGINE_POWER = 13.0f;     // :157
 constexpr float SIDE_ENGINE_POWER = 0.6f;      // :158
 constexpr int CHUNKS = 11;                     // :503
 constexpr int KMAXC = 6;                       // contact slots in the kernel's layout
-constexpr int KSTATE = 68, KAUX = 26;
+constexpr int KMAXP = 12;                      // broad-phase pair bytes in the kernel's layout
+constexpr int KSTATE = 80, KAUX = 29;
 enum : int32_t { F_GAME_OVER = 1, F_LEG0 = 2, F_LEG1 = 4, F_FUSELAGE = 8, F_AWAKE = 16, F_FIRST_STEP = 32, F_CONTINUOUS = 64 };
 
 void sincos_det_hook(float a, float* s, float* c) { oracle::det::sincosf_det(a, s, c); }
@@ -266,14 +267,10 @@ struct LunarSim {
     // ---- translation to / from the kernel's per-lander layout ---------------------------------------------
     Body* bodyOf(int k) const { return k == 0 ? fuselage.unit : legs[k - 1].unit; }
 
-    // touching contacts in the kernel's canonical order: body ascending, then edge number ascending
+    // touching contacts in creation order (the order the kernel keeps its slots in)
     std::vector<Contact*> touchingSorted() const {
         std::vector<Contact*> v;
-        for (Contact* c : world->contactList) if (c->touching) v.push_back(c);
-        std::sort(v.begin(), v.end(), [](Contact* a, Contact* b) {
-            const int ka = a->fixtureB->body->userIndex * 16 + a->fixtureA->userIndex, kb = b->fixtureB->body->userIndex * 16 + b->fixtureA->userIndex;
-            return ka < kb;
-        });
+        for (Contact* c : world->contactList) if (c->touching && (int)v.size() < KMAXC) v.push_back(c);
         return v;
     }
 
@@ -296,6 +293,10 @@ struct LunarSim {
         for (int i = 0; i < CHUNKS; ++i) s[k++] = smoothY[i];
         s[k++] = prevShaping;
         s[k++] = fuselage.unit->force.x; s[k++] = fuselage.unit->force.y; s[k++] = fuselage.unit->torque;
+        for (int i = 0; i < 3; ++i) {
+            const AABB& f = world->proxies[bodyOf(i)->fixtures[0]->proxyId].fat;
+            s[k++] = f.lo.x; s[k++] = f.lo.y; s[k++] = f.hi.x; s[k++] = f.hi.y;
+        }
         k = 0;
         uint32_t touch[3] = {0u, 0u, 0u};
         for (Contact* c : tc) touch[c->fixtureB->body->userIndex] |= 1u << c->fixtureA->userIndex;
@@ -320,6 +321,15 @@ struct LunarSim {
             }
         }
         a[k++] = windIdx; a[k++] = torqueIdx;
+        uint32_t pw[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+        int np = 0;
+        for (Contact* c : world->contactList) {
+            if (np >= KMAXP) break;
+            const uint32_t pr = (uint32_t)(c->fixtureB->body->userIndex * 16 + c->fixtureA->userIndex);
+            pw[np >> 2] = (pw[np >> 2] & ~(0xffu << (8 * (np & 3)))) | (pr << (8 * (np & 3)));
+            ++np;
+        }
+        for (int i = 0; i < 3; ++i) a[k++] = (int32_t)pw[i];
     }
 
     // Builds a world in the given state: bodies, joints and terrain as Reset makes them, then poses, velocities,
@@ -363,9 +373,24 @@ struct LunarSim {
         continuous = (flags & F_CONTINUOUS) != 0;
         legJoint[0]->limitState = (LimitState)a[4]; legJoint[1]->limitState = (LimitState)a[5];
         windIdx = a[6 + 3 * KMAXC]; torqueIdx = a[7 + 3 * KMAXC];
-        // contacts: the broad phase creates the pairs whose fat boxes overlap; the stored slots mark the touching ones
-        world->findNewContacts();
+        // broad phase: the stored proxy boxes, and the contacts that exist, re-created in their creation order
+        while (!world->contactList.empty()) world->destroyContact(world->contactList.back());   // pairs met while the bodies were being placed
+        world->moveBuffer.clear();
         world->newFixture = false;
+        for (int i = 0; i < 3; ++i) {
+            AABB& f = world->proxies[bodyOf(i)->fixtures[0]->proxyId].fat;
+            const float* q = s + 68 + 4 * i;
+            f.lo = Vec2(q[0], q[1]); f.hi = Vec2(q[2], q[3]);
+        }
+        for (int n = 0; n < KMAXP; ++n) {
+            const uint32_t pr = ((uint32_t)a[26 + (n >> 2)] >> (8 * (n & 3))) & 0xffu;
+            if (pr == 0xffu) break;
+            const int body = (int)(pr >> 4), edge = (int)(pr & 15u);
+            Fixture* fe = nullptr;
+            for (auto& f : moon->fixtures) if (f->userIndex == edge) fe = f.get();
+            world->addPair(bodyOf(body)->fixtures[0].get(), fe);
+        }
+        for (int i = 0; i < 3; ++i) bodyOf(i)->awake = awake;   // (creating a contact wakes its bodies)
         for (int slot = 0; slot < KMAXC; ++slot) {
             const int32_t pair = a[6 + 3 * slot];
             if (pair < 0) continue;

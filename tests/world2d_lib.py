@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W2D_DIR = os.path.join(ROOT, "oracle", "world2d")
 LIB_PATH = os.path.join(W2D_DIR, "libworld2d.so")
 
-STATE_DIM, AUX_DIM = 68, 26
+STATE_DIM, AUX_DIM = 80, 29
 STREAM_RESET, STREAM_ACTION, STREAM_DYNAMICS, STREAM_CTOR = 0, 1, 2, 3
 F_GAME_OVER, F_LEG0, F_LEG1, F_FUSELAGE, F_AWAKE, F_FIRST_STEP, F_CONTINUOUS = 1, 2, 4, 8, 16, 32, 64
 
