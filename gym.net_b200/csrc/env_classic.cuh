@@ -136,7 +136,7 @@ struct CartPole {
 // ------------------------------------------------------------------------------------------------
 // Pendulum-v1 (not in the reference, README.md:76; spec = upstream gym 0.26 pendulum.py)
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ float fmodf_cold(float a, float b) { return fmodf(a, b); }
+static __device__ __noinline__ float fmodf_cold(float a, float b) { return fmodf(a, b); }
 
 // Python float `a % b` for b > 0 (upstream angle_normalize): fmod is exact, so the result is defined by IEEE
 // alone.  For |a| <= 2^21 (every angle a pendulum reaches) fmod is computed without branches or conversions:
@@ -445,7 +445,7 @@ __device__ __forceinline__ double acrobot_integrate_f64(double s[4], int action)
     return -cos(s[0]) - cos(s[1] + s[0]);
 }
 
-__device__ __noinline__ unsigned acrobot_done_f64(float s0, float s1, float s2, float s3, int action) {
+static __device__ __noinline__ unsigned acrobot_done_f64(float s0, float s1, float s2, float s3, int action) {
     double sd[4] = {(double)s0, (double)s1, (double)s2, (double)s3};
     return (unsigned)(acrobot_integrate_f64(sd, action) > 1.0);
 }

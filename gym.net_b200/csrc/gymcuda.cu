@@ -21,7 +21,7 @@
 #include "kernels.cuh"
 #include "normalize.cuh"
 #ifdef GYMCUDA_WITH_LUNAR
-#include "lunar.cuh"
+#include "lunar_launch.h"
 #endif
 
 using namespace gymcuda;
@@ -111,8 +111,8 @@ static bool kind_info(int kind, KindInfo* ki) {
         case GYMCUDA_MOUNTAINCAR_CONT: *ki = {MountainCarCont::SD, 3, MountainCarCont::OD, MountainCarCont::AD, MountainCarCont::ACTN, MountainCarCont::DEFAULT_LIMIT}; return true;
         case GYMCUDA_ACROBOT: *ki = {Acrobot::SD, 3, Acrobot::OD, Acrobot::AD, Acrobot::ACTN, Acrobot::DEFAULT_LIMIT}; return true;
 #ifdef GYMCUDA_WITH_LUNAR
-        case GYMCUDA_LUNARLANDER: *ki = {LunarLander::SD, LunarLander::AUX, 8, 1, 4, 0}; return true;
-        case GYMCUDA_LUNARLANDER_CONT: *ki = {LunarLanderCont::SD, LunarLanderCont::AUX, 8, 2, 0, 0}; return true;
+        case GYMCUDA_LUNARLANDER: *ki = {LUNAR_STATE_DIM, LUNAR_AUX_DIM, 8, 1, 4, 0}; return true;
+        case GYMCUDA_LUNARLANDER_CONT: *ki = {LUNAR_STATE_DIM, LUNAR_AUX_DIM, 8, 2, 0, 0}; return true;
 #endif
         default: return false;
     }
@@ -131,6 +131,8 @@ struct gymcuda_env {
     int32_t *d_sbd, *d_ept, *d_episode, *d_seeds, *d_aux;
     EnvParams prm;
     int32_t *d_perm, *d_block_free;   // LunarLander contact partition
+    cudaStream_t side_stream;         // LunarLander: the kernel of the second partition class runs here, concurrently
+    cudaEvent_t ev_fork, ev_join;
     int sm_count;                     // multiprocessors of the device (launch heuristics)
     int auxw;   // int32 words per env in d_aux (LunarLander only)
     // I/O staging for the host-buffer entry points
@@ -226,13 +228,8 @@ static cudaError_t launch_reset(gymcuda_env* e, const ResetArgs& a) {
     return cudaGetLastError();
 }
 
-#ifdef GYMCUDA_WITH_LUNAR
-#define LUNAR_CASES(FN, ...)                                                      \
-    case GYMCUDA_LUNARLANDER: return launch_##FN<LunarLander>(e, __VA_ARGS__);     \
-    case GYMCUDA_LUNARLANDER_CONT: return launch_##FN<LunarLanderCont>(e, __VA_ARGS__);
-#else
-#define LUNAR_CASES(FN, ...)
-#endif
+static bool is_lunar(const gymcuda_env* e) { return e->cfg.env_kind == GYMCUDA_LUNARLANDER || e->cfg.env_kind == GYMCUDA_LUNARLANDER_CONT; }
+static bool is_lunar_cont(const gymcuda_env* e) { return e->cfg.env_kind == GYMCUDA_LUNARLANDER_CONT; }
 
 #define DISPATCH(FN, ...)                                                                \
     switch (e->cfg.env_kind) {                                                           \
@@ -241,39 +238,71 @@ static cudaError_t launch_reset(gymcuda_env* e, const ResetArgs& a) {
         case GYMCUDA_MOUNTAINCAR: return launch_##FN<MountainCar>(e, __VA_ARGS__);       \
         case GYMCUDA_MOUNTAINCAR_CONT: return launch_##FN<MountainCarCont>(e, __VA_ARGS__); \
         case GYMCUDA_ACROBOT: return launch_##FN<Acrobot>(e, __VA_ARGS__);               \
-        LUNAR_CASES(FN, __VA_ARGS__)                                                     \
         default: return cudaErrorInvalidValue;                                           \
     }
 
-static cudaError_t dispatch_step(gymcuda_env* e, const StepArgs& a) { DISPATCH(step, a) }
-static cudaError_t dispatch_rollout(gymcuda_env* e, const RolloutArgs& a) { DISPATCH(rollout, a) }
+// LunarLander: stable partition of the env ids by "a broad-phase contact pair exists" (kernels.cuh): d_perm lists the
+// free-flight landers first, d_block_free[nb] is their number.  The two classes are stepped by two kernels, the second
+// on a side stream (fork / join with events: legal under stream capture), so the long dependent chains of the landers
+// near the ground overlap the bulk of the batch instead of following it.
+static cudaError_t lunar_step(gymcuda_env* e, StepArgs a) {
+#ifdef GYMCUDA_WITH_LUNAR
+    const bool cont = is_lunar_cont(e), ar = e->auto_reset, lim = e->limit > 0;
+    const int grid = (e->n + STEP_BLOCK - 1) / STEP_BLOCK;
+    if (a.world > 0 || e->n < 4 * STEP_BLOCK) {   // fused gather (one kernel signals the peers) or a tiny batch: one launch, general kernel
+        a.perm = nullptr; a.part = 0;
+        return lunar_launch_step(cont, true, ar, lim, grid, e->stream, a);
+    }
+    const int nb = (e->n + PART_BLOCK - 1) / PART_BLOCK;
+    partition_count_kernel<<<nb, PART_BLOCK, 0, e->stream>>>(e->d_aux, e->n, e->d_block_free);
+    partition_scan_kernel<<<1, 1024, 0, e->stream>>>(e->d_block_free, nb);
+    partition_scatter_kernel<<<nb, PART_BLOCK, 0, e->stream>>>(e->d_aux, e->n, e->d_block_free, nb, e->d_perm);
+    a.perm = e->d_perm; a.split = e->d_block_free + nb;
+    cudaError_t ce = cudaEventRecord(e->ev_fork, e->stream);
+    if (ce != cudaSuccess) return ce;
+    if ((ce = cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0)) != cudaSuccess) return ce;
+    a.part = 2;   // landers with a contact pair: few, long
+    if ((ce = lunar_launch_step(cont, true, ar, lim, grid, e->side_stream, a)) != cudaSuccess) return ce;
+    if ((ce = cudaEventRecord(e->ev_join, e->side_stream)) != cudaSuccess) return ce;
+    a.part = 1;   // free flight: the bulk
+    if ((ce = lunar_launch_step(cont, false, ar, lim, grid, e->stream, a)) != cudaSuccess) return ce;
+    return cudaStreamWaitEvent(e->stream, e->ev_join, 0);
+#else
+    (void)e; (void)a;
+    return cudaErrorInvalidValue;
+#endif
+}
+
+static cudaError_t dispatch_step(gymcuda_env* e, const StepArgs& a) {
+    if (is_lunar(e)) return lunar_step(e, a);
+    DISPATCH(step, a)
+}
+static cudaError_t dispatch_rollout(gymcuda_env* e, const RolloutArgs& a) { DISPATCH(rollout, a) }   // (LunarLander: gymcuda_rollout_random_device loops over steps)
 template <class E>
 static cudaError_t launch_sample(gymcuda_env* e, const SampleArgs& a) {
     sample_kernel<E><<<(e->n + 127) / 128, 128, 0, e->stream>>>(a);
     return cudaGetLastError();
 }
-static cudaError_t dispatch_reset(gymcuda_env* e, const ResetArgs& a) { DISPATCH(reset, a) }
-static cudaError_t dispatch_sample(gymcuda_env* e, const SampleArgs& a) { DISPATCH(sample, a) }
+static cudaError_t dispatch_reset(gymcuda_env* e, const ResetArgs& a) {
+#ifdef GYMCUDA_WITH_LUNAR
+    if (is_lunar(e)) return lunar_launch_reset(is_lunar_cont(e), (e->n + 127) / 128, e->stream, a);
+#endif
+    DISPATCH(reset, a)
+}
+static cudaError_t dispatch_sample(gymcuda_env* e, const SampleArgs& a) {
+#ifdef GYMCUDA_WITH_LUNAR
+    if (is_lunar(e)) return lunar_launch_sample(is_lunar_cont(e), (e->n + 127) / 128, e->stream, a);
+#endif
+    DISPATCH(sample, a)
+}
 
 // constructor draws (LunarLander only): at create and whenever the generator is replaced by Seed()
 static cudaError_t dispatch_ctor(gymcuda_env* e, const ResetArgs& a) {
 #ifdef GYMCUDA_WITH_LUNAR
-    const int grid = (e->n + 127) / 128;
-    if (e->cfg.env_kind == GYMCUDA_LUNARLANDER) ctor_kernel<LunarLander><<<grid, 128, 0, e->stream>>>(a);
-    else if (e->cfg.env_kind == GYMCUDA_LUNARLANDER_CONT) ctor_kernel<LunarLanderCont><<<grid, 128, 0, e->stream>>>(a);
+    if (is_lunar(e)) return lunar_launch_ctor(is_lunar_cont(e), (e->n + 127) / 128, e->stream, a);
 #endif
     (void)e; (void)a;
     return cudaGetLastError();
-}
-
-// LunarLander: stable partition of the env ids by "has a touching contact" (kernels.cuh); null otherwise
-static const int32_t* contact_partition(gymcuda_env* e) {
-    if (!e->d_perm) return nullptr;
-    const int nb = (e->n + PART_BLOCK - 1) / PART_BLOCK;
-    partition_count_kernel<<<nb, PART_BLOCK, 0, e->stream>>>(e->d_aux, e->n, e->d_block_free);
-    partition_scan_kernel<<<1, 1024, 0, e->stream>>>(e->d_block_free, nb);
-    partition_scatter_kernel<<<nb, PART_BLOCK, 0, e->stream>>>(e->d_aux, e->n, e->d_block_free, nb, e->d_perm);
-    return e->d_perm;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -314,6 +343,9 @@ int gymcuda_destroy(gymcuda_env* e) {
     for (int r = 0; r < e->g_world; ++r) if (e->g_peer[r] && r != e->g_rank) cudaIpcCloseMemHandle(e->g_peer[r]);
     cudaFree(e->g_local);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    if (e->side_stream) { cudaStreamSynchronize(e->side_stream); cudaStreamDestroy(e->side_stream); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux); cudaFree(e->d_perm); cudaFree(e->d_block_free);
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
@@ -337,10 +369,11 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     if (e->auxw > 0) {
         CU_TRY(cudaMalloc(&e->d_aux, n * (size_t)e->auxw * 4));
         CU_TRY(cudaMemsetAsync(e->d_aux, 0, n * (size_t)e->auxw * 4, e->stream));
-        if (e->n >= 2048) {   // worth three tiny launches only for batches that fill the GPU
-            CU_TRY(cudaMalloc(&e->d_perm, n * 4));
-            CU_TRY(cudaMalloc(&e->d_block_free, ((n + PART_BLOCK - 1) / PART_BLOCK + 1) * 4));
-        }
+        CU_TRY(cudaMalloc(&e->d_perm, n * 4));
+        CU_TRY(cudaMalloc(&e->d_block_free, ((n + PART_BLOCK - 1) / PART_BLOCK + 1) * 4));
+        CU_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     }
     CU_TRY(cudaMalloc(&e->d_sbd, n * 4));
     CU_TRY(cudaMalloc(&e->d_ept, n * 4));
@@ -529,8 +562,9 @@ int gymcuda_reset_masked(gymcuda_env* e, const uint8_t* mask, float* obs_out) {
 // ------------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------------
+// d_actions == nullptr (and no broadcast): the random policy -- ActionSpace.Sample() of step t evaluated in the kernel, also written to sampled_out
 static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int32_t bcast, float* d_obs,
-                       float* d_reward, uint8_t* d_done, bool gather = false) {
+                       float* d_reward, uint8_t* d_done, bool gather = false, void* sampled_out = nullptr) {
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
     StepArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
@@ -538,7 +572,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
-    a.perm = contact_partition(e);
+    if (!d_actions && !use_bcast) { a.sample = 1; a.act_out = sampled_out; }
     if (gather) {
         e->g_seq += 1;
         a.world = e->g_world; a.rank = e->g_rank; a.gseq = e->g_seq;
@@ -671,11 +705,21 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
     if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
+    if (is_lunar(e)) {   // k step launches with the policy sampled in the kernel (lunar_kernels.cu)
+        const size_t n = (size_t)e->n;
+        for (int j = 0; j < k_steps; ++j) {
+            int rc = step_launch(e, nullptr, 0, 0, d_obs ? d_obs + (size_t)j * n * e->ki.od : e->d_obs, d_reward ? d_reward + (size_t)j * n : e->d_reward,
+                                 d_done ? d_done + (size_t)j * n : e->d_done, false,
+                                 d_actions ? reinterpret_cast<uint8_t*>(d_actions) + (size_t)j * n * e->ki.ad * 4 : nullptr);
+            if (rc) return rc;
+        }
+        e->last_obs = nullptr;
+        return GYMCUDA_OK;
+    }
     RolloutArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = d_actions; a.stats = e->d_stats; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
-    a.perm = contact_partition(e);
     CU_TRY(dispatch_rollout(e, a));
     e->t += (uint64_t)k_steps;
     e->env_steps += (unsigned long long)e->n * (unsigned long long)k_steps;

@@ -46,6 +46,10 @@ struct StepArgs {
     int32_t* episode;
     const int32_t* seeds;
     const int32_t* perm;               // thread -> env map (LunarLander contact partition), null = identity
+    const int32_t* split;              // with perm: device count of the envs in the first class of the partition
+    int part;                          // 0: every position; 1: positions [0, *split) (first class); 2: positions [*split, n)
+    int sample;                        // 1: the action is ActionSpace.Sample() of step t (the rollout's random policy), `actions` is not read
+    void* act_out;                     // sampled actions are also written here (may be null)
     const void* actions;
     float* obs;
     float* reward;
@@ -255,7 +259,11 @@ template <class E, bool AUTO_RESET, bool LIMIT>
 __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     using S = typename E::S;
     using Act = typename E::Act;
-    const int tix = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    int tix = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    int hi = p.n;
+    if (p.part == 1) hi = *p.split;
+    if (p.part == 2) tix += *p.split;
+    if (tix >= hi) tix = p.n;          // not in this launch's class: idle (the compaction below still needs the whole block)
     int i = tix;
     bool done = false;
     bool invalid = false;
@@ -266,7 +274,16 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     if (tix < p.n) {
         if (p.perm) i = p.perm[tix];
         S s = E::load(p.state, p.aux, p.n, i, p.prm);
-        const Act a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
+        Act a;
+        if (p.sample) {
+            ActionGen<E> gen;
+            const uint64_t sseed = seed_of(p.seeds, p.seed, i);
+            gen.init(sseed, p.env_off + (uint32_t)i, p.t);
+            a = gen.next(sseed, p.env_off + (uint32_t)i, p.t);
+            if (p.act_out) reinterpret_cast<Act*>(p.act_out)[i] = a;
+        } else {
+            a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
+        }
         int32_t sbd = -1;
         if (E::HAS_SBD && !AUTO_RESET) sbd = p.sbd[i];
         int32_t ept = 0;
@@ -316,7 +333,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     if (lane == 0) warp_cnt[warp] = __popc(m);
     // the done bytes of the CTA go out as one 128 B line (32 lanes x 4 B) instead of four 32 B pieces: over PCIe
     // (zero-copy host buffers) every store instruction is a packet, and over HBM it is one full sector group
-    const bool packed = p.perm == nullptr && (reinterpret_cast<uintptr_t>(p.done) & 3u) == 0;
+    const bool packed = p.perm == nullptr && p.part == 0 && (reinterpret_cast<uintptr_t>(p.done) & 3u) == 0;
     if (packed) done_tile[threadIdx.x] = done_byte;
     else if (tix < p.n) p.done[i] = done_byte;
     if (mi != 0 && lane == 0) {
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
 // this rank's buffer: one thread per peer spins on that peer's arrival flag.  Bounded: after ~2 s without
 // the flag (a peer died or never launched its step) it gives up and raises `timeout_flag` (mapped host
 // memory) instead of hanging the GPU.
-__global__ void gather_wait_kernel(const uint32_t* flags, int world, uint32_t gseq, int* timeout_flag) {
+static __global__ void gather_wait_kernel(const uint32_t* flags, int world, uint32_t gseq, int* timeout_flag) {
     const int r = threadIdx.x;
     if (r < world) {
         const volatile uint32_t* f = flags + r;
@@ -624,19 +641,23 @@ __global__ void __launch_bounds__(128) reset_kernel(const ResetArgs p) {
 }
 
 // ---------------------------------------------------------------- contact partition (LunarLander)
-// A lander with a touching contact runs a several times longer solver path than one in free flight, and a
-// warp runs as long as its slowest lane.  A STABLE partition of the env ids by "has a touching contact"
-// (warp ballot + block counts + scan, the machinery of the done compaction) puts the expensive landers in
-// their own warps; stability keeps each class in ascending env order, so the field-major loads of a warp
-// still fall in a handful of neighbouring sectors.  Results are unaffected: which thread steps an env is
-// invisible to it.
+// A lander near the ground (one whose broad phase holds a contact pair) runs the narrow phase and, when it touches, a
+// several times longer solver path than one in free flight; a warp runs as long as its slowest lane and a launch as
+// long as its slowest warp.  A STABLE partition of the env ids by "a contact pair exists" (warp ballot + block counts +
+// scan, the machinery of the done compaction) splits the batch into two classes that are stepped by two different
+// kernels, concurrently: the free-flight class by step_kernel<LunarLanderT<C, false>> (no narrow phase, no contact rows,
+// no contact slots loaded or stored: fewer registers, more resident warps), the other by <C, true>.  A lander cannot
+// change class inside a step -- pairs are created by FindNewContacts at the END of World.Step -- so the class is known
+// from the stored state.  Stability keeps each class in ascending env order, so the field-major loads of a warp still
+// fall in a handful of neighbouring sectors.  Results are unaffected: which thread steps an env is invisible to it.
 constexpr int PART_BLOCK = 256;
+constexpr int LUNAR_PAIRS_WORD = 26;   // aux word of lunar::Lander::pairs[0] (lunar.cuh static_asserts it)
 
 __device__ __forceinline__ bool lander_in_contact(const int32_t* aux, int n, int i) {
-    return (aux[i] | aux[(size_t)n + i] | aux[2 * (size_t)n + i]) != 0;   // touch[0..2]: first three aux words
+    return aux[(size_t)LUNAR_PAIRS_WORD * (size_t)n + i] != -1;   // first word of the broad-phase pair list: 0xffffffff = no contact exists
 }
 
-__global__ void __launch_bounds__(PART_BLOCK) partition_count_kernel(const int32_t* aux, int n, int32_t* block_free) {
+static __global__ void __launch_bounds__(PART_BLOCK) partition_count_kernel(const int32_t* aux, int n, int32_t* block_free) {
     const int i = blockIdx.x * PART_BLOCK + threadIdx.x;
     const bool free_flight = i < n && !lander_in_contact(aux, n, i);
     const int c = __syncthreads_count(free_flight);
@@ -644,7 +665,7 @@ __global__ void __launch_bounds__(PART_BLOCK) partition_count_kernel(const int32
 }
 
 // single block: exclusive scan of the per-block counts, in place; block_free[nb] = total
-__global__ void __launch_bounds__(1024) partition_scan_kernel(int32_t* block_free, int nb) {
+static __global__ void __launch_bounds__(1024) partition_scan_kernel(int32_t* block_free, int nb) {
     __shared__ int carry;
     __shared__ int warp_sum[32];
     if (threadIdx.x == 0) carry = 0;
@@ -673,7 +694,7 @@ __global__ void __launch_bounds__(1024) partition_scan_kernel(int32_t* block_fre
     if (threadIdx.x == 0) block_free[nb] = carry;
 }
 
-__global__ void __launch_bounds__(PART_BLOCK) partition_scatter_kernel(const int32_t* aux, int n, const int32_t* block_free, int nb, int32_t* perm) {
+static __global__ void __launch_bounds__(PART_BLOCK) partition_scatter_kernel(const int32_t* aux, int n, const int32_t* block_free, int nb, int32_t* perm) {
     __shared__ int warp_free[PART_BLOCK / 32];
     const int i = blockIdx.x * PART_BLOCK + threadIdx.x;
     const bool in = i < n;

@@ -61,6 +61,8 @@ constexpr int VELOCITY_ITERATIONS = 180, POSITION_ITERATIONS = 60;   // :723-724
 constexpr float DEFAULT_FRICTION = 0.2f;
 
 constexpr int MAXC = 6;   // touching manifolds kept per lander
+constexpr int MAXP = 12;  // broad-phase pairs (contacts that exist, touching or not) kept per lander, in creation order
+constexpr float AABB_EXTENSION = 0.1f, AABB_MULTIPLIER = 2.0f;   // Settings.AABBExtension / AABBMultiplier
 
 // ---------------------------------------------------------------- small vector algebra (b2Math)
 struct V2 { float x, y; };
@@ -131,6 +133,8 @@ struct Lander {
     V2 force;                  // force accumulator of the fuselage (ApplyForce in Reset, :496)
     float torque;
     uint32_t touch[3];         // bit e of touch[body]: polygon `body` was touching edge e after the last Collide
+    float fat[3][4];           // broad-phase proxy box of each polygon (lo.x, lo.y, hi.x, hi.y): replaced only when the swept tight box leaves it
+    uint32_t pairs[3];         // the contacts that exist (fat boxes overlap), in creation order: byte k = body * 16 + edge, 0xff = none
     int32_t flags;
     int32_t wind_idx, torque_idx;
     float gravity, wind_power, turbulence_power;
@@ -138,8 +142,8 @@ struct Lander {
     float obs[8];
 };
 
-constexpr int STATE_DIM = 21 + 8 + 4 * MAXC + CHUNKS + 1 + 3;        // 68
-constexpr int AUX_DIM = 3 + 1 + 2 + 3 * MAXC + 2 + 2;                  // touch[3], flags, limit[2], slots, wind idx, ep_t, episode
+constexpr int STATE_DIM = 21 + 8 + 4 * MAXC + CHUNKS + 1 + 3 + 12;   // 80
+constexpr int AUX_DIM = 3 + 1 + 2 + 3 * MAXC + 2 + 3 + 2;              // touch[3], flags, limit[2], slots, wind idx, pairs[3], ep_t, episode
 
 __device__ __forceinline__ void zero_lander(Lander& L) {
     for (int i = 0; i < 3; ++i) { L.b[i].c = mk(0.0f, 0.0f); L.b[i].a = 0.0f; L.b[i].v = mk(0.0f, 0.0f); L.b[i].w = 0.0f; L.b[i].sleep_time = 0.0f; L.touch[i] = 0u; }
@@ -149,6 +153,7 @@ __device__ __forceinline__ void zero_lander(Lander& L) {
     L.prev_shaping = 0.0f; L.force = mk(0.0f, 0.0f); L.torque = 0.0f; L.flags = 0;
     L.wind_idx = 0; L.torque_idx = 0; L.gravity = 0.0f; L.wind_power = 0.0f; L.turbulence_power = 0.0f; L.use_wind = 0;
     for (int i = 0; i < 8; ++i) L.obs[i] = 0.0f;
+    for (int i = 0; i < 3; ++i) { L.pairs[i] = 0xffffffffu; for (int j = 0; j < 4; ++j) L.fat[i][j] = 0.0f; }
 }
 
 // ---------------------------------------------------------------- geometry helpers
@@ -189,7 +194,7 @@ __device__ __forceinline__ int clip_segment(ClipVertex out[2], const ClipVertex 
 }
 
 // Edge A (static, identity transform, no adjacent vertices) vs polygon B with transform (p, q).
-__device__ __noinline__ void collide_edge_polygon(Manifold* m, V2 v1, V2 v2, const Shape& sh, V2 p, Rot q) {
+static __device__ __noinline__ void collide_edge_polygon(Manifold* m, V2 v1, V2 v2, const Shape& sh, V2 p, Rot q) {
     m->count = 0;
     m->type = 0;
     const V2 centroid = rmul(q, sh.centroid) + p;
@@ -344,67 +349,222 @@ __device__ __forceinline__ void set_awake(Lander& L, bool awake) {
     }
 }
 
+// ---------------------------------------------------------------- broad phase (b2BroadPhase / b2Fixture::Synchronize)
+// A contact EXISTS while the fat boxes of its two fixtures overlap -- created by FindNewContacts (appended to the world's
+// contact list, pushed on the FRONT of the body's contact list), destroyed by Collide when they stop overlapping -- and is
+// TOUCHING while its manifold has points.  The order of creation is state: Collide fires BeginContact / EndContact in
+// creation order ("last BeginContact wins", LunarLanderEnv.cs:316-329) and the island takes a body's contacts newest first.
+struct Box { float lx, ly, hx, hy; };
+__device__ __forceinline__ Box body_box(const Shape& sh, V2 p, Rot q) {   // b2PolygonShape::ComputeAABB
+    V2 lo = rmul(q, sh.v[0]) + p, hi = lo;
+    for (int i = 1; i < sh.count; ++i) {
+        const V2 w = rmul(q, sh.v[i]) + p;
+        lo = mk(minf(lo.x, w.x), minf(lo.y, w.y)); hi = mk(maxf(hi.x, w.x), maxf(hi.y, w.y));
+    }
+    return Box{lo.x - POLYGON_RADIUS, lo.y - POLYGON_RADIUS, hi.x + POLYGON_RADIUS, hi.y + POLYGON_RADIUS};
+}
+__device__ __forceinline__ Box edge_fat_box(const Lander& L, int e) {     // b2EdgeShape::ComputeAABB grown once by aabbExtension (static: never moves)
+    V2 v1, v2;
+    edge_points(L, e, &v1, &v2);
+    const float lx = minf(v1.x, v2.x) - POLYGON_RADIUS, ly = minf(v1.y, v2.y) - POLYGON_RADIUS;
+    const float hx = maxf(v1.x, v2.x) + POLYGON_RADIUS, hy = maxf(v1.y, v2.y) + POLYGON_RADIUS;
+    return Box{lx - AABB_EXTENSION, ly - AABB_EXTENSION, hx + AABB_EXTENSION, hy + AABB_EXTENSION};
+}
+__device__ __forceinline__ bool boxes_overlap(const Box& a, const Box& b) {
+    if (b.lx - a.hx > 0.0f || b.ly - a.hy > 0.0f) return false;
+    if (a.lx - b.hx > 0.0f || a.ly - b.hy > 0.0f) return false;
+    return true;
+}
+__device__ __forceinline__ Box fat_of(const Lander& L, int body) { return Box{L.fat[body][0], L.fat[body][1], L.fat[body][2], L.fat[body][3]}; }
+__device__ __forceinline__ uint32_t pair_at(const Lander& L, int k) { return (L.pairs[k >> 2] >> (8 * (k & 3))) & 0xffu; }
+__device__ __forceinline__ void pair_put(Lander& L, int k, uint32_t v) { L.pairs[k >> 2] = (L.pairs[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (v << (8 * (k & 3))); }
+__device__ __forceinline__ int pair_count(const Lander& L) { int n = 0; while (n < MAXP && pair_at(L, n) != 0xffu) ++n; return n; }
+
+// ---------------------------------------------------------------- register-resident constraint rows
+// The 180 velocity and up to 60 position iterations are one long dependent float32 chain per lander, and a launch lasts as
+// long as its slowest lander.  In the common configuration -- at most ONE touching manifold per body -- the rows below keep
+// every operand of that chain in registers with compile-time body indices: no local-memory round trip, no loop bookkeeping,
+// no body multiplexing inside the iterations, and the chains of the three bodies are independent straight-line code the
+// scheduler can interleave.  Anything else (two manifolds on one body: a polygon astride a terrain vertex) takes the general
+// loops over the ActiveContact array.  Both evaluate the same operations in the same (island) order: same bits.
+struct VelRow {
+    V2 normal, rb0, rb1;
+    float ni0, ni1, ti0, ti1, nm0, nm1, tm0, tm1, friction;
+    float k11, k12, k22, i11, i12, i21, i22;
+    int count;   // velocity-constraint points of the body's manifold; 0 = the body touches nothing
+};
+struct PosRow { V2 local_normal, local_point, lp0, lp1; int type, count; };
+
+__device__ __forceinline__ void friction_point(V2& vB, float& wB, float mB, float iB, V2 tangent, V2 rb, float tangent_mass, float friction, float normal_impulse, float& tangent_impulse) {
+    const V2 dv = vB + cross_sv(wB, rb);
+    const float vt = dot(dv, tangent);
+    float lambda = tangent_mass * (-vt);
+    const float max_friction = friction * normal_impulse;
+    const float new_impulse = clampf(tangent_impulse + lambda, -max_friction, max_friction);
+    lambda = new_impulse - tangent_impulse;
+    tangent_impulse = new_impulse;
+    const V2 P = lambda * tangent;
+    vB = vB + mB * P;
+    wB = wB + iB * cross(rb, P);
+}
+
+// b2ContactSolver::SolveVelocityConstraints for one manifold of a body against the static ground (friction first, then the
+// normal row or the 2-point block LCP by enumeration of its four cases)
+__device__ __forceinline__ void solve_velocity_row(VelRow& r, V2& vB, float& wB, float mB, float iB) {
+    const V2 normal = r.normal;
+    const V2 tangent = cross_vs(normal, 1.0f);
+    friction_point(vB, wB, mB, iB, tangent, r.rb0, r.tm0, r.friction, r.ni0, r.ti0);
+    if (r.count == 2) friction_point(vB, wB, mB, iB, tangent, r.rb1, r.tm1, r.friction, r.ni1, r.ti1);
+    if (r.count == 1) {
+        const V2 dv = vB + cross_sv(wB, r.rb0);
+        const float vn = dot(dv, normal);
+        float lambda = -r.nm0 * vn;   // velocity bias 0: restitution 0 (:242, :268)
+        const float new_impulse = maxf(r.ni0 + lambda, 0.0f);
+        lambda = new_impulse - r.ni0;
+        r.ni0 = new_impulse;
+        const V2 P = lambda * normal;
+        vB = vB + mB * P;
+        wB = wB + iB * cross(r.rb0, P);
+    } else {
+        const V2 aa = mk(r.ni0, r.ni1);
+        const V2 dv1 = vB + cross_sv(wB, r.rb0);
+        const V2 dv2 = vB + cross_sv(wB, r.rb1);
+        const float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+        V2 b = mk(vn1, vn2);
+        b = b - mk(r.k11 * aa.x + r.k12 * aa.y, r.k12 * aa.x + r.k22 * aa.y);
+        // the four candidates, evaluated without branches, first valid one taken
+        const V2 x1 = -mk(r.i11 * b.x + r.i12 * b.y, r.i21 * b.x + r.i22 * b.y);
+        const bool ok1 = x1.x >= 0.0f && x1.y >= 0.0f;
+        const float x2 = -r.nm0 * b.x;
+        const bool ok2 = x2 >= 0.0f && (r.k12 * x2 + b.y) >= 0.0f;
+        const float y3 = -r.nm1 * b.y;
+        const bool ok3 = y3 >= 0.0f && (r.k12 * y3 + b.x) >= 0.0f;
+        const bool ok4 = b.x >= 0.0f && b.y >= 0.0f;
+        V2 x = mk(0.0f, 0.0f);
+        if (ok3) x = mk(0.0f, y3);
+        if (ok2) x = mk(x2, 0.0f);
+        if (ok1) x = x1;
+        if (ok1 || ok2 || ok3 || ok4) {
+            const V2 d = x - aa;
+            const V2 P1 = d.x * normal, P2 = d.y * normal;
+            vB = vB + mB * (P1 + P2);
+            wB = wB + iB * (cross(r.rb0, P1) + cross(r.rb1, P2));
+            r.ni0 = x.x;
+            r.ni1 = x.y;
+        }
+    }
+}
+
+// one point of b2ContactSolver::SolvePositionConstraints (pseudo-impulse with Baumgarte, body against the static ground)
+__device__ __forceinline__ void position_point(int type, V2 local_normal, V2 local_point, V2 lp, V2 centroid, float mB, float iB, V2& cB, float& aB, float& min_separation) {
+    const Rot qB = rot(aB);
+    const V2 pB = cB - rmul(qB, centroid);
+    V2 normal, point;
+    float separation;
+    if (type == MF_FACE_A) {
+        normal = local_normal;
+        const V2 clip = rmul(qB, lp) + pB;
+        separation = dot(clip - local_point, normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+        point = clip;
+    } else {
+        normal = rmul(qB, local_normal);
+        const V2 plane = rmul(qB, local_point) + pB;
+        separation = dot(lp - plane, normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+        point = lp;
+        normal = -normal;
+    }
+    const V2 rB = point - cB;
+    min_separation = minf(min_separation, separation);
+    const float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
+    const float rnB = cross(rB, normal);
+    const float K = mB + iB * rnB * rnB;
+    const float impulse = K > 0.0f ? -C / K : 0.0f;
+    const V2 P = impulse * normal;
+    cB = cB + mB * P;
+    aB = aB + iB * cross(rB, P);
+}
+
+// HAS_PAIRS = false: the caller guarantees that no contact exists (the pair list is empty) -- the narrow phase and every
+// contact row compile out (the free-flight kernel).
+template <bool HAS_PAIRS>
 __device__ __noinline__ void world_step(Lander& L) {
     const float h = DT;
     const float dt_ratio = (L.flags & F_FIRST_STEP) ? 0.0f : 1.0f;   // inv_dt0 * dt: 0 on a new World, then 50 * 0.02f = 1
-    ActiveContact ac[MAXC];
+    ActiveContact ac[HAS_PAIRS ? MAXC : 1];
     int nc = 0;
 
-    // ---- ContactManager.Collide: update every (polygon, edge) pair whose AABBs can overlap
-    if (L.flags & F_AWAKE) {
-        for (int body = 0; body < 3; ++body) {
-            const Shape& sh = SHAPES[body];
-            const Rot q = rot(L.b[body].a);
-            const V2 p = L.b[body].c - rmul(q, sh.centroid);
-            float xmin = 3.4028234663852886e38f, xmax = -3.4028234663852886e38f, ymin = 3.4028234663852886e38f;
-            for (int i = 0; i < sh.count; ++i) {
-                const V2 w = rmul(q, sh.v[i]) + p;
-                xmin = minf(xmin, w.x); xmax = maxf(xmax, w.x); ymin = minf(ymin, w.y);
+    // ---- ContactManager.Collide: every existing contact, in creation order
+    if (HAS_PAIRS && (L.flags & F_AWAKE)) {
+        Rot q[3]; V2 p[3];
+#pragma unroll
+        for (int body = 0; body < 3; ++body) { q[body] = rot(L.b[body].a); p[body] = L.b[body].c - rmul(q[body], SHAPES[body].centroid); }
+        const int np = pair_count(L);
+        int kept = 0;
+        for (int k = 0; k < np; ++k) {
+            const uint32_t pr = pair_at(L, k);
+            const int body = (int)(pr >> 4), e = (int)(pr & 15u);
+            const bool was = (L.touch[body] >> e) & 1u;
+            if (!boxes_overlap(edge_fat_box(L, e), fat_of(L, body))) {   // the fat boxes parted: the contact is destroyed
+                if (was) { end_contact(L, body); L.touch[body] &= ~(1u << e); }
+                continue;
             }
-            const float margin = 0.1f;   // aabbExtension: a pair farther than this cannot be touching
-            uint32_t now = 0;
-            for (int e = 0; e < NUM_EDGES; ++e) {
-                V2 v1, v2;
-                edge_points(L, e, &v1, &v2);
-                const bool overlap = xmax + margin >= v1.x && xmin - margin <= v2.x &&
-                                     ymin - margin <= maxf(v1.y, v2.y);
-                Manifold m;
-                m.count = 0;
-                if (overlap) collide_edge_polygon(&m, v1, v2, sh, p, q);
-                const bool touching = m.count > 0 && nc < MAXC;
-                const bool was = (L.touch[body] >> e) & 1u;
-                if (touching) {
-                    now |= 1u << e;
-                    ActiveContact& c = ac[nc++];
-                    c.body = body; c.edge = e; c.count = m.count; c.m = m;
-                    for (int k = 0; k < 2; ++k) { c.p[k].normal_impulse = 0.0f; c.p[k].tangent_impulse = 0.0f; }
-                    // b2Contact::Update: match old manifold points by id, copy their impulses (warm start)
-                    const int32_t pair = body * 16 + e;
-                    for (int s = 0; s < MAXC; ++s) {
-                        if (L.c[s].pair != pair) continue;
-                        for (int k = 0; k < m.count; ++k)
-                            for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
-                                if (L.c[s].key[o] != NO_KEY && L.c[s].key[o] == m.key[k]) {
-                                    c.p[k].normal_impulse = L.c[s].ni[o]; c.p[k].tangent_impulse = L.c[s].ti[o];
-                                }
-                    }
+            pair_put(L, kept++, pr);
+            V2 v1, v2;
+            edge_points(L, e, &v1, &v2);
+            Manifold m;
+            collide_edge_polygon(&m, v1, v2, SHAPES[body], GETB(p, body), GETB(q, body));
+            const bool touching = m.count > 0 && nc < MAXC;
+            if (touching) {
+                L.touch[body] |= 1u << e;
+                ActiveContact& c = ac[nc++];
+                c.body = body; c.edge = e; c.count = m.count; c.m = m;
+                for (int j = 0; j < 2; ++j) { c.p[j].normal_impulse = 0.0f; c.p[j].tangent_impulse = 0.0f; }
+                // b2Contact::Update: match old manifold points by id, copy their impulses (warm start)
+                const int32_t pair = body * 16 + e;
+                for (int sl = 0; sl < MAXC; ++sl) {
+                    if (L.c[sl].pair != pair) continue;
+                    for (int j = 0; j < m.count; ++j)
+                        for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
+                            if (L.c[sl].key[o] != NO_KEY && L.c[sl].key[o] == m.key[j]) {
+                                c.p[j].normal_impulse = L.c[sl].ni[o]; c.p[j].tangent_impulse = L.c[sl].ti[o];
+                            }
                 }
-                if (touching && !was) begin_contact(L, body);
-                if (!touching && was) end_contact(L, body);
+            } else {
+                L.touch[body] &= ~(1u << e);
             }
-            L.touch[body] = now;
+            if (touching && !was) begin_contact(L, body);
+            if (!touching && was) end_contact(L, body);
         }
+        for (int k = kept; k < np; ++k) pair_put(L, k, 0xffu);
+    }
+    // island order of the touching contacts: bodies in DFS order (fuselage, leg 0, leg 1), each body's contacts newest first;
+    // four bits per entry.  `row_of[B]` = index of body B's manifold when every body has at most one (the register path).
+    uint32_t order = 0u;
+    int row_of[3] = {-1, -1, -1};
+    bool simple = true;
+    if (HAS_PAIRS) {
+        int no = 0;
+#pragma unroll
+        for (int body = 0; body < 3; ++body)
+            for (int k = nc - 1; k >= 0; --k)
+                if (ac[k].body == body) {
+                    order |= (uint32_t)k << (4 * no++);
+                    if (row_of[body] >= 0) simple = false;
+                    row_of[body] = k;
+                }
     }
 
     // ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1}
     if (L.flags & F_AWAKE) {
         V2 c[3], v[3];
         float a[3], w[3];
+        V2 c0[3]; float a0[3];   // the sweep's c0 / a0: the pose this step started from
         Joint Jl[2] = {L.j[0], L.j[1]};   // joint accumulators live in registers during the iterations
         const V2 gravity = mk(0.0f, L.gravity);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             c[i] = L.b[i].c; a[i] = L.b[i].a; v[i] = L.b[i].v; w[i] = L.b[i].w;
+            c0[i] = c[i]; a0[i] = a[i];
             const V2 f = i == 0 ? L.force : mk(0.0f, 0.0f);
             const float tq = i == 0 ? L.torque : 0.0f;
             v[i] = v[i] + h * (gravity + SHAPES[i].inv_mass * f);
@@ -413,7 +573,7 @@ __device__ __noinline__ void world_step(Lander& L) {
             w[i] = w[i] * (1.0f / (1.0f + h * 0.0f));
         }
 
-        // contact solver: InitializeVelocityConstraints
+        // contact solver: InitializeVelocityConstraints (any order: rows do not interact here)
         for (int k = 0; k < nc; ++k) {
             ActiveContact& cc = ac[k];
             const int B = cc.body;
@@ -474,9 +634,9 @@ __device__ __noinline__ void world_step(Lander& L) {
                 }
             }
         }
-        // contact solver: WarmStart
-        for (int k = 0; k < nc; ++k) {
-            ActiveContact& cc = ac[k];
+        // contact solver: WarmStart, island order
+        for (int kk = 0; kk < nc; ++kk) {
+            ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
             const int B = cc.body;
             V2 vB = GETB(v, B); float wB = GETB(w, B);
             const V2 tangent = cross_vs(cc.normal, 1.0f);
@@ -539,8 +699,8 @@ __device__ __noinline__ void world_step(Lander& L) {
             w[B] = w[B] + iB * (cross(W.rb, P) + J.motor + J.iz);
         }
 
-        // velocity iterations
-        for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+        // one velocity iteration of the two revolute joints (b2RevoluteJoint::SolveVelocityConstraints), leg1's then leg0's
+        auto solve_joints_velocity = [&]() {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int ji = 1 - jj;
@@ -606,76 +766,59 @@ __device__ __noinline__ void world_step(Lander& L) {
                     w[B] = w[B] + iB * cross(W.rb, impulse);
                 }
             }
-            for (int k = 0; k < nc; ++k) {
-                ActiveContact& cc = ac[k];
-                const int B = cc.body;
-                V2 vB = GETB(v, B); float wB = GETB(w, B);   // only velocities change in a velocity iteration
-                const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
-                const V2 normal = cc.normal;
-                const V2 tangent = cross_vs(normal, 1.0f);
-                // friction first
-                for (int j = 0; j < cc.count; ++j) {
-                    VelPoint& vp = cc.p[j];
-                    const V2 dv = vB + cross_sv(wB, vp.rb);
-                    const float vt = dot(dv, tangent);
-                    float lambda = vp.tangent_mass * (-vt);
-                    const float max_friction = cc.friction * vp.normal_impulse;
-                    const float new_impulse = clampf(vp.tangent_impulse + lambda, -max_friction, max_friction);
-                    lambda = new_impulse - vp.tangent_impulse;
-                    vp.tangent_impulse = new_impulse;
-                    const V2 P = lambda * tangent;
-                    vB = vB + mB * P;
-                    wB = wB + iB * cross(vp.rb, P);
+        };
+
+        // ---- velocity iterations
+        if (!HAS_PAIRS || nc == 0) {
+            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) solve_joints_velocity();
+        } else if (simple) {
+            VelRow row[3];
+#pragma unroll
+            for (int B = 0; B < 3; ++B) {
+                VelRow& r = row[B];
+                r.count = 0;
+                if (row_of[B] >= 0) {
+                    const ActiveContact& cc = ac[row_of[B]];
+                    r.normal = cc.normal; r.rb0 = cc.p[0].rb; r.rb1 = cc.p[1].rb;
+                    r.ni0 = cc.p[0].normal_impulse; r.ni1 = cc.p[1].normal_impulse; r.ti0 = cc.p[0].tangent_impulse; r.ti1 = cc.p[1].tangent_impulse;
+                    r.nm0 = cc.p[0].normal_mass; r.nm1 = cc.p[1].normal_mass; r.tm0 = cc.p[0].tangent_mass; r.tm1 = cc.p[1].tangent_mass;
+                    r.friction = cc.friction;
+                    r.k11 = cc.k11; r.k12 = cc.k12; r.k22 = cc.k22; r.i11 = cc.nm11; r.i12 = cc.nm12; r.i21 = cc.nm21; r.i22 = cc.nm22;
+                    r.count = cc.count;
                 }
-                if (cc.count == 1) {
-                    VelPoint& vp = cc.p[0];
-                    const V2 dv = vB + cross_sv(wB, vp.rb);
-                    const float vn = dot(dv, normal);
-                    float lambda = -vp.normal_mass * (vn - vp.velocity_bias);
-                    const float new_impulse = maxf(vp.normal_impulse + lambda, 0.0f);
-                    lambda = new_impulse - vp.normal_impulse;
-                    vp.normal_impulse = new_impulse;
-                    const V2 P = lambda * normal;
-                    vB = vB + mB * P;
-                    wB = wB + iB * cross(vp.rb, P);
-                } else {
-                    VelPoint& cp1 = cc.p[0];
-                    VelPoint& cp2 = cc.p[1];
-                    const V2 aa = mk(cp1.normal_impulse, cp2.normal_impulse);
-                    const V2 dv1 = vB + cross_sv(wB, cp1.rb);
-                    const V2 dv2 = vB + cross_sv(wB, cp2.rb);
-                    float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-                    V2 b = mk(vn1 - cp1.velocity_bias, vn2 - cp2.velocity_bias);
-                    b = b - mk(cc.k11 * aa.x + cc.k12 * aa.y, cc.k12 * aa.x + cc.k22 * aa.y);
-                    V2 x;
-                    bool solved = false;
-                    // case 1: both active
-                    x = -mk(cc.nm11 * b.x + cc.nm12 * b.y, cc.nm21 * b.x + cc.nm22 * b.y);
-                    if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
-                    if (!solved) {   // case 2: x2 = 0
-                        x = mk(-cp1.normal_mass * b.x, 0.0f);
-                        vn2 = cc.k12 * x.x + b.y;
-                        if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
-                    }
-                    if (!solved) {   // case 3: x1 = 0
-                        x = mk(0.0f, -cp2.normal_mass * b.y);
-                        vn1 = cc.k12 * x.y + b.x;
-                        if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
-                    }
-                    if (!solved) {   // case 4: both zero
-                        x = mk(0.0f, 0.0f);
-                        if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
-                    }
-                    if (solved) {
-                        const V2 d = x - aa;
-                        const V2 P1 = d.x * normal, P2 = d.y * normal;
-                        vB = vB + mB * (P1 + P2);
-                        wB = wB + iB * (cross(cp1.rb, P1) + cross(cp2.rb, P2));
-                        cp1.normal_impulse = x.x;
-                        cp2.normal_impulse = x.y;
-                    }
+            }
+            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+                solve_joints_velocity();
+#pragma unroll
+                for (int B = 0; B < 3; ++B)
+                    if (row[B].count > 0) solve_velocity_row(row[B], v[B], w[B], SHAPES[B].inv_mass, SHAPES[B].inv_inertia);
+            }
+#pragma unroll
+            for (int B = 0; B < 3; ++B)
+                if (row_of[B] >= 0) {
+                    ActiveContact& cc = ac[row_of[B]];
+                    cc.p[0].normal_impulse = row[B].ni0; cc.p[0].tangent_impulse = row[B].ti0;
+                    if (cc.count == 2) { cc.p[1].normal_impulse = row[B].ni1; cc.p[1].tangent_impulse = row[B].ti1; }
                 }
-                SETB(v, B, vB); SETB(w, B, wB);
+        } else {
+            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+                solve_joints_velocity();
+                for (int kk = 0; kk < nc; ++kk) {
+                    ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
+                    const int B = cc.body;
+                    V2 vB = GETB(v, B); float wB = GETB(w, B);   // only velocities change in a velocity iteration
+                    VelRow r;
+                    r.normal = cc.normal; r.rb0 = cc.p[0].rb; r.rb1 = cc.p[1].rb;
+                    r.ni0 = cc.p[0].normal_impulse; r.ni1 = cc.p[1].normal_impulse; r.ti0 = cc.p[0].tangent_impulse; r.ti1 = cc.p[1].tangent_impulse;
+                    r.nm0 = cc.p[0].normal_mass; r.nm1 = cc.p[1].normal_mass; r.tm0 = cc.p[0].tangent_mass; r.tm1 = cc.p[1].tangent_mass;
+                    r.friction = cc.friction;
+                    r.k11 = cc.k11; r.k12 = cc.k12; r.k22 = cc.k22; r.i11 = cc.nm11; r.i12 = cc.nm12; r.i21 = cc.nm21; r.i22 = cc.nm22;
+                    r.count = cc.count;
+                    solve_velocity_row(r, vB, wB, SHAPES[B].inv_mass, SHAPES[B].inv_inertia);
+                    cc.p[0].normal_impulse = r.ni0; cc.p[0].tangent_impulse = r.ti0;
+                    if (cc.count == 2) { cc.p[1].normal_impulse = r.ni1; cc.p[1].tangent_impulse = r.ti1; }
+                    SETB(v, B, vB); SETB(w, B, wB);
+                }
             }
         }
 
@@ -696,52 +839,47 @@ __device__ __noinline__ void world_step(Lander& L) {
             a[i] = a[i] + h * w[i];
         }
 
-        // position iterations
+        // ---- position iterations
         // A position iteration is a pure function of the nine coordinates (c, a) of the three bodies.  Box2D's exit
         // test never fires while a leg rests on its joint limit (the limit is corrected down to angular_error ~
         // ANGULAR_SLOP + 1 ulp, just above what joints_okay accepts), but after two or three iterations the
         // corrections round to nothing: once an iteration returns bit-identical coordinates, the remaining ones
         // would too, so the loop stops there -- same result as all 60, position_solved stays false.
+        PosRow prow[3];
+        if (HAS_PAIRS && simple) {
+#pragma unroll
+            for (int B = 0; B < 3; ++B) {
+                prow[B].count = 0;
+                if (row_of[B] >= 0) {
+                    const Manifold& m = ac[row_of[B]].m;
+                    prow[B].local_normal = m.local_normal; prow[B].local_point = m.local_point; prow[B].lp0 = m.lp[0]; prow[B].lp1 = m.lp[1];
+                    prow[B].type = m.type; prow[B].count = m.count;
+                }
+            }
+        }
         bool position_solved = false;
         for (int it = 0; it < POSITION_ITERATIONS; ++it) {
             const V2 c_in[3] = {c[0], c[1], c[2]};
             const float a_in[3] = {a[0], a[1], a[2]};
             float min_separation = 0.0f;
-            for (int k = 0; k < nc; ++k) {
-                const ActiveContact& cc = ac[k];
-                const int B = cc.body;
-                V2 cB = GETB(c, B); float aB = GETB(a, B);   // only positions change in a position iteration
-                const float mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
-                for (int j = 0; j < cc.m.count; ++j) {
-                    const Rot qB = rot(aB);
-                    const V2 pB = cB - rmul(qB, SHAPES[B].centroid);
-                    V2 normal, point;
-                    float separation;
-                    if (cc.m.type == MF_FACE_A) {
-                        normal = cc.m.local_normal;
-                        const V2 plane = cc.m.local_point;
-                        const V2 clip = rmul(qB, cc.m.lp[j]) + pB;
-                        separation = dot(clip - plane, normal) - POLYGON_RADIUS - POLYGON_RADIUS;
-                        point = clip;
-                    } else {
-                        normal = rmul(qB, cc.m.local_normal);
-                        const V2 plane = rmul(qB, cc.m.local_point) + pB;
-                        const V2 clip = cc.m.lp[j];
-                        separation = dot(clip - plane, normal) - POLYGON_RADIUS - POLYGON_RADIUS;
-                        point = clip;
-                        normal = -normal;
+            if (HAS_PAIRS && nc > 0) {
+                if (simple) {
+#pragma unroll
+                    for (int B = 0; B < 3; ++B) {
+                        const PosRow& m = prow[B];
+                        if (m.count > 0) position_point(m.type, m.local_normal, m.local_point, m.lp0, SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, c[B], a[B], min_separation);
+                        if (m.count > 1) position_point(m.type, m.local_normal, m.local_point, m.lp1, SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, c[B], a[B], min_separation);
                     }
-                    const V2 rB = point - cB;
-                    min_separation = minf(min_separation, separation);
-                    const float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
-                    const float rnB = cross(rB, normal);
-                    const float K = mB + iB * rnB * rnB;
-                    const float impulse = K > 0.0f ? -C / K : 0.0f;
-                    const V2 P = impulse * normal;
-                    cB = cB + mB * P;
-                    aB = aB + iB * cross(rB, P);
+                } else {
+                    for (int kk = 0; kk < nc; ++kk) {
+                        const ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
+                        const int B = cc.body;
+                        V2 cB = GETB(c, B); float aB = GETB(a, B);   // only positions change in a position iteration
+                        for (int j = 0; j < cc.m.count; ++j)
+                            position_point(cc.m.type, cc.m.local_normal, cc.m.local_point, cc.m.lp[j], SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, cB, aB, min_separation);
+                        SETB(c, B, cB); SETB(a, B, aB);
+                    }
                 }
-                SETB(c, B, cB); SETB(a, B, aB);
             }
             const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
             bool joints_okay = true;
@@ -798,22 +936,24 @@ __device__ __noinline__ void world_step(Lander& L) {
             if (moved == 0) break;   // fixed point
         }
 
-        // copy back, store impulses (b2ContactSolver::StoreImpulses)
+        // copy back, store impulses (b2ContactSolver::StoreImpulses): slots in creation order
 #pragma unroll
         for (int i = 0; i < 3; ++i) { L.b[i].c = c[i]; L.b[i].a = a[i]; L.b[i].v = v[i]; L.b[i].w = w[i]; }
         L.j[0] = Jl[0]; L.j[1] = Jl[1];
-        for (int s = 0; s < MAXC; ++s) {
-            ContactSlot& cs = L.c[s];
-            if (s < nc) {
-                cs.pair = ac[s].body * 16 + ac[s].edge;
-                for (int k = 0; k < 2; ++k) {
-                    const bool live = k < ac[s].m.count;
-                    cs.key[k] = live ? ac[s].m.key[k] : NO_KEY;
-                    cs.ni[k] = live ? ac[s].p[k].normal_impulse : 0.0f;
-                    cs.ti[k] = live ? ac[s].p[k].tangent_impulse : 0.0f;
+        if (HAS_PAIRS) {
+            for (int s = 0; s < MAXC; ++s) {
+                ContactSlot& cs = L.c[s];
+                if (s < nc) {
+                    cs.pair = ac[s].body * 16 + ac[s].edge;
+                    for (int k = 0; k < 2; ++k) {
+                        const bool live = k < ac[s].m.count;
+                        cs.key[k] = live ? ac[s].m.key[k] : NO_KEY;
+                        cs.ni[k] = live ? ac[s].p[k].normal_impulse : 0.0f;
+                        cs.ti[k] = live ? ac[s].p[k].tangent_impulse : 0.0f;
+                    }
+                } else {
+                    cs.pair = -1; cs.key[0] = cs.key[1] = NO_KEY; cs.ni[0] = cs.ni[1] = cs.ti[0] = cs.ti[1] = 0.0f;
                 }
-            } else {
-                cs.pair = -1; cs.key[0] = cs.key[1] = NO_KEY; cs.ni[0] = cs.ni[1] = cs.ti[0] = cs.ti[1] = 0.0f;
             }
         }
 
@@ -831,6 +971,42 @@ __device__ __noinline__ void world_step(Lander& L) {
             }
         }
         if (min_sleep >= TIME_TO_SLEEP && position_solved) set_awake(L, false);
+
+        // b2Body::SynchronizeFixtures: the proxy box must hold the tight boxes of the start and end pose of the step; when it
+        // does not, it is replaced by their union grown by aabbExtension and stretched along twice the displacement
+        uint32_t moved = 0u;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const Rot q1 = rot(a0[i]), q2 = rot(a[i]);
+            const V2 p1 = c0[i] - rmul(q1, SHAPES[i].centroid), p2 = c[i] - rmul(q2, SHAPES[i].centroid);
+            const Box b1 = body_box(SHAPES[i], p1, q1), b2 = body_box(SHAPES[i], p2, q2);
+            const Box u = Box{minf(b1.lx, b2.lx), minf(b1.ly, b2.ly), maxf(b1.hx, b2.hx), maxf(b1.hy, b2.hy)};
+            const Box f = fat_of(L, i);
+            if (f.lx <= u.lx && f.ly <= u.ly && u.hx <= f.hx && u.hy <= f.hy) continue;
+            Box n = Box{u.lx - AABB_EXTENSION, u.ly - AABB_EXTENSION, u.hx + AABB_EXTENSION, u.hy + AABB_EXTENSION};
+            const V2 d = AABB_MULTIPLIER * (p2 - p1);
+            if (d.x < 0.0f) n.lx = n.lx + d.x; else n.hx = n.hx + d.x;
+            if (d.y < 0.0f) n.ly = n.ly + d.y; else n.hy = n.hy + d.y;
+            L.fat[i][0] = n.lx; L.fat[i][1] = n.ly; L.fat[i][2] = n.hx; L.fat[i][3] = n.hy;
+            moved |= 1u << i;
+        }
+        // ContactManager.FindNewContacts: pairs of a moved proxy, sorted by proxy id (body, then edge in creation order: the
+        // base edge was created first, :541, then the ten terrain edges), appended unless they exist already
+        if (moved) {
+            int np = pair_count(L);
+            for (int i = 0; i < 3; ++i) {
+                if (!((moved >> i) & 1u)) continue;
+                const Box f = fat_of(L, i);
+                for (int ee = 0; ee < NUM_EDGES; ++ee) {
+                    const int e = ee == 0 ? BASE_EDGE : ee - 1;
+                    if (!boxes_overlap(f, edge_fat_box(L, e))) continue;
+                    const uint32_t pr = (uint32_t)(i * 16 + e);
+                    bool exists = false;
+                    for (int k = 0; k < np; ++k) if (pair_at(L, k) == pr) exists = true;
+                    if (!exists && np < MAXP) pair_put(L, np++, pr);
+                }
+            }
+        }
     }
     // ClearForces
     L.force = mk(0.0f, 0.0f);
@@ -863,6 +1039,7 @@ __device__ __forceinline__ void observe(const Lander& L, float* o) {   // LunarL
 struct StepResult { float reward; uint8_t done; };
 
 // LunarLanderEnv.Step (:574-774).  `t` indexes the DYNAMICS stream (the two dispersion draws, :611-612).
+template <bool HAS_PAIRS = true>
 __device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action) {
     const bool continuous = (L.flags & F_CONTINUOUS) != 0;
     float a0 = 0.0f, a1 = 0.0f;
@@ -872,7 +1049,12 @@ __device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, 
         const float wind_mag = (float)(tanh(sin(0.02 * L.wind_idx) + sin(3.14159265358979323846 * 0.01 * L.wind_idx))) * L.wind_power;
         L.wind_idx += 1;
         set_awake(L, true);
-        L.force = L.force + mk(wind_mag, 0.0f);
+        {   // Body.ApplyForce(Vector2) applies the force at the body ORIGIN (Farseer lineage: ApplyForce(ref force, ref _xf.p)), so it also makes a torque about the centre
+            const Rot qw = rot(L.b[0].a);
+            const V2 origin = L.b[0].c - rmul(qw, SHAPES[0].centroid);
+            L.force = L.force + mk(wind_mag, 0.0f);
+            L.torque = L.torque + ((origin.x - L.b[0].c.x) * 0.0f - (origin.y - L.b[0].c.y) * wind_mag);
+        }
         const float torque_mag = (float)(tanh(sin(0.02 * L.torque_idx) + sin(3.14159265358979323846 * 0.01 * L.torque_idx))) * L.turbulence_power;
         L.torque_idx += 1;
         L.torque = L.torque + torque_mag;
@@ -909,7 +1091,7 @@ __device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, 
         apply_linear_impulse(L, impulse, impulse_pos);                                        // :714
     }
 
-    world_step(L);                                                                            // :721-725
+    world_step<HAS_PAIRS>(L);                                                                 // :721-725
     if (L.flags & F_FUSELAGE) L.flags |= F_GAME_OVER;                                         // :726-729
 
     // observation (:733-747)
@@ -946,6 +1128,10 @@ __device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, ui
     const Block b0 = draw(seed, gid, index, STREAM_RESET, 0), b1 = draw(seed, gid, index, STREAM_RESET, 1),
                 b2 = draw(seed, gid, index, STREAM_RESET, 2), b3 = draw(seed, gid, index, STREAM_RESET, 3);
     L.force = mk(uniformf(-INITIAL_RANDOM, INITIAL_RANDOM, b0.w0), uniformf(-INITIAL_RANDOM, INITIAL_RANDOM, b0.w1));   // :496
+    {   // ... applied at the body origin while the fuselage still sits at (0, 0), rotation 0 (:496 precedes :561): torque about the centre of mass
+        const V2 c_at_creation = rmul(rot(0.0f), SHAPES[0].centroid) + mk(0.0f, 0.0f);
+        L.torque = (0.0f - c_at_creation.x) * L.force.y - (0.0f - c_at_creation.y) * L.force.x;
+    }
     L.prev_shaping = -3.4028234663852886e38f;                                                  // :498
     float height[CHUNKS + 1];
     const uint32_t hw[12] = {b0.w2, b0.w3, b1.w0, b1.w1, b1.w2, b1.w3, b2.w0, b2.w1, b2.w2, b2.w3, b3.w0, b3.w1};
@@ -968,9 +1154,11 @@ __device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, ui
         L.b[i].a = ang;
         L.b[i].c = rmul(rot(ang), SHAPES[i].centroid) + pos;
         L.b[i].v = mk(0.0f, 0.0f); L.b[i].w = 0.0f; L.b[i].sleep_time = 0.0f;
+        const Box bx = body_box(SHAPES[i], pos, rot(ang));   // Body.Position setter -> MoveProxy with no displacement
+        L.fat[i][0] = bx.lx - AABB_EXTENSION; L.fat[i][1] = bx.ly - AABB_EXTENSION; L.fat[i][2] = bx.hx + AABB_EXTENSION; L.fat[i][3] = bx.hy + AABB_EXTENSION;
     }
     const float zero[2] = {0.0f, 0.0f};
-    step(L, seed, gid, t, 0, zero);                                                            // :567-571
+    step<false>(L, seed, gid, t, 0, zero);                                                     // :567-571 (a new world: no contact exists yet)
 }
 
 

@@ -1,0 +1,45 @@
+// LunarLander kernels of libgymcuda: the generic step / reset / sample / ctor kernels (kernels.cuh) instantiated for
+// the LunarLander traits (lunar.cuh over lunar_core.cuh), and their host launchers (lunar_launch.h).
+// The fused k-step rollout of the other envs has no LunarLander instance: one lander step is a few hundred
+// microseconds of dependent arithmetic, so a rollout is k step launches with the random policy sampled in the kernel
+// (StepArgs::sample), each launch split over the two classes of the contact partition.
+#include "lunar_launch.h"
+
+#include "lunar.cuh"
+
+namespace gymcuda {
+
+static_assert(LUNAR_PAIRS_WORD == lunar::AUXD - 3, "kernels.cuh: aux word of the broad-phase pair list");
+static_assert(LUNAR_STATE_DIM == LunarLander::SD && LUNAR_AUX_DIM == LunarLander::AUX, "lunar_launch.h: state layout");
+
+template <bool C, bool P>
+static void launch_step_t(bool auto_reset, bool limit, int grid, cudaStream_t s, const StepArgs& a) {
+    using E = LunarLanderT<C, P>;
+    if (auto_reset && limit) step_kernel<E, true, true><<<grid, STEP_BLOCK, 0, s>>>(a);
+    else if (auto_reset) step_kernel<E, true, false><<<grid, STEP_BLOCK, 0, s>>>(a);
+    else if (limit) step_kernel<E, false, true><<<grid, STEP_BLOCK, 0, s>>>(a);
+    else step_kernel<E, false, false><<<grid, STEP_BLOCK, 0, s>>>(a);
+}
+
+cudaError_t lunar_launch_step(bool continuous, bool has_pairs, bool auto_reset, bool limit, int grid, cudaStream_t s, const StepArgs& a) {
+    if (continuous) { if (has_pairs) launch_step_t<true, true>(auto_reset, limit, grid, s, a); else launch_step_t<true, false>(auto_reset, limit, grid, s, a); }
+    else { if (has_pairs) launch_step_t<false, true>(auto_reset, limit, grid, s, a); else launch_step_t<false, false>(auto_reset, limit, grid, s, a); }
+    return cudaGetLastError();
+}
+
+cudaError_t lunar_launch_reset(bool continuous, int grid, cudaStream_t s, const ResetArgs& a) {
+    if (continuous) reset_kernel<LunarLanderCont><<<grid, 128, 0, s>>>(a); else reset_kernel<LunarLander><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t lunar_launch_sample(bool continuous, int grid, cudaStream_t s, const SampleArgs& a) {
+    if (continuous) sample_kernel<LunarLanderCont><<<grid, 128, 0, s>>>(a); else sample_kernel<LunarLander><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t lunar_launch_ctor(bool continuous, int grid, cudaStream_t s, const ResetArgs& a) {
+    if (continuous) ctor_kernel<LunarLanderCont><<<grid, 128, 0, s>>>(a); else ctor_kernel<LunarLander><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace gymcuda

@@ -160,15 +160,16 @@ def test_step_kernel_rejects_invalid_actions_and_broadcasts(hs):
 
 @pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 5000, 270000])
 def test_contact_partition_is_a_stable_partition(hs, n):
-    """partition_count / partition_scan / partition_scatter (gymcuda.cu: contact_partition): free-flight landers first,
-    landers with a touching contact after them, each class in ascending env order; 270 000 envs make the single-CTA scan
-    walk more than one 1024-wide tile of block counts."""
+    """partition_count / partition_scan / partition_scatter (gymcuda.cu: lunar_step): free-flight landers first, landers
+    whose broad phase holds a contact pair after them, each class in ascending env order; 270 000 envs make the single-CTA
+    scan walk more than one 1024-wide tile of block counts."""
     rng = np.random.default_rng(n)
     sim = HostSim(hs, O.LUNARLANDER, n, 1)
     sim.aux[:] = 0
     touching = rng.random(n) < (0.3 if n < 100000 else 0.02)
-    which = rng.integers(0, 3, n)
-    sim.aux[which[touching], np.nonzero(touching)[0]] = rng.integers(1, 64, int(touching.sum()))
+    pairs_word = 26                                   # lunar::Lander::pairs[0]: 0xffffffff = no contact exists
+    sim.aux[pairs_word, :] = -1
+    sim.aux[pairs_word, np.nonzero(touching)[0]] = rng.integers(0, 0x2a, int(touching.sum())) | ~np.int32(0xff)
     perm, block_free = sim.partition()
     want = np.concatenate([np.nonzero(~touching)[0], np.nonzero(touching)[0]]).astype(np.int32)
     assert np.array_equal(perm, want)

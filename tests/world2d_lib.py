@@ -152,3 +152,148 @@ class LunarWorld:
         v = np.zeros((8, 2), np.float32); n = np.zeros((8, 2), np.float32)
         k = lib().w2d_lunar_polygon(self.h, body, _p(v), _p(n))
         return v[:k], n[:k]
+
+
+def pid_action(s):
+    """The reference test's heuristic (tests/Gym.Tests/Envs/Aether/LunarLanderEnvironment.cs:102-150), discrete."""
+    angle_targ = min(max(s[0] * 0.5 + s[2] * 1.0, -0.4), 0.4)
+    hover_targ = 0.55 * abs(s[0])
+    angle_todo = (angle_targ - s[4]) * 0.5 - s[5] * 1.0
+    hover_todo = (hover_targ - s[1]) * 0.5 - s[3] * 0.5
+    if s[6] > 0 or s[7] > 0:
+        angle_todo = 0.0
+        hover_todo = -s[3] * 0.5
+    if hover_todo > abs(angle_todo) and hover_todo > 0.05:
+        return 2
+    if angle_todo < -0.05:
+        return 3
+    if angle_todo > 0.05:
+        return 1
+    return 0
+
+
+def generate_transitions(count, seed=2024, T=1000, landers=64, p_pid=(1.0, 1.0, 0.7, 0.3), continuous=False, rng_seed=5, max_episode=600, **opts):
+    """`count` single-step transitions of the generic oracle, free-running over `landers` episodes at a time (restarted
+    when done) under a mix of the PID heuristic and random actions, so that free flight, touch-down on one and two legs,
+    belly contact, resting and falling asleep all occur (lander k follows the heuristic with probability p_pid[k % len]).  Transition i is stepped with the dispersion draws of
+    (seed, env id i, step index T): exactly what env i of a batch does after set_state(..., t=T).
+    Returns dict of arrays: state0, aux0, action, state1, aux1, obs, reward, done."""
+    rng = np.random.default_rng(rng_seed)
+    out = {k: [] for k in ("state0", "aux0", "action", "state1", "aux1", "obs", "reward", "done")}
+    worlds, obs_now, age = [], [], []
+    episode = 0
+
+    def fresh():
+        nonlocal episode
+        wi, ti = ctor_draws(seed, 1000000 + episode)
+        w = LunarWorld(continuous=int(continuous), wind_idx=wi, torque_idx=ti, **opts)
+        o = w.reset(reset_draws(seed, 1000000 + episode, 0), step_draws(seed, 1000000 + episode, 0))
+        episode += 1
+        return w, o
+
+    for _ in range(landers):
+        w, o = fresh()
+        worlds.append(w); obs_now.append(o); age.append(0)
+    i = 0
+    while i < count:
+        for k in range(landers):
+            if i >= count:
+                break
+            w = worlds[k]
+            s0, a0 = w.export_state()
+            if continuous:
+                act = rng.uniform(-1, 1, 2).astype(np.float32)
+                if rng.random() < p_pid[k % len(p_pid)]:   # the heuristic's continuous branch (:128-132)
+                    s = obs_now[k]
+                    angle_targ = min(max(s[0] * 0.5 + s[2] * 1.0, -0.4), 0.4)
+                    hover_targ = 0.55 * abs(s[0])
+                    angle_todo = (angle_targ - s[4]) * 0.5 - s[5] * 1.0
+                    hover_todo = (hover_targ - s[1]) * 0.5 - s[3] * 0.5
+                    if s[6] > 0 or s[7] > 0:
+                        angle_todo = 0.0
+                        hover_todo = -s[3] * 0.5
+                    act = np.clip(np.array([hover_todo * 20 - 1, -angle_todo * 20], np.float32), -1, 1)
+            else:
+                act = pid_action(obs_now[k]) if rng.random() < p_pid[k % len(p_pid)] else int(rng.integers(0, 4))
+            o, r, d = w.step(act, step_draws(seed, i, T))
+            s1, a1 = w.export_state()
+            out["state0"].append(s0); out["aux0"].append(a0); out["action"].append(act)
+            out["state1"].append(s1); out["aux1"].append(a1); out["obs"].append(o); out["reward"].append(r); out["done"].append(d)
+            i += 1
+            age[k] += 1
+            obs_now[k] = o
+            if d or age[k] >= max_episode:
+                w.close()
+                worlds[k], obs_now[k] = fresh()
+                age[k] = 0
+    for w in worlds:
+        w.close()
+    res = {k: np.array(v) for k, v in out.items()}
+    res["action"] = res["action"].astype(np.float32 if continuous else np.int32)
+    res["done"] = res["done"].astype(np.uint8)
+    res["reward"] = res["reward"].astype(np.float32)
+    return res
+
+
+def categories(aux0, state0):
+    """Coarse class of a pre-step state, for coverage reports: free / near (pairs, not touching) / legs / belly / asleep."""
+    touch = aux0[:, 0:3]
+    flags = aux0[:, 3]
+    free = aux0[:, 26] == -1
+    cat = np.full(len(aux0), "near", dtype=object)
+    cat[free] = "free"
+    legs = (touch[:, 1] != 0) | (touch[:, 2] != 0)
+    cat[legs & (touch[:, 0] == 0)] = "legs"
+    cat[(touch[:, 1] != 0) & (touch[:, 2] != 0) & (touch[:, 0] == 0)] = "two_legs"
+    cat[touch[:, 0] != 0] = "belly"
+    cat[(flags & F_AWAKE) == 0] = "asleep"
+    return cat
+
+
+# Single-step sensitivity to the sin/cos implementation.  The generic oracle run with the engine's deterministic float32
+# sincos agrees with the engine bit for bit; run with the reference's (float)Math.Sin((double)a) it differs from ITSELF by
+# the bounds below, because a one-ulp change of a rotation row is amplified by the conditioning of the revolute-joint rows
+# (leg inertia 1.1e-4 against 0.78 for the fuselage: inverse inertias 8934 and 1.28) and by the 2-point block solver's
+# split of a leg's load between its two manifold points.  (index groups of the 80-word state, absolute error against
+# max(|value|, 1) unless noted)
+TOLERANCES = (
+    ("fuselage pose", [0, 1, 2], 1e-5),
+    ("fuselage velocity", [3, 4, 5], 2e-4),
+    ("leg poses", [7, 8, 9, 14, 15, 16], 1e-4),
+    ("leg velocities", [10, 11, 12, 17, 18, 19], 2e-3),
+    ("sleep timers", [6, 13, 20], 0.0),
+    ("joint impulses", list(range(21, 29)), 5e-3),
+    ("contact impulses", list(range(29, 53)), 1e-2),
+    ("terrain", list(range(53, 64)), 0.0),
+    ("shaping, force, torque", list(range(64, 68)), 1e-2),
+    ("proxy boxes", list(range(68, 80)), 1e-5),
+)
+OBS_ATOL, REWARD_ATOL = 2e-4, 1e-2
+
+
+def compare_transitions(tag, want, got_state, got_aux, got_obs, got_reward, got_done, exact):
+    """want: dict from generate_transitions; got_*: the engine's results for the same inputs.  Integer words (contact flags,
+    touching masks, limit states, contact ids, pair lists) and done must be identical; floats identical (exact) or within
+    TOLERANCES (the generic oracle on the reference's sin/cos)."""
+    aux1 = want["aux1"]
+    bad_aux = np.argwhere(got_aux[:, :AUX_DIM] != aux1)
+    assert len(bad_aux) == 0, "%s: %d int words differ, first (transition, word) %s: got %d want %d" % (
+        tag, len(bad_aux), tuple(bad_aux[0]), got_aux[tuple(bad_aux[0])], aux1[tuple(bad_aux[0])])
+    assert np.array_equal(np.asarray(got_done).astype(np.uint8), want["done"]), "%s: done flags differ" % tag
+    gs = np.asarray(got_state, np.float32)[:, :STATE_DIM]; ws = np.asarray(want["state1"], np.float32)
+    go = np.asarray(got_obs, np.float32); wo = np.asarray(want["obs"], np.float32)
+    gr = np.asarray(got_reward, np.float32); wr = np.asarray(want["reward"], np.float32)
+    if exact:
+        for name, g, w in (("state", gs, ws), ("obs", go, wo), ("reward", gr, wr)):
+            same = (g == w) | (np.isnan(g) & np.isnan(w))
+            assert same.all(), "%s: %s differs in %d values (bit-exact mode), max |diff| %.3e, first at %s" % (
+                tag, name, int((~same).sum()), float(np.abs(g.astype(np.float64) - w).max()), tuple(np.argwhere(~same)[0]))
+        return
+    for name, idx, tol in TOLERANCES:
+        g = gs[:, idx].astype(np.float64); w = ws[:, idx].astype(np.float64)
+        err = np.abs(g - w) / np.maximum(np.abs(w), 1.0)
+        assert err.max() <= tol, "%s: %s: error %.3e > %.1e at transition %d" % (tag, name, float(err.max()), tol, int(err.max(axis=1).argmax()))
+    assert np.abs(go.astype(np.float64) - wo).max() <= OBS_ATOL, "%s: observation error %.3e" % (tag, float(np.abs(go.astype(np.float64) - wo).max()))
+    big = want["done"] != 0   # the terminal +-100 are exact
+    assert np.array_equal(gr[big], wr[big])
+    assert np.abs(gr.astype(np.float64) - wr)[~big].max() <= REWARD_ATOL, "%s: reward error %.3e" % (tag, float(np.abs(gr.astype(np.float64) - wr)[~big].max()))
