@@ -14,6 +14,8 @@ behind MEASURED_PEAKS.json); `roofline.sustained` repeats the measurement after 
 next to a memset and a copy timed live in the same state.
 `e2e` is the same metric through the host-buffer C-ABI call (gymcuda_step) with pinned HOST action /
 obs / reward / done buffers: H2D + kernel + D2H inside the timed region, every step.
+After the headline, the same process measures the other BASELINE.json configs and appends them as `envs` to the one JSON
+line (SURVEY 8d configs 3-5 and the L2-busting 16 777 216-env CartPole step run), each with the roofline that binds it.
 Prints exactly one JSON line on rank 0.
 """
 import argparse
@@ -48,6 +50,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-envs", action="store_true", help="skip the `envs` block (the other BASELINE.json configs)")
     return ap.parse_args()
 
 
@@ -134,8 +137,10 @@ def oracle_cpu_rate(env_name, n, seconds, threads, chunk=32):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is C#
-    (no dotnet/mono in this image) so oracle/_ref cannot be built; the CPU oracle port is timed on
-    all host cores.  One bench step = `inner` batched steps of all num_envs envs (a bounded sample)."""
+    (no dotnet/mono in this image) so oracle/_ref cannot be built; the CPU oracle port (C++ restatement of
+    CartPoleEnv.Step in the C#'s double arithmetic) is timed on all host cores.  One bench step = a bounded sample:
+    `inner` batched steps of all num_envs envs, repeated until the step has lasted >= 3 s / steps (so the whole timed
+    region is >= 3 s whatever --steps is: a 0.1 s sample disagreed by 30 % with the 10 s one in round 1)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
@@ -143,19 +148,27 @@ def run_reference(args, rank, world):
     o, acts = _oracle_setup(args.env, n, cores, inner)
     for w in range(max(1, args.warmup)):
         o.step_many(acts)
+    per_step_s = max(3.0 / max(1, args.steps), 0.05)
+    calls = 0
     t0 = time.perf_counter()
     for s in range(args.steps):
-        o.step_many(acts)
+        ts = time.perf_counter()
+        while True:
+            o.step_many(acts); calls += 1
+            if time.perf_counter() - ts >= per_step_s:
+                break
     el = time.perf_counter() - t0
-    value = n * inner * args.steps / el
+    value = n * inner * calls / el
+    one_core, one_sample = oracle_cpu_rate(args.env, min(n, 4096), 2.0, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s, %d envs, random policy, auto-reset" % (args.env, n),
-                   "sample_per_step": "%d batched steps of all %d envs" % (inner, n)},
+                   "sample_per_step": "batched steps of all %d envs for >= %.2f s (%d batched steps in total)" % (n, per_step_s, inner * calls)},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d envs x %d steps, oracle F64 port of CartPoleEnv.Step (C# unavailable: no dotnet)" % (n, inner * args.steps)},
+                         "sample": "%d envs x %d steps in %.1f s, C++ port (oracle F64) of CartPoleEnv.Step -- the C# itself cannot run here: no dotnet" % (n, inner * calls, el),
+                         "one_core": {"value": one_core, "sample": one_sample}},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -204,6 +217,117 @@ def measure_gather(env, torch, dist, dev, rank, world, n, od, ad, t_act, steps=2
     return {"unit": "us per step of %d envs per GPU, max over ranks" % n, "step_only": timed(plain),
             "step_then_ncclAllGather": timed(nccl), "step_fused_p2p_gather": timed(fused),
             "gathered_bytes_per_rank": world * n * od * 4}
+
+
+
+# warp-instructions issued per env step of the fused rollout kernel (ncu smsp__inst_executed / env steps, profiles/):
+# the FP32-issue roofline of an env whose step is arithmetic-bound = thread-instructions/s over lanes x SMSPs x clock
+INSTR_PER_ENV_STEP = {"Acrobot-v1": 500.0}
+
+
+def measure_envs(G, torch, dist, dev, rank, world, local_rank, peak, sm_mhz):
+    """SURVEY 8d configs 3-5 + config 2's L2-busting per-launch run, measured after the headline in the same process.
+    Every number is a whole-job aggregate (all ranks, max over ranks of the device time)."""
+    out = {}
+    stream = torch.cuda.current_stream()
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    def rollout_case(name, n, K, reps, **kw):
+        env = G.make(name, n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True, **kw)
+        env.SetStream(stream.cuda_stream)
+        env.ResetBatch()
+        od, ad = env.obs_dim, env.act_dim
+        o = torch.empty((K, n, od), dtype=torch.float32, device=dev); r = torch.empty((K, n), dtype=torch.float32, device=dev)
+        d = torch.empty((K, n), dtype=torch.uint8, device=dev); a = torch.empty((K, n, ad), dtype=torch.int32 if env.act_n > 0 else torch.float32, device=dev)
+        ms = timed(lambda: env.RolloutRandomDevice(K, o.data_ptr(), r.data_ptr(), d.data_ptr(), a.data_ptr()), reps)
+        rate = world * n * K / (ms * 1e-3)
+        b = od * 4 + 4 + 1 + ad * 4
+        res = {"mode": "fused rollout, %d env steps per launch" % K, "num_envs_per_gpu": n, "env_steps_per_s": rate, "ms_per_launch": ms,
+               "algorithmic_bytes_per_env_step": b, "hbm_gbs_per_gpu": rate / world * b / 1e9, "hbm_frac": rate / world * b / 1e9 / peak}
+        env.Close()
+        del o, r, d, a
+        return res
+
+    # config 3: Pendulum-v1 + MountainCarContinuous-v0, 262 144 envs, continuous Box actions -- HBM-write bound
+    for name in ("Pendulum-v1", "MountainCarContinuous-v0"):
+        res = rollout_case(name, 262144, 128, 10)
+        res["bound"] = "hbm"; res["frac"] = res["hbm_frac"]
+        out[name] = res
+    # config 4: Acrobot-v1, 131 072 envs per GPU (1 048 576 at 8 GPUs), independent shards -- FP32-issue bound
+    res = rollout_case("Acrobot-v1", 131072, 128, 10)
+    lanes_per_s = 148 * 4 * 32 * (sm_mhz or 1965.0) * 1e6
+    res["bound"] = "fp32_issue"
+    res["instr_per_env_step"] = INSTR_PER_ENV_STEP["Acrobot-v1"]
+    res["achieved_thread_instr_per_s_per_gpu"] = res["env_steps_per_s"] / world * INSTR_PER_ENV_STEP["Acrobot-v1"]
+    res["peak_thread_instr_per_s_per_gpu"] = lanes_per_s
+    res["frac"] = res["achieved_thread_instr_per_s_per_gpu"] / lanes_per_s
+    res["note"] = "RK4 of the book dynamics: 8 sincos + ~150 flop per step; one warp-instruction per cycle and sub-partition is the ceiling (148 SMs x 4 x 32 lanes x SM clock)"
+    out["Acrobot-v1"] = res
+
+    # config 5: LunarLander-v2, 65 536 landers per GPU (524 288 at 8), auto-reset + done compaction, one launch group per step
+    n = 65536
+    env = G.make("LunarLander-v2", n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True, time_limit=1000)
+    env.SetStream(stream.cuda_stream)
+    env.ResetBatch()
+    o = torch.empty((n, 8), dtype=torch.float32, device=dev); r = torch.empty((n,), dtype=torch.float32, device=dev); d = torch.empty((n,), dtype=torch.uint8, device=dev)
+    acts = torch.randint(0, 4, (n,), dtype=torch.int32, device=dev)
+    step = lambda: env.StepDevice(acts.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr())   # noqa: E731
+    for _ in range(150):   # from the reset state (every lander in free flight at the top) to the steady mix of flight / touch-down / reset
+        step()
+    ms = timed(step, 100, warm=0)
+    sb = 2 * (env.state_dim + env.aux_dim) * 4 + 4 + 32 + 4 + 1
+    lunar = {"mode": "one step per launch group (partition + free-flight kernel + contact kernel), device-resident actions", "num_envs_per_gpu": n,
+             "env_steps_per_s": world * n / (ms * 1e-3), "ms_per_step": ms, "bound": "fp32_latency",
+             "algorithmic_bytes_per_env_step": sb, "hbm_frac": n / (ms * 1e-3) * sb / 1e9 / peak,
+             "legs_down_frac": float((o[:, 6:] > 0).any(1).float().mean().item()),
+             "note": "180 velocity + up to 60 position iterations of sequential impulses per lander: the step lasts as long as the dependent float32 chain of "
+                     "the slowest lander in contact; HBM is idle (hbm_frac)"}
+    if world > 1:
+        try:
+            g = measure_gather(env, torch, dist, dev, rank, world, n, 8, 1, acts.view(1, n, 1), steps=50)
+            lunar["obs_allgather"] = g
+            lunar["env_steps_per_s_with_ncclAllGather"] = world * n / (g["step_then_ncclAllGather"] * 1e-6)
+            lunar["env_steps_per_s_with_fused_gather"] = world * n / (g["step_fused_p2p_gather"] * 1e-6)
+        except Exception as ex:
+            lunar["obs_allgather"] = {"error": repr(ex)[:300]}
+    env.Close()
+    del o, r, d, acts
+    out["LunarLander-v2"] = lunar
+
+    # config 2, per-launch mode, L2-busting: CartPole step_kernel at 16 777 216 envs (state 256 MiB >> the 126 MB L2), 41 B per env step
+    n = 16777216
+    env = G.make("CartPole-v1", n, seed=0, device=local_rank, env_id_offset=0, auto_reset=True)
+    env.SetStream(stream.cuda_stream)
+    env.ResetBatch()
+    o = torch.empty((n, 4), dtype=torch.float32, device=dev); r = torch.empty((n,), dtype=torch.float32, device=dev); d = torch.empty((n,), dtype=torch.uint8, device=dev)
+    acts = torch.randint(0, 2, (n,), dtype=torch.int32, device=dev)
+    ms = timed(lambda: env.StepDevice(acts.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr()), 20)
+    rate = n / (ms * 1e-3)
+    # state 16 R + 16 W, action 4 R, reward 4 W, done 1 W = 41 (SURVEY 8d); the separate observation copy the ABI asks for adds 16 W
+    out["CartPole-v1 step_kernel @16777216"] = {
+        "mode": "one step per launch (gymcuda_step_device), per GPU", "num_envs_per_gpu": n, "env_steps_per_s_per_gpu": rate, "ms_per_launch": ms, "bound": "hbm",
+        "algorithmic_bytes_per_env_step": 41, "hbm_gbs_per_gpu": rate * 41 / 1e9, "frac": rate * 41 / 1e9 / peak,
+        "bytes_moved_per_env_step_with_obs_copy": 57, "hbm_gbs_with_obs_copy": rate * 57 / 1e9, "frac_with_obs_copy": rate * 57 / 1e9 / peak}
+    env.Close()
+    return out
 
 
 def main():
@@ -392,12 +516,26 @@ def main():
         except Exception as ex:   # the optional collective must never cost the headline line
             gather = {"error": repr(ex)[:300]}
 
+    # ---- the other BASELINE.json configs (SURVEY 8d configs 3-5, config 2's 16 M-env per-launch run)
+    envs = None
+    if not args.no_envs:
+        env.Close()
+        env = None
+        del t_obs, t_rew, t_done, t_act
+        torch.cuda.empty_cache()
+        try:
+            envs = measure_envs(G, torch, dist, dev, rank, world, local_rank, peak, clocks.get("sm_mhz"))
+        except Exception as ex:   # never costs the headline line
+            envs = {"error": repr(ex)[:400]}
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port of the reference's CPU path
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, sample = oracle_cpu_rate(args.env, n, args.cpu_seconds, cores)
-        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        v1, sample1 = oracle_cpu_rate(args.env, min(n, 4096), 3.0, 1)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+               "one_core": {"value": v1, "sample": sample1}}
 
     if rank == 0:
         line = {
@@ -408,11 +546,12 @@ def main():
                                    "fused rollout launch of %d env steps per env" % (args.env, n, K),
                        "num_envs_per_gpu": n, "inner_steps": K, "parallelism": "independent env shards, no collective",
                        "l2": "outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (launch_bytes / 1e6)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "obs_allgather": gather,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "obs_allgather": gather, "envs": envs,
             "gpu_launches": args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    env.Close()
+    if env is not None:
+        env.Close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -104,3 +104,12 @@ def test_sleeping_landers_and_the_step_that_puts_them_to_sleep():
         if found >= 3:
             break
     assert found >= 1, "no PID episode ended asleep on the pad"
+
+
+def test_golden_fixture_from_the_generic_oracle_against_the_twin():
+    import os
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "lunar_world2d.npz"))
+    for name, exact in (("det", True), ("ref", False)):
+        tr = {k.split("/", 1)[1]: fx[k] for k in fx.files if k.startswith(name + "/")}
+        st, ax, obs, rew, done = twin_step(tr)
+        W.compare_transitions("fixture " + name, tr, st, ax, obs, rew, done, exact=exact)

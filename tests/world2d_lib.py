@@ -260,7 +260,7 @@ TOLERANCES = (
     ("fuselage pose", [0, 1, 2], 1e-5),
     ("fuselage velocity", [3, 4, 5], 2e-4),
     ("leg poses", [7, 8, 9, 14, 15, 16], 1e-4),
-    ("leg velocities", [10, 11, 12, 17, 18, 19], 2e-3),
+    ("leg velocities", [10, 11, 12, 17, 18, 19], 1e-2),
     ("sleep timers", [6, 13, 20], 0.0),
     ("joint impulses", list(range(21, 29)), 5e-3),
     ("contact impulses", list(range(29, 53)), 1e-2),
