@@ -22,7 +22,7 @@
 
 namespace gymcuda {
 
-struct StepOut { float reward; unsigned done; };   // done: 0 / 1 in a full register (a byte-sized bool costs PRMT packing around calls)
+struct StepOut { float reward; unsigned done; unsigned did_reset = 0u; };   // done: 0 / 1 in a full register (a byte-sized bool costs PRMT packing around calls); did_reset: the env already replaced its state by a new episode (LunarLander's fused crash reset)
 
 // constructor arguments of the env (LunarLanderEnv.cs:381); unused by the classic-control family
 struct EnvParams { float gravity, wind_power, turbulence_power; int32_t use_wind; };

@@ -50,6 +50,7 @@ struct StepArgs {
     int part;                          // 0: every position; 1: positions [0, *split) (first class); 2: positions [*split, n)
     int sample;                        // 1: the action is ActionSpace.Sample() of step t (the rollout's random policy), `actions` is not read
     void* act_out;                     // sampled actions are also written here (may be null)
+    float* terminal_obs;               // [n][OD], may be null: under auto-reset, the observation of the TERMINAL state of the envs whose step returned done (the returned obs is the post-reset one)
     const void* actions;
     float* obs;
     float* reward;
@@ -255,6 +256,10 @@ __device__ __forceinline__ uint64_t seed_of(const int32_t* seeds, uint64_t seed,
 // ---------------------------------------------------------------- step
 constexpr int STEP_BLOCK = 128;
 
+// envs whose step can fold the auto-reset in (E::FUSED_RESET + E::step_ar): LunarLander
+template <class E, class = void> struct FusedReset : std::false_type {};
+template <class E> struct FusedReset<E, std::enable_if_t<E::FUSED_RESET>> : std::true_type {};
+
 template <class E, bool AUTO_RESET, bool LIMIT>
 __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     using S = typename E::S;
@@ -293,7 +298,14 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
         if (!invalid) {
             const uint64_t seed = seed_of(p.seeds, p.seed, i);
             const uint32_t gid = p.env_off + (uint32_t)i;
-            r = E::step(s, a, sbd, seed, gid, p.t);
+            int32_t ep_ord = 0;
+            if constexpr (FusedReset<E>::value) {
+                if (AUTO_RESET) ep_ord = p.episode[i];
+                const bool allow = AUTO_RESET && p.terminal_obs == nullptr;
+                r = E::step_ar(s, a, seed, gid, p.t, allow, (uint32_t)ep_ord);
+            } else {
+                r = E::step(s, a, sbd, seed, gid, p.t);
+            }
             if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }   // truncation folded into done
             if (p.ep_ret) {   // episode statistics (the caller-side bookkeeping of BasePlaySession.cs:58-69)
                 float ret = p.ep_ret[i] + r.reward;
@@ -301,8 +313,11 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
                 p.ep_ret[i] = ret;
             }
             if (AUTO_RESET && r.done) {
-                const int32_t ep = p.episode[i];
-                E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
+                const int32_t ep = FusedReset<E>::value ? ep_ord : p.episode[i];
+                if (!r.did_reset) {
+                    if (p.terminal_obs) { float to[E::OD]; E::obs(s, to); store_obs<E::OD, false>(p.terminal_obs, (size_t)i, to); }
+                    E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
+                }
                 p.episode[i] = ep + 1;
                 sbd = -1;
                 ept = 0;

@@ -70,6 +70,7 @@ struct LunarLanderT {
     static constexpr bool HAS_SBD = false;
     static constexpr bool REJECT_INVALID = true;    // InvalidActionError (LunarLanderEnv.cs:604-607)
     static constexpr bool HAS_SMALL = false;
+    static constexpr bool FUSED_RESET = true;       // step_autoreset: a crash and the zero step of the next episode share one solve
     static constexpr bool ROLLOUT_CHUNK = false;    // one step is thousands of instructions: no unrolling
     static constexpr bool PREGEN_RESET = false;     // resets are rare and a full zero step: done in place
     static constexpr float ACT_LOW = -1.0f, ACT_HIGH = 1.0f;
@@ -99,6 +100,17 @@ struct LunarLanderT {
         const float act[2] = {a.x, a.y};
         const lunar::StepResult r = lunar::step<HAS_PAIRS>(L, seed, gid, t, 0, act);
         return StepOut{r.reward, (unsigned)(r.done != 0)};
+    }
+    // step with the auto-reset folded in (lunar_core.cuh step_autoreset); `ordinal` = the env's next RESET draw index
+    __device__ static __forceinline__ StepOut step_ar(S& L, int32_t a, uint64_t seed, uint32_t gid, uint64_t t, bool allow, uint32_t ordinal) {
+        const float none[2] = {0.0f, 0.0f};
+        const lunar::StepResult r = lunar::step_autoreset<HAS_PAIRS>(L, seed, gid, t, (int)a, none, allow, (uint64_t)ordinal);
+        return StepOut{r.reward, (unsigned)(r.done != 0), (unsigned)r.did_reset};
+    }
+    __device__ static __forceinline__ StepOut step_ar(S& L, float2 a, uint64_t seed, uint32_t gid, uint64_t t, bool allow, uint32_t ordinal) {
+        const float act[2] = {a.x, a.y};
+        const lunar::StepResult r = lunar::step_autoreset<HAS_PAIRS>(L, seed, gid, t, 0, act, allow, (uint64_t)ordinal);
+        return StepOut{r.reward, (unsigned)(r.done != 0), (unsigned)r.did_reset};
     }
     __device__ static __forceinline__ void obs(const S& L, float* o) { lunar::observe(L, o); }
     // LunarLanderEnv ctor (:409-410): _wind_idx / _torque_idx = randint(-9999, 9999), once per generator

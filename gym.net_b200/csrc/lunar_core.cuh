@@ -382,18 +382,21 @@ __device__ __forceinline__ int pair_count(const Lander& L) { int n = 0; while (n
 
 // ---------------------------------------------------------------- register-resident constraint rows
 // The 180 velocity and up to 60 position iterations are one long dependent float32 chain per lander, and a launch lasts as
-// long as its slowest lander.  In the common configuration -- at most ONE touching manifold per body -- the rows below keep
-// every operand of that chain in registers with compile-time body indices: no local-memory round trip, no loop bookkeeping,
-// no body multiplexing inside the iterations, and the chains of the three bodies are independent straight-line code the
-// scheduler can interleave.  Anything else (two manifolds on one body: a polygon astride a terrain vertex) takes the general
-// loops over the ActiveContact array.  Both evaluate the same operations in the same (island) order: same bits.
+// long as its slowest lander.  The first ROWS manifolds of the island (in island order) keep every operand of that chain in
+// registers; the iteration loops are the SAME loops for every lane of a warp -- two joints, then row 0, row 1, ... each
+// skipped by the lanes that have fewer rows -- so a warp that mixes landers without contact, with one manifold and with four
+// executes the joints once per iteration, not once per kind of lander (ncu, round 2: the three separate loops of the first
+// version ran back to back in almost every warp, 6.5 of 32 lanes active).  Same operations in the same order as plain
+// per-contact loops: same bits.
 struct VelRow {
     V2 normal, rb0, rb1;
     float ni0, ni1, ti0, ti1, nm0, nm1, tm0, tm1, friction;
     float k11, k12, k22, i11, i12, i21, i22;
-    int count;   // velocity-constraint points of the body's manifold; 0 = the body touches nothing
+    float inv_mass, inv_inertia;
+    int count, body;   // velocity-constraint points of the manifold, the body it acts on
 };
-struct PosRow { V2 local_normal, local_point, lp0, lp1; int type, count; };
+struct PosRow { V2 local_normal, local_point, lp0, lp1, centroid; float inv_mass, inv_inertia; int type, count, body; };
+constexpr int ROWS = 4;   // manifolds kept in registers (island order); a lander with more (rare) runs the rest from local memory
 
 __device__ __forceinline__ void friction_point(V2& vB, float& wB, float mB, float iB, V2 tangent, V2 rb, float tangent_mass, float friction, float normal_impulse, float& tangent_impulse) {
     const V2 dv = vB + cross_sv(wB, rb);
@@ -486,14 +489,14 @@ __device__ __forceinline__ void position_point(int type, V2 local_normal, V2 loc
 
 // HAS_PAIRS = false: the caller guarantees that no contact exists (the pair list is empty) -- the narrow phase and every
 // contact row compile out (the free-flight kernel).
-template <bool HAS_PAIRS>
-__device__ __noinline__ void world_step(Lander& L) {
-    const float h = DT;
-    const float dt_ratio = (L.flags & F_FIRST_STEP) ? 0.0f : 1.0f;   // inv_dt0 * dt: 0 on a new World, then 50 * 0.02f = 1
-    ActiveContact ac[HAS_PAIRS ? MAXC : 1];
-    int nc = 0;
+// the touching manifolds of a step (creation order) and their island order
+struct Contacts { ActiveContact ac[MAXC]; int nc; uint32_t order; };
 
-    // ---- ContactManager.Collide: every existing contact, in creation order
+// ---- ContactManager.Collide: every existing contact, in creation order
+template <bool HAS_PAIRS>
+__device__ __forceinline__ void collide(Lander& L, Contacts& C) {
+    ActiveContact* ac = C.ac;
+    int nc = 0;
     if (HAS_PAIRS && (L.flags & F_AWAKE)) {
         Rot q[3]; V2 p[3];
 #pragma unroll
@@ -538,23 +541,26 @@ __device__ __noinline__ void world_step(Lander& L) {
         for (int k = kept; k < np; ++k) pair_put(L, k, 0xffu);
     }
     // island order of the touching contacts: bodies in DFS order (fuselage, leg 0, leg 1), each body's contacts newest first;
-    // four bits per entry.  `row_of[B]` = index of body B's manifold when every body has at most one (the register path).
+    // four bits per entry
     uint32_t order = 0u;
-    int row_of[3] = {-1, -1, -1};
-    bool simple = true;
     if (HAS_PAIRS) {
         int no = 0;
 #pragma unroll
         for (int body = 0; body < 3; ++body)
             for (int k = nc - 1; k >= 0; --k)
-                if (ac[k].body == body) {
-                    order |= (uint32_t)k << (4 * no++);
-                    if (row_of[body] >= 0) simple = false;
-                    row_of[body] = k;
-                }
+                if (ac[k].body == body) order |= (uint32_t)k << (4 * no++);
     }
+    C.nc = nc; C.order = order;
+}
 
-    // ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1}
+// ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1} -- then the broad-phase update and ClearForces
+template <bool HAS_PAIRS>
+__device__ __forceinline__ void solve(Lander& L, Contacts& C) {
+    const float h = DT;
+    const float dt_ratio = (L.flags & F_FIRST_STEP) ? 0.0f : 1.0f;   // inv_dt0 * dt: 0 on a new World, then 50 * 0.02f = 1
+    ActiveContact* ac = C.ac;
+    const int nc = HAS_PAIRS ? C.nc : 0;
+    const uint32_t order = C.order;
     if (L.flags & F_AWAKE) {
         V2 c[3], v[3];
         float a[3], w[3];
@@ -768,58 +774,63 @@ __device__ __noinline__ void world_step(Lander& L) {
             }
         };
 
-        // ---- velocity iterations
-        if (!HAS_PAIRS || nc == 0) {
-            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) solve_joints_velocity();
-        } else if (simple) {
-            VelRow row[3];
+        // ---- velocity iterations: one loop for every lane
+        VelRow row[HAS_PAIRS ? ROWS : 1];
+        if (HAS_PAIRS) {
 #pragma unroll
-            for (int B = 0; B < 3; ++B) {
-                VelRow& r = row[B];
-                r.count = 0;
-                if (row_of[B] >= 0) {
-                    const ActiveContact& cc = ac[row_of[B]];
-                    r.normal = cc.normal; r.rb0 = cc.p[0].rb; r.rb1 = cc.p[1].rb;
-                    r.ni0 = cc.p[0].normal_impulse; r.ni1 = cc.p[1].normal_impulse; r.ti0 = cc.p[0].tangent_impulse; r.ti1 = cc.p[1].tangent_impulse;
-                    r.nm0 = cc.p[0].normal_mass; r.nm1 = cc.p[1].normal_mass; r.tm0 = cc.p[0].tangent_mass; r.tm1 = cc.p[1].tangent_mass;
-                    r.friction = cc.friction;
-                    r.k11 = cc.k11; r.k12 = cc.k12; r.k22 = cc.k22; r.i11 = cc.nm11; r.i12 = cc.nm12; r.i21 = cc.nm21; r.i22 = cc.nm22;
-                    r.count = cc.count;
+            for (int r = 0; r < ROWS; ++r) {
+                VelRow& q = row[r];
+                q.count = 0; q.body = 0;
+                if (r < nc) {
+                    const ActiveContact& cc = ac[(order >> (4 * r)) & 15u];
+                    q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
+                    q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
+                    q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
+                    q.friction = cc.friction;
+                    q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
+                    q.inv_mass = SHAPES[cc.body].inv_mass; q.inv_inertia = SHAPES[cc.body].inv_inertia;
+                    q.count = cc.count; q.body = cc.body;
                 }
             }
-            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
-                solve_joints_velocity();
+        }
+#pragma unroll 1
+        for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+            solve_joints_velocity();
+            if (HAS_PAIRS) {
 #pragma unroll
-                for (int B = 0; B < 3; ++B)
-                    if (row[B].count > 0) solve_velocity_row(row[B], v[B], w[B], SHAPES[B].inv_mass, SHAPES[B].inv_inertia);
-            }
-#pragma unroll
-            for (int B = 0; B < 3; ++B)
-                if (row_of[B] >= 0) {
-                    ActiveContact& cc = ac[row_of[B]];
-                    cc.p[0].normal_impulse = row[B].ni0; cc.p[0].tangent_impulse = row[B].ti0;
-                    if (cc.count == 2) { cc.p[1].normal_impulse = row[B].ni1; cc.p[1].tangent_impulse = row[B].ti1; }
-                }
-        } else {
-            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
-                solve_joints_velocity();
-                for (int kk = 0; kk < nc; ++kk) {
+                for (int r = 0; r < ROWS; ++r)
+                    if (row[r].count > 0) {
+                        const int B = row[r].body;
+                        V2 vB = GETB(v, B); float wB = GETB(w, B);   // only velocities change in a velocity iteration
+                        solve_velocity_row(row[r], vB, wB, row[r].inv_mass, row[r].inv_inertia);
+                        SETB(v, B, vB); SETB(w, B, wB);
+                    }
+                for (int kk = ROWS; kk < nc; ++kk) {   // beyond the register rows (rare): from local memory
                     ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
                     const int B = cc.body;
-                    V2 vB = GETB(v, B); float wB = GETB(w, B);   // only velocities change in a velocity iteration
-                    VelRow r;
-                    r.normal = cc.normal; r.rb0 = cc.p[0].rb; r.rb1 = cc.p[1].rb;
-                    r.ni0 = cc.p[0].normal_impulse; r.ni1 = cc.p[1].normal_impulse; r.ti0 = cc.p[0].tangent_impulse; r.ti1 = cc.p[1].tangent_impulse;
-                    r.nm0 = cc.p[0].normal_mass; r.nm1 = cc.p[1].normal_mass; r.tm0 = cc.p[0].tangent_mass; r.tm1 = cc.p[1].tangent_mass;
-                    r.friction = cc.friction;
-                    r.k11 = cc.k11; r.k12 = cc.k12; r.k22 = cc.k22; r.i11 = cc.nm11; r.i12 = cc.nm12; r.i21 = cc.nm21; r.i22 = cc.nm22;
-                    r.count = cc.count;
-                    solve_velocity_row(r, vB, wB, SHAPES[B].inv_mass, SHAPES[B].inv_inertia);
-                    cc.p[0].normal_impulse = r.ni0; cc.p[0].tangent_impulse = r.ti0;
-                    if (cc.count == 2) { cc.p[1].normal_impulse = r.ni1; cc.p[1].tangent_impulse = r.ti1; }
+                    V2 vB = GETB(v, B); float wB = GETB(w, B);
+                    VelRow q;
+                    q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
+                    q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
+                    q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
+                    q.friction = cc.friction;
+                    q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
+                    q.count = cc.count; q.body = B;
+                    solve_velocity_row(q, vB, wB, SHAPES[B].inv_mass, SHAPES[B].inv_inertia);
+                    cc.p[0].normal_impulse = q.ni0; cc.p[0].tangent_impulse = q.ti0;
+                    if (cc.count == 2) { cc.p[1].normal_impulse = q.ni1; cc.p[1].tangent_impulse = q.ti1; }
                     SETB(v, B, vB); SETB(w, B, wB);
                 }
             }
+        }
+        if (HAS_PAIRS) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                if (r < nc) {
+                    ActiveContact& cc = ac[(order >> (4 * r)) & 15u];
+                    cc.p[0].normal_impulse = row[r].ni0; cc.p[0].tangent_impulse = row[r].ti0;
+                    if (cc.count == 2) { cc.p[1].normal_impulse = row[r].ni1; cc.p[1].tangent_impulse = row[r].ti1; }
+                }
         }
 
         // integrate positions
@@ -845,40 +856,45 @@ __device__ __noinline__ void world_step(Lander& L) {
         // ANGULAR_SLOP + 1 ulp, just above what joints_okay accepts), but after two or three iterations the
         // corrections round to nothing: once an iteration returns bit-identical coordinates, the remaining ones
         // would too, so the loop stops there -- same result as all 60, position_solved stays false.
-        PosRow prow[3];
-        if (HAS_PAIRS && simple) {
+        PosRow prow[HAS_PAIRS ? ROWS : 1];
+        if (HAS_PAIRS) {
 #pragma unroll
-            for (int B = 0; B < 3; ++B) {
-                prow[B].count = 0;
-                if (row_of[B] >= 0) {
-                    const Manifold& m = ac[row_of[B]].m;
-                    prow[B].local_normal = m.local_normal; prow[B].local_point = m.local_point; prow[B].lp0 = m.lp[0]; prow[B].lp1 = m.lp[1];
-                    prow[B].type = m.type; prow[B].count = m.count;
+            for (int r = 0; r < ROWS; ++r) {
+                prow[r].count = 0; prow[r].body = 0; prow[r].type = 0;
+                if (r < nc) {
+                    const ActiveContact& cc = ac[(order >> (4 * r)) & 15u];
+                    const Manifold& m = cc.m;
+                    prow[r].local_normal = m.local_normal; prow[r].local_point = m.local_point; prow[r].lp0 = m.lp[0]; prow[r].lp1 = m.lp[1];
+                    prow[r].centroid = SHAPES[cc.body].centroid; prow[r].inv_mass = SHAPES[cc.body].inv_mass; prow[r].inv_inertia = SHAPES[cc.body].inv_inertia;
+                    prow[r].type = m.type; prow[r].count = m.count; prow[r].body = cc.body;
                 }
             }
         }
         bool position_solved = false;
+#pragma unroll 1
         for (int it = 0; it < POSITION_ITERATIONS; ++it) {
             const V2 c_in[3] = {c[0], c[1], c[2]};
             const float a_in[3] = {a[0], a[1], a[2]};
             float min_separation = 0.0f;
-            if (HAS_PAIRS && nc > 0) {
-                if (simple) {
+            if (HAS_PAIRS) {
 #pragma unroll
-                    for (int B = 0; B < 3; ++B) {
-                        const PosRow& m = prow[B];
-                        if (m.count > 0) position_point(m.type, m.local_normal, m.local_point, m.lp0, SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, c[B], a[B], min_separation);
-                        if (m.count > 1) position_point(m.type, m.local_normal, m.local_point, m.lp1, SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, c[B], a[B], min_separation);
-                    }
-                } else {
-                    for (int kk = 0; kk < nc; ++kk) {
-                        const ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
-                        const int B = cc.body;
+                for (int r = 0; r < ROWS; ++r) {
+                    const PosRow& m = prow[r];
+                    if (m.count > 0) {
+                        const int B = m.body;
                         V2 cB = GETB(c, B); float aB = GETB(a, B);   // only positions change in a position iteration
-                        for (int j = 0; j < cc.m.count; ++j)
-                            position_point(cc.m.type, cc.m.local_normal, cc.m.local_point, cc.m.lp[j], SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, cB, aB, min_separation);
+                        position_point(m.type, m.local_normal, m.local_point, m.lp0, m.centroid, m.inv_mass, m.inv_inertia, cB, aB, min_separation);
+                        if (m.count > 1) position_point(m.type, m.local_normal, m.local_point, m.lp1, m.centroid, m.inv_mass, m.inv_inertia, cB, aB, min_separation);
                         SETB(c, B, cB); SETB(a, B, aB);
                     }
+                }
+                for (int kk = ROWS; kk < nc; ++kk) {
+                    const ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
+                    const int B = cc.body;
+                    V2 cB = GETB(c, B); float aB = GETB(a, B);
+                    for (int j = 0; j < cc.m.count; ++j)
+                        position_point(cc.m.type, cc.m.local_normal, cc.m.local_point, cc.m.lp[j], SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, cB, aB, min_separation);
+                    SETB(c, B, cB); SETB(a, B, aB);
                 }
             }
             const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
@@ -1036,11 +1052,11 @@ __device__ __forceinline__ void observe(const Lander& L, float* o) {   // LunarL
     o[7] = (L.flags & F_LEG1) ? 1.0f : 0.0f;
 }
 
-struct StepResult { float reward; uint8_t done; };
+struct StepResult { float reward; uint8_t done; uint8_t did_reset; };
+struct Powers { float m_power, s_power; };
 
-// LunarLanderEnv.Step (:574-774).  `t` indexes the DYNAMICS stream (the two dispersion draws, :611-612).
-template <bool HAS_PAIRS = true>
-__device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action) {
+// LunarLanderEnv.Step up to the physics (:574-716): wind, engine impulses.  `t` indexes the DYNAMICS stream (the two dispersion draws, :611-612).
+__device__ __forceinline__ Powers pre_physics(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action) {
     const bool continuous = (L.flags & F_CONTINUOUS) != 0;
     float a0 = 0.0f, a1 = 0.0f;
     if (continuous) { a0 = clampf(c_action[0], -1.0f, 1.0f); a1 = clampf(c_action[1], -1.0f, 1.0f); }   // :600
@@ -1090,12 +1106,13 @@ __device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, 
         const V2 impulse = mk(-ox * SIDE_ENGINE_POWER * s_power, -oy * SIDE_ENGINE_POWER * s_power);   // :709
         apply_linear_impulse(L, impulse, impulse_pos);                                        // :714
     }
+    return Powers{m_power, s_power};
+}
 
-    world_step<HAS_PAIRS>(L);                                                                 // :721-725
+// LunarLanderEnv.Step after the physics (:726-772): GameOver, observation, shaping reward, termination
+__device__ __forceinline__ StepResult post_physics(Lander& L, Powers pw) {
     if (L.flags & F_FUSELAGE) L.flags |= F_GAME_OVER;                                         // :726-729
-
-    // observation (:733-747)
-    observe(L, L.obs);
+    observe(L, L.obs);                                                                        // :733-747
     const float px = L.obs[0], py = L.obs[1], vx = L.obs[2], vy = L.obs[3], angle = L.obs[4];
     const float l0 = L.obs[6], l1 = L.obs[7];
     // reward (:748-760)
@@ -1107,17 +1124,27 @@ __device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, 
     shaping += 10.0f * l1;
     if (L.prev_shaping != -3.4028234663852886e38f) reward = shaping - L.prev_shaping;          // float.MinValue sentinel
     L.prev_shaping = shaping;
-    reward -= m_power * 0.3f;
-    reward -= s_power * 0.03f;
+    reward -= pw.m_power * 0.3f;
+    reward -= pw.s_power * 0.03f;
     uint8_t done = 0;
     if ((L.flags & F_GAME_OVER) || px > 1.0f) { done = 1; reward = -100.0f; }                 // :762 one-sided: no `< -1` check
     if (!(L.flags & F_AWAKE)) { done = 1; reward = 100.0f; }                                  // :767
-    return StepResult{reward, done};
+    return StepResult{reward, done, 0};
 }
 
-// LunarLanderEnv.Reset (:489-572).  `index` = episode ordinal; draws: sub-block 0 = (fx, fy, h0, h1),
-// 1 = (h2..h5), 2 = (h6..h9), 3 = (h10, h11).  Ends with the zero step (:567-571) at step index `t`.
-__device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, uint64_t index, bool continuous, uint64_t t,
+// LunarLanderEnv.Step (:574-774)
+template <bool HAS_PAIRS = true>
+__device__ __noinline__ StepResult step(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action) {
+    const Powers pw = pre_physics(L, seed, gid, t, i_action, c_action);
+    Contacts C;
+    collide<HAS_PAIRS>(L, C);
+    solve<HAS_PAIRS>(L, C);                                                                   // :721-725
+    return post_physics(L, pw);
+}
+
+// LunarLanderEnv.Reset (:489-572) up to its zero step.  `index` = episode ordinal; draws: sub-block 0 = (fx, fy, h0, h1),
+// 1 = (h2..h5), 2 = (h6..h9), 3 = (h10, h11).
+__device__ __forceinline__ void reset_prepare(Lander& L, uint64_t seed, uint32_t gid, uint64_t index, bool continuous,
                   float gravity, int use_wind, float wind_power, float turbulence_power) {
     const int32_t wi = L.wind_idx, ti = L.torque_idx;   // drawn in the constructor, persist across episodes (:409-410)
     zero_lander(L);
@@ -1157,9 +1184,47 @@ __device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, ui
         const Box bx = body_box(SHAPES[i], pos, rot(ang));   // Body.Position setter -> MoveProxy with no displacement
         L.fat[i][0] = bx.lx - AABB_EXTENSION; L.fat[i][1] = bx.ly - AABB_EXTENSION; L.fat[i][2] = bx.hx + AABB_EXTENSION; L.fat[i][3] = bx.hy + AABB_EXTENSION;
     }
+}
+
+// LunarLanderEnv.Reset (:489-572): ends with the zero step (:567-571) at step index `t`
+__device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, uint64_t index, bool continuous, uint64_t t,
+                  float gravity, int use_wind, float wind_power, float turbulence_power) {
+    reset_prepare(L, seed, gid, index, continuous, gravity, use_wind, wind_power, turbulence_power);
     const float zero[2] = {0.0f, 0.0f};
     step<false>(L, seed, gid, t, 0, zero);                                                     // :567-571 (a new world: no contact exists yet)
 }
 
+// Step with the in-kernel auto-reset folded in.  A lander whose fuselage touched the ground in this step's Collide is over
+// (GameOver, :726-729: reward -100, done) whatever its solve would give, and under auto-reset its state is replaced by a new
+// episode whose first act is a whole World.Step of its own (the zero step of Reset, :567-571).  Both solves would run one after
+// the other in the slowest lane of the warp; instead the lander is re-created right after Collide and THIS step's solve is the
+// new episode's zero step: same outputs (reward -100, done, the observation after the zero step) and same state, one solve
+// instead of two.  Not taken when the old solve could still matter: the island could fall asleep in this very step (done with
+// +100 overrides -100, :767), or the caller wants the terminal observation (`allow` false).
+template <bool HAS_PAIRS = true>
+__device__ __noinline__ StepResult step_autoreset(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action,
+                                                  bool allow, uint64_t next_ordinal) {
+    Powers pw = pre_physics(L, seed, gid, t, i_action, c_action);
+    Contacts C;
+    collide<HAS_PAIRS>(L, C);
+    bool early = false;
+    if (HAS_PAIRS && allow && (L.flags & (F_FUSELAGE | F_GAME_OVER)) && (L.flags & F_AWAKE)) {
+        bool may_sleep = true;   // the island sleeps only if EVERY body's timer reaches timeToSleep: one that cannot, after this step, rules it out
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (!(L.b[i].sleep_time + DT >= TIME_TO_SLEEP)) may_sleep = false;
+        if (!may_sleep) {
+            const bool continuous = (L.flags & F_CONTINUOUS) != 0;
+            reset_prepare(L, seed, gid, next_ordinal, continuous, L.gravity, L.use_wind, L.wind_power, L.turbulence_power);
+            const float zero[2] = {0.0f, 0.0f};
+            pw = pre_physics(L, seed, gid, t + 1, 0, zero);   // the zero step of the new episode (:567-571)
+            C.nc = 0; C.order = 0u;
+            early = true;
+        }
+    }
+    solve<HAS_PAIRS>(L, C);                                                                   // :721-725
+    StepResult r = post_physics(L, pw);
+    if (early) r = StepResult{-100.0f, 1, 1};
+    return r;
+}
 
 }}  // namespace gymcuda::lunar

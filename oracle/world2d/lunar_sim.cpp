@@ -478,6 +478,14 @@ void w2d_lunar_step(void* h, int32_t i_action, const float* c_action, const floa
 }
 void w2d_lunar_export(void* h, float* state68, int32_t* aux26) { static_cast<LunarSim*>(h)->exportState(state68, aux26); }
 void w2d_lunar_import(void* h, const float* state68, const int32_t* aux26) { static_cast<LunarSim*>(h)->importState(state68, aux26); }
+/* analysis: record the iteration at which the velocity / position sweeps first repeat (out[6]: vel at, vel period, pos at, pos period, pos iterations run, contacts touching) */
+void w2d_lunar_record_cycles(void* h, int32_t on) { static_cast<LunarSim*>(h)->world->recordCycles = on != 0; }
+void w2d_lunar_cycle_info(void* h, int32_t* out) {
+    World* w = static_cast<LunarSim*>(h)->world.get();
+    out[0] = w->velCycleAt; out[1] = w->velCyclePeriod; out[2] = w->posCycleAt; out[3] = w->posCyclePeriod; out[4] = w->posIterationsRun;
+    int t = 0; for (Contact* c : w->contactList) if (c->touching) ++t;
+    out[5] = t;
+}
 int32_t w2d_lunar_toi_events(void* h) { return static_cast<LunarSim*>(h)->toiEvents; }
 int32_t w2d_lunar_num_contacts(void* h) { return (int32_t)static_cast<LunarSim*>(h)->world->contactList.size(); }
 

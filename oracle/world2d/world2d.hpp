@@ -1424,6 +1424,9 @@ public:
         cp1.normalImpulse = x.x;
         cp2.normalImpulse = x.y;
     }
+    template <class F> void hashImpulses(F&& mix) const {
+        for (const ContactVelocityConstraint& vc : vcs_) for (int j = 0; j < vc.pointCount; ++j) { mix(vc.points[j].normalImpulse); mix(vc.points[j].tangentImpulse); }
+    }
     void storeImpulses() {
         for (size_t i = 0; i < vcs_.size(); ++i) {
             const ContactVelocityConstraint& vc = vcs_[i];
@@ -1548,6 +1551,10 @@ public:
     uint64_t contactSerial = 0;
     // statistics of the last step (for tests / reports)
     int lastToiEvents = 0;
+    // analysis hook (tools/lunar_cycle_study.py): when set, the island solver records after which velocity / position iteration
+    // the iterated state first repeats with period 1..4 (an exact fixed point or limit cycle of the float32 Gauss-Seidel sweep)
+    bool recordCycles = false;
+    int velCycleAt = -1, velCyclePeriod = 0, posCycleAt = -1, posCyclePeriod = 0, posIterationsRun = 0;
 
     explicit World(const Vec2& g, const WorldOptions& o = WorldOptions()) : gravity(g), opt(o) {}
 
@@ -1753,9 +1760,20 @@ public:
         contactSolver.initializeVelocityConstraints();
         if (step.warmStarting) contactSolver.warmStart();
         for (Joint* j : island.joints) j->initVelocityConstraints(solverData);
+        std::vector<uint64_t> hist;
+        velCycleAt = -1; velCyclePeriod = 0;
         for (int i = 0; i < step.velocityIterations; ++i) {
             for (Joint* j : island.joints) j->solveVelocityConstraints(solverData);
             contactSolver.solveVelocityConstraints();
+            if (recordCycles && velCycleAt < 0) {
+                uint64_t hsh = 1469598103934665603ull;
+                auto mix = [&hsh](float f) { uint32_t u; std::memcpy(&u, &f, 4); hsh = (hsh ^ u) * 1099511628211ull; };
+                for (int b = 0; b < n; ++b) { mix(island.velocities[b].v.x); mix(island.velocities[b].v.y); mix(island.velocities[b].w); }
+                for (Joint* j : island.joints) { RevoluteJoint* r = static_cast<RevoluteJoint*>(j); mix(r->impulse.x); mix(r->impulse.y); mix(r->impulse.z); mix(r->motorImpulse); }
+                contactSolver.hashImpulses(mix);
+                for (int p = 1; p <= 4 && p <= (int)hist.size(); ++p) if (hist[hist.size() - p] == hsh) { velCycleAt = i; velCyclePeriod = p; break; }
+                hist.push_back(hsh);
+            }
         }
         contactSolver.storeImpulses();
         for (int i = 0; i < n; ++i) {
@@ -1771,11 +1789,21 @@ public:
             island.velocities[i].v = v; island.velocities[i].w = w;
         }
         bool positionSolved = false;
+        std::vector<uint64_t> phist;
+        posCycleAt = -1; posCyclePeriod = 0; posIterationsRun = 0;
         for (int i = 0; i < step.positionIterations; ++i) {
             const bool contactsOkay = contactSolver.solvePositionConstraints();
             bool jointsOkay = true;
             for (Joint* j : island.joints) { const bool jointOkay = j->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
+            posIterationsRun = i + 1;
             if (contactsOkay && jointsOkay) { positionSolved = true; break; }
+            if (recordCycles && posCycleAt < 0) {
+                uint64_t hsh = 1469598103934665603ull;
+                auto mix = [&hsh](float f) { uint32_t u; std::memcpy(&u, &f, 4); hsh = (hsh ^ u) * 1099511628211ull; };
+                for (int b = 0; b < n; ++b) { mix(island.positions[b].c.x); mix(island.positions[b].c.y); mix(island.positions[b].a); }
+                for (int p = 1; p <= 4 && p <= (int)phist.size(); ++p) if (phist[phist.size() - p] == hsh) { posCycleAt = i; posCyclePeriod = p; break; }
+                phist.push_back(hsh);
+            }
         }
         for (int i = 0; i < n; ++i) {
             Body* b = island.bodies[i];
