@@ -1014,8 +1014,9 @@ int gymcuda_normalize_get(gymcuda_env* e, double* obs_mean, double* obs_var, dou
         if (obs_var) obs_var[j] = var > 0.0 ? var : 0.0;
     }
     if (return_var) {
-        const double mean = c > 0.0 ? acc[2 * NORM_MAX_OD] / c : 0.0;
-        const double var = c > 0.0 ? acc[2 * NORM_MAX_OD + 1] / c - mean * mean : 1.0;
+        const double cr = acc[NORM_VALUES + 1];   // the returns have their own count (a call may carry observations only)
+        const double mean = cr > 0.0 ? acc[2 * NORM_MAX_OD] / cr : 0.0;
+        const double var = cr > 0.0 ? acc[2 * NORM_MAX_OD + 1] / cr - mean * mean : 1.0;
         *return_var = var > 0.0 ? var : 0.0;
     }
     if (count) *count = c;

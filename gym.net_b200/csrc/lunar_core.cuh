@@ -22,6 +22,7 @@
 // aux[f * n + i] (int32), so every load/store of the 32 lanes of a warp is one coalesced 128 B line.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "detmath.cuh"
@@ -396,7 +397,6 @@ struct VelRow {
     int count, body;   // velocity-constraint points of the manifold, the body it acts on
 };
 struct PosRow { V2 local_normal, local_point, lp0, lp1, centroid; float inv_mass, inv_inertia; int type, count, body; };
-constexpr int ROWS = 4;   // manifolds kept in registers (island order); a lander with more (rare) runs the rest from local memory
 
 __device__ __forceinline__ void friction_point(V2& vB, float& wB, float mB, float iB, V2 tangent, V2 rb, float tangent_mass, float friction, float normal_impulse, float& tangent_impulse) {
     const V2 dv = vB + cross_sv(wB, rb);
@@ -489,6 +489,199 @@ __device__ __forceinline__ void position_point(int type, V2 local_normal, V2 loc
 
 // HAS_PAIRS = false: the caller guarantees that no contact exists (the pair list is empty) -- the narrow phase and every
 // contact row compile out (the free-flight kernel).
+
+// ---- branch-free inner loops ------------------------------------------------------------------------------------------
+// A velocity or position iteration below is ONE basic block: every data-dependent choice (limit active / released /
+// inactive, one- or two-point manifold, the four cases of the block solver, face-A / face-B manifolds, a body without a
+// manifold) is a select over values that are all computed, never a branch.  The chains of the three bodies' contact rows
+// are independent inside an iteration, and with no branch between them the scheduler interleaves them: the launch is bound
+// by the dependent float32 latency of its slowest lander, and instruction-level parallelism is the only thing that shortens
+// it (ncu, round 2: the branchy version issued 0.25 instructions per cycle on the sub-partitions that hold such a lander).
+// Every selected value is produced by exactly the operations of the plain per-contact loops: same bits.
+
+// b2RevoluteJoint::SolveVelocityConstraints of joint ji (fuselage A = 0, leg B = 1 + ji).  limit_state is never
+// LIMIT_EQUAL for these joints (|upper - lower| = 0.5 >= 2 angularSlop, set by InitVelocityConstraints every step).
+template <int ji>
+__device__ __forceinline__ void joint_velocity(Joint& J, const JointWork& W, V2& vA, float& wA, V2& vB, float& wB) {
+    constexpr int A = 0, B = 1 + ji;
+    const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+    {   // motor
+        const float Cdot = wB - wA - JOINTS[ji].motor_speed;
+        float impulse = -W.motor_mass * Cdot;
+        const float old_impulse = J.motor;
+        const float max_impulse = DT * MAX_MOTOR_TORQUE;
+        J.motor = clampf(old_impulse + impulse, -max_impulse, max_impulse);
+        impulse = J.motor - old_impulse;
+        wA = wA - iA * impulse;
+        wB = wB + iB * impulse;
+    }
+    const bool active = J.limit_state != LIMIT_INACTIVE;
+    const V2 Cdot1 = vB + cross_sv(wB, W.rb) - vA - cross_sv(wA, W.ra);
+    const float Cdot2 = wB - wA;
+    // impulse = -mass.Solve33(Cdot), mass symmetric: ex=(exx,eyx,ezx) ey=(eyx,eyy,ezy) ez=(ezx,ezy,ezz); cross(ey, ez) and 1 / det from JointWork
+    const float exx = W.m_exx, exy = W.m_eyx, exz = W.m_ezx;
+    const float eyx = W.m_eyx, eyy = W.m_eyy, eyz = W.m_ezy;
+    const float ezx = W.m_ezx, ezy = W.m_ezy, ezz = W.m_ezz;
+    const float bx = Cdot1.x, by = Cdot1.y, bz = Cdot2;
+    const float det = W.inv_det33;
+    const float sx = det * (bx * W.c1x + by * W.c1y + bz * W.c1z);
+    const float c2x = by * ezz - bz * ezy, c2y = bz * ezx - bx * ezz, c2z = bx * ezy - by * ezx;   // cross(b, ez)
+    const float sy = det * (exx * c2x + exy * c2y + exz * c2z);
+    const float c3x = eyy * bz - eyz * by, c3y = eyz * bx - eyx * bz, c3z = eyx * by - eyy * bx;   // cross(ey, b)
+    const float sz = det * (exx * c3x + exy * c3y + exz * c3z);
+    const float new_impulse = J.iz + (-sz);
+    const bool release = active && (J.limit_state == LIMIT_AT_LOWER ? new_impulse < 0.0f : new_impulse > 0.0f);
+    // the 2x2 solve of the released limit (rhs = -Cdot1 + impulse.z * ez.xy) and of the inactive limit (rhs = -Cdot) is one solve of the selected rhs
+    const V2 rhs_released = -Cdot1 + J.iz * mk(W.m_ezx, W.m_ezy);
+    const V2 rhs_inactive = -Cdot1;
+    const V2 rhs = active ? rhs_released : rhs_inactive;
+    const V2 red = solve22_pre(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, W.inv_det22, rhs);
+    const bool full = active && !release;
+    const float imx = full ? -sx : red.x, imy = full ? -sy : red.y;
+    const float imz = full ? -sz : -J.iz;        // (inactive: not used)
+    J.ix += imx; J.iy += imy;
+    J.iz = full ? J.iz + imz : (release ? 0.0f : J.iz);
+    const V2 P = mk(imx, imy);
+    const float ta = cross(W.ra, P), tb = cross(W.rb, P);
+    vA = vA - mA * P;
+    wA = wA - iA * (active ? ta + imz : ta);
+    vB = vB + mB * P;
+    wB = wB + iB * (active ? tb + imz : tb);
+}
+
+// b2ContactSolver::SolveVelocityConstraints for the manifold of one body against the static ground, committed only if the
+// row exists (r.count > 0): friction of the points, then the normal row (one point) or the block LCP (two points).
+__device__ __forceinline__ void velocity_row_select(VelRow& r, V2& v, float& w) {
+    const bool has = r.count > 0, two = r.count == 2;
+    const float mB = r.inv_mass, iB = r.inv_inertia;
+    const V2 normal = r.normal;
+    const V2 tangent = cross_vs(normal, 1.0f);
+    V2 vB = v; float wB = w;
+    float ti0 = r.ti0, ti1 = r.ti1;
+    friction_point(vB, wB, mB, iB, tangent, r.rb0, r.tm0, r.friction, r.ni0, ti0);
+    {
+        V2 v2 = vB; float w2 = wB; float t2 = ti1;
+        friction_point(v2, w2, mB, iB, tangent, r.rb1, r.tm1, r.friction, r.ni1, t2);
+        vB = two ? v2 : vB; wB = two ? w2 : wB; ti1 = two ? t2 : ti1;
+    }
+    // one point
+    V2 v1; float w1, n1;
+    {
+        const V2 dv = vB + cross_sv(wB, r.rb0);
+        const float vn = dot(dv, normal);
+        float lambda = -r.nm0 * vn;   // velocity bias 0: restitution 0 (:242, :268)
+        n1 = maxf(r.ni0 + lambda, 0.0f);
+        lambda = n1 - r.ni0;
+        const V2 P = lambda * normal;
+        v1 = vB + mB * P;
+        w1 = wB + iB * cross(r.rb0, P);
+    }
+    // two points: the LCP by enumeration, first valid candidate
+    V2 v2p; float w2p, n20, n21;
+    {
+        const V2 aa = mk(r.ni0, r.ni1);
+        const V2 dv1 = vB + cross_sv(wB, r.rb0);
+        const V2 dv2 = vB + cross_sv(wB, r.rb1);
+        const float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+        V2 b = mk(vn1, vn2);
+        b = b - mk(r.k11 * aa.x + r.k12 * aa.y, r.k12 * aa.x + r.k22 * aa.y);
+        const V2 x1 = -mk(r.i11 * b.x + r.i12 * b.y, r.i21 * b.x + r.i22 * b.y);
+        const bool ok1 = x1.x >= 0.0f && x1.y >= 0.0f;
+        const float x2 = -r.nm0 * b.x;
+        const bool ok2 = x2 >= 0.0f && (r.k12 * x2 + b.y) >= 0.0f;
+        const float y3 = -r.nm1 * b.y;
+        const bool ok3 = y3 >= 0.0f && (r.k12 * y3 + b.x) >= 0.0f;
+        const bool ok4 = b.x >= 0.0f && b.y >= 0.0f;
+        V2 x = mk(0.0f, 0.0f);
+        x = ok3 ? mk(0.0f, y3) : x;
+        x = ok2 ? mk(x2, 0.0f) : x;
+        x = ok1 ? x1 : x;
+        const bool solved = ok1 || ok2 || ok3 || ok4;
+        const V2 d = x - aa;
+        const V2 P1 = d.x * normal, P2 = d.y * normal;
+        const V2 vs = vB + mB * (P1 + P2);
+        const float ws = wB + iB * (cross(r.rb0, P1) + cross(r.rb1, P2));
+        v2p = solved ? vs : vB; w2p = solved ? ws : wB;
+        n20 = solved ? x.x : r.ni0; n21 = solved ? x.y : r.ni1;
+    }
+    const V2 vn_ = two ? v2p : v1;
+    const float wn_ = two ? w2p : w1;
+    v = has ? vn_ : v;
+    w = has ? wn_ : w;
+    r.ti0 = has ? ti0 : r.ti0; r.ti1 = has ? ti1 : r.ti1;
+    r.ni0 = has ? (two ? n20 : n1) : r.ni0;
+    r.ni1 = (has && two) ? n21 : r.ni1;
+}
+
+// rotation of a body angle known to be far below the 32768 rad where the argument reduction changes path (checked once per step)
+__device__ __forceinline__ Rot rot_in_range(float a) { Rot q; const float2 sc = sincos_det<true>(a); q.s = sc.x; q.c = sc.y; return q; }
+
+// one point of b2ContactSolver::SolvePositionConstraints, both manifold types computed, committed only if `on`
+template <bool IN_RANGE>
+__device__ __forceinline__ void position_point_select(bool on, int type, V2 local_normal, V2 local_point, V2 lp, V2 centroid, float mB, float iB,
+                                                      V2& c, float& a, float& min_separation) {
+    const Rot qB = IN_RANGE ? rot_in_range(a) : rot(a);
+    const V2 pB = c - rmul(qB, centroid);
+    // face A: the plane is the (static) edge's, the clip point rides on the body
+    const V2 clipA = rmul(qB, lp) + pB;
+    const float sepA = dot(clipA - local_point, local_normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+    // face B: the plane rides on the body, the clip point is the edge's
+    const V2 nB = rmul(qB, local_normal);
+    const V2 planeB = rmul(qB, local_point) + pB;
+    const float sepB = dot(lp - planeB, nB) - POLYGON_RADIUS - POLYGON_RADIUS;
+    const bool faceA = type == MF_FACE_A;
+    const V2 normal = faceA ? local_normal : -nB;
+    const V2 point = faceA ? clipA : lp;
+    const float separation = faceA ? sepA : sepB;
+    const V2 rB = point - c;
+    const float ms = minf(min_separation, separation);
+    const float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
+    const float rnB = cross(rB, normal);
+    const float K = mB + iB * rnB * rnB;
+    // K >= inv_mass > 0 for a real row; -C / K is 0 or far from the subnormal range (C is a multiple of ulp(linearSlop) ~ 5e-10 scaled by 0.2)
+    const float impulse = K > 0.0f ? div_inrange(-C, K) : 0.0f;
+    const V2 P = impulse * normal;
+    const V2 cn = c + mB * P;
+    const float an = a + iB * cross(rB, P);
+    c = on ? cn : c;
+    a = on ? an : a;
+    min_separation = on ? ms : min_separation;
+}
+
+// b2RevoluteJoint::SolvePositionConstraints of joint ji; returns position_error <= linearSlop && angular_error <= angularSlop
+template <int ji, bool IN_RANGE>
+__device__ __forceinline__ bool joint_position(const Joint& J, float motor_mass, V2& cA, float& aA, V2& cB, float& aB) {
+    constexpr int A = 0, B = 1 + ji;
+    const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
+    const bool active = J.limit_state != LIMIT_INACTIVE, lower = J.limit_state == LIMIT_AT_LOWER;
+    const float angle = aB - aA - JOINTS[ji].ref_angle;
+    const float Cl = angle - JOINTS[ji].lower, Cu = angle - JOINTS[ji].upper;
+    const float angular_error = active ? (lower ? -Cl : Cu) : 0.0f;
+    const float Cl2 = clampf(Cl + ANGULAR_SLOP, -MAX_ANGULAR_CORRECTION, 0.0f);
+    const float Cu2 = clampf(Cu - ANGULAR_SLOP, 0.0f, MAX_ANGULAR_CORRECTION);
+    const float limit_impulse = -motor_mass * (lower ? Cl2 : Cu2);
+    const float aAn = aA - iA * limit_impulse, aBn = aB + iB * limit_impulse;
+    aA = active ? aAn : aA;
+    aB = active ? aBn : aB;
+    const Rot qA = IN_RANGE ? rot_in_range(aA) : rot(aA), qB = IN_RANGE ? rot_in_range(aB) : rot(aB);
+    const V2 rA = rmul(qA, mk(0.0f, 0.0f) - SHAPES[A].centroid);
+    const V2 rB = rmul(qB, JOINTS[ji].anchor_b - SHAPES[B].centroid);
+    const V2 C = cB + rB - cA - rA;
+    const float position_error = sqrtf(dot(C, C));
+    const float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+    const float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+    const float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+    // b2Mat22::Solve; the determinant of this K is of order (1 / m_leg)^2: normal, never 0 -- its reciprocal without the range check of `/`
+    float det = kxx * kyy - kxy * kxy;
+    det = det != 0.0f ? div_inrange(1.0f, det) : det;
+    const V2 impulse = -solve22_pre(kxx, kxy, kxy, kyy, det, C);
+    cA = cA - mA * impulse;
+    aA = aA - iA * cross(rA, impulse);
+    cB = cB + mB * impulse;
+    aB = aB + iB * cross(rB, impulse);
+    return position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+}
+
 // the touching manifolds of a step (creation order) and their island order
 struct Contacts { ActiveContact ac[MAXC]; int nc; uint32_t order; };
 
@@ -705,131 +898,80 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
             w[B] = w[B] + iB * (cross(W.rb, P) + J.motor + J.iz);
         }
 
-        // one velocity iteration of the two revolute joints (b2RevoluteJoint::SolveVelocityConstraints), leg1's then leg0's
-        auto solve_joints_velocity = [&]() {
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int ji = 1 - jj;
-                const int A = 0, B = 1 + ji;
-                Joint& J = Jl[ji];
-                const JointWork& W = jw[ji];
-                const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
-                // motor
-                if (J.limit_state != LIMIT_EQUAL) {
-                    const float Cdot = w[B] - w[A] - JOINTS[ji].motor_speed;
-                    float impulse = -W.motor_mass * Cdot;
-                    const float old_impulse = J.motor;
-                    const float max_impulse = h * MAX_MOTOR_TORQUE;
-                    J.motor = clampf(old_impulse + impulse, -max_impulse, max_impulse);
-                    impulse = J.motor - old_impulse;
-                    w[A] = w[A] - iA * impulse;
-                    w[B] = w[B] + iB * impulse;
-                }
-                if (J.limit_state != LIMIT_INACTIVE) {
-                    const V2 Cdot1 = v[B] + cross_sv(w[B], W.rb) - v[A] - cross_sv(w[A], W.ra);
-                    const float Cdot2 = w[B] - w[A];
-                    // impulse = -mass.Solve33(Cdot), mass symmetric: ex=(exx,eyx,ezx) ey=(eyx,eyy,ezy) ez=(ezx,ezy,ezz)
-                    const float exx = W.m_exx, exy = W.m_eyx, exz = W.m_ezx;
-                    const float eyx = W.m_eyx, eyy = W.m_eyy, eyz = W.m_ezy;
-                    const float ezx = W.m_ezx, ezy = W.m_ezy, ezz = W.m_ezz;
-                    const float bx = Cdot1.x, by = Cdot1.y, bz = Cdot2;
-                    // cross(ey, ez) and 1 / det: from JointWork
-                    const float c1x = W.c1x, c1y = W.c1y, c1z = W.c1z, det = W.inv_det33;
-                    const float sx = det * (bx * c1x + by * c1y + bz * c1z);
-                    // cross(b, ez)
-                    const float c2x = by * ezz - bz * ezy, c2y = bz * ezx - bx * ezz, c2z = bx * ezy - by * ezx;
-                    const float sy = det * (exx * c2x + exy * c2y + exz * c2z);
-                    // cross(ey, b)
-                    const float c3x = eyy * bz - eyz * by, c3y = eyz * bx - eyx * bz, c3z = eyx * by - eyy * bx;
-                    const float sz = det * (exx * c3x + exy * c3y + exz * c3z);
-                    float imx = -sx, imy = -sy, imz = -sz;
-                    if (J.limit_state == LIMIT_EQUAL) {
-                        J.ix += imx; J.iy += imy; J.iz += imz;
-                    } else {
-                        const float new_impulse = J.iz + imz;
-                        const bool release = J.limit_state == LIMIT_AT_LOWER ? new_impulse < 0.0f : new_impulse > 0.0f;
-                        if (release) {
-                            const V2 rhs = -Cdot1 + J.iz * mk(W.m_ezx, W.m_ezy);
-                            const V2 reduced = solve22_pre(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, W.inv_det22, rhs);
-                            imx = reduced.x; imy = reduced.y; imz = -J.iz;
-                            J.ix += reduced.x; J.iy += reduced.y; J.iz = 0.0f;
-                        } else {
-                            J.ix += imx; J.iy += imy; J.iz += imz;
-                        }
-                    }
-                    const V2 P = mk(imx, imy);
-                    v[A] = v[A] - mA * P;
-                    w[A] = w[A] - iA * (cross(W.ra, P) + imz);
-                    v[B] = v[B] + mB * P;
-                    w[B] = w[B] + iB * (cross(W.rb, P) + imz);
-                } else {
-                    const V2 Cdot = v[B] + cross_sv(w[B], W.rb) - v[A] - cross_sv(w[A], W.ra);
-                    const V2 impulse = solve22_pre(W.m_exx, W.m_eyx, W.m_eyx, W.m_eyy, W.inv_det22, -Cdot);
-                    J.ix += impulse.x; J.iy += impulse.y;
-                    v[A] = v[A] - mA * impulse;
-                    w[A] = w[A] - iA * cross(W.ra, impulse);
-                    v[B] = v[B] + mB * impulse;
-                    w[B] = w[B] + iB * cross(W.rb, impulse);
-                }
-            }
-        };
-
-        // ---- velocity iterations: one loop for every lane
-        VelRow row[HAS_PAIRS ? ROWS : 1];
+        // ---- velocity iterations: one branch-free loop body for every lane.  Register rows: the newest manifold of each body
+        // (rows of different bodies commute: they share no variable); a body's older manifolds (a polygon astride a terrain
+        // vertex) follow from local memory, in island order, skipped by the whole warp when no lane has one.
+        VelRow row[HAS_PAIRS ? 3 : 1];
+        uint32_t extra = 0u;   // island positions (4 bits each) of the manifolds that are not a body's newest
+        int nextra = 0;
+        bool warp_rows = false, warp_extra = false;
         if (HAS_PAIRS) {
+            int first_of[3] = {-1, -1, -1};
+            for (int kk = 0; kk < nc; ++kk) {
+                const int k = (int)((order >> (4 * kk)) & 15u);
+                const int B = ac[k].body;
+                if (GETB(first_of, B) < 0) { SETB(first_of, B, k); }
+                else { extra |= (uint32_t)k << (4 * nextra++); }
+            }
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                VelRow& q = row[r];
-                q.count = 0; q.body = 0;
-                if (r < nc) {
-                    const ActiveContact& cc = ac[(order >> (4 * r)) & 15u];
+            for (int B = 0; B < 3; ++B) {
+                VelRow& q = row[B];
+                q.count = 0; q.body = B;
+                q.inv_mass = SHAPES[B].inv_mass; q.inv_inertia = SHAPES[B].inv_inertia;
+                q.normal = mk(0.0f, 1.0f); q.rb0 = q.rb1 = mk(0.0f, 0.0f);
+                q.ni0 = q.ni1 = q.ti0 = q.ti1 = q.nm0 = q.nm1 = q.tm0 = q.tm1 = q.friction = 0.0f;
+                q.k11 = q.k12 = q.k22 = q.i11 = q.i12 = q.i21 = q.i22 = 0.0f;
+                if (first_of[B] >= 0) {
+                    const ActiveContact& cc = ac[first_of[B]];
                     q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
                     q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
                     q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
                     q.friction = cc.friction;
                     q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
-                    q.inv_mass = SHAPES[cc.body].inv_mass; q.inv_inertia = SHAPES[cc.body].inv_inertia;
-                    q.count = cc.count; q.body = cc.body;
+                    q.count = cc.count;
                 }
             }
+            const unsigned am = __activemask();
+            warp_rows = __ballot_sync(am, nc > 0) != 0u;
+            warp_extra = __ballot_sync(am, nextra > 0) != 0u;
         }
 #pragma unroll 1
         for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
-            solve_joints_velocity();
-            if (HAS_PAIRS) {
+            joint_velocity<1>(Jl[1], jw[1], v[0], w[0], v[2], w[2]);   // island order: leg 1's joint, then leg 0's
+            joint_velocity<0>(Jl[0], jw[0], v[0], w[0], v[1], w[1]);
+            if (HAS_PAIRS && warp_rows) {
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r)
-                    if (row[r].count > 0) {
-                        const int B = row[r].body;
+                for (int B = 0; B < 3; ++B) velocity_row_select(row[B], v[B], w[B]);
+                if (warp_extra) {
+                    for (int kk = 0; kk < nextra; ++kk) {
+                        ActiveContact& cc = ac[(extra >> (4 * kk)) & 15u];
+                        const int B = cc.body;
                         V2 vB = GETB(v, B); float wB = GETB(w, B);   // only velocities change in a velocity iteration
-                        solve_velocity_row(row[r], vB, wB, row[r].inv_mass, row[r].inv_inertia);
+                        VelRow q;
+                        q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
+                        q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
+                        q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
+                        q.friction = cc.friction;
+                        q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
+                        q.inv_mass = SHAPES[B].inv_mass; q.inv_inertia = SHAPES[B].inv_inertia;
+                        q.count = cc.count; q.body = B;
+                        velocity_row_select(q, vB, wB);
+                        cc.p[0].normal_impulse = q.ni0; cc.p[0].tangent_impulse = q.ti0;
+                        cc.p[1].normal_impulse = q.ni1; cc.p[1].tangent_impulse = q.ti1;
                         SETB(v, B, vB); SETB(w, B, wB);
                     }
-                for (int kk = ROWS; kk < nc; ++kk) {   // beyond the register rows (rare): from local memory
-                    ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
-                    const int B = cc.body;
-                    V2 vB = GETB(v, B); float wB = GETB(w, B);
-                    VelRow q;
-                    q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
-                    q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
-                    q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
-                    q.friction = cc.friction;
-                    q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
-                    q.count = cc.count; q.body = B;
-                    solve_velocity_row(q, vB, wB, SHAPES[B].inv_mass, SHAPES[B].inv_inertia);
-                    cc.p[0].normal_impulse = q.ni0; cc.p[0].tangent_impulse = q.ti0;
-                    if (cc.count == 2) { cc.p[1].normal_impulse = q.ni1; cc.p[1].tangent_impulse = q.ti1; }
-                    SETB(v, B, vB); SETB(w, B, wB);
                 }
             }
         }
         if (HAS_PAIRS) {
+            int first_of[3] = {-1, -1, -1};
+            for (int kk = nc - 1; kk >= 0; --kk) { const int k = (int)((order >> (4 * kk)) & 15u); SETB(first_of, ac[k].body, k); }
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r)
-                if (r < nc) {
-                    ActiveContact& cc = ac[(order >> (4 * r)) & 15u];
-                    cc.p[0].normal_impulse = row[r].ni0; cc.p[0].tangent_impulse = row[r].ti0;
-                    if (cc.count == 2) { cc.p[1].normal_impulse = row[r].ni1; cc.p[1].tangent_impulse = row[r].ti1; }
+            for (int B = 0; B < 3; ++B)
+                if (first_of[B] >= 0) {
+                    ActiveContact& cc = ac[first_of[B]];
+                    cc.p[0].normal_impulse = row[B].ni0; cc.p[0].tangent_impulse = row[B].ti0;
+                    cc.p[1].normal_impulse = row[B].ni1; cc.p[1].tangent_impulse = row[B].ti1;
                 }
         }
 
@@ -856,101 +998,64 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
         // ANGULAR_SLOP + 1 ulp, just above what joints_okay accepts), but after two or three iterations the
         // corrections round to nothing: once an iteration returns bit-identical coordinates, the remaining ones
         // would too, so the loop stops there -- same result as all 60, position_solved stays false.
-        PosRow prow[HAS_PAIRS ? ROWS : 1];
+        PosRow prow[HAS_PAIRS ? 3 : 1];
         if (HAS_PAIRS) {
+            int first_of[3] = {-1, -1, -1};
+            for (int kk = nc - 1; kk >= 0; --kk) { const int k = (int)((order >> (4 * kk)) & 15u); SETB(first_of, ac[k].body, k); }
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                prow[r].count = 0; prow[r].body = 0; prow[r].type = 0;
-                if (r < nc) {
-                    const ActiveContact& cc = ac[(order >> (4 * r)) & 15u];
-                    const Manifold& m = cc.m;
-                    prow[r].local_normal = m.local_normal; prow[r].local_point = m.local_point; prow[r].lp0 = m.lp[0]; prow[r].lp1 = m.lp[1];
-                    prow[r].centroid = SHAPES[cc.body].centroid; prow[r].inv_mass = SHAPES[cc.body].inv_mass; prow[r].inv_inertia = SHAPES[cc.body].inv_inertia;
-                    prow[r].type = m.type; prow[r].count = m.count; prow[r].body = cc.body;
+            for (int B = 0; B < 3; ++B) {
+                PosRow& q = prow[B];
+                q.count = 0; q.body = B; q.type = MF_FACE_A;
+                q.centroid = SHAPES[B].centroid; q.inv_mass = SHAPES[B].inv_mass; q.inv_inertia = SHAPES[B].inv_inertia;
+                q.local_normal = mk(0.0f, 1.0f); q.local_point = q.lp0 = q.lp1 = mk(0.0f, 0.0f);
+                if (first_of[B] >= 0) {
+                    const Manifold& m = ac[first_of[B]].m;
+                    q.local_normal = m.local_normal; q.local_point = m.local_point; q.lp0 = m.lp[0]; q.lp1 = m.lp[1];
+                    q.type = m.type; q.count = m.count;
                 }
             }
         }
+        // every body angle far inside the single-path range of the argument reduction (a step turns a body by at most pi / 2)?
+        const bool small_angles = fabsf(a[0]) < 30000.0f && fabsf(a[1]) < 30000.0f && fabsf(a[2]) < 30000.0f;
         bool position_solved = false;
+        auto position_iterations = [&](auto in_range_tag) {
+            constexpr bool IN_RANGE = decltype(in_range_tag)::value;
 #pragma unroll 1
-        for (int it = 0; it < POSITION_ITERATIONS; ++it) {
-            const V2 c_in[3] = {c[0], c[1], c[2]};
-            const float a_in[3] = {a[0], a[1], a[2]};
-            float min_separation = 0.0f;
-            if (HAS_PAIRS) {
+            for (int it = 0; it < POSITION_ITERATIONS; ++it) {
+                const V2 c_in[3] = {c[0], c[1], c[2]};
+                const float a_in[3] = {a[0], a[1], a[2]};
+                float min_separation = 0.0f;
+                if (HAS_PAIRS && warp_rows) {
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const PosRow& m = prow[r];
-                    if (m.count > 0) {
-                        const int B = m.body;
-                        V2 cB = GETB(c, B); float aB = GETB(a, B);   // only positions change in a position iteration
-                        position_point(m.type, m.local_normal, m.local_point, m.lp0, m.centroid, m.inv_mass, m.inv_inertia, cB, aB, min_separation);
-                        if (m.count > 1) position_point(m.type, m.local_normal, m.local_point, m.lp1, m.centroid, m.inv_mass, m.inv_inertia, cB, aB, min_separation);
-                        SETB(c, B, cB); SETB(a, B, aB);
+                    for (int B = 0; B < 3; ++B) {
+                        const PosRow& m = prow[B];
+                        position_point_select<IN_RANGE>(m.count > 0, m.type, m.local_normal, m.local_point, m.lp0, m.centroid, m.inv_mass, m.inv_inertia, c[B], a[B], min_separation);
+                        position_point_select<IN_RANGE>(m.count > 1, m.type, m.local_normal, m.local_point, m.lp1, m.centroid, m.inv_mass, m.inv_inertia, c[B], a[B], min_separation);
+                    }
+                    if (warp_extra) {
+                        for (int kk = 0; kk < nextra; ++kk) {
+                            const ActiveContact& cc = ac[(extra >> (4 * kk)) & 15u];
+                            const int B = cc.body;
+                            V2 cB = GETB(c, B); float aB = GETB(a, B);   // only positions change in a position iteration
+                            for (int j = 0; j < cc.m.count; ++j)
+                                position_point(cc.m.type, cc.m.local_normal, cc.m.local_point, cc.m.lp[j], SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, cB, aB, min_separation);
+                            SETB(c, B, cB); SETB(a, B, aB);
+                        }
                     }
                 }
-                for (int kk = ROWS; kk < nc; ++kk) {
-                    const ActiveContact& cc = ac[(order >> (4 * kk)) & 15u];
-                    const int B = cc.body;
-                    V2 cB = GETB(c, B); float aB = GETB(a, B);
-                    for (int j = 0; j < cc.m.count; ++j)
-                        position_point(cc.m.type, cc.m.local_normal, cc.m.local_point, cc.m.lp[j], SHAPES[B].centroid, SHAPES[B].inv_mass, SHAPES[B].inv_inertia, cB, aB, min_separation);
-                    SETB(c, B, cB); SETB(a, B, aB);
-                }
-            }
-            const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
-            bool joints_okay = true;
+                const bool contacts_okay = min_separation >= -3.0f * LINEAR_SLOP;
+                const bool j1 = joint_position<1, IN_RANGE>(Jl[1], jw[1].motor_mass, c[0], a[0], c[2], a[2]);
+                const bool j0 = joint_position<0, IN_RANGE>(Jl[0], jw[0].motor_mass, c[0], a[0], c[1], a[1]);
+                if (contacts_okay && j1 && j0) { position_solved = true; break; }
+                int moved = 0;
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int ji = 1 - jj;
-                const int A = 0, B = 1 + ji;
-                const Joint& J = Jl[ji];
-                const float mA = SHAPES[A].inv_mass, iA = SHAPES[A].inv_inertia, mB = SHAPES[B].inv_mass, iB = SHAPES[B].inv_inertia;
-                float angular_error = 0.0f;
-                if (J.limit_state != LIMIT_INACTIVE) {
-                    const float angle = a[B] - a[A] - JOINTS[ji].ref_angle;
-                    float limit_impulse = 0.0f;
-                    const float motor_mass = jw[ji].motor_mass;
-                    if (J.limit_state == LIMIT_EQUAL) {
-                        const float C = clampf(angle - JOINTS[ji].lower, -MAX_ANGULAR_CORRECTION, MAX_ANGULAR_CORRECTION);
-                        limit_impulse = -motor_mass * C;
-                        angular_error = fabsf(C);
-                    } else if (J.limit_state == LIMIT_AT_LOWER) {
-                        float C = angle - JOINTS[ji].lower;
-                        angular_error = -C;
-                        C = clampf(C + ANGULAR_SLOP, -MAX_ANGULAR_CORRECTION, 0.0f);
-                        limit_impulse = -motor_mass * C;
-                    } else {
-                        float C = angle - JOINTS[ji].upper;
-                        angular_error = C;
-                        C = clampf(C - ANGULAR_SLOP, 0.0f, MAX_ANGULAR_CORRECTION);
-                        limit_impulse = -motor_mass * C;
-                    }
-                    a[A] = a[A] - iA * limit_impulse;
-                    a[B] = a[B] + iB * limit_impulse;
-                }
-                const Rot qA = rot(a[A]), qB = rot(a[B]);
-                const V2 rA = rmul(qA, mk(0.0f, 0.0f) - SHAPES[A].centroid);
-                const V2 rB = rmul(qB, JOINTS[ji].anchor_b - SHAPES[B].centroid);
-                const V2 C = c[B] + rB - c[A] - rA;
-                const float position_error = sqrtf(dot(C, C));
-                const float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
-                const float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
-                const float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
-                const V2 impulse = -solve22(kxx, kxy, kxy, kyy, C);
-                c[A] = c[A] - mA * impulse;
-                a[A] = a[A] - iA * cross(rA, impulse);
-                c[B] = c[B] + mB * impulse;
-                a[B] = a[B] + iB * cross(rB, impulse);
-                joints_okay = joints_okay && (position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP);
+                for (int i = 0; i < 3; ++i)
+                    moved |= (__float_as_int(c[i].x) ^ __float_as_int(c_in[i].x)) | (__float_as_int(c[i].y) ^ __float_as_int(c_in[i].y)) |
+                             (__float_as_int(a[i]) ^ __float_as_int(a_in[i]));
+                if (moved == 0) break;   // fixed point
             }
-            if (contacts_okay && joints_okay) { position_solved = true; break; }
-            int moved = 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                moved |= (__float_as_int(c[i].x) ^ __float_as_int(c_in[i].x)) | (__float_as_int(c[i].y) ^ __float_as_int(c_in[i].y)) |
-                         (__float_as_int(a[i]) ^ __float_as_int(a_in[i]));
-            if (moved == 0) break;   // fixed point
-        }
+        };
+        if (small_angles) position_iterations(std::true_type{}); else position_iterations(std::false_type{});
 
         // copy back, store impulses (b2ContactSolver::StoreImpulses): slots in creation order
 #pragma unroll

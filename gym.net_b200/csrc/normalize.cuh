@@ -17,9 +17,10 @@ namespace gymcuda {
 constexpr int NORM_MAX_OD = 8;
 constexpr int NORM_BLOCK = 256;
 constexpr int NORM_VALUES = 2 * NORM_MAX_OD + 2;   // per-env contributions: obs_j, obs_j^2, ret, ret^2
-constexpr int NORM_ACC = NORM_VALUES + 1;          // + the number of envs accumulated so far
+constexpr int NORM_ACC = NORM_VALUES + 2;          // + the numbers of envs accumulated so far: [18] into the observation sums, [19] into the return sums
 
-// acc (double): [0..7] sum obs_j, [8..15] sum obs_j^2, [16] sum ret, [17] sum ret^2, [18] count
+// acc (double): [0..7] sum obs_j, [8..15] sum obs_j^2, [16] sum ret, [17] sum ret^2, [18] count of observations, [19] count of returns
+// (two counts: a call may carry only observations -- the batch Reset returns -- or only rewards, and must not dilute the other statistic)
 struct NormArgs {
     float* obs;            // [n][od], may be null
     float* reward;         // [n], may be null
@@ -65,7 +66,10 @@ __global__ void __launch_bounds__(NORM_BLOCK) norm_update_kernel(const NormArgs 
         for (int w = 0; w < NORM_BLOCK / 32; ++w) s += part[w][threadIdx.x];
         if (s != 0.0) atomicAdd(&p.acc[threadIdx.x], s);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.acc[NORM_VALUES], (double)p.n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (p.obs) atomicAdd(&p.acc[NORM_VALUES], (double)p.n);
+        if (p.reward) atomicAdd(&p.acc[NORM_VALUES + 1], (double)p.n);
+    }
 }
 
 __device__ __forceinline__ float norm_clip(float x, float c) { return x < -c ? -c : (x > c ? c : x); }
@@ -73,9 +77,8 @@ __device__ __forceinline__ float norm_clip(float x, float c) { return x < -c ? -
 __global__ void __launch_bounds__(NORM_BLOCK) norm_apply_kernel(const NormArgs p) {
     const int i = blockIdx.x * NORM_BLOCK + threadIdx.x;
     if (i >= p.n) return;
-    const double count = p.acc[NORM_VALUES];
-    if (count <= 0.0) return;   // nothing accumulated yet: leave the batch as it is
-    if (p.obs) {
+    const double count = p.acc[NORM_VALUES], count_ret = p.acc[NORM_VALUES + 1];
+    if (p.obs && count > 0.0) {   // nothing accumulated yet: leave the batch as it is
 #pragma unroll
         for (int j = 0; j < NORM_MAX_OD; ++j)
             if (j < p.od) {
@@ -86,9 +89,9 @@ __global__ void __launch_bounds__(NORM_BLOCK) norm_apply_kernel(const NormArgs p
                 p.obs[at] = norm_clip((float)(((double)p.obs[at] - mean) / sqrt(var + (double)p.eps)), p.clip_obs);
             }
     }
-    if (p.reward) {
-        const double mean = p.acc[2 * NORM_MAX_OD] / count;
-        double var = p.acc[2 * NORM_MAX_OD + 1] / count - mean * mean;
+    if (p.reward && count_ret > 0.0) {
+        const double mean = p.acc[2 * NORM_MAX_OD] / count_ret;
+        double var = p.acc[2 * NORM_MAX_OD + 1] / count_ret - mean * mean;
         var = var > 0.0 ? var : 0.0;
         p.reward[i] = norm_clip((float)((double)p.reward[i] / sqrt(var + (double)p.eps)), p.clip_reward);
     }

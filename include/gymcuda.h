@@ -188,7 +188,8 @@ int gymcuda_get_stats(gymcuda_env* env, gymcuda_stats* out, int reset_counters);
 int gymcuda_normalize_config(gymcuda_env* env, float gamma, float epsilon, float clip_obs, float clip_reward);
 int gymcuda_normalize_device(gymcuda_env* env, float* d_obs, float* d_reward, const uint8_t* d_done, int update);
 int gymcuda_normalize(gymcuda_env* env, float* obs, float* reward, const uint8_t* done, int update);
-/* obs_mean / obs_var: [obs_dim]; any pointer may be NULL.  count = envs accumulated so far. */
+/* obs_mean / obs_var: [obs_dim]; any pointer may be NULL.  count = observations accumulated so far (the returns keep
+ * their own count: a call that carries only observations, e.g. the batch Reset returned, does not dilute return_var). */
 int gymcuda_normalize_get(gymcuda_env* env, double* obs_mean, double* obs_var, double* return_var, double* count);
 int gymcuda_normalize_reset(gymcuda_env* env);
 

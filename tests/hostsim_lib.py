@@ -167,7 +167,7 @@ class NormalizeModel:
     def __init__(self, n, od, gamma=0.99, eps=1e-8, clip_obs=10.0, clip_reward=10.0):
         self.n, self.od = n, od
         self.gamma, self.eps, self.clip_obs, self.clip_reward = np.float32(gamma), np.float32(eps), np.float32(clip_obs), np.float32(clip_reward)
-        self.s = np.zeros(od); self.q = np.zeros(od); self.sr = 0.0; self.qr = 0.0; self.count = 0.0
+        self.s = np.zeros(od); self.q = np.zeros(od); self.sr = 0.0; self.qr = 0.0; self.count = 0.0; self.count_ret = 0.0   # separate counts: obs-only / reward-only calls
         self.ret = np.zeros(n, np.float32)
 
     def __call__(self, obs, reward, done, update=True):
@@ -176,21 +176,20 @@ class NormalizeModel:
             if obs is not None:
                 x = obs.astype(np.float64)
                 self.s += x.sum(axis=0); self.q += (x * x).sum(axis=0)
+                self.count += self.n
             if reward is not None:
                 r = (self.ret * self.gamma).astype(np.float32) + reward          # float32 multiply, then float32 add
                 r64 = r.astype(np.float64)
                 self.sr += r64.sum(); self.qr += (r64 * r64).sum()
                 self.ret = np.where(done != 0, np.float32(0), r).astype(np.float32) if done is not None else r
-            self.count += self.n
-        if self.count <= 0:
-            return obs, reward
-        out_o = out_r = None
-        if obs is not None:
+                self.count_ret += self.n
+        out_o, out_r = obs, reward
+        if obs is not None and self.count > 0:
             mean = self.s / self.count
             var = np.maximum(self.q / self.count - mean * mean, 0.0)
             out_o = np.clip(((obs.astype(np.float64) - mean) / np.sqrt(var + np.float64(self.eps))).astype(np.float32), -self.clip_obs, self.clip_obs)
-        if reward is not None:
-            mean = self.sr / self.count
-            var = max(self.qr / self.count - mean * mean, 0.0)
+        if reward is not None and self.count_ret > 0:
+            mean = self.sr / self.count_ret
+            var = max(self.qr / self.count_ret - mean * mean, 0.0)
             out_r = np.clip((reward.astype(np.float64) / np.sqrt(var + np.float64(self.eps))).astype(np.float32), -self.clip_reward, self.clip_reward)
         return out_o, out_r

@@ -300,7 +300,7 @@ def test_normalize_kernels_against_numpy(hs, n, od):
     from hostsim_lib import NormalizeModel, _p
     rng = np.random.default_rng(n)
     model = NormalizeModel(n, od, gamma=0.97, eps=1e-6, clip_obs=1.5, clip_reward=4.0)
-    acc = np.zeros(19, np.float64); ret = np.zeros(n, np.float32)
+    acc = np.zeros(20, np.float64); ret = np.zeros(n, np.float32)
     scale = rng.uniform(0.1, 30.0, od); shift = rng.uniform(-5, 5, od)
     for it in range(6):
         obs = (rng.standard_normal((n, od)) * scale + shift).astype(F32)
@@ -312,10 +312,15 @@ def test_normalize_kernels_against_numpy(hs, n, od):
         hs.hostsim_normalize(_p(got_o), _p(got_r), _p(done), _p(ret), _p(acc), n, od, 0.97, 1e-6, 1.5, 4.0, int(update))
         assert np.allclose(got_o, want_o, rtol=1e-6, atol=1e-6) and np.allclose(got_r, want_r, rtol=1e-6, atol=1e-6)
         assert np.array_equal(ret, model.ret)
-        assert acc[18] == model.count and np.allclose(acc[:od], model.s, rtol=1e-12) and np.allclose(acc[8:8 + od], model.q, rtol=1e-12)
+        assert acc[18] == model.count and acc[19] == model.count_ret and np.allclose(acc[:od], model.s, rtol=1e-12) and np.allclose(acc[8:8 + od], model.q, rtol=1e-12)
         assert (np.abs(got_o) <= 1.5).all() and (np.abs(got_o) == 1.5).any()         # the clip is active
     # obs only / reward only
     obs = rng.standard_normal((n, od)).astype(F32); got = obs.copy()
     want, _ = model(obs, None, None, True)
     hs.hostsim_normalize(_p(got), None, None, _p(ret), _p(acc), n, od, 0.97, 1e-6, 1.5, 4.0, 1)
     assert np.allclose(got, want, rtol=1e-6, atol=1e-6)
+    assert acc[18] == model.count and acc[19] == model.count_ret and acc[18] == acc[19] + n   # the obs-only call did not touch the return count
+    rew = rng.uniform(-2, 3, n).astype(F32); got_r = rew.copy()
+    _, want_r = model(None, rew, None, True)
+    hs.hostsim_normalize(None, _p(got_r), None, _p(ret), _p(acc), n, od, 0.97, 1e-6, 1.5, 4.0, 1)
+    assert np.allclose(got_r, want_r, rtol=1e-6, atol=1e-6) and acc[18] == acc[19]
