@@ -327,6 +327,25 @@ def measure_envs(G, torch, dist, dev, rank, world, local_rank, peak, sm_mhz):
         "algorithmic_bytes_per_env_step": 41, "hbm_gbs_per_gpu": rate * 41 / 1e9, "frac": rate * 41 / 1e9 / peak,
         "bytes_moved_per_env_step_with_obs_copy": 57, "hbm_gbs_with_obs_copy": rate * 57 / 1e9, "frac_with_obs_copy": rate * 57 / 1e9 / peak}
     env.Close()
+    del o, r, d, acts
+
+    # caller-supplied actions, k steps per launch (gymcuda_step_many_device): what a device-resident learner that produces
+    # blocks of actions gets instead of k per-launch steps -- CartPole, 65 536 envs, 512 steps per launch
+    n, K = 65536, 512
+    env = G.make("CartPole-v1", n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True)
+    env.SetStream(stream.cuda_stream)
+    env.ResetBatch()
+    o = torch.empty((K, n, 4), dtype=torch.float32, device=dev); r = torch.empty((K, n), dtype=torch.float32, device=dev)
+    d = torch.empty((K, n), dtype=torch.uint8, device=dev)
+    acts = torch.randint(0, 2, (K, n), dtype=torch.int32, device=dev)
+    ms = timed(lambda: env.StepManyDevice(K, acts.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr()), 10)
+    rate = world * n * K / (ms * 1e-3)
+    out["CartPole-v1 step_many @65536"] = {
+        "mode": "gymcuda_step_many_device: %d env steps per launch with caller-supplied device-resident actions" % K, "num_envs_per_gpu": n,
+        "env_steps_per_s": rate, "ms_per_launch": ms, "bound": "hbm", "algorithmic_bytes_per_env_step": 25,
+        "hbm_gbs_per_gpu": rate / world * 25 / 1e9, "frac": rate / world * 25 / 1e9 / peak,
+        "note": "action 4 B read + obs 16 B + reward 4 B + done 1 B written per env step; the per-launch gymcuda_step_device figure of the same batch is in profiles/"}
+    env.Close()
     return out
 
 

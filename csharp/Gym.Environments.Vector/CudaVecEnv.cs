@@ -13,7 +13,12 @@ using Gym.Spaces;
 using NumSharp;
 
 namespace Gym.Environments.Vector {
-    public class CudaVecEnv : VecEnv, IDisposable {
+    // IVecEnv is re-implemented explicitly: VecEnv.Seed(int) / Seed(int[]) are NOT virtual (VecEnv.cs:44-53) and loop over the
+    // (here empty) Environments list, so `public new void Seed` alone would be reached only through a CudaVecEnv-typed
+    // reference -- through an IVecEnv or VecEnv reference the base would run and silently seed nothing.  Listing IVecEnv
+    // again makes the interface map to the members below; a VecEnv-typed (base class) reference still binds statically to
+    // the base methods, which is why INTEGRATION.md proposes `virtual` on the two base methods as the one-line upstream patch.
+    public class CudaVecEnv : VecEnv, IVecEnv, IDisposable {
         private readonly GymCudaHandle _h;
         private readonly GymCudaSpaceInfo _info;
         private readonly float[] _obs, _reward;
@@ -75,16 +80,23 @@ namespace Gym.Environments.Vector {
         }
 
         public override void Close() {
+            if (_terminalPin.IsAllocated) { Native.gymcuda_host_unregister(_terminalPin.AddrOfPinnedObject()); _terminalPin.Free(); }
             foreach (var h in _pins) { Native.gymcuda_host_unregister(h.AddrOfPinnedObject()); h.Free(); }
             _pins.Clear();
             _h.Dispose();
         }
         public void Dispose() { Close(); }
 
+        // Seed widening (the same rule in gym.net_b200/vector.py): the 32-bit pattern of the int, zero-extended -- Seed(-1) is
+        // 0x00000000FFFFFFFF in both hosts.
         public new void Seed(int seed) { Native.Check(Native.gymcuda_seed(_h, (ulong) (uint) seed)); }
         public new void Seed(int[] seed) { Native.Check(Native.gymcuda_seed_each(_h, seed, seed.Length)); }   // length check -> ArgumentException, as VecEnv.cs:49
+        void IVecEnv.Seed(int seed) { Seed(seed); }
+        void IVecEnv.Seed(int[] seed) { Seed(seed); }
 
         // ---- batched API ---------------------------------------------------------------------
+        // `actions`: a pageable managed array is marshalled (pinned for the call) and staged by the library (one H2D copy); an
+        // array registered once with PinActions() is read in place by the kernel -- no per-call pin, no copy.
         public (float[] obs, float[] reward, byte[] done) Step(int[] actions) {
             Native.Check(Native.gymcuda_step(_h, actions, _obs, _reward, _done));
             return (_obs, _reward, _done);
@@ -93,6 +105,28 @@ namespace Gym.Environments.Vector {
             Native.Check(Native.gymcuda_step(_h, actions, _obs, _reward, _done));
             return (_obs, _reward, _done);
         }
+        /// <summary>k steps with caller-supplied actions [k][numEnvs] in one launch (gymcuda_step_many); outputs [k][numEnvs]...</summary>
+        public void StepMany(int kSteps, int[] actions, float[] obs, float[] reward, byte[] done) {
+            Native.Check(Native.gymcuda_step_many(_h, kSteps, actions, obs, reward, done));
+        }
+        public void StepMany(int kSteps, float[] actions, float[] obs, float[] reward, byte[] done) {
+            Native.Check(Native.gymcuda_step_many(_h, kSteps, actions, obs, reward, done));
+        }
+        /// <summary>Under auto-reset: the array (numEnvs * ObsDim, kept pinned until replaced) receives the observation of the
+        /// TERMINAL state of every env whose step returns done; null turns the side buffer off.</summary>
+        public void SetTerminalObservations(float[] buffer) {
+            if (_terminalPin.IsAllocated) {
+                Native.Check(Native.gymcuda_set_terminal_obs(_h, IntPtr.Zero));
+                Native.gymcuda_host_unregister(_terminalPin.AddrOfPinnedObject()); _terminalPin.Free();
+            }
+            if (buffer == null) return;
+            if (buffer.Length != NumberOfEnvironments * _info.ObsDim) throw new ArgumentException("expected numEnvs * ObsDim floats", nameof(buffer));
+            _terminalPin = GCHandle.Alloc(buffer, GCHandleType.Pinned);
+            Native.Check(Native.gymcuda_host_register(_terminalPin.AddrOfPinnedObject(), (UIntPtr) (ulong) (sizeof(float) * buffer.Length)));
+            Native.Check(Native.gymcuda_set_terminal_obs(_h, _terminalPin.AddrOfPinnedObject()));
+        }
+        private GCHandle _terminalPin;
+
         public float[] Reset(byte[] mask) { Native.Check(Native.gymcuda_reset_masked(_h, mask, _obs)); return _obs; }
         public void RolloutRandom(int kSteps, float[] obs, float[] reward, byte[] done, int[] actions) {
             Native.Check(Native.gymcuda_rollout_random(_h, kSteps, obs, reward, done, actions));
@@ -146,12 +180,12 @@ namespace Gym.Environments.Vector {
     public sealed class LunarLanderVecEnv : CudaVecEnv {
         public LunarLanderVecEnv(int numEnvs, bool continuous = false, float gravity = -10f, bool enableWind = false,
                                  float windPower = 15f, float turbulencePower = 1.5f, ulong seed = 0, int device = 0,
-                                 uint envIdOffset = 0, bool autoReset = false)
+                                 uint envIdOffset = 0, bool autoReset = false, int timeLimit = 0)
             : base(continuous ? GymCudaEnvKind.LunarLanderContinuous : GymCudaEnvKind.LunarLander, numEnvs,
                    new Box(np.array(new float[] {-1.5f, -1.5f, -5f, -5f, (float) -Math.PI, -5f, 0f, 0f}),
                            np.array(new float[] {1.5f, 1.5f, 5f, 5f, (float) Math.PI, 5f, 1f, 1f})),
                    continuous ? (Space) new Box(-1f, 1f, new Shape(2)) : new Discrete(4),
-                   seed, device, envIdOffset, autoReset, 0,
+                   seed, device, envIdOffset, autoReset, timeLimit,
                    c => { c.Value.Gravity = gravity; c.Value.EnableWind = enableWind ? 1 : 0; c.Value.WindPower = windPower; c.Value.TurbulencePower = turbulencePower; }) { }
     }
 

@@ -68,6 +68,12 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_step(GymCudaHandle env, float[] actions, float[] obs, float[] reward, byte[] done);
         [DllImport(Lib)] internal static extern int gymcuda_step_device(GymCudaHandle env, IntPtr dActions, IntPtr dObs, IntPtr dReward, IntPtr dDone);
         [DllImport(Lib)] internal static extern int gymcuda_step_broadcast(GymCudaHandle env, int action, float[] obs, float[] reward, byte[] done);
+        [DllImport(Lib)] internal static extern int gymcuda_step_many_device(GymCudaHandle env, int kSteps, IntPtr dActions, IntPtr dObs, IntPtr dReward, IntPtr dDone);
+        [DllImport(Lib)] internal static extern int gymcuda_step_many(GymCudaHandle env, int kSteps, int[] actions, float[] obs, float[] reward, byte[] done);
+        [DllImport(Lib)] internal static extern int gymcuda_step_many(GymCudaHandle env, int kSteps, float[] actions, float[] obs, float[] reward, byte[] done);
+        [DllImport(Lib)] internal static extern int gymcuda_set_terminal_obs(GymCudaHandle env, IntPtr buffer);
+        [DllImport(Lib)] internal static extern int gymcuda_box_sample_device(int device, IntPtr cudaStream, ulong seed, ulong index, IntPtr dLow, IntPtr dHigh, int dim, int count, int asInt, IntPtr dOut);
+        [DllImport(Lib)] internal static extern int gymcuda_box_sample(int device, ulong seed, ulong index, float[] low, float[] high, int dim, int count, int asInt, float[] output);
         [DllImport(Lib)] internal static extern int gymcuda_rollout_random_device(GymCudaHandle env, int kSteps, IntPtr dObs, IntPtr dReward, IntPtr dDone, IntPtr dActions);
         [DllImport(Lib)] internal static extern int gymcuda_rollout_random(GymCudaHandle env, int kSteps, float[] obs, float[] reward, byte[] done, int[] actions);
         [DllImport(Lib)] internal static extern int gymcuda_sample_actions(GymCudaHandle env, byte[] mask, int[] actionsOut);

@@ -59,10 +59,15 @@ SYMBOLS = {
     "gymcuda_step": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "gymcuda_step_device": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "gymcuda_step_broadcast": (_I, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "gymcuda_step_many_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "gymcuda_step_many": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "gymcuda_set_terminal_obs": (_I, [_VP, _VP]),
     "gymcuda_rollout_random_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_rollout_random": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_sample_actions": (_I, [_VP, _VP, _VP]),
     "gymcuda_sample_actions_device": (_I, [_VP, _VP, _VP]),
+    "gymcuda_box_sample_device": (_I, [_I, _VP, _U64, _U64, _VP, _VP, _I, _I, _I, _VP]),
+    "gymcuda_box_sample": (_I, [_I, _U64, _U64, _VP, _VP, _I, _I, _I, _VP]),
     "gymcuda_done_indices": (_I, [_VP, _VP, C.POINTER(C.c_int32)]),
     "gymcuda_done_indices_device": (_I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     "gymcuda_get_state": (_I, [_VP, _VP, _VP, C.POINTER(_U64)]),

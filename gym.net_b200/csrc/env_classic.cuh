@@ -450,6 +450,18 @@ static __device__ __noinline__ unsigned acrobot_done_f64(float s0, float s1, flo
     return (unsigned)(acrobot_integrate_f64(sd, action) > 1.0);
 }
 
+// Engine arithmetic v3: beyond (9, 18) rad/s -- towards the corners of the velocity clamp box (4 pi, 9 pi), where one RK4
+// step of 0.2 s changes the velocities by tens of rad/s and amplifies float32 rounding about a hundredfold (up to 2.5e-4
+// relative, against the 1e-5 of north_star) -- the step is the upstream double-precision RK4, rounded to float32 once.
+// Out of line and rare: random-policy episodes stay below (6, 12) rad/s, so rollouts never take it.
+constexpr float ACROBOT_F32_MAX_V1 = 9.0f, ACROBOT_F32_MAX_V2 = 18.0f;
+struct AcroFast { float v0, v1, v2, v3; unsigned done; };
+static __device__ __noinline__ AcroFast acrobot_step_f64(float s0, float s1, float s2, float s3, int action) {
+    double sd[4] = {(double)s0, (double)s1, (double)s2, (double)s3};
+    const unsigned done = (unsigned)(acrobot_integrate_f64(sd, action) > 1.0);
+    return AcroFast{(float)sd[0], (float)sd[1], (float)sd[2], (float)sd[3], done};
+}
+
 struct Acrobot {
     static constexpr int SD = 4, OD = 6, AD = 1, ACTN = 3, DEFAULT_LIMIT = 500;
     static constexpr bool HAS_SBD = false;
@@ -489,6 +501,12 @@ struct Acrobot {
     template <bool SMALL = false>
     __device__ static __forceinline__ StepOut step(S& s, Act a, int32_t&, uint64_t, uint32_t, uint64_t) {
         const float o0 = s.v[0], o1 = s.v[1], o2 = s.v[2], o3 = s.v[3];
+        if (fabsf(o2) > ACROBOT_F32_MAX_V1 || fabsf(o3) > ACROBOT_F32_MAX_V2) {   // fast links: double-precision step (rare)
+            const AcroFast f = acrobot_step_f64(o0, o1, o2, o3, (int)a);
+            s.v[0] = f.v0; s.v[1] = f.v1; s.v[2] = f.v2; s.v[3] = f.v3;
+            s.t = acrobot_trig<false>(s.v);
+            return StepOut{f.done ? 0.0f : -1.0f, f.done};
+        }
         const AcroTrig t0 = s.t;   // the first RK4 stage reuses the trig of the current state
         acrobot_rk4_f32<SMALL>(s.v, (int)a, t0);
         s.t = acrobot_trig<SMALL>(s.v);

@@ -18,8 +18,11 @@
 #include <type_traits>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: the ranges cost a null-pointer test unless a profiler injects itself
+
 #include "kernels.cuh"
 #include "normalize.cuh"
+#include "box_sample.cuh"
 #ifdef GYMCUDA_WITH_LUNAR
 #include "lunar_launch.h"
 #endif
@@ -139,7 +142,7 @@ struct gymcuda_env {
     void* d_actions;
     uint8_t* d_out;          // obs | reward | done
     float *d_obs, *d_reward;
-    uint8_t *d_done, *d_mask;
+    uint8_t *d_done, *d_mask, *d_sample_mask;
     const void* alias_host[4]; void* alias_dev[4];   // cache of mapped_alias()
     unsigned alias_epoch;
     void* scratch[4]; size_t scratch_cap[4];   // device scratch of gymcuda_rollout_random (host buffers)
@@ -151,12 +154,17 @@ struct gymcuda_env {
     double* d_sums;
     bool ep_stats, done_bits;
     const float* last_obs;   // device pointer of the most recent observations
+    // terminal observations under auto-reset (gymcuda_set_terminal_obs)
+    float* term_dev;         // what the step kernel writes: the caller's device / mapped buffer, or d_term_own
+    float* term_host;        // pageable caller buffer: d_term_own is copied into it by the host-buffer step calls
+    float* d_term_own;
     // observation / reward normalisation (normalize.cuh), allocated by the first call
     double* d_norm_acc; float* d_norm_ret;
     float norm_gamma, norm_eps, norm_clip_obs, norm_clip_reward;
     // pinned scratch: [0..1] stats, [2] done_count
     unsigned long long* h_small;
     unsigned long long invalid_seen, env_steps;
+    bool async_steps;        // *_device steps were enqueued since the last synchronisation: their rejected actions are not yet reported
     // nccl
     void* comm;
     int rank, world;
@@ -169,6 +177,15 @@ struct gymcuda_env {
     size_t act_bytes() const { return (size_t)n * ki.ad * 4; }
     size_t obs_bytes() const { return (size_t)n * ki.od * 4; }
 };
+
+// NVTX range around an entry point (tracing): visible in Nsight Systems timelines as gymcuda/<name>
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define TRACE(name) NvtxRange _nvtx_range("gymcuda/" name)
 
 static int check(const gymcuda_env* e) {
     if (!e) return fail(GYMCUDA_EINVAL, "null gymcuda_env handle");
@@ -347,10 +364,10 @@ int gymcuda_destroy(gymcuda_env* e) {
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux); cudaFree(e->d_perm); cudaFree(e->d_block_free);
-    cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask);
+    cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask); cudaFree(e->d_sample_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
     for (int k = 0; k < 4; ++k) cudaFree(e->scratch[k]);
-    cudaFree(e->d_norm_acc); cudaFree(e->d_norm_ret);
+    cudaFree(e->d_norm_acc); cudaFree(e->d_norm_ret); cudaFree(e->d_term_own);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -546,6 +563,7 @@ static int reset_impl(gymcuda_env* e, const uint8_t* d_mask, float* obs_host) {
 
 int gymcuda_reset(gymcuda_env* e, float* obs_out) {
     ENTER(e);
+    TRACE("reset");
     int rc = reset_impl(e, nullptr, obs_out);
     if (rc == GYMCUDA_OK) e->has_state = true;
     return rc;
@@ -553,6 +571,7 @@ int gymcuda_reset(gymcuda_env* e, float* obs_out) {
 
 int gymcuda_reset_masked(gymcuda_env* e, const uint8_t* mask, float* obs_out) {
     ENTER(e);
+    TRACE("reset_masked");
     if (!mask) return fail(GYMCUDA_EINVAL, "mask is null");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "reset_masked before the first full Reset()");
     CU_TRY(cudaMemcpyAsync(e->d_mask, mask, (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
@@ -572,6 +591,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
+    a.terminal_obs = e->auto_reset ? e->term_dev : nullptr;
     if (!d_actions && !use_bcast) { a.sample = 1; a.act_out = sampled_out; }
     if (gather) {
         e->g_seq += 1;
@@ -628,6 +648,21 @@ static void* mapped_alias(gymcuda_env* e, const void* host, int slot, size_t ali
     return dev;
 }
 
+// Before a host-buffer step: rejected actions of earlier asynchronous *_device steps belong to THOSE calls (reported by
+// gymcuda_sync); if the caller never asked, they are dropped here rather than blamed on the step that follows.
+static int drain_async_invalid(gymcuda_env* e) {
+    if (!e->async_steps) return GYMCUDA_OK;
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->async_steps = false;
+    if (*e->h_invalid) {
+        *e->h_invalid = 0;
+        CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        e->invalid_seen = e->h_small[1];
+    }
+    return GYMCUDA_OK;
+}
+
 static int step_finish_host(gymcuda_env* e, float* obs, float* reward, uint8_t* done) {
     const size_t ob = e->obs_bytes(), n = (size_t)e->n;
     const bool adjacent = obs && reward && done && reinterpret_cast<uint8_t*>(obs) + ob == reinterpret_cast<uint8_t*>(reward) &&
@@ -639,6 +674,7 @@ static int step_finish_host(gymcuda_env* e, float* obs, float* reward, uint8_t* 
         if (reward) CU_TRY(cudaMemcpyAsync(reward, e->d_reward, n * 4, cudaMemcpyDeviceToHost, e->stream));
         if (done) CU_TRY(cudaMemcpyAsync(done, e->d_done, n, cudaMemcpyDeviceToHost, e->stream));
     }
+    if (e->term_host) CU_TRY(cudaMemcpyAsync(e->term_host, e->d_term_own, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     if (*e->h_invalid) {   // written through mapped memory by the kernel: no extra copy on the common path
         *e->h_invalid = 0;
@@ -653,8 +689,10 @@ static int step_finish_host(gymcuda_env* e, float* obs, float* reward, uint8_t* 
 
 int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward, uint8_t* done) {
     ENTER(e);
+    TRACE("step");
     if (!actions) return fail(GYMCUDA_EINVAL, "actions is null");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
+    if (int rc = drain_async_invalid(e)) return rc;
     // Zero-copy path: when all four host buffers are page-locked, the kernel reads the actions and
     // writes obs / reward / done straight through their device aliases -- the H2D and D2H traffic
     // crosses PCIe inside the step kernel, overlapped with the math, with no DMA set-up per buffer.
@@ -666,6 +704,7 @@ int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward,
         int rc = step_launch(e, za, 0, 0, (float*)zo, (float*)zr, (uint8_t*)zd);
         if (rc) return rc;
         e->last_obs = nullptr;   // the observations were written to host memory only
+        if (e->term_host) CU_TRY(cudaMemcpyAsync(e->term_host, e->d_term_own, e->obs_bytes(), cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
         if (*e->h_invalid) return step_finish_host(e, nullptr, nullptr, nullptr);
         return GYMCUDA_OK;
@@ -683,7 +722,9 @@ int gymcuda_step(gymcuda_env* e, const void* actions, float* obs, float* reward,
 
 int gymcuda_step_broadcast(gymcuda_env* e, int32_t action, float* obs, float* reward, uint8_t* done) {
     ENTER(e);
+    TRACE("step_broadcast");
     if (e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "IVecEnv.Step(int action) needs a Discrete action space");
+    if (int rc0 = drain_async_invalid(e)) return rc0;
     int rc = step_launch(e, nullptr, 1, action, e->d_obs, e->d_reward, e->d_done);
     if (rc) return rc;
     return step_finish_host(e, obs, reward, done);
@@ -691,10 +732,95 @@ int gymcuda_step_broadcast(gymcuda_env* e, int32_t action, float* obs, float* re
 
 int gymcuda_step_device(gymcuda_env* e, const void* d_actions, float* d_obs, float* d_reward, uint8_t* d_done) {
     ENTER(e);
+    TRACE("step_device");
     if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
     if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
+    e->async_steps = true;
     return step_launch(e, d_actions, 0, 0, d_obs ? d_obs : e->d_obs, d_reward ? d_reward : e->d_reward,
                        d_done ? d_done : e->d_done);
+}
+
+int gymcuda_set_terminal_obs(gymcuda_env* e, float* buffer) {
+    ENTER(e);
+    CU_TRY(cudaStreamSynchronize(e->stream));   // steps in flight still write the previous buffer
+    e->term_dev = nullptr; e->term_host = nullptr;
+    if (!buffer) return GYMCUDA_OK;
+    if (!e->auto_reset) return fail(GYMCUDA_EINVAL, "terminal observations exist only under GYMCUDA_FLAG_AUTO_RESET (without it Step returns the terminal observation itself)");
+    cudaPointerAttributes at;
+    cudaError_t ce = cudaPointerGetAttributes(&at, buffer);
+    if (ce != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; at.devicePointer = nullptr; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+        if (!is_aligned(buffer, OBS_ALIGN)) return fail(GYMCUDA_EINVAL, "device terminal-observation buffer must be 16-byte aligned");
+        e->term_dev = buffer;
+    } else if (at.type == cudaMemoryTypeHost && at.devicePointer && is_aligned(at.devicePointer, OBS_ALIGN)) {
+        e->term_dev = static_cast<float*>(at.devicePointer);   // page-locked and mapped: written in place over PCIe
+    } else {   // pageable (or unaligned page-locked) host memory: staged
+        if (!e->d_term_own) CU_TRY(cudaMalloc(&e->d_term_own, e->obs_bytes()));
+        // the staging copy starts as the caller's buffer: rows of envs that have not finished an episode keep their contents
+        CU_TRY(cudaMemcpyAsync(e->d_term_own, buffer, e->obs_bytes(), cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        e->term_dev = e->d_term_own;
+        e->term_host = buffer;
+    }
+    return GYMCUDA_OK;
+}
+
+// k steps with caller-supplied actions: the rollout kernel's generic variant reading `actions_in` (classic envs), k step
+// launches for LunarLander
+int gymcuda_step_many_device(gymcuda_env* e, int k_steps, const void* d_actions, float* d_obs, float* d_reward, uint8_t* d_done) {
+    ENTER(e);
+    TRACE("step_many_device");
+    if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
+    if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
+    if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
+    e->async_steps = true;
+    const size_t n = (size_t)e->n;
+    if (is_lunar(e)) {
+        for (int j = 0; j < k_steps; ++j) {
+            int rc = step_launch(e, reinterpret_cast<const uint8_t*>(d_actions) + (size_t)j * n * e->ki.ad * 4, 0, 0,
+                                 d_obs ? d_obs + (size_t)j * n * e->ki.od : e->d_obs, d_reward ? d_reward + (size_t)j * n : e->d_reward,
+                                 d_done ? d_done + (size_t)j * n : e->d_done);
+            if (rc) return rc;
+        }
+        return GYMCUDA_OK;
+    }
+    RolloutArgs a{};
+    a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
+    a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.actions = nullptr; a.actions_in = d_actions; a.host_invalid = e->d_invalid_flag;
+    a.stats = e->d_stats; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
+    a.n = e->n; a.k_steps = k_steps; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
+    CU_TRY(dispatch_rollout(e, a));
+    e->t += (uint64_t)k_steps;
+    e->env_steps += (unsigned long long)e->n * (unsigned long long)k_steps;
+    e->last_obs = nullptr;
+    return GYMCUDA_OK;
+}
+
+static cudaError_t scratch_reserve(gymcuda_env* e, int slot, size_t bytes, void** out);
+
+int gymcuda_step_many(gymcuda_env* e, int k_steps, const void* actions, float* obs, float* reward, uint8_t* done) {
+    ENTER(e);
+    TRACE("step_many");
+    if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
+    if (!actions) return fail(GYMCUDA_EINVAL, "actions is null");
+    if (int rc0 = drain_async_invalid(e)) return rc0;
+    const size_t kn = (size_t)k_steps * (size_t)e->n;
+    void *d_obs = nullptr, *d_reward = nullptr, *d_done = nullptr, *d_act = nullptr;
+#define SM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    SM_TRY(scratch_reserve(e, 0, obs ? kn * e->ki.od * 4 : 0, &d_obs));
+    SM_TRY(scratch_reserve(e, 1, reward ? kn * 4 : 0, &d_reward));
+    SM_TRY(scratch_reserve(e, 2, done ? kn : 0, &d_done));
+    SM_TRY(scratch_reserve(e, 3, kn * e->ki.ad * 4, &d_act));
+    SM_TRY(cudaMemcpyAsync(d_act, actions, kn * e->ki.ad * 4, cudaMemcpyHostToDevice, e->stream));
+    int rc = gymcuda_step_many_device(e, k_steps, d_act, (float*)d_obs, (float*)d_reward, (uint8_t*)d_done);
+    if (rc) return rc;
+    e->async_steps = false;   // synchronised below
+    if (obs) SM_TRY(cudaMemcpyAsync(obs, d_obs, kn * e->ki.od * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (reward) SM_TRY(cudaMemcpyAsync(reward, d_reward, kn * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (done) SM_TRY(cudaMemcpyAsync(done, d_done, kn, cudaMemcpyDeviceToHost, e->stream));
+#undef SM_TRY
+    return step_finish_host(e, nullptr, nullptr, nullptr);   // synchronise + report rejected actions
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -702,6 +828,7 @@ int gymcuda_step_device(gymcuda_env* e, const void* d_actions, float* d_obs, flo
 // ------------------------------------------------------------------------------------------------
 int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, float* d_reward, uint8_t* d_done, void* d_actions) {
     ENTER(e);
+    TRACE("rollout_random_device");
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
     if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
@@ -784,10 +911,10 @@ int gymcuda_sample_actions(gymcuda_env* e, const uint8_t* mask, void* actions_ou
     if (!actions_out) return fail(GYMCUDA_EINVAL, "actions_out is null");
     if (mask && e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "Box.sample cannot be provided a mask.");
     uint8_t* d_mask = nullptr;
-    if (mask) {
-        CU_TRY(cudaMalloc(&d_mask, (size_t)e->n * e->ki.actn));
-        cudaError_t ce = cudaMemcpyAsync(d_mask, mask, (size_t)e->n * e->ki.actn, cudaMemcpyHostToDevice, e->stream);
-        if (ce != cudaSuccess) { cudaFree(d_mask); return fail(GYMCUDA_ECUDA, "mask copy failed: %s", cudaGetErrorString(ce)); }
+    if (mask) {   // [n][act_n] bytes, kept for the life of the handle (a policy that masks does so every step)
+        if (!e->d_sample_mask) CU_TRY(cudaMalloc(&e->d_sample_mask, (size_t)e->n * e->ki.actn));
+        d_mask = e->d_sample_mask;
+        CU_TRY(cudaMemcpyAsync(d_mask, mask, (size_t)e->n * e->ki.actn, cudaMemcpyHostToDevice, e->stream));
     }
     int rc = gymcuda_sample_actions_device(e, d_mask, e->d_actions);
     if (rc == GYMCUDA_OK) {
@@ -795,7 +922,39 @@ int gymcuda_sample_actions(gymcuda_env* e, const uint8_t* mask, void* actions_ou
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
         if (ce != cudaSuccess) rc = fail(GYMCUDA_ECUDA, "sample copy failed: %s", cudaGetErrorString(ce));
     }
-    cudaFree(d_mask);
+    return rc;
+}
+
+// Box.Sample() of an arbitrary box (box_sample.cuh)
+int gymcuda_box_sample_device(int device, void* cuda_stream, uint64_t seed, uint64_t index, const float* d_low, const float* d_high,
+                              int dim, int count, int as_int, float* d_out) {
+    if (!d_low || !d_high || !d_out) return fail(GYMCUDA_EINVAL, "low / high / out is null");
+    if (dim <= 0 || count <= 0) return fail(GYMCUDA_EINVAL, "dim and count must be > 0");
+    CU_TRY(cudaSetDevice(device));
+    BoxSampleArgs a{d_low, d_high, d_out, dim, (long long)dim * (long long)count, as_int, seed, index};
+    const long long blocks = (a.total + 255) / 256;
+    if (blocks > 0x7fffffffll) return fail(GYMCUDA_EINVAL, "count * dim too large");
+    box_sample_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+    CU_TRY(cudaGetLastError());
+    return GYMCUDA_OK;
+}
+
+int gymcuda_box_sample(int device, uint64_t seed, uint64_t index, const float* low, const float* high, int dim, int count,
+                       int as_int, float* out) {
+    if (!low || !high || !out) return fail(GYMCUDA_EINVAL, "low / high / out is null");
+    if (dim <= 0 || count <= 0) return fail(GYMCUDA_EINVAL, "dim and count must be > 0");
+    CU_TRY(cudaSetDevice(device));
+    float* d = nullptr;
+    const size_t total = (size_t)dim * (size_t)count;
+    CU_TRY(cudaMalloc(&d, (total + 2 * (size_t)dim) * 4));
+    float *d_low = d + total, *d_high = d_low + dim;
+    cudaError_t ce = cudaMemcpy(d_low, low, (size_t)dim * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_high, high, (size_t)dim * 4, cudaMemcpyHostToDevice);
+    int rc = GYMCUDA_OK;
+    if (ce == cudaSuccess) rc = gymcuda_box_sample_device(device, nullptr, seed, index, d_low, d_high, dim, count, as_int, d);
+    if (ce == cudaSuccess && rc == GYMCUDA_OK) ce = cudaMemcpy(out, d, total * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(GYMCUDA_ECUDA, "box sample failed: %s", cudaGetErrorString(ce));
     return rc;
 }
 
@@ -1036,7 +1195,9 @@ int gymcuda_set_stream(gymcuda_env* e, void* cuda_stream) {
 int gymcuda_sync(gymcuda_env* e) {
     ENTER(e);
     CU_TRY(cudaStreamSynchronize(e->stream));
+    e->async_steps = false;
     if (e->h_invalid[1]) { const int who = e->h_invalid[1] - 1; e->h_invalid[1] = 0; return fail(GYMCUDA_ENCCL, "gather wait timed out: rank %d never published its observations", who); }
+    if (*e->h_invalid) return step_finish_host(e, nullptr, nullptr, nullptr);   // actions rejected by the asynchronous *_device steps since the last report
     return GYMCUDA_OK;
 }
 
@@ -1148,6 +1309,7 @@ int gymcuda_step_gather_device(gymcuda_env* e, const void* d_actions, float* d_r
     if (!e->g_local) return fail(GYMCUDA_EINVAL, "gather buffer not created");
     if (int rc = check_device_buffers(e, d_actions, nullptr, d_reward)) return rc;
     for (int r = 0; r < e->g_world; ++r) if (!e->g_peer[r]) return fail(GYMCUDA_EINVAL, "gymcuda_gather_open has not mapped rank %d", r);
+    e->async_steps = true;
     int rc = step_launch(e, d_actions, 0, 0, nullptr, d_reward ? d_reward : e->d_reward, d_done ? d_done : e->d_done, true);
     if (rc) return rc;
     const float* base = reinterpret_cast<const float*>(e->g_local) + (size_t)(e->g_seq & 1u) * e->g_world * (size_t)e->n * e->ki.od;

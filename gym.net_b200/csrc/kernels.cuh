@@ -91,6 +91,8 @@ struct RolloutArgs {
     float* reward;     // [k][n]       may be null
     uint8_t* done;     // [k][n]       may be null
     void* actions;     // [k][n][AD]   may be null
+    const void* actions_in;   // [k][n][AD] caller-supplied actions (gymcuda_step_many*): null = the in-kernel random policy.  Generic variant (ALL_OUT = false) only.
+    int* host_invalid;        // with actions_in: mapped host flag raised when an action is rejected
     unsigned long long* stats;
     float* ep_ret;
     double* sums;
@@ -151,6 +153,7 @@ template <> struct ActCast<float2> { __device__ static __forceinline__ float2 fr
 template <class E> struct ActIO {
     using Act = typename E::Act;
     __device__ static __forceinline__ Act load(const void* base, int i) { return reinterpret_cast<const Act*>(base)[i]; }
+    __device__ static __forceinline__ Act load_at(const void* base, size_t idx) { return __ldcs(reinterpret_cast<const Act*>(base) + idx); }
     __device__ static __forceinline__ Act bcast(int32_t a) { return ActCast<Act>::from_int(a); }
     __device__ static __forceinline__ void store(void* base, size_t idx, Act a) { __stcs(reinterpret_cast<Act*>(base) + idx, a); }
 };
@@ -491,7 +494,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
         const uint64_t seed = seed_of(p.seeds, p.seed, i);
         const uint32_t gid = p.env_off + (uint32_t)i;
         ActionGen<E> gen;
-        gen.init(seed, gid, p.t);
+        bool supplied = false;   // the actions come from the caller (gymcuda_step_many*), not from the policy stream
+        if constexpr (!ALL_OUT) supplied = p.actions_in != nullptr;
+        if (!supplied) gen.init(seed, gid, p.t);
+        unsigned rejected = 0;
         const size_t n = (size_t)p.n;
         // next initial state, pre-generated: consumed at `done`, refilled for all lanes of the warp that
         // need it every REFILL steps (one Philox evaluation per warp per refill instead of per done)
@@ -608,7 +614,25 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
                 E::reset(next, seed, gid, (uint32_t)ep, p.t + (uint64_t)k, p.prm);
                 have = 1;
             }
-            const Act a = gen.next(seed, gid, p.t + (uint64_t)k);
+            Act a;
+            if constexpr (!ALL_OUT) {
+                if (supplied) {
+                    a = ActIO<E>::load_at(p.actions_in, (size_t)k * n + (size_t)i);
+                    if (E::REJECT_INVALID && !E::valid(a)) {
+                        // like step_kernel: the env is not stepped; this row of the trajectory holds its unchanged observation
+                        rejected += 1;
+                        const size_t idx = (size_t)k * n + (size_t)i;
+                        if (p.obs) { float o[E::OD]; E::obs(s, o); store_obs<E::OD, true>(p.obs, idx, o); }
+                        if (p.reward) __stcs(p.reward + idx, 0.0f);
+                        if (p.done) __stcs(p.done + idx, (uint8_t)0);
+                        continue;
+                    }
+                } else {
+                    a = gen.next(seed, gid, p.t + (uint64_t)k);
+                }
+            } else {
+                a = gen.next(seed, gid, p.t + (uint64_t)k);
+            }
             if constexpr (ALL_OUT && E::HAS_SMALL && !E::ROLLOUT_CHUNK) {
                 // envs too large to unroll (Acrobot): the same warp vote, per step, picks the reduced-range step
                 if (__all_sync(__activemask(), E::small_ok(s))) { body(k, a, std::true_type{}, std::true_type{}); continue; }
@@ -620,6 +644,13 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
         E::store(p.state, p.aux, p.n, i, s);
         if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
         if (LIMIT) p.ep_t[i] = ept;
+        if constexpr (!ALL_OUT) {
+            if (rejected) {
+                atomicAdd(&p.stats[1], (unsigned long long)rejected);
+                *reinterpret_cast<volatile int*>(p.host_invalid) = 1;
+                __threadfence_system();
+            }
+        }
     }
     // episodes finished: warp reduce, one atomic per warp
 #pragma unroll

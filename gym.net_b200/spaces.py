@@ -74,6 +74,21 @@ class Box(Space):
             sample = np.floor(sample)
         return sample.astype(self.DType)
 
+    def SampleBatch(self, count, seed=0, index=0, device=0):
+        """`count` samples of this box drawn ON THE GPU (gymcuda_box_sample): the same four-way split per component
+        (Box.cs:81-84) from the engine's Philox stream -- sample c, component j is a pure function of (seed, index + c, j).
+        Returns [count, *Shape] in this box's dtype.  No CPU fallback: raises without a CUDA device."""
+        import ctypes as C
+        from . import _native as N
+        dim = int(np.prod(self.Shape))
+        low = np.ascontiguousarray(self.Low, np.float32).reshape(dim)
+        high = np.ascontiguousarray(self.High, np.float32).reshape(dim)
+        out = np.empty((int(count), dim), np.float32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().gymcuda_box_sample(int(device), int(seed) & (2**64 - 1), int(index), vp(low), vp(high), dim, int(count),
+                                           1 if self.DType.kind in "iu" else 0, vp(out)))
+        return out.reshape((int(count),) + self.Shape).astype(self.DType)
+
     def Contains(self, x):
         if not isinstance(x, np.ndarray):
             raise NotImplementedError(repr(x))   # NotSupportedException (Box.cs:95)

@@ -32,6 +32,13 @@ class Step:
             self.Reward, self.Done, self.Information, self.Observation)
 
 
+def _widen_seed(seed):
+    """int -> the 64-bit engine seed, by the rule of the C# shim ((ulong)(uint) seed for the reference's 32-bit Seed(int)): a
+    negative seed is its 32-bit two's-complement pattern, zero-extended; non-negative seeds up to 2^64 - 1 pass through."""
+    seed = int(seed)
+    return seed & 0xFFFFFFFF if seed < 0 else seed & (2**64 - 1)
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -53,7 +60,7 @@ class CudaVecEnv:
         L = N.lib()
         cfg = N.Config()
         N.check(L.gymcuda_config_default(C.byref(cfg), self.ENV_KIND, int(num_envs)))
-        cfg.device, cfg.seed, cfg.env_id_offset = int(device), int(seed) & (2**64 - 1), int(env_id_offset)
+        cfg.device, cfg.seed, cfg.env_id_offset = int(device), _widen_seed(seed), int(env_id_offset)
         cfg.flags = ((N.FLAG_AUTO_RESET if auto_reset else 0) | (N.FLAG_EPISODE_STATS if episode_stats else 0)
                      | (N.FLAG_DONE_BITS if done_bits else 0))
         cfg.time_limit = int(time_limit)
@@ -105,7 +112,7 @@ class CudaVecEnv:
     def Seed(self, seed):
         """Seed(int) (VecEnv.cs:44-46) or Seed(int[]) (VecEnv.cs:48-53)."""
         if np.isscalar(seed):
-            N.check(self._L.gymcuda_seed(self._h, int(seed) & (2**64 - 1)))
+            N.check(self._L.gymcuda_seed(self._h, _widen_seed(seed)))
         else:
             s = np.ascontiguousarray(seed, dtype=np.int32)
             N.check(self._L.gymcuda_seed_each(self._h, _ptr(s), int(s.size)))
@@ -141,6 +148,43 @@ class CudaVecEnv:
         obs, rew, done = self._out()
         N.check(self._L.gymcuda_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
         return obs, rew, done
+
+    def StepMany(self, actions, want=("obs", "reward", "done")):
+        """k env steps with caller-supplied actions [k][n](, act_dim) in one launch (gymcuda_step_many)."""
+        n = self.NumberOfEnvironments
+        if self.act_n > 0:
+            a = np.ascontiguousarray(actions, dtype=np.int32)
+            if a.ndim != 2 or a.shape[1] != n:
+                raise ValueError("expected actions of shape [k][%d]" % n)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32)
+            a = a.reshape(a.shape[0], n, self.act_dim)
+        k = a.shape[0]
+        obs = np.empty((k, n, self.obs_dim), np.float32) if "obs" in want else None
+        rew = np.empty((k, n), np.float32) if "reward" in want else None
+        done = np.empty((k, n), np.uint8) if "done" in want else None
+        N.check(self._L.gymcuda_step_many(self._h, k, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
+        return obs, rew, done
+
+    def StepManyDevice(self, k_steps, d_actions, d_obs=0, d_reward=0, d_done=0):
+        N.check(self._L.gymcuda_step_many_device(self._h, int(k_steps), C.c_void_p(d_actions), C.c_void_p(d_obs or None),
+                                                 C.c_void_p(d_reward or None), C.c_void_p(d_done or None)))
+
+    def SetTerminalObs(self, buffer):
+        """Under auto-reset: `buffer` ([n][obs_dim] float32 numpy array, a raw device pointer, or None to turn the side
+        buffer off) receives the observation of the TERMINAL state of every env whose step returns done (the step itself
+        returns the post-reset observation).  The array must stay alive while it is registered."""
+        if buffer is None:
+            self._terminal = None
+            N.check(self._L.gymcuda_set_terminal_obs(self._h, None))
+        elif isinstance(buffer, int):
+            self._terminal = None
+            N.check(self._L.gymcuda_set_terminal_obs(self._h, C.c_void_p(buffer)))
+        else:
+            if buffer.dtype != np.float32 or buffer.shape != (self.NumberOfEnvironments, self.obs_dim) or not buffer.flags.c_contiguous:
+                raise ValueError("terminal-observation buffer must be a C-contiguous float32 [num_envs][obs_dim] array")
+            self._terminal = buffer
+            N.check(self._L.gymcuda_set_terminal_obs(self._h, _ptr(buffer)))
 
     def RolloutRandom(self, k_steps, want=("obs", "reward", "done", "actions")):
         n, k = self.NumberOfEnvironments, int(k_steps)

@@ -136,6 +136,25 @@ int gymcuda_step_device(gymcuda_env* env, const void* d_actions, float* d_obs, f
                         uint8_t* d_done);
 /* Broadcast of one action to every env: the shipped IVecEnv.Step(int action) (IVecEnv.cs:14). */
 int gymcuda_step_broadcast(gymcuda_env* env, int32_t action, float* obs, float* reward, uint8_t* done);
+/* k_steps env steps with CALLER-SUPPLIED actions in ONE launch (the rollout kernel fed from `actions` [k_steps][num_envs]
+ * (x act_dim) instead of the in-kernel policy): the state stays in registers between the steps, auto-reset / time limit /
+ * statistics as in gymcuda_step, outputs [k_steps][num_envs]... each optional (NULL = not written).  For learners that
+ * produce a block of actions at a time (open-loop plans, action repeats, the alternating-action loop of the reference's
+ * test, tests/Gym.Tests/Envs/Classic/CartpoleEnvironment.cs:19-26): one launch and no state round trip per step instead
+ * of k.  An invalid action leaves that env unstepped for that step (obs = its current observation, reward 0, done 0) and is
+ * counted; the host-buffer call then returns GYMCUDA_EACTION like gymcuda_step.  LunarLander: k step launches. */
+int gymcuda_step_many_device(gymcuda_env* env, int k_steps, const void* d_actions, float* d_obs, float* d_reward,
+                             uint8_t* d_done);
+int gymcuda_step_many(gymcuda_env* env, int k_steps, const void* actions, float* obs, float* reward, uint8_t* done);
+
+/* ---- terminal observations under auto-reset (SURVEY 8b "Auto-reset": "optionally the terminal obs in a side buffer") ----
+ * With GYMCUDA_FLAG_AUTO_RESET a step that ends an episode returns the POST-reset observation; value bootstrapping at a
+ * time-limit truncation needs the observation of the state the episode ended in.  `buffer` [num_envs][obs_dim] float32:
+ * every later gymcuda_step* call writes that observation into the rows of the envs whose step returned done (other rows are
+ * left as they are).  buffer may be device memory or page-locked host memory (written by the kernel in place; 16-byte
+ * aligned), or pageable host memory (staged: copied whole by the host-buffer step calls before they return).  NULL turns
+ * the side buffer off.  Not written by the fused rollouts (gymcuda_rollout_random*, gymcuda_step_many*). */
+int gymcuda_set_terminal_obs(gymcuda_env* env, float* buffer);
 
 /* ---- fused random-policy rollout (Discrete.Sample / Box.Sample inside the kernel) ------------- */
 /* k_steps env steps in ONE launch, state in registers, trajectory streamed out.  Every output
@@ -152,6 +171,18 @@ int gymcuda_rollout_random(gymcuda_env* env, int k_steps, float* obs, float* rew
  * uniform over the valid entries, Start when none); a mask on a Box space is GYMCUDA_EINVAL (Box.cs:70-73). */
 int gymcuda_sample_actions(gymcuda_env* env, const uint8_t* mask, void* actions_out);
 int gymcuda_sample_actions_device(gymcuda_env* env, const uint8_t* d_mask, void* d_actions_out);
+/* Box.Sample() of an ARBITRARY box on device (src/Gym/Spaces/Box.cs:69-90), the reference's four-way split per component:
+ * low and high finite -> uniform(low, high); only low finite -> low + exponential(1); only high finite -> high +
+ * exponential(1) (the reference ADDS the draw to High, Box.cs:83 -- upstream gym subtracts it; the reference's behaviour is
+ * kept); neither -> normal(0.5, 1) (Box.cs:81: mean 0.5, the reference's constant).  out [count][dim] float32; sample c,
+ * component j is a pure function of (seed, index + c, j): Philox stream 4, one 32-bit word for uniform / exponential
+ * (-log1p(-u), u = (w >> 8) * 2^-24), two words for the normal (Box-Muller).  as_int != 0 floors the values (the reference
+ * floors for integer dtypes, Box.cs:85-88).  low / high / out: device pointers (*_device, asynchronous on `cuda_stream`) or
+ * host pointers (synchronous). */
+int gymcuda_box_sample_device(int device, void* cuda_stream, uint64_t seed, uint64_t index, const float* d_low,
+                              const float* d_high, int dim, int count, int as_int, float* d_out);
+int gymcuda_box_sample(int device, uint64_t seed, uint64_t index, const float* low, const float* high, int dim,
+                       int count, int as_int, float* out);
 
 /* ---- done compaction (valid after a step) ------------------------------------------------------ */
 /* Indices (local env ids, ascending within a thread block, block order unspecified) of the envs

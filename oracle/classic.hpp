@@ -352,8 +352,18 @@ inline float acrobot_integrate_f32(float s[4], int action) {
     return -c1 - c12;
 }
 
+// Engine arithmetic v3: a state whose link velocities are beyond (9, 18) rad/s -- towards the corners of the clamp box
+// (4 pi, 9 pi), where one RK4 step of 0.2 s amplifies float32 rounding about a hundredfold -- is stepped with the
+// upstream double-precision RK4 and rounded to float32 once.
+static const float ACROBOT_F32_MAX_V1 = 9.0f, ACROBOT_F32_MAX_V2 = 18.0f;
+
 inline StepOut acrobot_step_f32(float s[4], int action) {
     double sd[4] = {s[0], s[1], s[2], s[3]};
+    if (std::fabs(s[2]) > ACROBOT_F32_MAX_V1 || std::fabs(s[3]) > ACROBOT_F32_MAX_V2) {
+        const bool done = acrobot_integrate<double>(sd, action) > 1.0;
+        for (int i = 0; i < 4; ++i) s[i] = (float)sd[i];
+        return StepOut{done ? 0.0f : -1.0f, (uint8_t)done};
+    }
     float v = acrobot_integrate_f32(s, action);
     bool done = v > 1.0f;
     if (std::fabs(v - 1.0f) <= 2e-5f) done = acrobot_integrate<double>(sd, action) > 1.0;

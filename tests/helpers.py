@@ -47,9 +47,9 @@ def random_states(name, rng, n):
     elif name in ("MountainCar-v0", "MountainCarContinuous-v0"):
         s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(n, 2))
     elif name == "Acrobot-v1":
-        # velocities up to ~2x what random-policy episodes reach; at the clamp bounds (4pi, 9pi) the
-        # accelerations are ~1e3 rad/s^2 and float32 RK4 no longer holds 1e-5 (precision)
-        s = rng.uniform([-3.14, -3.14, -6.0, -12.0], [3.14, 3.14, 6.0, 12.0], size=(n, 4))
+        # the whole reachable state box: angles wrapped to [-pi, pi], velocities clamped to (4 pi, 9 pi); beyond (9, 18)
+        # rad/s the engine steps in double precision, so 1e-5 holds over all of it
+        s = rng.uniform([-3.14159, -3.14159, -12.5663, -28.2743], [3.14159, 3.14159, 12.5663, 28.2743], size=(n, 4))
     else:
         raise KeyError(name)
     return s.astype(np.float32)

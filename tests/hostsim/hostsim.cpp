@@ -86,6 +86,9 @@ void sim_reset(const Bufs& b, float* obs, int n, uint32_t env_off, uint64_t seed
 //      stands in for __shared__.  The kernels run as written, warp-cooperative parts included.
 static int g_simt = 0;
 static const int32_t* g_seeds = nullptr;
+static float* g_terminal_obs = nullptr;
+static const void* g_actions_in = nullptr;
+static int* g_rollout_invalid = nullptr;
 static void set_block(unsigned b, unsigned grid, unsigned block) { blockIdx.x = b; gridDim.x = grid; blockDim.x = block; }
 static void set_thread(unsigned t) { threadIdx.x = t; }
 
@@ -191,6 +194,7 @@ int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* 
     a.obs = obs; a.reward = reward; a.done = done; a.actions = actions; a.stats = stats; a.ep_ret = ep_ret; a.sums = sums;
     a.done_bits = done_bits; a.n = n; a.k_steps = k_steps; a.env_off = env_off; a.seed = seed; a.t = t; a.limit = limit;
     a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
+    a.actions_in = g_actions_in; a.host_invalid = g_rollout_invalid; g_actions_in = nullptr; g_rollout_invalid = nullptr;
     switch (kind) {
         case 0: return rollout_dispatch<CartPole>(a, auto_reset, all_out, block);
         case 1: return rollout_dispatch<Pendulum>(a, auto_reset, all_out, block);
@@ -219,6 +223,11 @@ void hostsim_set_gather(int world, int rank, uint32_t gseq, float** peer_obs, ui
     for (int r = 0; r < world; ++r) { g_gather.peer_obs[r] = peer_obs[r]; g_gather.peer_flags[r] = peer_flags[r]; }
 }
 
+// The NEXT hostsim_step_kernel call writes terminal observations here (gymcuda_set_terminal_obs); the NEXT hostsim_rollout
+// call reads its actions from `actions_in` (gymcuda_step_many*) and raises *host_invalid when it rejects one.
+void hostsim_set_terminal_obs(float* buf) { g_terminal_obs = buf; }
+void hostsim_set_actions_in(const void* actions_in, int* host_invalid) { g_actions_in = actions_in; g_rollout_invalid = host_invalid; }
+
 // gather_wait_kernel: returns the timeout flag (0, or 1 + the rank that never published)
 int hostsim_gather_wait(const uint32_t* flags, int world, uint32_t gseq) {
     int timeout_flag = 0;
@@ -241,6 +250,7 @@ int hostsim_step_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32
     a.world = g_gather.world; a.rank = g_gather.rank; a.gseq = g_gather.gseq; a.block_counter = g_gather.block_counter;
     for (int r = 0; r < g_gather.world; ++r) { a.peer_obs[r] = g_gather.peer_obs[r]; a.peer_flags[r] = g_gather.peer_flags[r]; }
     g_gather.world = 0;   // one launch
+    a.terminal_obs = g_terminal_obs; g_terminal_obs = nullptr;
     switch (kind) {
         case 0: return k_step<CartPole>(a, auto_reset);
         case 1: return k_step<Pendulum>(a, auto_reset);

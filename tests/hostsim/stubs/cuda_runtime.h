@@ -37,6 +37,7 @@ static hostsim_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
 static inline void __threadfence_system() {}
 static inline void __nanosleep(unsigned) {}
 static inline long long clock64() { static long long ticks = 0; return ticks += 1000000000ll; }   // every look at the clock is 1e9 cycles later

@@ -27,6 +27,8 @@ def build():
     L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
     L.hostsim_rollout.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, I, I, I, U32, U64, U64, I, I, I, I, F, F, F, I]
     L.hostsim_set_simt.argtypes = [I]
+    L.hostsim_set_terminal_obs.argtypes = [V]
+    L.hostsim_set_actions_in.argtypes = [V, V]
     L.hostsim_set_seeds.argtypes = [V]
     L.hostsim_set_schedule.argtypes = [I, U64]
     L.hostsim_step_kernel.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, V, V, V, I, V, I, U32, U64, U64, I, I, I, C.c_int32, U32, F, F, F, I]
@@ -81,21 +83,30 @@ class HostSim:
         self.t += 1
         return obs, rew, done, bad
 
-    def rollout(self, k, all_out=True, block=64, ep_ret=None, sums=None, done_bits=0):
+    def rollout(self, k, all_out=True, block=64, ep_ret=None, sums=None, done_bits=0, actions_in=None):
+        """actions_in [k][n](, ad): gymcuda_step_many* (the generic variant fed with the caller's actions; all_out must be False);
+        self.rollout_invalid then holds [host flag, rejected count]."""
         n = self.n
         obs = np.empty((k, n, self.od), np.float32); rew = np.empty((k, n), np.float32); done = np.empty((k, n), np.uint8)
         act = np.empty((k, n), np.int32) if self.actn > 0 else np.empty((k, n, self.ad), np.float32)
         stats = np.zeros(2, np.uint64)
+        if actions_in is not None:
+            assert not all_out
+            a_in = np.ascontiguousarray(actions_in); flag = np.zeros(1, np.int32)
+            self.L.hostsim_set_actions_in(_p(a_in), _p(flag))
+            act = None
         rc = self.L.hostsim_rollout(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode), _p(obs),
-                                    _p(rew), _p(done), _p(act), _p(stats), None if ep_ret is None else _p(ep_ret),
+                                    _p(rew), _p(done), None if act is None else _p(act), _p(stats), None if ep_ret is None else _p(ep_ret),
                                     None if sums is None else _p(sums), done_bits, n, k, self.off, self.seed, self.t, self.limit,
                                     int(self.auto), int(all_out), block, *self.prm)
         assert rc == 0, rc
         self.t += k
+        if actions_in is not None:
+            self.rollout_invalid = (int(flag[0]), int(stats[1]))
         return obs, rew, done, act, int(stats[0])
 
     # ---- the kernels themselves (run them under hostsim_set_simt(1)) ------------------------------------------------
-    def step_kernel(self, actions, *, perm=None, ep_ret=None, sums=None, done_bits=0, bcast=None, done_offset=0):
+    def step_kernel(self, actions, *, perm=None, ep_ret=None, sums=None, done_bits=0, bcast=None, done_offset=0, terminal_obs=None):
         """step_kernel as gymcuda_step_device launches it.  Returns obs, reward, done, done_idx[:count], invalid flag.
         self.stats ([episodes, invalid]) and self.done_count ([2], by parity of the launch number) persist like on the device."""
         n = self.n
@@ -105,6 +116,8 @@ class HostSim:
         obs = np.empty((n, self.od), np.float32); rew = np.empty(n, np.float32)
         done_buf = np.zeros(n + 8, np.uint8); done = done_buf[done_offset:done_offset + n]   # offset != 0 mod 4: unpacked done stores
         idx = np.full(n, -1, np.int32); flag = np.zeros(2, np.int32)
+        if terminal_obs is not None:
+            self.L.hostsim_set_terminal_obs(_p(terminal_obs))
         rc = self.L.hostsim_step_kernel(self.kind, _p(self.state), _p(self.aux), _p(self.sbd), _p(self.ept), _p(self.episode),
                                         None if perm is None else _p(perm), None if a is None else _p(a), _p(obs), _p(rew),
                                         C.c_void_p(done_buf.ctypes.data + done_offset), _p(idx), _p(self.done_count), _p(self.stats),

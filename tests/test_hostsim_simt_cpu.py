@@ -324,3 +324,78 @@ def test_normalize_kernels_against_numpy(hs, n, od):
     _, want_r = model(None, rew, None, True)
     hs.hostsim_normalize(None, _p(got_r), None, _p(ret), _p(acc), n, od, 0.97, 1e-6, 1.5, 4.0, 1)
     assert np.allclose(got_r, want_r, rtol=1e-6, atol=1e-6) and acc[18] == acc[19]
+
+
+def terminal_checker(kind, n, seed, off, time_limit):
+    """Two oracles: A runs with auto-reset (what the kernel does); before every step its state is copied into B, which runs
+    WITHOUT auto-reset -- B's observation after the step is the terminal observation of every env whose step ended an episode."""
+    a = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=True, mode=O.MODE_F32, time_limit=time_limit)
+    b = O.OracleEnv(kind, n, seed=seed, env_id_offset=off, auto_reset=False, mode=O.MODE_F32, time_limit=time_limit)
+    return a, b
+
+
+@pytest.mark.parametrize("name,kind,n,limit,k", [("CartPole-v1", O.CARTPOLE, 300, 0, 60), ("MountainCar-v0", O.MOUNTAINCAR, 70, 25, 60),
+                                                   ("Acrobot-v1", O.ACROBOT, 90, 20, 45), ("LunarLander-v2", O.LUNARLANDER, 40, 90, 200)],
+                         ids=["CartPole-v1", "MountainCar-v0", "Acrobot-v1", "LunarLander-v2"])
+def test_step_kernel_terminal_observations(hs, name, kind, n, limit, k):
+    """gymcuda_set_terminal_obs: rows of the side buffer of the envs whose step returned done == the observation of the state
+    the episode ended in (terminated or truncated by the time limit); the other rows are not touched; the step's own outputs
+    and the state are what they are without the side buffer (LunarLander: the fused crash + zero-step solve is bypassed)."""
+    rng = np.random.default_rng(17)
+    a, b = terminal_checker(kind, n, 5, 77, limit)
+    sim = HostSim(hs, kind, n, 5, 77)
+    if limit:
+        sim.limit = limit
+    assert np.array_equal(sim.reset_kernel(), a.reset())
+    b.reset()
+    term = np.full((n, sim.od), -7.0, F32)
+    seen = 0
+    for _ in range(k):
+        act = rng.integers(0, sim.actn, n).astype(np.int32)
+        st, aux, t = a.get_state()
+        b.set_state(st, aux, t)
+        want_o, want_r, want_d = a.step(act)
+        term_o, _, term_d = b.step(act)
+        before = term.copy()
+        got_o, got_r, got_d, _, _ = sim.step_kernel(act, terminal_obs=term)
+        assert np.array_equal(got_o, want_o) and np.array_equal(got_r, want_r) and np.array_equal(got_d, want_d)
+        d = want_d != 0
+        assert np.array_equal(term[d], term_o[d]) and np.array_equal(term[~d], before[~d])
+        seen += int(d.sum())
+        assert same_state(a, sim)
+    assert seen > 0
+
+
+@pytest.mark.parametrize("name,kind,n", [("CartPole-v1", O.CARTPOLE, 100), ("Pendulum-v1", O.PENDULUM, 70), ("MountainCar-v0", O.MOUNTAINCAR, 64),
+                                         ("MountainCarContinuous-v0", O.MOUNTAINCAR_CONT, 33), ("Acrobot-v1", O.ACROBOT, 50)],
+                         ids=["CartPole-v1", "Pendulum-v1", "MountainCar-v0", "MountainCarContinuous-v0", "Acrobot-v1"])
+def test_rollout_kernel_with_caller_supplied_actions(hs, name, kind, n):
+    """gymcuda_step_many*: the generic rollout variant fed from `actions_in` == k oracle steps with those actions (auto-reset,
+    default time limits); an invalid action leaves its env unstepped for that step, is counted and raises the host flag."""
+    rng = np.random.default_rng(23)
+    o, sim = pair(hs, kind, n)
+    k = 37
+    if sim.actn > 0:
+        acts = rng.integers(0, sim.actn, (k, n)).astype(np.int32)
+    else:
+        acts = rng.uniform(-2.5, 2.5, (k, n, sim.ad)).astype(F32)
+    bad = np.zeros((k, n), bool)
+    if kind != O.CARTPOLE:           # CartPole accepts anything (Debug.Assert only, CartPoleEnv.cs:139)
+        bad = rng.random((k, n)) < 0.03
+        if sim.actn > 0:
+            acts[bad] = 7
+        else:
+            acts[bad] = np.nan
+    obs, rew, done, _, episodes = sim.rollout(k, all_out=False, actions_in=acts)
+    want_eps = 0
+    for j in range(k):
+        wo, wr, wd = o.step(acts[j])
+        assert o.invalid == int(bad[j].sum())
+        ok = ~bad[j]
+        assert np.array_equal(obs[j][ok], wo[ok]) and np.array_equal(rew[j][ok], wr[ok]) and np.array_equal(done[j][ok], wd[ok])
+        assert np.array_equal(obs[j][bad[j]], wo[bad[j]])              # unchanged observation of the unstepped env
+        assert not rew[j][bad[j]].any() and not done[j][bad[j]].any()
+        want_eps += int(wd.sum())
+    assert episodes == want_eps
+    assert sim.rollout_invalid == (int(bad.any()), int(bad.sum()))
+    assert same_state(o, sim)
