@@ -164,6 +164,7 @@ struct gymcuda_env {
     // pinned scratch: [0..1] stats, [2] done_count
     unsigned long long* h_small;
     unsigned long long invalid_seen, env_steps;
+    bool stats_pending;      // the episode count of the latest step launch is still in d_done_count, not in d_stats[0]
     bool async_steps;        // *_device steps were enqueued since the last synchronisation: their rejected actions are not yet reported
     // nccl
     void* comm;
@@ -203,8 +204,16 @@ static int check(const gymcuda_env* e) {
 // ------------------------------------------------------------------------------------------------
 template <class E>
 static cudaError_t launch_step(gymcuda_env* e, const StepArgs& a) {
-    const int grid = (e->n + STEP_BLOCK - 1) / STEP_BLOCK;
     const bool ar = e->auto_reset, lim = e->limit > 0;
+    if (e->n >= STEP_BIG_BATCH) {   // a million envs and more: 1024-thread CTAs (kernels.cuh)
+        const int grid = (e->n + STEP_BLOCK_BIG - 1) / STEP_BLOCK_BIG;
+        if (ar && lim) step_kernel<E, true, true, STEP_BLOCK_BIG><<<grid, STEP_BLOCK_BIG, 0, e->stream>>>(a);
+        else if (ar) step_kernel<E, true, false, STEP_BLOCK_BIG><<<grid, STEP_BLOCK_BIG, 0, e->stream>>>(a);
+        else if (lim) step_kernel<E, false, true, STEP_BLOCK_BIG><<<grid, STEP_BLOCK_BIG, 0, e->stream>>>(a);
+        else step_kernel<E, false, false, STEP_BLOCK_BIG><<<grid, STEP_BLOCK_BIG, 0, e->stream>>>(a);
+        return cudaGetLastError();
+    }
+    const int grid = (e->n + STEP_BLOCK - 1) / STEP_BLOCK;
     if (ar && lim) step_kernel<E, true, true><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
     else if (ar) step_kernel<E, true, false><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
     else if (lim) step_kernel<E, false, true><<<grid, STEP_BLOCK, 0, e->stream>>>(a);
@@ -590,7 +599,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
-    a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq;
+    a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq; a.fold_prev = e->stats_pending ? 1 : 0;
     a.terminal_obs = e->auto_reset ? e->term_dev : nullptr;
     if (!d_actions && !use_bcast) { a.sample = 1; a.act_out = sampled_out; }
     if (gather) {
@@ -603,6 +612,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
         a.block_counter = reinterpret_cast<unsigned*>(e->g_local + e->g_counter_off);
     }
     CU_TRY(dispatch_step(e, a));
+    e->stats_pending = true;   // this launch's episode count sits in done_count[seq & 1] until the next launch folds it into stats[0]
     e->t += 1;
     e->seq += 1;
     e->env_steps += (unsigned long long)e->n;
@@ -1078,12 +1088,15 @@ int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
     ENTER(e);
     if (!out) return fail(GYMCUDA_EINVAL, "out is null");
     CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    int32_t* pending = reinterpret_cast<int32_t*>(e->h_small + 2);   // (h_small[2] doubles as the done_count scratch of gymcuda_done_indices)
+    *pending = 0;
+    if (e->stats_pending) CU_TRY(cudaMemcpyAsync(pending, e->d_done_count + ((e->seq - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     double* hs = reinterpret_cast<double*>(e->h_small + 4);
     hs[0] = hs[1] = 0.0;
     if (e->d_sums) CU_TRY(cudaMemcpyAsync(hs, e->d_sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     out->env_steps = e->env_steps;
-    out->episodes = e->h_small[0];
+    out->episodes = e->h_small[0] + (unsigned long long)*pending;
     out->invalid_actions = e->h_small[1];
     out->return_sum = hs[0];
     out->length_sum = (uint64_t)(hs[1] + 0.5);
@@ -1093,6 +1106,7 @@ int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
         CU_TRY(cudaStreamSynchronize(e->stream));
         e->env_steps = 0;
         e->invalid_seen = 0;
+        e->stats_pending = false;   // reported and discarded: the next launch must not add it again
     }
     return GYMCUDA_OK;
 }

@@ -70,6 +70,7 @@ struct StepArgs {
     int use_bcast;
     int32_t bcast_action;
     uint32_t seq;                      // step-launch sequence number of this handle
+    int fold_prev;                     // 1: done_count[(seq + 1) & 1] still holds the episode count of the previous step launch, not yet added to stats[0]
     EnvParams prm;
     // fused observation gather over NVLink peer memory (world == 0: off)
     int world, rank;
@@ -258,16 +259,23 @@ __device__ __forceinline__ uint64_t seed_of(const int32_t* seeds, uint64_t seed,
 
 // ---------------------------------------------------------------- step
 constexpr int STEP_BLOCK = 128;
+#ifndef GYMCUDA_STEP_BLOCK_BIG
+#define GYMCUDA_STEP_BLOCK_BIG 256
+#endif
+constexpr int STEP_BLOCK_BIG = GYMCUDA_STEP_BLOCK_BIG;   // CTA of the batches of STEP_BIG_BATCH envs and more (classic envs)
+constexpr int STEP_BIG_BATCH = 1 << 20;
 
 // envs whose step can fold the auto-reset in (E::FUSED_RESET + E::step_ar): LunarLander
 template <class E, class = void> struct FusedReset : std::false_type {};
 template <class E> struct FusedReset<E, std::enable_if_t<E::FUSED_RESET>> : std::true_type {};
 
-template <class E, bool AUTO_RESET, bool LIMIT>
-__global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
+// STEP_BLOCK = the launch shape at the config sizes; batches of a million envs and more run 1024-thread CTAs (one
+// same-address atomic per CTA on the done counter: 131 072 of them per launch at 16.7 M envs cost ~90 us, measured)
+template <class E, bool AUTO_RESET, bool LIMIT, int BLOCK = STEP_BLOCK>
+__global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
     using S = typename E::S;
     using Act = typename E::Act;
-    int tix = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    int tix = blockIdx.x * BLOCK + threadIdx.x;
     int hi = p.n;
     if (p.part == 1) hi = *p.split;
     if (p.part == 2) tix += *p.split;
@@ -276,6 +284,13 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     bool done = false;
     bool invalid = false;
     bool trunc_only = false;
+    // Auto-reset of the classic envs is DEFERRED to the end of the kernel: a reset is a Philox block + the uniform maps
+    // (~100 instructions) that a warp pays in full as soon as ONE of its lanes finished an episode (CartPole under the
+    // random policy: 4.5 % of the envs per step, i.e. 77 % of the warps); the done envs of the whole CTA are instead listed
+    // in shared memory (the ranks of the done compaction below) and reset side by side by its first lanes -- one warp
+    // instead of four pays, and the 16 M-env step drops from issue-bound to DRAM-bound.  Same draws, same results.
+    constexpr bool DEFER = AUTO_RESET && !FusedReset<E>::value;
+    bool deferred = false;
     float fin_ret = 0.0f;
     int32_t fin_len = 0;
     uint8_t done_byte = 0;
@@ -316,35 +331,78 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
                 p.ep_ret[i] = ret;
             }
             if (AUTO_RESET && r.done) {
-                const int32_t ep = FusedReset<E>::value ? ep_ord : p.episode[i];
-                if (!r.did_reset) {
+                if constexpr (DEFER) {
                     if (p.terminal_obs) { float to[E::OD]; E::obs(s, to); store_obs<E::OD, false>(p.terminal_obs, (size_t)i, to); }
-                    E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
+                    deferred = true;   // new state, episode ordinal and observation: written by the CTA's reset pass below
+                } else {
+                    const int32_t ep = FusedReset<E>::value ? ep_ord : p.episode[i];
+                    if (!r.did_reset) {
+                        if (p.terminal_obs) { float to[E::OD]; E::obs(s, to); store_obs<E::OD, false>(p.terminal_obs, (size_t)i, to); }
+                        E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
+                    }
+                    p.episode[i] = ep + 1;
                 }
-                p.episode[i] = ep + 1;
                 sbd = -1;
                 ept = 0;
             }
-            E::store(p.state, p.aux, p.n, i, s);
+            if (!deferred) E::store(p.state, p.aux, p.n, i, s);
             if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
             if (LIMIT) p.ep_t[i] = ept;
         }
-        float o[E::OD];
-        E::obs(s, o);
-        if (p.obs) store_obs<E::OD, false>(p.obs, (size_t)i, o);
-        // step + all-gather in one kernel: the observation goes straight into slot `rank` of EVERY rank's
-        // gather buffer with peer stores over NVLink (the local copy is just the peer == rank case)
-        for (int r = 0; r < p.world; ++r)
-            store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
+        if (!deferred) {
+            float o[E::OD];
+            E::obs(s, o);
+            if (p.obs) store_obs<E::OD, false>(p.obs, (size_t)i, o);
+            // step + all-gather in one kernel: the observation goes straight into slot `rank` of EVERY rank's
+            // gather buffer with peer stores over NVLink (the local copy is just the peer == rank case)
+            for (int r = 0; r < p.world; ++r)
+                store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
+        }
         p.reward[i] = r.reward;
         done_byte = (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done;
         done = r.done != 0;
     }
 
+    // ---- envs whose step is long and uneven (LunarLander: FusedReset): WARP-granular epilogue, no CTA barrier -- a warp
+    // whose landers are done retires at once and frees its registers instead of waiting at __syncthreads() for the
+    // slowest lander of the CTA (ncu, round 2: 7-10 % of the warp time of both lunar kernels sat at that barrier).
+    // One atomicAdd per warp with a finished episode: 2048 warps per 65 536-lander launch, no contention to speak of.
+    if constexpr (FusedReset<E>::value) {
+        if (p.world == 0) {   // (the fused gather needs the CTA-level "last block" signal: general path below)
+            const unsigned lane_w = threadIdx.x & 31;
+            const unsigned mw = __ballot_sync(0xffffffffu, done);
+            const unsigned miw = __ballot_sync(0xffffffffu, invalid);
+            if (tix < p.n) p.done[i] = done_byte;
+            if (miw != 0 && lane_w == 0) {
+                atomicAdd(&p.stats[1], (unsigned long long)__popc(miw));
+                *reinterpret_cast<volatile int*>(p.host_invalid) = 1;
+                __threadfence_system();
+            }
+            if (mw != 0) {
+                int base = 0;
+                if (lane_w == 0) base = atomicAdd(p.done_count + (p.seq & 1), __popc(mw));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (done && p.done_idx != nullptr) p.done_idx[base + __popc(mw & ((1u << lane_w) - 1u))] = i;
+                if (p.sums != nullptr) {
+                    double rs = done ? (double)fin_ret : 0.0, ls = done ? (double)fin_len : 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); ls += __shfl_xor_sync(0xffffffffu, ls, o); }
+                    if (lane_w == 0) { atomicAdd(&p.sums[0], rs); atomicAdd(&p.sums[1], ls); }
+                }
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0 && p.part != 2) {   // fold the previous launch's count, zero the next launch's counter (see below)
+                int32_t* prev = p.done_count + ((p.seq + 1) & 1);
+                if (p.fold_prev) p.stats[0] += (unsigned long long)*prev;
+                *prev = 0;
+            }
+            return;
+        }
+    }
+
     // ---- done compaction: warp ballot + popc prefix -> block scan -> one atomicAdd per block
-    __shared__ int warp_cnt[STEP_BLOCK / 32];
+    __shared__ int warp_cnt[BLOCK / 32];
     __shared__ int block_base;
-    __shared__ __align__(16) uint8_t done_tile[STEP_BLOCK];
+    __shared__ __align__(16) uint8_t done_tile[BLOCK];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, done);
     const unsigned mi = __ballot_sync(0xffffffffu, invalid);
@@ -362,25 +420,49 @@ __global__ void __launch_bounds__(STEP_BLOCK) step_kernel(const StepArgs p) {
     __syncthreads();
     int warp_off = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < STEP_BLOCK / 32; ++w) {
+    for (int w = 0; w < BLOCK / 32; ++w) {
         const int c = warp_cnt[w];
         if (w < (int)warp) warp_off += c;
         total += c;
     }
-    if (packed && threadIdx.x < STEP_BLOCK / 4) {
-        const int first = blockIdx.x * STEP_BLOCK + 4 * (int)threadIdx.x;
+    if (packed && threadIdx.x < BLOCK / 4) {
+        const int first = blockIdx.x * BLOCK + 4 * (int)threadIdx.x;
         if (first + 3 < p.n) *reinterpret_cast<uint32_t*>(p.done + first) = *reinterpret_cast<const uint32_t*>(done_tile + 4 * threadIdx.x);
-        else for (int k = first; k < p.n && k < first + 4; ++k) p.done[k] = done_tile[k - blockIdx.x * STEP_BLOCK];
+        else for (int k = first; k < p.n && k < first + 4; ++k) p.done[k] = done_tile[k - blockIdx.x * BLOCK];
+    }
+    if constexpr (DEFER) {
+        if (total > 0) {   // block-uniform
+            __shared__ int reset_list[BLOCK];
+            if (deferred) reset_list[warp_off + __popc(m & ((1u << lane) - 1u))] = i;
+            __syncthreads();
+            for (int j = (int)threadIdx.x; j < total; j += BLOCK) {
+                const int e = reset_list[j];
+                const int32_t ep = p.episode[e];
+                S s{};
+                E::reset(s, seed_of(p.seeds, p.seed, e), p.env_off + (uint32_t)e, (uint32_t)ep, p.t + 1, p.prm);
+                p.episode[e] = ep + 1;
+                E::store(p.state, p.aux, p.n, e, s);
+                float o[E::OD];
+                E::obs(s, o);
+                if (p.obs) store_obs<E::OD, false>(p.obs, (size_t)e, o);
+                for (int r = 0; r < p.world; ++r)
+                    store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)e, o);
+            }
+        }
     }
     int32_t* count = p.done_count + (p.seq & 1);
     if (threadIdx.x == 0) {
         int base = 0;
-        if (total > 0) {
-            base = atomicAdd(count, total);
-            atomicAdd(&p.stats[0], (unsigned long long)total);
-        }
+        if (total > 0) base = atomicAdd(count, total);   // the only contended atomic of the launch: one per CTA with a finished episode
         block_base = base;
-        if (blockIdx.x == 0) p.done_count[(p.seq + 1) & 1] = 0;   // zero the next step's counter
+        if (blockIdx.x == 0 && p.part != 2) {
+            // the other counter holds the total of the PREVIOUS step launch (complete: same stream): it joins the running
+            // number of finished episodes here -- one plain add per launch instead of one more atomic per CTA -- and is
+            // zeroed for the next launch.  (The host adds the not-yet-folded count of the latest launch when it reports.)
+            int32_t* prev = p.done_count + ((p.seq + 1) & 1);
+            if (p.fold_prev) p.stats[0] += (unsigned long long)*prev;
+            *prev = 0;
+        }
     }
     if (p.done_idx != nullptr && total > 0) {
         __syncthreads();

@@ -47,6 +47,7 @@ constexpr int BASE_EDGE = 10;
 
 // Box2D-2.3 / Farseer-3.5 lineage settings
 constexpr float LINEAR_SLOP = 0.005f;
+constexpr float LINEAR_SLOP_SQ_MAX = 2.5000001187436283e-05f;   // largest float32 x with sqrtf(x) <= LINEAR_SLOP (joint_position)
 constexpr float ANGULAR_SLOP = 0.03490658849477768f;          // (2.0f / 180.0f * Pi) folded in float32 like the C# / C++ constant expression (NOT the double product rounded once: 0.034906584769…)
 constexpr float POLYGON_RADIUS = 0.01f;                      // 2 * linearSlop
 constexpr float BAUMGARTE = 0.2f;
@@ -58,7 +59,15 @@ constexpr float VELOCITY_THRESHOLD = 1.0f;
 constexpr float TIME_TO_SLEEP = 0.5f;
 constexpr float LINEAR_SLEEP_TOL = 0.01f;
 constexpr float ANGULAR_SLEEP_TOL = 0.03490658849477768f;
-constexpr int VELOCITY_ITERATIONS = 180, POSITION_ITERATIONS = 60;   // :723-724
+// (the two macros exist for timing probes only -- tools/lunar_split_probe.py builds variants with 1 iteration to see where a
+// step's time goes; the product is always built with the reference's counts)
+#ifndef LUNAR_VEL_ITERS
+#define LUNAR_VEL_ITERS 180
+#endif
+#ifndef LUNAR_POS_ITERS
+#define LUNAR_POS_ITERS 60
+#endif
+constexpr int VELOCITY_ITERATIONS = LUNAR_VEL_ITERS, POSITION_ITERATIONS = LUNAR_POS_ITERS;   // :723-724
 constexpr float DEFAULT_FRICTION = 0.2f;
 
 constexpr int MAXC = 6;   // touching manifolds kept per lander
@@ -192,6 +201,30 @@ __device__ __forceinline__ int clip_segment(ClipVertex out[2], const ClipVertex 
         ++n;
     }
     return n;
+}
+
+// The first exit of b2CollideEdgeAndPolygon -- ComputeEdgeSeparation: the polygon's deepest vertex is further than the
+// contact radius from the edge's line -- evaluated INLINE with exactly the operations of collide_edge_polygon below (same
+// bits: every operation is a single IEEE operation, nothing is contracted).  A lander near the ground holds six to nine
+// broad-phase pairs (fat boxes overlap) of which one or two touch: only those pay the out-of-line narrow phase, with its
+// vertex arrays in local memory (round 2, per-warp clocks: Collide was 108 k of a contact warp's 840 k cycles).
+__device__ __forceinline__ bool edge_polygon_apart(V2 v1, V2 v2, int body, V2 p, Rot q) {
+    const V2 centroid = rmul(q, SHAPES[body].centroid) + p;
+    V2 edge1 = v2 - v1;
+    {
+        const float len = sqrtf(edge1.x * edge1.x + edge1.y * edge1.y);
+        const float inv = 1.0f / len;
+        edge1 = mk(edge1.x * inv, edge1.y * inv);
+    }
+    const V2 normal1 = mk(edge1.y, -edge1.x);
+    const float offset1 = dot(normal1, centroid - v1);
+    const V2 normal = offset1 >= 0.0f ? normal1 : -normal1;
+    float edge_sep = 3.4028234663852886e38f;
+    const int count = SHAPES[body].count;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (i < count) { const float s = dot(normal, (rmul(q, SHAPES[body].v[i]) + p) - v1); if (s < edge_sep) edge_sep = s; }
+    return edge_sep > 2.0f * POLYGON_RADIUS;
 }
 
 // Edge A (static, identity transform, no adjacent vertices) vs polygon B with transform (p, q).
@@ -549,10 +582,23 @@ __device__ __forceinline__ void joint_velocity(Joint& J, const JointWork& W, V2&
     wB = wB + iB * (active ? tb + imz : tb);
 }
 
+// A select the compiler cannot turn back into a branch: the condition is an all-ones / all-zeros word whose origin is hidden
+// behind an empty asm, applied with integer and / or (one LOP3).  With plain `c ? a : b` nvcc sinks a row's whole
+// computation under `if (row exists)` -- three divergent regions per iteration, executed one after the other (ncu, round 2:
+// 12 of 32 lanes active in the row code) -- and the three independent chains can no longer be interleaved.
+__device__ __forceinline__ int opaque_mask(bool c) {
+    int m = c ? -1 : 0;
+    asm volatile("" : "+r"(m));
+    return m;
+}
+__device__ __forceinline__ float msel(int m, float a, float b) { return __int_as_float((__float_as_int(a) & m) | (__float_as_int(b) & ~m)); }
+__device__ __forceinline__ V2 msel(int m, V2 a, V2 b) { return mk(msel(m, a.x, b.x), msel(m, a.y, b.y)); }
+
 // b2ContactSolver::SolveVelocityConstraints for the manifold of one body against the static ground, committed only if the
 // row exists (r.count > 0): friction of the points, then the normal row (one point) or the block LCP (two points).
 __device__ __forceinline__ void velocity_row_select(VelRow& r, V2& v, float& w) {
-    const bool has = r.count > 0, two = r.count == 2;
+    const bool two = r.count == 2;
+    const int has = opaque_mask(r.count > 0), has2 = opaque_mask(r.count == 2);
     const float mB = r.inv_mass, iB = r.inv_inertia;
     const V2 normal = r.normal;
     const V2 tangent = cross_vs(normal, 1.0f);
@@ -606,11 +652,11 @@ __device__ __forceinline__ void velocity_row_select(VelRow& r, V2& v, float& w) 
     }
     const V2 vn_ = two ? v2p : v1;
     const float wn_ = two ? w2p : w1;
-    v = has ? vn_ : v;
-    w = has ? wn_ : w;
-    r.ti0 = has ? ti0 : r.ti0; r.ti1 = has ? ti1 : r.ti1;
-    r.ni0 = has ? (two ? n20 : n1) : r.ni0;
-    r.ni1 = (has && two) ? n21 : r.ni1;
+    v = msel(has, vn_, v);
+    w = msel(has, wn_, w);
+    r.ti0 = msel(has, ti0, r.ti0); r.ti1 = msel(has, ti1, r.ti1);
+    r.ni0 = msel(has, two ? n20 : n1, r.ni0);
+    r.ni1 = msel(has2, n21, r.ni1);
 }
 
 // rotation of a body angle known to be far below the 32768 rad where the argument reduction changes path (checked once per step)
@@ -638,8 +684,11 @@ __device__ __forceinline__ void position_point_select(bool on, int type, V2 loca
     const float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
     const float rnB = cross(rB, normal);
     const float K = mB + iB * rnB * rnB;
-    // K >= inv_mass > 0 for a real row; -C / K is 0 or far from the subnormal range (C is a multiple of ulp(linearSlop) ~ 5e-10 scaled by 0.2)
-    const float impulse = K > 0.0f ? div_inrange(-C, K) : 0.0f;
+    // K >= inv_mass > 0 for a real row; -C / K is 0 or far from the subnormal range (C is a multiple of ulp(linearSlop) ~ 5e-10 scaled by 0.2).
+    // The `K > 0` of b2ContactSolver (false only for a NaN here) is kept as an opaque-mask select: as a branch it put a
+    // convergence barrier around every one of the six points of an iteration and serialised the three bodies' chains.
+    const int kpos = opaque_mask(K > 0.0f);
+    const float impulse = msel(kpos, div_inrange(-C, msel(kpos, K, 1.0f)), 0.0f);
     const V2 P = impulse * normal;
     const V2 cn = c + mB * P;
     const float an = a + iB * cross(rB, P);
@@ -667,7 +716,10 @@ __device__ __forceinline__ bool joint_position(const Joint& J, float motor_mass,
     const V2 rA = rmul(qA, mk(0.0f, 0.0f) - SHAPES[A].centroid);
     const V2 rB = rmul(qB, JOINTS[ji].anchor_b - SHAPES[B].centroid);
     const V2 C = cB + rB - cA - rA;
-    const float position_error = sqrtf(dot(C, C));
+    // position_error = sqrt(dot(C, C)) is only compared with linearSlop: sqrt is correctly rounded and monotonic, so
+    // `sqrtf(x) <= LINEAR_SLOP` holds exactly for x <= LINEAR_SLOP_SQ_MAX, the largest float32 whose rounded root does not
+    // exceed LINEAR_SLOP (0x1.a36e3p-16; tests/test_host_helpers.py checks the boundary) -- no MUFU.RSQ + fix-up call in the loop
+    const float position_error_sq = dot(C, C);
     const float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
     const float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
     const float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
@@ -679,7 +731,7 @@ __device__ __forceinline__ bool joint_position(const Joint& J, float motor_mass,
     aA = aA - iA * cross(rA, impulse);
     cB = cB + mB * impulse;
     aB = aB + iB * cross(rB, impulse);
-    return position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+    return position_error_sq <= LINEAR_SLOP_SQ_MAX && angular_error <= ANGULAR_SLOP;
 }
 
 // the touching manifolds of a step (creation order) and their island order
@@ -708,23 +760,32 @@ __device__ __forceinline__ void collide(Lander& L, Contacts& C) {
             V2 v1, v2;
             edge_points(L, e, &v1, &v2);
             Manifold m;
-            collide_edge_polygon(&m, v1, v2, SHAPES[body], GETB(p, body), GETB(q, body));
+            m.count = 0; m.type = 0;
+            if (!edge_polygon_apart(v1, v2, body, GETB(p, body), GETB(q, body)))
+                collide_edge_polygon(&m, v1, v2, SHAPES[body], GETB(p, body), GETB(q, body));
             const bool touching = m.count > 0 && nc < MAXC;
             if (touching) {
                 L.touch[body] |= 1u << e;
+                // b2Contact::Update: match old manifold points by id, copy their impulses (warm start).  Matched into scalars
+                // first: stores through ac[nc] inside the slot / point / id loops were expanded by the compiler into one copy
+                // per possible nc (10 000 instructions of selects)
+                const int32_t pair = body * 16 + e;
+                float wni[2] = {0.0f, 0.0f}, wti[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int sl = 0; sl < MAXC; ++sl) {
+                    const bool slot = L.c[sl].pair == pair;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int o = 1; o >= 0; --o) {   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
+                            const bool hit = slot && j < m.count && L.c[sl].key[o] != NO_KEY && L.c[sl].key[o] == m.key[j];
+                            wni[j] = hit ? L.c[sl].ni[o] : wni[j];
+                            wti[j] = hit ? L.c[sl].ti[o] : wti[j];
+                        }
+                }
                 ActiveContact& c = ac[nc++];
                 c.body = body; c.edge = e; c.count = m.count; c.m = m;
-                for (int j = 0; j < 2; ++j) { c.p[j].normal_impulse = 0.0f; c.p[j].tangent_impulse = 0.0f; }
-                // b2Contact::Update: match old manifold points by id, copy their impulses (warm start)
-                const int32_t pair = body * 16 + e;
-                for (int sl = 0; sl < MAXC; ++sl) {
-                    if (L.c[sl].pair != pair) continue;
-                    for (int j = 0; j < m.count; ++j)
-                        for (int o = 1; o >= 0; --o)   // the FIRST old point with this id wins (b2Contact::Update breaks at the first match; a face-B manifold can carry the same id twice)
-                            if (L.c[sl].key[o] != NO_KEY && L.c[sl].key[o] == m.key[j]) {
-                                c.p[j].normal_impulse = L.c[sl].ni[o]; c.p[j].tangent_impulse = L.c[sl].ti[o];
-                            }
-                }
+                for (int j = 0; j < 2; ++j) { c.p[j].normal_impulse = wni[j]; c.p[j].tangent_impulse = wti[j]; }
             } else {
                 L.touch[body] &= ~(1u << e);
             }
@@ -745,6 +806,15 @@ __device__ __forceinline__ void collide(Lander& L, Contacts& C) {
     }
     C.nc = nc; C.order = order;
 }
+
+// Timing probe only (tools/lunar_phase_probe.py builds a variant with -DLUNAR_PHASE_CLOCKS): clock64() of every thread at the
+// phase boundaries of a step, read back through gymcuda_debug_lunar_phase.  Never defined in the product build.
+#ifdef LUNAR_PHASE_CLOCKS
+__device__ long long g_lunar_phase[2][10][65536];
+#define LUNAR_PHASE(HP, k) do { const unsigned _t = blockIdx.x * blockDim.x + threadIdx.x; if (_t < 65536u) g_lunar_phase[(HP) ? 1 : 0][k][_t] = clock64(); } while (0)
+#else
+#define LUNAR_PHASE(HP, k) do {} while (0)
+#endif
 
 // ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1} -- then the broad-phase update and ClearForces
 template <bool HAS_PAIRS>
@@ -935,6 +1005,7 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
             warp_rows = __ballot_sync(am, nc > 0) != 0u;
             warp_extra = __ballot_sync(am, nextra > 0) != 0u;
         }
+        LUNAR_PHASE(HAS_PAIRS, 3);
 #pragma unroll 1
         for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
             joint_velocity<1>(Jl[1], jw[1], v[0], w[0], v[2], w[2]);   // island order: leg 1's joint, then leg 0's
@@ -975,6 +1046,7 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
                 }
         }
 
+        LUNAR_PHASE(HAS_PAIRS, 4);
         // integrate positions
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -1056,6 +1128,7 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
             }
         };
         if (small_angles) position_iterations(std::true_type{}); else position_iterations(std::false_type{});
+        LUNAR_PHASE(HAS_PAIRS, 5);
 
         // copy back, store impulses (b2ContactSolver::StoreImpulses): slots in creation order
 #pragma unroll
@@ -1309,9 +1382,12 @@ __device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, ui
 template <bool HAS_PAIRS = true>
 __device__ __noinline__ StepResult step_autoreset(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action,
                                                   bool allow, uint64_t next_ordinal) {
+    LUNAR_PHASE(HAS_PAIRS, 0);
     Powers pw = pre_physics(L, seed, gid, t, i_action, c_action);
+    LUNAR_PHASE(HAS_PAIRS, 1);
     Contacts C;
     collide<HAS_PAIRS>(L, C);
+    LUNAR_PHASE(HAS_PAIRS, 2);
     bool early = false;
     if (HAS_PAIRS && allow && (L.flags & (F_FUSELAGE | F_GAME_OVER)) && (L.flags & F_AWAKE)) {
         bool may_sleep = true;   // the island sleeps only if EVERY body's timer reaches timeToSleep: one that cannot, after this step, rules it out
@@ -1327,8 +1403,10 @@ __device__ __noinline__ StepResult step_autoreset(Lander& L, uint64_t seed, uint
         }
     }
     solve<HAS_PAIRS>(L, C);                                                                   // :721-725
+    LUNAR_PHASE(HAS_PAIRS, 6);
     StepResult r = post_physics(L, pw);
     if (early) r = StepResult{-100.0f, 1, 1};
+    LUNAR_PHASE(HAS_PAIRS, 7);
     return r;
 }
 

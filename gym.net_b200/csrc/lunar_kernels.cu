@@ -43,3 +43,10 @@ cudaError_t lunar_launch_ctor(bool continuous, int grid, cudaStream_t s, const R
 }
 
 }  // namespace gymcuda
+
+#ifdef LUNAR_PHASE_CLOCKS
+// timing probe only (see lunar_core.cuh): [2][10][65536] clock64 samples of the last launches
+extern "C" int gymcuda_debug_lunar_phase(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, gymcuda::lunar::g_lunar_phase, sizeof(long long) * 2 * 10 * 65536);
+}
+#endif

@@ -245,7 +245,7 @@ int hostsim_step_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32
     a.state = state; a.aux = aux; a.sbd = sbd; a.ep_t = ep_t; a.episode = episode; a.seeds = g_seeds; a.perm = perm; a.actions = actions;
     a.obs = obs; a.reward = reward; a.done = done; a.done_idx = done_idx; a.done_count = done_count; a.stats = stats; a.ep_ret = ep_ret;
     a.sums = sums; a.done_bits = done_bits; a.host_invalid = host_invalid; a.n = n; a.env_off = env_off; a.seed = seed; a.t = t;
-    a.limit = limit; a.use_bcast = use_bcast; a.bcast_action = bcast_action; a.seq = seq;
+    a.limit = limit; a.use_bcast = use_bcast; a.bcast_action = bcast_action; a.seq = seq; a.fold_prev = 1;
     a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
     a.world = g_gather.world; a.rank = g_gather.rank; a.gseq = g_gather.gseq; a.block_counter = g_gather.block_counter;
     for (int r = 0; r < g_gather.world; ++r) { a.peer_obs[r] = g_gather.peer_obs[r]; a.peer_flags[r] = g_gather.peer_flags[r]; }

@@ -25,7 +25,7 @@
 namespace simt {
 
 enum State { RUNNING = 0, WAIT_WARP, WAIT_AMASK, WAIT_BLOCK, DONE };
-enum Op { OP_BALLOT = 1, OP_ALL, OP_SHFL_XOR, OP_SHFL_UP, OP_SYNCWARP };
+enum Op { OP_BALLOT = 1, OP_ALL, OP_SHFL_XOR, OP_SHFL_UP, OP_SYNCWARP, OP_SHFL_IDX };
 
 struct Fiber {
     ucontext_t ctx;
@@ -120,6 +120,7 @@ static void resolve_warp(Cta& c, int w) {
                 case OP_ALL: r = ballot == group ? 1u : 0u; break;
                 case OP_SHFL_XOR: { const int src = lane ^ arg; r = (src < 32 && ((group >> src) & 1u)) ? vals[src] : vals[lane]; break; }
                 case OP_SHFL_UP: { const int src = lane - arg; r = (src >= 0 && ((group >> src) & 1u)) ? vals[src] : vals[lane]; break; }
+                case OP_SHFL_IDX: { const int src = arg & 31; r = ((group >> src) & 1u) ? vals[src] : vals[lane]; break; }
                 case OP_SYNCWARP: r = 0; break;
             }
             release(c, j, r);

@@ -56,6 +56,10 @@ template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int o) {
     if (!simt::active()) return T(0);   // one-lane warp: lanes that do not exist contribute nothing
     return simt::from_bits<T>(simt::wait(simt::WAIT_WARP, simt::OP_SHFL_XOR, mask, simt::to_bits(v), o));
 }
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) {
+    if (!simt::active()) return v;      // one-lane warp: lane 0 is this lane
+    return simt::from_bits<T>(simt::wait(simt::WAIT_WARP, simt::OP_SHFL_IDX, mask, simt::to_bits(v), src));
+}
 template <class T> static inline T __shfl_up_sync(unsigned mask, T v, int o) {
     if (!simt::active()) return v;
     return simt::from_bits<T>(simt::wait(simt::WAIT_WARP, simt::OP_SHFL_UP, mask, simt::to_bits(v), o));

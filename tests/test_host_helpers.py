@@ -21,3 +21,20 @@ def test_shards_tile_the_global_batch():
             assert o == off and n >= 1
             off += n
         assert off == total
+
+
+def test_linear_slop_squared_threshold_is_the_exact_sqrt_boundary():
+    """lunar_core.cuh joint_position compares dot(C, C) with LINEAR_SLOP_SQ_MAX instead of sqrtf(dot(C, C)) with linearSlop:
+    the constant must be the LARGEST float32 whose correctly rounded square root does not exceed float32(0.005)."""
+    import math
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gym.net_b200", "csrc", "lunar_core.cuh")).read()
+    c = np.float32(float(re.search(r"LINEAR_SLOP_SQ_MAX = ([0-9.e+-]+)f", src).group(1)))
+    slop = np.float32(0.005)
+    root = lambda x: np.float32(math.sqrt(float(x)))   # double sqrt rounded once: the correctly rounded float32 root
+    assert root(c) <= slop and root(np.nextafter(c, np.float32(np.inf), dtype=np.float32)) > slop
+    x = c
+    for _ in range(1000):   # monotone on both sides of the boundary
+        x = np.nextafter(x, np.float32(-np.inf), dtype=np.float32)
+        assert root(x) <= slop

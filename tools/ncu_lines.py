@@ -4,7 +4,7 @@
 ncu's SASS page gives per-instruction executed counts and stall samples; nvdisasm -gi on the same
 cubin gives the (inlined) source line of every instruction.  Joined and aggregated per source line:
 
-  python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel-substring> [top-N]
+  python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel-substring (demangled, report)> [mangled-substring (cubin)] [top-N]
 """
 import csv
 import os
@@ -14,7 +14,7 @@ import sys
 import tempfile
 
 
-HELPERS = {"lunar_core.cuh": (64, 84), "detmath.cuh": (1, 10 ** 6), "philox.cuh": (1, 10 ** 6)}
+HELPERS = {"lunar_core.cuh": (72, 94), "detmath.cuh": (1, 10 ** 6), "philox.cuh": (1, 10 ** 6)}
 
 
 def is_helper(loc):
@@ -25,12 +25,15 @@ def is_helper(loc):
 def line_table(lib, kernel):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-    table, cur, group, infn = {}, None, [], False
+    # every cubin of the library (one per translation unit); `kernel` is matched against the MANGLED section name
+    dis = "".join(subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+                  for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))
+    table, cur, group, infn, taken = {}, None, [], False, None
     for ln in dis.splitlines():
         if ln.startswith("//--------------------- .text."):
-            infn = kernel in ln
+            infn = kernel in ln and taken in (None, ln)
+            if infn:
+                taken = ln
             continue
         if not infn:
             continue
@@ -49,18 +52,25 @@ def line_table(lib, kernel):
 
 
 def main():
-    rep, lib, kernel = sys.argv[1:4]
-    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    table = line_table(lib, kernel)
+    rep, lib, kernel = sys.argv[1:4]   # kernel: substring of the demangled name in the report
+    mangled = sys.argv[4] if len(sys.argv) > 4 and not sys.argv[4].isdigit() else kernel   # substring of the mangled name in the cubin
+    top = int(sys.argv[-1]) if sys.argv[-1].isdigit() else 40
+    table = line_table(lib, mangled)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # one section per profiled launch: a "Kernel Name" row, the header row, then the instructions; take the first section
+    # whose kernel name contains the pattern (all blanks removed on both sides)
+    squeeze = lambda t: t.replace(" ", "").replace("(bool)", "").replace("gymcuda::", "")   # noqa: E731
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = next((i for i in starts if squeeze(kernel) in squeeze(rows[i][1])), starts[0] if starts else -1)
+    hi = next(i for i, r in enumerate(rows) if i > sec and r and r[0] == "Address")
+    end = next((i for i in starts if i > hi), len(rows))
     hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
     base = None
     agg = {}
     tot_i = tot_s = 0
-    for r in rows[hi + 1:]:
+    for r in rows[hi + 1:end]:
         if len(r) < len(hdr):
             continue
         addr = int(r[ix["Address"]], 16) if r[ix["Address"]].startswith("0x") else int(r[ix["Address"]])
