@@ -18,6 +18,7 @@
 #include <type_traits>
 #include <vector>
 
+#include <algorithm>
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: the ranges cost a null-pointer test unless a profiler injects itself
 
 #include "kernels.cuh"
@@ -1324,6 +1325,29 @@ int gymcuda_step_gather_device(gymcuda_env* e, const void* d_actions, float* d_r
     if (int rc = check_device_buffers(e, d_actions, nullptr, d_reward)) return rc;
     for (int r = 0; r < e->g_world; ++r) if (!e->g_peer[r]) return fail(GYMCUDA_EINVAL, "gymcuda_gather_open has not mapped rank %d", r);
     e->async_steps = true;
+    if (is_lunar(e) && e->n >= 4 * STEP_BLOCK) {
+        // several kernels per step (contact partition): the step fills this rank's own slot, gather_push_kernel sends it to the peers
+        e->g_seq += 1;
+        const size_t slot = (size_t)e->n * e->ki.od;
+        const size_t at = ((size_t)(e->g_seq & 1u) * e->g_world + e->g_rank) * slot;
+        float* own = reinterpret_cast<float*>(e->g_local) + at;
+        int rc = step_launch(e, d_actions, 0, 0, own, d_reward ? d_reward : e->d_reward, d_done ? d_done : e->d_done);
+        if (rc) return rc;
+        PushArgs pa{};
+        pa.src = reinterpret_cast<const float4*>(own); pa.world = e->g_world; pa.rank = e->g_rank; pa.gseq = e->g_seq; pa.n4 = slot / 4;
+        pa.block_counter = reinterpret_cast<unsigned*>(e->g_local + e->g_counter_off);
+        for (int r = 0; r < e->g_world; ++r) {
+            pa.dst[r] = reinterpret_cast<float4*>(reinterpret_cast<float*>(e->g_peer[r]) + at);
+            pa.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(e->g_peer[r]) + e->g_flags_off);
+        }
+        const int grid = (int)std::min<size_t>((pa.n4 + 255) / 256, (size_t)e->sm_count * 4);
+        gather_push_kernel<<<grid, 256, 0, e->stream>>>(pa);
+        CU_TRY(cudaGetLastError());
+        const float* base0 = reinterpret_cast<const float*>(e->g_local) + (size_t)(e->g_seq & 1u) * e->g_world * slot;
+        e->last_obs = own;
+        if (d_gathered) *d_gathered = base0;
+        return GYMCUDA_OK;
+    }
     int rc = step_launch(e, d_actions, 0, 0, nullptr, d_reward ? d_reward : e->d_reward, d_done ? d_done : e->d_done, true);
     if (rc) return rc;
     const float* base = reinterpret_cast<const float*>(e->g_local) + (size_t)(e->g_seq & 1u) * e->g_world * (size_t)e->n * e->ki.od;

@@ -90,6 +90,34 @@ def main():
         np.save(os.path.join(out_dir, "gathered_lunar.npy"), out2.cpu().numpy())
     dist.barrier()
     ll.Close()
+    # LunarLander with the observation gather: the partitioned step (three partition kernels + two step kernels) fills the
+    # rank's own slot, gather_push_kernel sends it to the peers -- against ncclAllGather of the same step, 30 steps
+    n3, off3 = G.shard_envs(4096, rank, world)
+    lg = G.LunarLanderVecEnv(n3, seed=9, device=local, env_id_offset=off3, auto_reset=True, time_limit=25)
+    lg.CommInit(_second_id(rank), rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, lg.GatherCreate(rank, world))
+    lg.GatherOpen(handles)
+    lg.ResetBatch()
+    g_rew = torch.empty((n3,), dtype=torch.float32, device="cuda"); g_done = torch.empty((n3,), dtype=torch.uint8, device="cuda")
+    ref3 = torch.empty((world, n3, 8), dtype=torch.float32, device="cuda")
+    ok = True
+    for step in range(30):
+        a = torch.randint(0, 4, (n3,), dtype=torch.int32, device="cuda", generator=gen)
+        torch.cuda.synchronize()
+        ptr = lg.StepGatherDevice(a.data_ptr(), g_rew.data_ptr(), g_done.data_ptr())
+        lg.GatherWait()
+        lg.AllGatherObs(ref3.data_ptr())
+        lg.Sync()
+        fused = torch.as_tensor(_RawCuda(ptr, (world, n3, 8)), device="cuda")
+        ok = ok and bool(torch.equal(fused, ref3))
+        dist.barrier()   # nobody starts the next step's pushes into a buffer a peer is still comparing
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "fused_lunar_ok.npy"), flag.numpy())
+    dist.barrier()
+    lg.Close()
     dist.destroy_process_group()
 
 

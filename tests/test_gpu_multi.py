@@ -58,6 +58,7 @@ def test_two_gpu_sharded_rollout_and_nccl_allgather(tmp_path):
     assert np.array_equal(gathered.reshape(-1, 4), full.Observe())
     full.Close()
     assert np.load(tmp_path / "fused_ok.npy")[0] == 1.0      # fused peer-store gather == ncclAllGather, 25 steps
+    assert np.load(tmp_path / "fused_lunar_ok.npy")[0] == 1.0   # LunarLander: partitioned step + peer push == ncclAllGather, 30 steps
     gl = np.load(tmp_path / "gathered_lunar.npy")
     ll = G.LunarLanderVecEnv(gl.shape[0] * gl.shape[1], seed=5, auto_reset=True)
     ll.ResetBatch()
