@@ -91,6 +91,7 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_normalize_get(GymCudaHandle env, double[] obsMean, double[] obsVar, out double returnVar, out double count);
         [DllImport(Lib)] internal static extern int gymcuda_normalize_reset(GymCudaHandle env);
         [DllImport(Lib)] internal static extern int gymcuda_set_stream(GymCudaHandle env, IntPtr cudaStream);
+        [DllImport(Lib)] internal static extern int gymcuda_set_device_clock(GymCudaHandle env, int on);
         [DllImport(Lib)] internal static extern int gymcuda_sync(GymCudaHandle env);
         [DllImport(Lib)] internal static extern int gymcuda_host_alloc(out IntPtr ptr, UIntPtr bytes);
         [DllImport(Lib)] internal static extern int gymcuda_host_free(IntPtr ptr);

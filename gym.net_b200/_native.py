@@ -80,6 +80,7 @@ SYMBOLS = {
     "gymcuda_normalize_get": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "gymcuda_normalize_reset": (_I, [_VP]),
     "gymcuda_set_stream": (_I, [_VP, _VP]),
+    "gymcuda_set_device_clock": (_I, [_VP, _I]),
     "gymcuda_sync": (_I, [_VP]),
     "gymcuda_host_alloc": (_I, [C.POINTER(_VP), C.c_size_t]),
     "gymcuda_host_free": (_I, [_VP]),

@@ -165,6 +165,8 @@ struct gymcuda_env {
     // pinned scratch: [0..1] stats, [2] done_count
     unsigned long long* h_small;
     unsigned long long invalid_seen, env_steps;
+    unsigned long long* d_clock;   // {t, seq} on the device (gymcuda_set_device_clock)
+    bool device_clock;
     bool stats_pending;      // the episode count of the latest step launch is still in d_done_count, not in d_stats[0]
     bool async_steps;        // *_device steps were enqueued since the last synchronisation: their rejected actions are not yet reported
     // nccl
@@ -337,6 +339,9 @@ static cudaError_t dispatch_ctor(gymcuda_env* e, const ResetArgs& a) {
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
+static int clock_pull(gymcuda_env* e);
+static int clock_push(gymcuda_env* e);
+
 int gymcuda_version(void) { return GYMCUDA_VERSION; }
 const char* gymcuda_last_error(void) { return g_last_error.c_str(); }
 
@@ -377,7 +382,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaFree(e->d_actions); cudaFree(e->d_out); cudaFree(e->d_mask); cudaFree(e->d_sample_mask);
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
     for (int k = 0; k < 4; ++k) cudaFree(e->scratch[k]);
-    cudaFree(e->d_norm_acc); cudaFree(e->d_norm_ret); cudaFree(e->d_term_own);
+    cudaFree(e->d_norm_acc); cudaFree(e->d_norm_ret); cudaFree(e->d_term_own); cudaFree(e->d_clock);
     cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -419,7 +424,7 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMalloc(&e->d_done_idx, n * 4));
     CU_TRY(cudaMalloc(&e->d_done_count, 2 * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&e->d_stats, 2 * sizeof(unsigned long long)));
-    CU_TRY(cudaHostAlloc((void**)&e->h_small, 6 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc((void**)&e->h_small, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     if (e->ep_stats) {
         CU_TRY(cudaMalloc(&e->d_ep_ret, n * 4));
         CU_TRY(cudaMalloc(&e->d_sums, 2 * sizeof(double)));
@@ -533,6 +538,7 @@ int gymcuda_space(const gymcuda_env* e, gymcuda_space_info* o) {
 // ------------------------------------------------------------------------------------------------
 int gymcuda_seed(gymcuda_env* e, uint64_t seed) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     e->seed = seed;
     CU_TRY(cudaStreamSynchronize(e->stream));
     if (e->d_seeds) { CU_TRY(cudaFree(e->d_seeds)); e->d_seeds = nullptr; }
@@ -540,11 +546,13 @@ int gymcuda_seed(gymcuda_env* e, uint64_t seed) {
     CU_TRY(cudaMemsetAsync(e->d_episode, 0, (size_t)e->n * 4, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->t = 0;
+    if (int _c = clock_push(e)) return _c;
     return run_ctor(e);
 }
 
 int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (!seeds) return fail(GYMCUDA_EINVAL, "seeds is null");
     // VecEnv.Seed(int[]) throws ArgumentException on a length mismatch (VecEnv.cs:49)
     if (n != e->n) return fail(GYMCUDA_EINVAL, "Number of seeds passed should be equals to number of environments");
@@ -553,6 +561,7 @@ int gymcuda_seed_each(gymcuda_env* e, const int32_t* seeds, int n) {
     CU_TRY(cudaMemsetAsync(e->d_episode, 0, (size_t)e->n * 4, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     e->t = 0;
+    if (int _c = clock_push(e)) return _c;
     return run_ctor(e);
 }
 
@@ -573,6 +582,7 @@ static int reset_impl(gymcuda_env* e, const uint8_t* d_mask, float* obs_host) {
 
 int gymcuda_reset(gymcuda_env* e, float* obs_out) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     TRACE("reset");
     int rc = reset_impl(e, nullptr, obs_out);
     if (rc == GYMCUDA_OK) e->has_state = true;
@@ -581,6 +591,7 @@ int gymcuda_reset(gymcuda_env* e, float* obs_out) {
 
 int gymcuda_reset_masked(gymcuda_env* e, const uint8_t* mask, float* obs_out) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     TRACE("reset_masked");
     if (!mask) return fail(GYMCUDA_EINVAL, "mask is null");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "reset_masked before the first full Reset()");
@@ -591,6 +602,24 @@ int gymcuda_reset_masked(gymcuda_env* e, const uint8_t* mask, float* obs_out) {
 // ------------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------------
+// ---- device-resident clock (gymcuda_set_device_clock) --------------------------------------------------------------
+// In this mode the step kernels read t and the launch sequence number from d_clock and a one-thread kernel advances it after
+// every step, so a captured step can be replayed; the host mirrors (e->t, e->seq) are exact only after clock_pull.
+static int clock_pull(gymcuda_env* e) {   // device -> host mirrors (synchronises; not legal while the stream is being captured)
+    if (!e->device_clock) return GYMCUDA_OK;
+    CU_TRY(cudaMemcpyAsync(e->h_small + 6, e->d_clock, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->t = e->h_small[6]; e->seq = (uint32_t)e->h_small[7];
+    return GYMCUDA_OK;
+}
+static int clock_push(gymcuda_env* e) {   // host mirrors -> device, after an entry point that advanced them on the host
+    if (!e->device_clock) return GYMCUDA_OK;
+    e->h_small[6] = e->t; e->h_small[7] = e->seq;
+    CU_TRY(cudaMemcpyAsync(e->d_clock, e->h_small + 6, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
 // d_actions == nullptr (and no broadcast): the random policy -- ActionSpace.Sample() of step t evaluated in the kernel, also written to sampled_out
 static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int32_t bcast, float* d_obs,
                        float* d_reward, uint8_t* d_done, bool gather = false, void* sampled_out = nullptr) {
@@ -601,6 +630,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq; a.fold_prev = e->stats_pending ? 1 : 0;
+    if (e->device_clock) { a.clock = e->d_clock; a.fold_prev = 1; }   // (entering the mode zeroed the other counter if nothing was pending)
     a.terminal_obs = e->auto_reset ? e->term_dev : nullptr;
     if (!d_actions && !use_bcast) { a.sample = 1; a.act_out = sampled_out; }
     if (gather) {
@@ -613,6 +643,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
         a.block_counter = reinterpret_cast<unsigned*>(e->g_local + e->g_counter_off);
     }
     CU_TRY(dispatch_step(e, a));
+    if (e->device_clock) { clock_tick_kernel<<<1, 1, 0, e->stream>>>(e->d_clock, 1ull); CU_TRY(cudaGetLastError()); }
     e->stats_pending = true;   // this launch's episode count sits in done_count[seq & 1] until the next launch folds it into stats[0]
     e->t += 1;
     e->seq += 1;
@@ -780,6 +811,7 @@ int gymcuda_set_terminal_obs(gymcuda_env* e, float* buffer) {
 // launches for LunarLander
 int gymcuda_step_many_device(gymcuda_env* e, int k_steps, const void* d_actions, float* d_obs, float* d_reward, uint8_t* d_done) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     TRACE("step_many_device");
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
@@ -805,7 +837,7 @@ int gymcuda_step_many_device(gymcuda_env* e, int k_steps, const void* d_actions,
     e->t += (uint64_t)k_steps;
     e->env_steps += (unsigned long long)e->n * (unsigned long long)k_steps;
     e->last_obs = nullptr;
-    return GYMCUDA_OK;
+    return clock_push(e);
 }
 
 static cudaError_t scratch_reserve(gymcuda_env* e, int slot, size_t bytes, void** out);
@@ -839,6 +871,7 @@ int gymcuda_step_many(gymcuda_env* e, int k_steps, const void* actions, float* o
 // ------------------------------------------------------------------------------------------------
 int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, float* d_reward, uint8_t* d_done, void* d_actions) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     TRACE("rollout_random_device");
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
@@ -862,7 +895,7 @@ int gymcuda_rollout_random_device(gymcuda_env* e, int k_steps, float* d_obs, flo
     e->t += (uint64_t)k_steps;
     e->env_steps += (unsigned long long)e->n * (unsigned long long)k_steps;
     e->last_obs = nullptr;   // the current observations are not materialised; gymcuda_observe recomputes them
-    return GYMCUDA_OK;
+    return clock_push(e);
 }
 
 // grow-only device scratch for the host-buffer rollout (a cudaMalloc + cudaFree pair per call costs more than a
@@ -907,6 +940,7 @@ int gymcuda_rollout_random(gymcuda_env* e, int k_steps, float* obs, float* rewar
 // ------------------------------------------------------------------------------------------------
 int gymcuda_sample_actions_device(gymcuda_env* e, const uint8_t* d_mask, void* d_actions_out) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (!d_actions_out) return fail(GYMCUDA_EINVAL, "d_actions_out is null");
     if (int rc = check_device_buffers(e, d_actions_out, nullptr, nullptr)) return rc;
     if (d_mask && e->ki.actn == 0) return fail(GYMCUDA_EINVAL, "Box.sample cannot be provided a mask.");   // Box.cs:70-73
@@ -974,6 +1008,7 @@ int gymcuda_box_sample(int device, uint64_t seed, uint64_t index, const float* l
 // ------------------------------------------------------------------------------------------------
 int gymcuda_done_indices(gymcuda_env* e, int32_t* idx, int32_t* count) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (!count) return fail(GYMCUDA_EINVAL, "count is null");
     if (e->seq == 0) { *count = 0; return GYMCUDA_OK; }
     int32_t* h = reinterpret_cast<int32_t*>(e->h_small + 2);
@@ -989,6 +1024,7 @@ int gymcuda_done_indices(gymcuda_env* e, int32_t* idx, int32_t* count) {
 
 int gymcuda_done_indices_device(gymcuda_env* e, const int32_t** d_idx, const int32_t** d_count) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (d_idx) *d_idx = e->d_done_idx;
     if (d_count) *d_count = e->seq == 0 ? e->d_done_count : e->d_done_count + ((e->seq - 1) & 1);
     return GYMCUDA_OK;
@@ -999,6 +1035,7 @@ int gymcuda_done_indices_device(gymcuda_env* e, const int32_t** d_idx, const int
 // ------------------------------------------------------------------------------------------------
 int gymcuda_get_state(gymcuda_env* e, float* state, int32_t* aux, uint64_t* t) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (e->auxw > 0) {   // LunarLander: device arrays are field-major [word][env]; the ABI is [env][word]
         const size_t n = (size_t)e->n; const int sd = e->ki.sd, ad = e->ki.aux, aw = e->auxw;
         std::vector<float> fs(n * sd); std::vector<int32_t> fa(n * aw), ept(n), epi(n);
@@ -1030,6 +1067,7 @@ int gymcuda_get_state(gymcuda_env* e, float* state, int32_t* aux, uint64_t* t) {
 
 int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, uint64_t t) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (e->auxw > 0) {
         if (!state || !aux) return fail(GYMCUDA_EINVAL, "LunarLander set_state needs both state and aux");
         const size_t n = (size_t)e->n; const int sd = e->ki.sd, ad = e->ki.aux, aw = e->auxw;
@@ -1045,7 +1083,7 @@ int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, ui
         CU_TRY(cudaMemcpyAsync(e->d_episode, epi.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
         e->t = t; e->has_state = true; e->last_obs = nullptr;
-        return GYMCUDA_OK;
+        return clock_push(e);
     }
     if (state) CU_TRY(cudaMemcpyAsync(e->d_state, state, (size_t)e->n * e->ki.sd * 4, cudaMemcpyHostToDevice, e->stream));
     std::vector<int32_t> sbd, ept, epi;
@@ -1060,7 +1098,7 @@ int gymcuda_set_state(gymcuda_env* e, const float* state, const int32_t* aux, ui
     e->t = t;
     e->has_state = true;
     e->last_obs = nullptr;
-    return GYMCUDA_OK;
+    return clock_push(e);
 }
 
 static int observe_device(gymcuda_env* e) {
@@ -1087,6 +1125,7 @@ int gymcuda_observe(gymcuda_env* e, float* obs) {
 
 int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
     ENTER(e);
+    if (int _c = clock_pull(e)) return _c;
     if (!out) return fail(GYMCUDA_EINVAL, "out is null");
     CU_TRY(cudaMemcpyAsync(e->h_small, e->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     int32_t* pending = reinterpret_cast<int32_t*>(e->h_small + 2);   // (h_small[2] doubles as the done_count scratch of gymcuda_done_indices)
@@ -1108,6 +1147,10 @@ int gymcuda_get_stats(gymcuda_env* e, gymcuda_stats* out, int reset_counters) {
         e->env_steps = 0;
         e->invalid_seen = 0;
         e->stats_pending = false;   // reported and discarded: the next launch must not add it again
+        if (e->device_clock && e->seq > 0) {   // (a captured launch always folds: discard the count itself)
+            CU_TRY(cudaMemsetAsync(e->d_done_count + ((e->seq - 1) & 1), 0, sizeof(int32_t), e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+        }
     }
     return GYMCUDA_OK;
 }
@@ -1200,6 +1243,20 @@ int gymcuda_normalize_get(gymcuda_env* e, double* obs_mean, double* obs_var, dou
 // ------------------------------------------------------------------------------------------------
 // streams, pinned memory
 // ------------------------------------------------------------------------------------------------
+int gymcuda_set_device_clock(gymcuda_env* e, int on) {
+    ENTER(e);
+    if (on) {
+        if (e->device_clock) return GYMCUDA_OK;
+        if (!e->d_clock) CU_TRY(cudaMalloc(&e->d_clock, 2 * sizeof(unsigned long long)));
+        if (!e->stats_pending && e->seq > 0) CU_TRY(cudaMemsetAsync(e->d_done_count + ((e->seq - 1) & 1), 0, sizeof(int32_t), e->stream));
+        e->device_clock = true;
+        return clock_push(e);
+    }
+    if (int rc = clock_pull(e)) return rc;   // the host mirrors are exact again
+    e->device_clock = false;
+    return GYMCUDA_OK;
+}
+
 int gymcuda_set_stream(gymcuda_env* e, void* cuda_stream) {
     ENTER(e);
     CU_TRY(cudaStreamSynchronize(e->stream));

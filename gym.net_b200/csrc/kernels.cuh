@@ -71,6 +71,7 @@ struct StepArgs {
     int32_t bcast_action;
     uint32_t seq;                      // step-launch sequence number of this handle
     int fold_prev;                     // 1: done_count[(seq + 1) & 1] still holds the episode count of the previous step launch, not yet added to stats[0]
+    const unsigned long long* clock;   // device-resident {t, seq} (gymcuda_set_device_clock): read instead of the baked `t` / `seq`, so that a captured launch can be replayed
     EnvParams prm;
     // fused observation gather over NVLink peer memory (world == 0: off)
     int world, rank;
@@ -260,7 +261,7 @@ __device__ __forceinline__ uint64_t seed_of(const int32_t* seeds, uint64_t seed,
 // ---------------------------------------------------------------- step
 constexpr int STEP_BLOCK = 128;
 #ifndef GYMCUDA_STEP_BLOCK_BIG
-#define GYMCUDA_STEP_BLOCK_BIG 256
+#define GYMCUDA_STEP_BLOCK_BIG 128
 #endif
 constexpr int STEP_BLOCK_BIG = GYMCUDA_STEP_BLOCK_BIG;   // CTA of the batches of STEP_BIG_BATCH envs and more (classic envs)
 constexpr int STEP_BIG_BATCH = 1 << 20;
@@ -269,10 +270,14 @@ constexpr int STEP_BIG_BATCH = 1 << 20;
 template <class E, class = void> struct FusedReset : std::false_type {};
 template <class E> struct FusedReset<E, std::enable_if_t<E::FUSED_RESET>> : std::true_type {};
 
-// STEP_BLOCK = the launch shape at the config sizes; batches of a million envs and more run 1024-thread CTAs (one
-// same-address atomic per CTA on the done counter: 131 072 of them per launch at 16.7 M envs cost ~90 us, measured)
+// STEP_BLOCK = the launch shape at every size.  (BLOCK is a parameter because larger CTAs were measured for the batches of a
+// million envs and more -- fewer same-address atomics on the done counter: 128 / 256 / 512 / 1024 threads give 160 / 166 / 182 /
+// 238 us per 16.7 M-env CartPole launch without finished episodes, so STEP_BLOCK_BIG stays at 128.)
 template <class E, bool AUTO_RESET, bool LIMIT, int BLOCK = STEP_BLOCK>
 __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
+    // step index and launch sequence number: baked arguments, or the device-resident clock a CUDA-graph replay advances
+    const uint64_t now_t = p.clock ? (uint64_t)p.clock[0] : p.t;
+    const uint32_t now_seq = p.clock ? (uint32_t)p.clock[1] : p.seq;
     using S = typename E::S;
     using Act = typename E::Act;
     int tix = blockIdx.x * BLOCK + threadIdx.x;
@@ -301,8 +306,8 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
         if (p.sample) {
             ActionGen<E> gen;
             const uint64_t sseed = seed_of(p.seeds, p.seed, i);
-            gen.init(sseed, p.env_off + (uint32_t)i, p.t);
-            a = gen.next(sseed, p.env_off + (uint32_t)i, p.t);
+            gen.init(sseed, p.env_off + (uint32_t)i, now_t);
+            a = gen.next(sseed, p.env_off + (uint32_t)i, now_t);
             if (p.act_out) reinterpret_cast<Act*>(p.act_out)[i] = a;
         } else {
             a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
@@ -320,9 +325,9 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             if constexpr (FusedReset<E>::value) {
                 if (AUTO_RESET) ep_ord = p.episode[i];
                 const bool allow = AUTO_RESET && p.terminal_obs == nullptr;
-                r = E::step_ar(s, a, seed, gid, p.t, allow, (uint32_t)ep_ord);
+                r = E::step_ar(s, a, seed, gid, now_t, allow, (uint32_t)ep_ord);
             } else {
-                r = E::step(s, a, sbd, seed, gid, p.t);
+                r = E::step(s, a, sbd, seed, gid, now_t);
             }
             if (LIMIT) { ept += 1; if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }   // truncation folded into done
             if (p.ep_ret) {   // episode statistics (the caller-side bookkeeping of BasePlaySession.cs:58-69)
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
                     const int32_t ep = FusedReset<E>::value ? ep_ord : p.episode[i];
                     if (!r.did_reset) {
                         if (p.terminal_obs) { float to[E::OD]; E::obs(s, to); store_obs<E::OD, false>(p.terminal_obs, (size_t)i, to); }
-                        E::reset(s, seed, gid, (uint32_t)ep, p.t + 1, p.prm);
+                        E::reset(s, seed, gid, (uint32_t)ep, now_t + 1, p.prm);
                     }
                     p.episode[i] = ep + 1;
                 }
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             }
             if (mw != 0) {
                 int base = 0;
-                if (lane_w == 0) base = atomicAdd(p.done_count + (p.seq & 1), __popc(mw));
+                if (lane_w == 0) base = atomicAdd(p.done_count + (now_seq & 1), __popc(mw));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (done && p.done_idx != nullptr) p.done_idx[base + __popc(mw & ((1u << lane_w) - 1u))] = i;
                 if (p.sums != nullptr) {
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
                 }
             }
             if (blockIdx.x == 0 && threadIdx.x == 0 && p.part != 2) {   // fold the previous launch's count, zero the next launch's counter (see below)
-                int32_t* prev = p.done_count + ((p.seq + 1) & 1);
+                int32_t* prev = p.done_count + ((now_seq + 1) & 1);
                 if (p.fold_prev) p.stats[0] += (unsigned long long)*prev;
                 *prev = 0;
             }
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
                 const int e = reset_list[j];
                 const int32_t ep = p.episode[e];
                 S s{};
-                E::reset(s, seed_of(p.seeds, p.seed, e), p.env_off + (uint32_t)e, (uint32_t)ep, p.t + 1, p.prm);
+                E::reset(s, seed_of(p.seeds, p.seed, e), p.env_off + (uint32_t)e, (uint32_t)ep, now_t + 1, p.prm);
                 p.episode[e] = ep + 1;
                 E::store(p.state, p.aux, p.n, e, s);
                 float o[E::OD];
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             }
         }
     }
-    int32_t* count = p.done_count + (p.seq & 1);
+    int32_t* count = p.done_count + (now_seq & 1);
     if (threadIdx.x == 0) {
         int base = 0;
         if (total > 0) base = atomicAdd(count, total);   // the only contended atomic of the launch: one per CTA with a finished episode
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             // the other counter holds the total of the PREVIOUS step launch (complete: same stream): it joins the running
             // number of finished episodes here -- one plain add per launch instead of one more atomic per CTA -- and is
             // zeroed for the next launch.  (The host adds the not-yet-folded count of the latest launch when it reports.)
-            int32_t* prev = p.done_count + ((p.seq + 1) & 1);
+            int32_t* prev = p.done_count + ((now_seq + 1) & 1);
             if (p.fold_prev) p.stats[0] += (unsigned long long)*prev;
             *prev = 0;
         }
@@ -489,6 +494,9 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
         }
     }
 }
+
+// advances the device-resident clock after the kernels of a step (device-clock mode only)
+static __global__ void clock_tick_kernel(unsigned long long* clock, unsigned long long steps) { clock[0] += steps; clock[1] += 1ull; }
 
 // Observation gather of an env whose step is several kernels (LunarLander: contact partition + two step kernels): the
 // step writes this rank's slot of its OWN gather buffer; this kernel then pushes the slot into the same slot of every

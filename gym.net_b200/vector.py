@@ -269,6 +269,10 @@ class CudaVecEnv:
         N.check(self._L.gymcuda_normalize_reset(self._h))
 
     # ---- device-pointer API (torch tensors / raw pointers) ------------------------------------------
+    def SetDeviceClock(self, on=True):
+        """Step index and launch sequence number on the device: makes a captured StepDevice replayable (CUDA graphs)."""
+        N.check(self._L.gymcuda_set_device_clock(self._h, 1 if on else 0))
+
     def SetStream(self, cuda_stream):
         N.check(self._L.gymcuda_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 

@@ -228,6 +228,15 @@ int gymcuda_normalize_reset(gymcuda_env* env);
 /* Use the caller's CUDA stream (cudaStream_t) for every launch and copy; NULL restores the
  * handle's own stream (to target the legacy default stream pass cudaStreamLegacy, not 0). */
 int gymcuda_set_stream(gymcuda_env* env, void* cuda_stream);
+/* CUDA-graph capture of gymcuda_step_device (and gymcuda_step_gather_device): by default the global step index `t` (it keys
+ * LunarLander's per-step dispersion draws) and the launch sequence number (it selects the done-list counter) are host
+ * state baked into the kernel arguments, so a REPLAYED launch would repeat them.  on != 0 moves both into device memory:
+ * the step kernels read them there and a one-thread kernel advances them after every step, so a captured step can be
+ * replayed any number of times and each replay is the next step -- bit-identical to the same steps launched one by one.
+ * Capture with the handle's stream set to the capturing stream (gymcuda_set_stream); the actions / outputs are the static
+ * buffers of the graph.  Every other entry point keeps working in this mode (it synchronises to read the clock back), but
+ * only the *_device step calls may be captured.  on == 0 returns to host-side counters (synchronises). */
+int gymcuda_set_device_clock(gymcuda_env* env, int on);
 int gymcuda_sync(gymcuda_env* env);
 int gymcuda_host_alloc(void** ptr, size_t bytes); /* pinned (page-locked) host memory */
 int gymcuda_host_free(void* ptr);

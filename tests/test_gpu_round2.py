@@ -244,3 +244,57 @@ def test_two_handles_from_two_host_threads():
     for tag, _, _ in specs:
         assert len(results[tag]) == len(results[tag + "_alone"])
         assert all(np.array_equal(x, y) for x, y in zip(results[tag], results[tag + "_alone"]))
+
+
+@pytest.mark.parametrize("name,n", [("CartPole-v1", 65536), ("Acrobot-v1", 4096), ("LunarLander-v2", 2048)])
+def test_step_device_under_cuda_graph_capture_and_replay(name, n):
+    """gymcuda_set_device_clock: a StepDevice captured into a CUDA graph and replayed k times == k steps of the oracle with the
+    same actions (LunarLander's per-step dispersion draws are keyed by the step index, which the replay must advance; the
+    done list and the episode counter must follow the replays too); then ordinary launches continue from the replayed state."""
+    import torch
+    k = 60
+    limit = 40 if name == "LunarLander-v2" else 0
+    o = O.OracleEnv(KINDS[name], n, seed=6, env_id_offset=10, auto_reset=True, mode=O.MODE_F32, time_limit=limit)
+    env = MAKE[name](n, seed=6, env_id_offset=10, auto_reset=True, time_limit=limit)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    dev = torch.device("cuda", 0)
+    s = torch.cuda.Stream(device=dev)
+    env.SetStream(s.cuda_stream)
+    env.SetDeviceClock(True)
+    act = torch.zeros(n, dtype=torch.int32, device=dev)
+    obs = torch.empty((n, env.obs_dim), device=dev); rew = torch.empty(n, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(12)
+    a0 = rng.integers(0, env.act_n, n).astype(np.int32)
+    with torch.cuda.stream(s):               # one ordinary launch first (also warms the lazily created resources)
+        act.copy_(torch.from_numpy(a0).to(dev))
+        env.StepDevice(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr())
+    s.synchronize()
+    wo, wr, wd = o.step(a0)
+    assert np.array_equal(obs.cpu().numpy(), wo)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        env.StepDevice(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr())
+    episodes = int(wd.sum())
+    for j in range(k):
+        a = rng.integers(0, env.act_n, n).astype(np.int32)
+        act.copy_(torch.from_numpy(a).to(dev))
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        wo, wr, wd = o.step(a)
+        assert np.array_equal(done.cpu().numpy(), wd), (name, j)
+        assert np.array_equal(obs.cpu().numpy(), wo) and np.array_equal(rew.cpu().numpy(), wr), (name, j)
+        episodes += int(wd.sum())
+        if j % 20 == 7:
+            assert np.array_equal(np.sort(env.DoneIndices()), np.nonzero(wd)[0])
+    assert env.Stats()["episodes"] == episodes
+    st, aux, t = o.get_state()
+    gs, ga, gt = env.GetState()
+    assert gt == t and np.array_equal(gs, st.astype(np.float32))
+    env.SetDeviceClock(False)               # back to host counters: ordinary steps continue the same trajectory
+    for _ in range(5):
+        a = rng.integers(0, env.act_n, n).astype(np.int32)
+        go, gr, gd = env.StepBatch(a)
+        wo, wr, wd = o.step(a)
+        assert np.array_equal(go, wo) and np.array_equal(gd, wd)
+    env.Close()
