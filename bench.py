@@ -346,6 +346,33 @@ def measure_envs(G, torch, dist, dev, rank, world, local_rank, peak, sm_mhz):
         "hbm_gbs_per_gpu": rate / world * 25 / 1e9, "frac": rate / world * 25 / 1e9 / peak,
         "note": "action 4 B read + obs 16 B + reward 4 B + done 1 B written per env step; the per-launch gymcuda_step_device figure of the same batch is in profiles/"}
     env.Close()
+    del o, r, d, acts
+
+    # per-launch steps without per-launch host cost: 16 gymcuda_step_device calls captured into ONE CUDA graph
+    # (gymcuda_set_device_clock makes the captured steps replayable), device-resident actions -- CartPole, 65 536 envs
+    n, G16 = 65536, 16
+    env = G.make("CartPole-v1", n, seed=0, device=local_rank, env_id_offset=rank * n, auto_reset=True)
+    env.SetStream(stream.cuda_stream)
+    env.ResetBatch()
+    env.SetDeviceClock(True)
+    o = torch.empty((n, 4), dtype=torch.float32, device=dev); r = torch.empty((n,), dtype=torch.float32, device=dev); d = torch.empty((n,), dtype=torch.uint8, device=dev)
+    acts = torch.randint(0, 2, (n,), dtype=torch.int32, device=dev)
+    step1 = lambda: env.StepDevice(acts.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr())   # noqa: E731
+    ms_plain = timed(step1, 200)
+    side = torch.cuda.Stream(device=dev)
+    env.SetStream(side.cuda_stream)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(G16):
+            step1()
+    env.SetStream(stream.cuda_stream)
+    ms_graph = timed(graph.replay, 50) / G16
+    out["CartPole-v1 step via CUDA graph @65536"] = {
+        "mode": "gymcuda_step_device captured %d times into one CUDA graph and replayed (device-resident step clock)" % G16, "num_envs_per_gpu": n,
+        "us_per_step_graph": ms_graph * 1e3, "us_per_step_plain_launch": ms_plain * 1e3, "env_steps_per_s": world * n / (ms_graph * 1e-3),
+        "bound": "launch_latency", "note": "one dependent chain of load -> step -> store -> counters per step; the working set lives in L2"}
+    env.SetDeviceClock(False)
+    env.Close()
     return out
 
 

@@ -150,6 +150,8 @@ struct gymcuda_env {
     volatile int* h_invalid; // mapped pinned flags: [0] set by the step kernel when it rejects an action,
     int* d_invalid_flag;     //                      [1] set by gather_wait_kernel on a timeout (1 + missing rank)
     int32_t *d_done_idx, *d_done_count;
+    int32_t *d_blk_cnt, *d_blk_off, *d_tmp_idx;   // per-CTA counts (and their exclusive scan) / sub-lists of the last step launch (the done list is built on demand)
+    bool done_list_stale;             // the last step launch left blk_cnt / tmp_idx, d_done_idx has not been built from them yet
     unsigned long long* d_stats;
     float* d_ep_ret;          // GYMCUDA_FLAG_EPISODE_STATS
     double* d_sums;
@@ -383,7 +385,7 @@ int gymcuda_destroy(gymcuda_env* e) {
     if (e->h_invalid) cudaFreeHost((void*)e->h_invalid);
     for (int k = 0; k < 4; ++k) cudaFree(e->scratch[k]);
     cudaFree(e->d_norm_acc); cudaFree(e->d_norm_ret); cudaFree(e->d_term_own); cudaFree(e->d_clock);
-    cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
+    cudaFree(e->d_done_idx); cudaFree(e->d_done_count); cudaFree(e->d_blk_cnt); cudaFree(e->d_blk_off); cudaFree(e->d_tmp_idx); cudaFree(e->d_stats); cudaFree(e->d_ep_ret); cudaFree(e->d_sums);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -423,6 +425,12 @@ static int create_impl(const gymcuda_config* cfg, gymcuda_env* e) {
     CU_TRY(cudaMalloc(&e->d_mask, n));
     CU_TRY(cudaMalloc(&e->d_done_idx, n * 4));
     CU_TRY(cudaMalloc(&e->d_done_count, 2 * sizeof(int32_t)));
+    {
+        const size_t nb = (n + STEP_BLOCK - 1) / STEP_BLOCK;
+        CU_TRY(cudaMalloc(&e->d_blk_cnt, (nb + 1) * sizeof(int32_t)));
+        CU_TRY(cudaMalloc(&e->d_blk_off, (nb + 1) * sizeof(int32_t)));
+        CU_TRY(cudaMalloc(&e->d_tmp_idx, nb * STEP_BLOCK * sizeof(int32_t)));
+    }
     CU_TRY(cudaMalloc(&e->d_stats, 2 * sizeof(unsigned long long)));
     CU_TRY(cudaHostAlloc((void**)&e->h_small, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     if (e->ep_stats) {
@@ -627,7 +635,7 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     StepArgs a{};
     a.state = e->d_state; a.aux = e->d_aux; a.prm = e->prm; a.sbd = e->d_sbd; a.ep_t = e->d_ept; a.episode = e->d_episode; a.seeds = e->d_seeds;
     a.actions = d_actions; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
-    a.done_idx = e->d_done_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
+    a.done_idx = e->d_done_idx; a.blk_cnt = e->d_blk_cnt; a.tmp_idx = e->d_tmp_idx; a.done_count = e->d_done_count; a.stats = e->d_stats; a.host_invalid = e->d_invalid_flag; a.ep_ret = e->d_ep_ret; a.sums = e->d_sums; a.done_bits = e->done_bits ? 1 : 0;
     a.n = e->n; a.env_off = e->cfg.env_id_offset; a.seed = e->seed; a.t = e->t; a.limit = e->limit;
     a.use_bcast = use_bcast; a.bcast_action = bcast; a.seq = e->seq; a.fold_prev = e->stats_pending ? 1 : 0;
     if (e->device_clock) { a.clock = e->d_clock; a.fold_prev = 1; }   // (entering the mode zeroed the other counter if nothing was pending)
@@ -643,6 +651,8 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
         a.block_counter = reinterpret_cast<unsigned*>(e->g_local + e->g_counter_off);
     }
     CU_TRY(dispatch_step(e, a));
+    // which epilogue ran: the warp-granular one of the partitioned LunarLander step writes d_done_idx itself
+    e->done_list_stale = !(is_lunar(e) && a.world == 0);
     if (e->device_clock) { clock_tick_kernel<<<1, 1, 0, e->stream>>>(e->d_clock, 1ull); CU_TRY(cudaGetLastError()); }
     e->stats_pending = true;   // this launch's episode count sits in done_count[seq & 1] until the next launch folds it into stats[0]
     e->t += 1;
@@ -1006,11 +1016,27 @@ int gymcuda_box_sample(int device, uint64_t seed, uint64_t index, const float* l
 // ------------------------------------------------------------------------------------------------
 // done compaction
 // ------------------------------------------------------------------------------------------------
+// builds d_done_idx from the per-CTA sub-lists of the last step launch (once per launch)
+static int done_list_build(gymcuda_env* e) {
+    // (under the device-resident clock a graph replay may have stepped since the last build without the host knowing: rebuild.
+    // The scan works on a copy, so building twice from the same launch gives the same list.)
+    if (!e->done_list_stale && !e->device_clock) return GYMCUDA_OK;
+    if (is_lunar(e) && !e->done_list_stale) return GYMCUDA_OK;   // partitioned LunarLander step: the kernel wrote the list itself
+    const int nb = (e->n + STEP_BLOCK - 1) / STEP_BLOCK;
+    CU_TRY(cudaMemcpyAsync(e->d_blk_off, e->d_blk_cnt, (size_t)(nb + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    partition_scan_kernel<<<1, 1024, 0, e->stream>>>(e->d_blk_off, nb);
+    done_list_scatter_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(e->d_blk_off, e->d_tmp_idx, nb, STEP_BLOCK, e->d_done_idx);
+    CU_TRY(cudaGetLastError());
+    e->done_list_stale = false;
+    return GYMCUDA_OK;
+}
+
 int gymcuda_done_indices(gymcuda_env* e, int32_t* idx, int32_t* count) {
     ENTER(e);
     if (int _c = clock_pull(e)) return _c;
     if (!count) return fail(GYMCUDA_EINVAL, "count is null");
     if (e->seq == 0) { *count = 0; return GYMCUDA_OK; }
+    if (idx) { if (int rc = done_list_build(e)) return rc; }
     int32_t* h = reinterpret_cast<int32_t*>(e->h_small + 2);
     CU_TRY(cudaMemcpyAsync(h, e->d_done_count + ((e->seq - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
@@ -1025,7 +1051,7 @@ int gymcuda_done_indices(gymcuda_env* e, int32_t* idx, int32_t* count) {
 int gymcuda_done_indices_device(gymcuda_env* e, const int32_t** d_idx, const int32_t** d_count) {
     ENTER(e);
     if (int _c = clock_pull(e)) return _c;
-    if (d_idx) *d_idx = e->d_done_idx;
+    if (d_idx) { if (int rc = done_list_build(e)) return rc; *d_idx = e->d_done_idx; }
     if (d_count) *d_count = e->seq == 0 ? e->d_done_count : e->d_done_count + ((e->seq - 1) & 1);
     return GYMCUDA_OK;
 }

@@ -55,7 +55,9 @@ struct StepArgs {
     float* obs;
     float* reward;
     uint8_t* done;
-    int32_t* done_idx;                 // may be null
+    int32_t* done_idx;                 // may be null; written directly only by the warp-granular epilogue (LunarLander)
+    int32_t* blk_cnt;                  // [CTAs + 1] finished episodes per CTA of this launch   } the CTA-level epilogue: the compact list is
+    int32_t* tmp_idx;                  // [CTAs * BLOCK] every CTA's own compact sub-list        } built on demand by done_list_scatter_kernel
     int32_t* done_count;               // [2], indexed by the parity of `seq`
     unsigned long long* stats;         // [0] episodes finished, [1] invalid actions
     float* ep_ret;                     // per-env running episode return (null: statistics off)
@@ -406,7 +408,6 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
 
     // ---- done compaction: warp ballot + popc prefix -> block scan -> one atomicAdd per block
     __shared__ int warp_cnt[BLOCK / 32];
-    __shared__ int block_base;
     __shared__ __align__(16) uint8_t done_tile[BLOCK];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, done);
@@ -455,11 +456,16 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             }
         }
     }
+    // The done LIST is not built here: a compact list needs an exclusive prefix over the CTAs, i.e. one same-address atomic
+    // WITH its return value per CTA, and at 131 072 CTAs (16.7 M envs) the queue on that one address alone lasts ~57 us while
+    // every CTA waits for its turn (measured: 160 us per launch without finished episodes, 217 us with).  Instead every CTA
+    // leaves its count and its own compact sub-list (blk_cnt, tmp_idx) and only adds to the step's counter with a
+    // fire-and-forget reduction; gymcuda_done_indices* builds the list when it is asked for (scan + scatter, kernels below).
     int32_t* count = p.done_count + (now_seq & 1);
+    if (done && p.tmp_idx != nullptr) p.tmp_idx[(size_t)blockIdx.x * BLOCK + warp_off + __popc(m & ((1u << lane) - 1u))] = i;
     if (threadIdx.x == 0) {
-        int base = 0;
-        if (total > 0) base = atomicAdd(count, total);   // the only contended atomic of the launch: one per CTA with a finished episode
-        block_base = base;
+        if (p.blk_cnt != nullptr) p.blk_cnt[blockIdx.x] = total;
+        if (total > 0) atomicAdd(count, total);   // result unused: RED
         if (blockIdx.x == 0 && p.part != 2) {
             // the other counter holds the total of the PREVIOUS step launch (complete: same stream): it joins the running
             // number of finished episodes here -- one plain add per launch instead of one more atomic per CTA -- and is
@@ -468,10 +474,6 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             if (p.fold_prev) p.stats[0] += (unsigned long long)*prev;
             *prev = 0;
         }
-    }
-    if (p.done_idx != nullptr && total > 0) {
-        __syncthreads();
-        if (done) p.done_idx[block_base + warp_off + __popc(m & ((1u << lane) - 1u))] = i;
     }
     if (p.sums != nullptr && m != 0) {   // finished episodes of this warp -> one atomic pair
         double rs = done ? (double)fin_ret : 0.0, ls = done ? (double)fin_len : 0.0;
@@ -881,6 +883,15 @@ static __global__ void __launch_bounds__(PART_BLOCK) partition_scatter_kernel(co
         if (free_flight) perm[free_base + free_rank] = i;
         else perm[total_free + (blockIdx.x * PART_BLOCK - free_base) + (local - free_rank)] = i;
     }
+}
+
+// The done list on demand (gymcuda_done_indices*): blk_off = exclusive scan of the per-CTA counts of the last step launch
+// (partition_scan_kernel, in place: blk_off[nb] = total), then one warp per CTA copies its sub-list to its place.
+static __global__ void __launch_bounds__(256) done_list_scatter_kernel(const int32_t* blk_off, const int32_t* tmp_idx, int nb, int block, int32_t* done_idx) {
+    const int b = blockIdx.x * 8 + (int)(threadIdx.x >> 5);
+    if (b >= nb) return;
+    const int base = blk_off[b], cnt = blk_off[b + 1] - base;
+    for (int k = (int)(threadIdx.x & 31); k < cnt; k += 32) done_idx[base + k] = tmp_idx[(size_t)b * block + k];
 }
 
 // ActionSpace.Sample() for every env at step index t: the same draws the rollout kernel consumes, so

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>   // the stub
 
 #include <functional>
+#include <vector>
 
 #include "env_classic.cuh"
 #include "lunar.cuh"
@@ -249,18 +250,29 @@ int hostsim_step_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32
     a.prm = EnvParams{gravity, wind_power, turbulence_power, use_wind};
     a.world = g_gather.world; a.rank = g_gather.rank; a.gseq = g_gather.gseq; a.block_counter = g_gather.block_counter;
     for (int r = 0; r < g_gather.world; ++r) { a.peer_obs[r] = g_gather.peer_obs[r]; a.peer_flags[r] = g_gather.peer_flags[r]; }
+    const bool block_epilogue = kind < 5 || g_gather.world > 0;   // LunarLander without the fused gather: warp-granular epilogue, writes done_idx itself
     g_gather.world = 0;   // one launch
     a.terminal_obs = g_terminal_obs; g_terminal_obs = nullptr;
+    // the CTA-level epilogue leaves per-CTA counts and sub-lists; the done list is built from them afterwards, as gymcuda_done_indices does
+    const int nb = (n + STEP_BLOCK - 1) / STEP_BLOCK;
+    std::vector<int32_t> blk_cnt((size_t)nb + 1, 0), tmp_idx((size_t)nb * STEP_BLOCK, -1);
+    a.blk_cnt = blk_cnt.data(); a.tmp_idx = tmp_idx.data();
+    int rc = -1;
     switch (kind) {
-        case 0: return k_step<CartPole>(a, auto_reset);
-        case 1: return k_step<Pendulum>(a, auto_reset);
-        case 2: return k_step<MountainCar>(a, auto_reset);
-        case 3: return k_step<MountainCarCont>(a, auto_reset);
-        case 4: return k_step<Acrobot>(a, auto_reset);
-        case 5: return k_step<LunarLander>(a, auto_reset);
-        case 6: return k_step<LunarLanderCont>(a, auto_reset);
+        case 0: rc = k_step<CartPole>(a, auto_reset); break;
+        case 1: rc = k_step<Pendulum>(a, auto_reset); break;
+        case 2: rc = k_step<MountainCar>(a, auto_reset); break;
+        case 3: rc = k_step<MountainCarCont>(a, auto_reset); break;
+        case 4: rc = k_step<Acrobot>(a, auto_reset); break;
+        case 5: rc = k_step<LunarLander>(a, auto_reset); break;
+        case 6: rc = k_step<LunarLanderCont>(a, auto_reset); break;
     }
-    return -1;
+    if (rc == 0 && block_epilogue && done_idx != nullptr) {
+        int32_t* cnt = blk_cnt.data(); const int32_t* tmp = tmp_idx.data();
+        launch(1, 1024, [&] { partition_scan_kernel(cnt, nb); });
+        launch((nb + 7) / 8, 256, [&] { done_list_scatter_kernel(cnt, tmp, nb, STEP_BLOCK, done_idx); });
+    }
+    return rc;
 }
 
 // reset_kernel (mask may be null = all)
