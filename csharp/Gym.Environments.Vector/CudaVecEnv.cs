@@ -137,6 +137,12 @@ namespace Gym.Environments.Vector {
             Array.Resize(ref idx, count);
             return idx;
         }
+        /// <summary>Env.Render for `envIds` (null: the first `count` envs), rasterised on the device: RGB8 [count][height][width][3].</summary>
+        public byte[] Render(int[] envIds, int count, int width = 600, int height = 400) {
+            var rgb = new byte[count * width * height * 3];
+            Native.Check(Native.gymcuda_render(_h, envIds, count, width, height, rgb));
+            return rgb;
+        }
         public GymCudaStats Stats(bool reset = false) { Native.Check(Native.gymcuda_get_stats(_h, out var s, reset ? 1 : 0)); return s; }
 
         // ---- observation / reward normalisation on device (what callers otherwise keep by hand, BasePlaySession.cs:58-69)

@@ -84,6 +84,8 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_get_state(GymCudaHandle env, float[] state, int[] aux, out ulong t);
         [DllImport(Lib)] internal static extern int gymcuda_set_state(GymCudaHandle env, float[] state, int[] aux, ulong t);
         [DllImport(Lib)] internal static extern int gymcuda_observe(GymCudaHandle env, float[] obs);
+        [DllImport(Lib)] internal static extern int gymcuda_render_device(GymCudaHandle env, IntPtr dEnvIds, int count, int width, int height, IntPtr dRgb);
+        [DllImport(Lib)] internal static extern int gymcuda_render(GymCudaHandle env, int[] envIds, int count, int width, int height, byte[] rgb);
         [DllImport(Lib)] internal static extern int gymcuda_get_stats(GymCudaHandle env, out GymCudaStats stats, int resetCounters);
         [DllImport(Lib)] internal static extern int gymcuda_normalize_config(GymCudaHandle env, float gamma, float epsilon, float clipObs, float clipReward);
         [DllImport(Lib)] internal static extern int gymcuda_normalize(GymCudaHandle env, float[] obs, float[] reward, byte[] done, int update);

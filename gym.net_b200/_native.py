@@ -73,6 +73,8 @@ SYMBOLS = {
     "gymcuda_get_state": (_I, [_VP, _VP, _VP, C.POINTER(_U64)]),
     "gymcuda_set_state": (_I, [_VP, _VP, _VP, _U64]),
     "gymcuda_observe": (_I, [_VP, _VP]),
+    "gymcuda_render_device": (_I, [_VP, _VP, _I, _I, _I, _VP]),
+    "gymcuda_render": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "gymcuda_get_stats": (_I, [_VP, C.POINTER(Stats), _I]),
     "gymcuda_normalize_config": (_I, [_VP, C.c_float, C.c_float, C.c_float, C.c_float]),
     "gymcuda_normalize_device": (_I, [_VP, _VP, _VP, _VP, _I]),

@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "normalize.cuh"
 #include "box_sample.cuh"
+#include "render.cuh"
 #ifdef GYMCUDA_WITH_LUNAR
 #include "lunar_launch.h"
 #endif
@@ -1269,6 +1270,46 @@ int gymcuda_normalize_get(gymcuda_env* e, double* obs_mean, double* obs_var, dou
 // ------------------------------------------------------------------------------------------------
 // streams, pinned memory
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Env.Render, headless and batched (render.cuh / lunar_render.cuh)
+// ------------------------------------------------------------------------------------------------
+int gymcuda_render_device(gymcuda_env* e, const int32_t* d_env_ids, int count, int width, int height, uint8_t* d_rgb) {
+    ENTER(e);
+    TRACE("render_device");
+    if (!d_rgb) return fail(GYMCUDA_EINVAL, "d_rgb is null");
+    if (count <= 0 || width <= 0 || height <= 0 || width > 4096 || height > 4096) return fail(GYMCUDA_EINVAL, "count, width and height must be positive (at most 4096 x 4096)");
+    if (!d_env_ids && count > e->n) return fail(GYMCUDA_EINVAL, "count %d exceeds the %d envs of the handle", count, e->n);
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "Render() before Reset()");
+    RenderArgs a{e->d_state, d_env_ids, d_rgb, e->n, count, width, height};
+    if (e->cfg.env_kind == GYMCUDA_CARTPOLE) {
+        const dim3 grid((unsigned)render_grid_x(width, height), (unsigned)count);
+        render_cartpole_kernel<<<grid, RENDER_BLOCK, 0, e->stream>>>(a);
+        CU_TRY(cudaGetLastError());
+        return GYMCUDA_OK;
+    }
+#ifdef GYMCUDA_WITH_LUNAR
+    if (is_lunar(e)) { CU_TRY(lunar_launch_render(e->stream, a)); return GYMCUDA_OK; }
+#endif
+    return fail(GYMCUDA_EINVAL, "Render() exists in the reference for CartPoleEnv and LunarLanderEnv only");
+}
+
+int gymcuda_render(gymcuda_env* e, const int32_t* env_ids, int count, int width, int height, uint8_t* rgb) {
+    ENTER(e);
+    if (!rgb) return fail(GYMCUDA_EINVAL, "rgb is null");
+    if (count <= 0 || width <= 0 || height <= 0 || width > 4096 || height > 4096) return fail(GYMCUDA_EINVAL, "count, width and height must be positive (at most 4096 x 4096)");
+    if (env_ids) for (int k = 0; k < count; ++k) if (env_ids[k] < 0 || env_ids[k] >= e->n) return fail(GYMCUDA_EINVAL, "env id %d out of range [0, %d)", env_ids[k], e->n);
+    const size_t bytes = (size_t)count * width * height * 3;
+    void *d_rgb = nullptr, *d_ids = nullptr;
+    cudaError_t ce = scratch_reserve(e, 0, bytes, &d_rgb);
+    if (ce == cudaSuccess && env_ids) ce = scratch_reserve(e, 3, (size_t)count * 4, &d_ids);
+    if (ce == cudaSuccess && env_ids) ce = cudaMemcpyAsync(d_ids, env_ids, (size_t)count * 4, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(ce == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "render staging failed: %s", cudaGetErrorString(ce)); }
+    if (int rc = gymcuda_render_device(e, static_cast<const int32_t*>(d_ids), count, width, height, static_cast<uint8_t*>(d_rgb))) return rc;
+    CU_TRY(cudaMemcpyAsync(rgb, d_rgb, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return GYMCUDA_OK;
+}
+
 int gymcuda_set_device_clock(gymcuda_env* e, int on) {
     ENTER(e);
     if (on) {

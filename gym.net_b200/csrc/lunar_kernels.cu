@@ -6,6 +6,7 @@
 #include "lunar_launch.h"
 
 #include "lunar.cuh"
+#include "lunar_render.cuh"
 
 namespace gymcuda {
 
@@ -39,6 +40,12 @@ cudaError_t lunar_launch_sample(bool continuous, int grid, cudaStream_t s, const
 
 cudaError_t lunar_launch_ctor(bool continuous, int grid, cudaStream_t s, const ResetArgs& a) {
     if (continuous) ctor_kernel<LunarLanderCont><<<grid, 128, 0, s>>>(a); else ctor_kernel<LunarLander><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t lunar_launch_render(cudaStream_t s, const RenderArgs& a) {
+    const dim3 grid((unsigned)render_grid_x(a.width, a.height), (unsigned)a.count);
+    render_lunar_kernel<<<grid, RENDER_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 

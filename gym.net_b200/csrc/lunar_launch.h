@@ -16,5 +16,7 @@ cudaError_t lunar_launch_step(bool continuous, bool has_pairs, bool auto_reset, 
 cudaError_t lunar_launch_reset(bool continuous, int grid, cudaStream_t stream, const ResetArgs& a);
 cudaError_t lunar_launch_sample(bool continuous, int grid, cudaStream_t stream, const SampleArgs& a);
 cudaError_t lunar_launch_ctor(bool continuous, int grid, cudaStream_t stream, const ResetArgs& a);
+struct RenderArgs;
+cudaError_t lunar_launch_render(cudaStream_t stream, const RenderArgs& a);   // LunarLanderEnv.Render (lunar_render.cuh)
 
 }  // namespace gymcuda

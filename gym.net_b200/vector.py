@@ -234,6 +234,18 @@ class CudaVecEnv:
         N.check(self._L.gymcuda_observe(self._h, _ptr(obs)))
         return obs
 
+    def Render(self, env_ids=None, width=600, height=400, count=None):
+        """Env.Render(mode: "rgb_array") for a subset of the batch, rasterised on the device: uint8 [count, height, width, 3]
+        (CartPole and LunarLander, the two envs the reference can render)."""
+        if env_ids is None:
+            k = int(count if count is not None else min(self.NumberOfEnvironments, 1))
+            ids = None
+        else:
+            ids = np.ascontiguousarray(env_ids, dtype=np.int32); k = int(ids.size)
+        out = np.empty((k, int(height), int(width), 3), np.uint8)
+        N.check(self._L.gymcuda_render(self._h, _ptr(ids), k, int(width), int(height), _ptr(out)))
+        return out
+
     def Stats(self, reset=False):
         s = N.Stats()
         N.check(self._L.gymcuda_get_stats(self._h, C.byref(s), 1 if reset else 0))

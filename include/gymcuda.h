@@ -197,6 +197,17 @@ int gymcuda_set_state(gymcuda_env* env, const float* state, const int32_t* aux, 
 /* Current observations of all envs (no stepping). */
 int gymcuda_observe(gymcuda_env* env, float* obs);
 
+/* ---- Env.Render, headless and batched -------------------------------------------------------------
+ * What CartPoleEnv.Render (CartPoleEnv.cs:69-135) and LunarLanderEnv.Render (LunarLanderEnv.cs:776-890) draw, rasterised on
+ * the device for `count` envs of the batch (env_ids, or envs 0..count-1 when NULL) into rgb [count][height][width][3] uint8:
+ * the reference's 600 x 400 canvas sampled at width x height pixel centres (600 x 400 gives the reference's frame; 84 x 84
+ * gives the down-sampled picture an image-based agent wants without materialising the large one).  Same primitives, colours
+ * and draw order as the reference; coverage is decided at the pixel centre with NO anti-aliasing (ImageSharp's edge blending
+ * is not reproduced), LunarLander's exhaust particles are not simulated and not drawn.  The other env kinds have no Render in
+ * the reference: GYMCUDA_EINVAL.  *_device: device pointers, asynchronous on the handle's stream. */
+int gymcuda_render_device(gymcuda_env* env, const int32_t* d_env_ids, int count, int width, int height, uint8_t* d_rgb);
+int gymcuda_render(gymcuda_env* env, const int32_t* env_ids, int count, int width, int height, uint8_t* rgb);
+
 /* ---- episode statistics: what callers keep by hand (examples/.../BasePlaySession.cs:58-69) -- accumulated
  * on device by every step / rollout ------------------------- */
 typedef struct gymcuda_stats {

@@ -298,3 +298,47 @@ def test_step_device_under_cuda_graph_capture_and_replay(name, n):
         wo, wr, wd = o.step(a)
         assert np.array_equal(go, wo) and np.array_equal(gd, wd)
     env.Close()
+
+
+def test_render_cartpole_and_lunarlander_headless_batched():
+    """Env.Render rasterised on the device for a subset of the batch, against the numpy restatement of the same
+    primitives / colours / draw order (tests/render_ref.py), at the reference's 600 x 400 and at a down-sampled size."""
+    import render_ref as RR
+    env = G.CartPoleVecEnv(64, seed=3, auto_reset=True); env.ResetBatch()
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        env.StepBatch(rng.integers(0, 2, 64).astype(np.int32))
+    st, _, _ = env.GetState()
+    ids = np.array([0, 17, 63], np.int32)
+    for (w, h) in ((600, 400), (150, 100)):
+        got = env.Render(ids, w, h)
+        assert got.shape == (3, h, w, 3) and got.dtype == np.uint8
+        for k, e in enumerate(ids):
+            want = RR.cartpole(st[e], w, h)
+            assert (got[k] != want).any(axis=2).mean() < 1e-3
+        colours = {tuple(c) for c in got[0].reshape(-1, 3)}
+        assert colours == {(255, 255, 255), (0, 0, 0), (204, 153, 102)}
+    first = env.Render(None, 600, 400, count=2)
+    assert np.array_equal(first[1], env.Render(np.array([1], np.int32))[0])
+    env.Close()
+    ll = G.LunarLanderVecEnv(48, seed=5, auto_reset=True); ll.ResetBatch()
+    for _ in range(30):
+        ll.StepBatch(rng.integers(0, 4, 48).astype(np.int32))
+    st, _, _ = ll.GetState()
+    ids = np.array([3, 40], np.int32)
+    for (w, h) in ((600, 400), (84, 84)):
+        got = ll.Render(ids, w, h)
+        for k, e in enumerate(ids):
+            want = RR.lunar(st[e], w, h)
+            assert (got[k] != want).any(axis=2).mean() < 1e-3
+    full = ll.Render(ids[:1], 600, 400)[0]
+    colours = {tuple(c) for c in full.reshape(-1, 3)}
+    assert {(0, 0, 0), (255, 255, 255), (255, 0, 0), (128, 102, 230), (204, 204, 0)} <= colours
+    assert (full[396] == 255).all(axis=1).mean() > 0.9                                   # ground near the bottom (the last row is the red base edge)
+    odd = ll.Render(ids[:1], 83, 61)[0]                                                  # pixel count not a multiple of 4: byte stores
+    assert (odd != RR.lunar(st[ids[0]], 83, 61)).any(axis=2).mean() < 2e-3
+    ll.Close()
+    pend = G.PendulumVecEnv(4); pend.ResetBatch()
+    with pytest.raises(ValueError):
+        pend.Render(None, 64, 64, count=1)               # the reference has no Render for it
+    pend.Close()

@@ -35,4 +35,35 @@ for _ in range(120):      # long enough for contacts: exercises the contact part
     obs, r, d = ll.StepBatch(np.full(2500, 0, np.int32))
 print("contacts", float((obs[:, 6:] > 0).any(1).mean()))
 ll.Close()
+# round-2 entry points: terminal observations, step_many (valid + rejected actions), the done list built on demand, Box.Sample,
+# the device-resident clock with a captured + replayed step
+import torch
+for name, n in (("CartPole-v1", 3001), ("Acrobot-v1", 777), ("LunarLander-v2", 700)):
+    env = G.make(name, n, seed=4, auto_reset=True, time_limit=20)
+    env.ResetBatch()
+    term = np.zeros((n, env.obs_dim), np.float32); env.SetTerminalObs(term)
+    acts = rng.integers(0, env.act_n, (30, n)).astype(np.int32)
+    env.StepMany(acts)
+    if name != "CartPole-v1":
+        acts[3, 5] = 99
+        try:
+            env.StepMany(acts[:6])
+        except G.InvalidActionError:
+            pass
+    for _ in range(4):
+        env.StepBatch(acts[0]); env.DoneIndices(); env.DoneIndices()
+    env.SetTerminalObs(None)
+    dev = torch.device("cuda", 0); s = torch.cuda.Stream(device=dev); env.SetStream(s.cuda_stream); env.SetDeviceClock(True)
+    a = torch.zeros(n, dtype=torch.int32, device=dev); o = torch.empty((n, env.obs_dim), device=dev); r = torch.empty(n, device=dev); d = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(s):
+        env.StepDevice(a.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr())
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        env.StepDevice(a.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr())
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize(); env.DoneIndices(); env.Stats(); env.SetDeviceClock(False)
+    env.Close()
+G.Box(np.array([-2.0, 1.5, -np.inf, -np.inf], np.float32), np.array([3.0, np.inf, -4.0, np.inf], np.float32)).SampleBatch(5000, seed=1)
 print("sanitize probe done")
