@@ -135,6 +135,17 @@ def oracle_cpu_rate(env_name, n, seconds, threads, chunk=32):
         env_name, n, chunk * calls, el, threads)
 
 
+def workload_config(args):
+    """The `config` of BOTH arms (the driver compares them): the workload, not how an arm executes it."""
+    n, K = args.num_envs, args.inner
+    bytes_per_step = n * K * 25 if args.env == "CartPole-v1" else None
+    cfg = {"workload": "%s, %d envs per GPU, random policy, auto-reset; one step = %d env steps of every env" % (args.env, n, K),
+           "num_envs_per_gpu": n, "inner_steps": K, "parallelism": "independent env shards, no collective"}
+    if bytes_per_step:
+        cfg["l2"] = "outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % ((bytes_per_step + n * 32) / 1e6)
+    return cfg
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is C#
     (no dotnet/mono in this image) so oracle/_ref cannot be built; the CPU oracle port (C++ restatement of
@@ -164,8 +175,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s, %d envs, random policy, auto-reset" % (args.env, n),
-                   "sample_per_step": "batched steps of all %d envs for >= %.2f s (%d batched steps in total)" % (n, per_step_s, inner * calls)},
+        "config": workload_config(args),
+        "reference_sample_per_step": "batched steps of all %d envs for >= %.2f s (%d batched steps in total)" % (n, per_step_s, inner * calls),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": "%d envs x %d steps in %.1f s, C++ port (oracle F64) of CartPoleEnv.Step -- the C# itself cannot run here: no dotnet" % (n, inner * calls, el),
                          "one_core": {"value": one_core, "sample": one_sample}},
@@ -281,6 +292,12 @@ def measure_envs(G, torch, dist, dev, rank, world, local_rank, peak, sm_mhz):
     res["frac"] = res["achieved_thread_instr_per_s_per_gpu"] / lanes_per_s
     res["note"] = "RK4 of the book dynamics: 8 sincos + ~150 flop per step; one warp-instruction per cycle and sub-partition is the ceiling (148 SMs x 4 x 32 lanes x SM clock)"
     out["Acrobot-v1"] = res
+    # config 4, the other reading of SURVEY 8d: N TOTAL fixed (1 048 576 envs split over the GPUs: strong scaling)
+    strong = rollout_case("Acrobot-v1", 1048576 // world, 128, 5)
+    strong["mode"] += "; 1 048 576 envs in TOTAL, %d per GPU (strong scaling)" % (1048576 // world)
+    strong["bound"] = "fp32_issue"
+    strong["frac"] = strong["env_steps_per_s"] / world * INSTR_PER_ENV_STEP["Acrobot-v1"] / lanes_per_s
+    out["Acrobot-v1 strong @1048576 total"] = strong
 
     # config 5: LunarLander-v2, 65 536 landers per GPU (524 288 at 8), auto-reset + done compaction, one launch group per step
     n = 65536
@@ -588,10 +605,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s, %d envs per GPU, random policy (in-kernel Philox), auto-reset; one step = one "
-                                   "fused rollout launch of %d env steps per env" % (args.env, n, K),
-                       "num_envs_per_gpu": n, "inner_steps": K, "parallelism": "independent env shards, no collective",
-                       "l2": "outputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (launch_bytes / 1e6)},
+            "config": workload_config(args),
+            "execution": "one step = ONE fused rollout launch (in-kernel Philox policy, state in registers, trajectory streamed to HBM)",
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "obs_allgather": gather, "envs": envs,
             "gpu_launches": args.steps, "clocks": clocks,
         }

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GYMCUDA_VERSION 100 /* 0.1.0 */
+#define GYMCUDA_VERSION 110 /* 0.1.10: round-2 additions (step_many, terminal obs, device clock, box sample, render); purely additive */
 
 typedef enum gymcuda_status {
     GYMCUDA_OK = 0,
