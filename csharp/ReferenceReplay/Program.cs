@@ -1,4 +1,4 @@
-// ReferenceReplay -- dumps what the UNMODIFIED reference computes, in the CSV layout tools/replay_reference_dump.py reads.
+// ReferenceReplay -- dumps what the UNMODIFIED reference computes, in the CSV layout tests/tools/replay_reference_dump.py reads.
 //
 //   cartpole_reference.csv      teacher-forced single steps of CartPoleEnv.Step (CartPoleEnv.cs:137-186): the private fields
 //                               `state` / `steps_beyond_done` (:40-41) are set by reflection, so every row is one transition

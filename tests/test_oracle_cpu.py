@@ -184,13 +184,13 @@ def test_partition_invariance_cpu():
 
 
 def test_free_running_drift_report_runs():
-    """SURVEY 8(c) T2, free-running half (tools/f32_vs_f64_drift.py): the float32 engine arithmetic against the float64
+    """SURVEY 8(c) T2, free-running half (tests/tools/f32_vs_f64_drift.py): the float32 engine arithmetic against the float64
     reference arithmetic with NO teacher forcing.  CartPole's episodes are short and its termination test is evaluated
     exactly, so the two agree on (almost) every `done` for hundreds of steps; chaotic Pendulum / Acrobot trajectories
     separate by construction -- which is why the parity criterion is per-step (teacher-forced), not per-trajectory."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("drift", os.path.join(root, "tools", "f32_vs_f64_drift.py"))
+    spec = importlib.util.spec_from_file_location("drift", os.path.join(root, "tests", "tools", "f32_vs_f64_drift.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
     r = mod.drift("CartPole-v1", 512, 300)
     assert r["frac_diverged"] <= 0.01 and r["max_rel_state_err_while_in_step"] < 0.05

@@ -1,4 +1,4 @@
-"""CPU: the off-box reference replay (csharp/ReferenceReplay -> tools/replay_reference_dump.py) checked end to end on
+"""CPU: the off-box reference replay (csharp/ReferenceReplay -> tests/tools/replay_reference_dump.py) checked end to end on
 SYNTHETIC dumps written in the dumper's CSV layout -- so that once a machine with a .NET SDK has produced the real dump,
 pinning the oracles to reference-executed vectors is one command.  If tests/golden/cartpole_reference.npz (the converted real
 dump) is present, the oracle is held to it here; it is absent in this image (no dotnet), and the test says so."""
@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 import replay_reference_dump as RR  # noqa: E402
@@ -40,7 +40,7 @@ def test_cartpole_dump_layout_and_check(tmp_path):
 def test_lunar_dump_layout_and_replay(tmp_path):
     """An episode of the generic engine (PID policy, engine draws) written in the dumper's layout replays without divergence
     under the options it was made with and diverges at the first touch-down under another BeginContact semantic."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
     import world2d_lib as W
     from lunar_pid_study import pid
     seed, gid = 1000, 3
@@ -80,6 +80,6 @@ def test_oracle_against_reference_executed_cartpole_vectors_if_present():
     path = os.path.join(ROOT, "tests", "golden", "cartpole_reference.npz")
     if not os.path.exists(path):
         pytest.skip("no reference-executed vectors in this image (no dotnet): run csharp/ReferenceReplay off-box, then "
-                    "tools/replay_reference_dump.py <dir> --write-golden")
+                    "tests/tools/replay_reference_dump.py <dir> --write-golden")
     fx = dict(np.load(path))
     RR.check_cartpole(fx)

@@ -5,7 +5,7 @@ states under the same action sequences -- no teacher forcing.  Per env family: t
 the two still agree on every `done`, and the histogram of the first step at which a `done` flag differs (after that
 the episodes are different episodes and the comparison ends for that env).  CPU only (the oracle is the checker).
 
-    python tools/f32_vs_f64_drift.py [n_envs] [steps]
+    python tests/tools/f32_vs_f64_drift.py [n_envs] [steps]
 """
 import json
 import os
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
 

@@ -3,7 +3,7 @@ LunarLanderEnvironment.cs:38-150; golden for NumSharp seed 1000: 1547 steps, ret
 oracle (oracle/world2d).  The NumSharp stream is unreproducible, so this reports DISTRIBUTIONS over many terrains /
 initial kicks drawn from the engine's Philox stream, not the golden itself.  TEST / ANALYSIS TOOL ONLY.
 
-    python tools/lunar_pid_study.py [episodes]  ->  profiles/lunar_pid_study_r2.txt
+    python tests/tools/lunar_pid_study.py [episodes]  ->  profiles/lunar_pid_study_r2.txt
 """
 import itertools
 import os
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import world2d_lib as W  # noqa: E402
 

@@ -3,7 +3,7 @@
 of this repo -- the step that turns "parity against our restatement" into "parity against the reference" (SURVEY 8f rank 1).
 TEST / ANALYSIS TOOL: it drives oracle/ (and, with --gpu, libgymcuda through the C ABI); nothing in the product uses it.
 
-    python tools/replay_reference_dump.py <dump_dir> [--gpu] [--write-golden]
+    python tests/tools/replay_reference_dump.py <dump_dir> [--gpu] [--write-golden]
 
   cartpole_reference.csv   every teacher-forced transition against oracle F64 (the reference's arithmetic: done / reward /
                            steps_beyond_done exact, next state <= 1e-12 relative -- .NET's Math.Sin / Cos and libm may differ
@@ -23,7 +23,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 
