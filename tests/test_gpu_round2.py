@@ -342,3 +342,44 @@ def test_render_cartpole_and_lunarlander_headless_batched():
     with pytest.raises(ValueError):
         pend.Render(None, 64, 64, count=1)               # the reference has no Render for it
     pend.Close()
+
+
+@pytest.mark.parametrize("n", [1, 33, 129, 1000])
+def test_round2_entry_points_on_small_and_ragged_batches(n):
+    """Batches of 1, 33, 129 and 1000 envs (one lane, a ragged second warp, a ragged second CTA, eight CTAs): the done list built
+    on demand, the deferred CTA-level reset pass, the terminal-observation buffer and step_many against the oracle."""
+    rng = np.random.default_rng(n)
+    a, b = oracle_pair("CartPole-v1", n, 7, 3, 12)
+    env = G.CartPoleVecEnv(n, seed=7, env_id_offset=3, auto_reset=True, time_limit=12)
+    assert np.array_equal(env.ResetBatch(), a.reset()); b.reset()
+    term = np.full((n, 4), -1.0, np.float32)
+    env.SetTerminalObs(term)
+    for _ in range(40):
+        act = rng.integers(0, 2, n).astype(np.int32)
+        st, aux, t = a.get_state(); b.set_state(st, aux, t)
+        wo, wr, wd = a.step(act); to, _, _ = b.step(act)
+        go, gr, gd = env.StepBatch(act)
+        assert np.array_equal(go, wo) and np.array_equal(gr, wr) and np.array_equal(gd, wd)
+        d = wd != 0
+        assert np.array_equal(term[d], to[d])
+        assert np.array_equal(np.sort(env.DoneIndices()), np.nonzero(wd)[0])
+        assert np.array_equal(np.sort(env.DoneIndices()), np.nonzero(wd)[0])     # asked twice: built once, same list
+    env.SetTerminalObs(None)
+    acts = rng.integers(0, 2, (25, n)).astype(np.int32)
+    obs, rew, done = env.StepMany(acts)
+    for j in range(25):
+        wo, wr, wd = a.step(acts[j])
+        assert np.array_equal(obs[j], wo) and np.array_equal(done[j], wd)
+    st, _, t = a.get_state(); gs, _, gt = env.GetState()
+    assert gt == t and np.array_equal(gs, st.astype(np.float32))
+    assert env.Stats()["episodes"] > 0
+    env.Close()
+    ll = G.LunarLanderVecEnv(n, seed=2, auto_reset=True, time_limit=15)      # n < 512: LunarLander's single-launch path
+    lt = O.OracleEnv(O.LUNARLANDER, n, seed=2, auto_reset=True, mode=O.MODE_F32, time_limit=15)
+    assert np.array_equal(ll.ResetBatch(), lt.reset())
+    for _ in range(20):
+        act = rng.integers(0, 4, n).astype(np.int32)
+        go, gr, gd = ll.StepBatch(act); wo, wr, wd = lt.step(act)
+        assert np.array_equal(go, wo) and np.array_equal(gd, wd)
+        assert np.array_equal(np.sort(ll.DoneIndices()), np.nonzero(wd)[0])
+    ll.Close()
