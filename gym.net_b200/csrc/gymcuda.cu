@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -227,21 +228,28 @@ static cudaError_t launch_step(gymcuda_env* e, const StepArgs& a) {
     return cudaGetLastError();
 }
 
-template <class E, bool ALL_OUT, int BLOCK>
+template <class E, bool ALL_OUT, int BLOCK, bool SUPPLIED = false>
 static void launch_rollout_variant(gymcuda_env* e, const RolloutArgs& a) {
     const int grid = (e->n + BLOCK - 1) / BLOCK;
     const bool ar = e->auto_reset, lim = e->limit > 0;
-    if (ar && lim) rollout_kernel<E, true, true, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
-    else if (ar) rollout_kernel<E, true, false, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
-    else if (lim) rollout_kernel<E, false, true, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
-    else rollout_kernel<E, false, false, ALL_OUT, BLOCK><<<grid, BLOCK, 0, e->stream>>>(a);
+    if (ar && lim) rollout_kernel<E, true, true, ALL_OUT, BLOCK, SUPPLIED><<<grid, BLOCK, 0, e->stream>>>(a);
+    else if (ar) rollout_kernel<E, true, false, ALL_OUT, BLOCK, SUPPLIED><<<grid, BLOCK, 0, e->stream>>>(a);
+    else if (lim) rollout_kernel<E, false, true, ALL_OUT, BLOCK, SUPPLIED><<<grid, BLOCK, 0, e->stream>>>(a);
+    else rollout_kernel<E, false, false, ALL_OUT, BLOCK, SUPPLIED><<<grid, BLOCK, 0, e->stream>>>(a);
 }
 
 template <class E>
 static cudaError_t launch_rollout(gymcuda_env* e, const RolloutArgs& a) {
     // ALL_OUT addresses the trajectory with one 32-bit row index: every row * envs + env must fit
     const bool idx32 = (unsigned long long)a.k_steps * (unsigned long long)a.n <= 0xffffffffull;
-    if (a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits && idx32) {
+    if (a.actions_in && a.obs && a.reward && a.done && !a.ep_ret && !a.done_bits && idx32) {
+        // gymcuda_step_many* with every output requested: the chunked all-outputs kernel reading the caller's actions
+        const long long wave = (long long)e->sm_count * ROLLOUT_BLOCK_WAVE;
+        bool one_wave = false;
+        if constexpr (E::ROLLOUT_CHUNK) one_wave = (long long)e->n <= wave && 4ll * e->n >= 3ll * wave;
+        if constexpr (E::ROLLOUT_CHUNK) { if (one_wave) { launch_rollout_variant<E, true, ROLLOUT_BLOCK_WAVE, true>(e, a); return cudaGetLastError(); } }
+        launch_rollout_variant<E, true, ROLLOUT_BLOCK, true>(e, a);
+    } else if (!a.actions_in && a.obs && a.reward && a.done && a.actions && !a.ep_ret && !a.done_bits && idx32) {
         // one wave of 16-warp CTAs, one per SM, when the batch fits and fills at least 3/4 of the SMs (kernels.cuh)
         const long long wave = (long long)e->sm_count * ROLLOUT_BLOCK_WAVE;
         bool one_wave = false;
@@ -293,8 +301,10 @@ static cudaError_t lunar_step(gymcuda_env* e, StepArgs a) {
     cudaError_t ce = cudaEventRecord(e->ev_fork, e->stream);
     if (ce != cudaSuccess) return ce;
     if ((ce = cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0)) != cudaSuccess) return ce;
-    a.part = 2;   // landers with a contact pair: few, long
-    if ((ce = lunar_launch_step(cont, true, ar, lim, grid, e->side_stream, a)) != cudaSuccess) return ce;
+    a.part = 2;   // landers with a contact pair: few, long.  GYMCUDA_LUNAR_TRIO=1: three lanes per lander (lunar_core.cuh; measured: no gain, off)
+    static const bool trio = [] { const char* v = getenv("GYMCUDA_LUNAR_TRIO"); return v && v[0] == '1'; }();
+    ce = trio ? lunar_launch_step_trio(cont, ar, lim, e->side_stream, a) : lunar_launch_step(cont, true, ar, lim, grid, e->side_stream, a);
+    if (ce != cudaSuccess) return ce;
     if ((ce = cudaEventRecord(e->ev_join, e->side_stream)) != cudaSuccess) return ce;
     a.part = 1;   // free flight: the bulk
     if ((ce = lunar_launch_step(cont, false, ar, lim, grid, e->stream, a)) != cudaSuccess) return ce;

@@ -272,6 +272,13 @@ constexpr int STEP_BIG_BATCH = 1 << 20;
 template <class E, class = void> struct FusedReset : std::false_type {};
 template <class E> struct FusedReset<E, std::enable_if_t<E::FUSED_RESET>> : std::true_type {};
 
+// envs stepped by three lanes each (E::TRIO: the contact class of LunarLander, lunar_core.cuh): a warp holds ten envs in its
+// lanes 0..29 (lane = 3 * slot + sub), lanes 30 and 31 idle; the three lanes of an env compute the same values and the first
+// one (sub == 0) does the global stores and takes part in the done / invalid votes
+template <class E, class = void> struct TrioEnv : std::false_type {};
+template <class E> struct TrioEnv<E, std::enable_if_t<E::TRIO>> : std::true_type {};
+constexpr int TRIO_ENVS_PER_WARP = 10;
+
 // STEP_BLOCK = the launch shape at every size.  (BLOCK is a parameter because larger CTAs were measured for the batches of a
 // million envs and more -- fewer same-address atomics on the done counter: 128 / 256 / 512 / 1024 threads give 160 / 166 / 182 /
 // 238 us per 16.7 M-env CartPole launch without finished episodes, so STEP_BLOCK_BIG stays at 128.)
@@ -283,6 +290,13 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
     using S = typename E::S;
     using Act = typename E::Act;
     int tix = blockIdx.x * BLOCK + threadIdx.x;
+    constexpr bool TRIO = TrioEnv<E>::value;
+    bool primary = true;               // this lane writes the env's results (TRIO: the first lane of the three)
+    if constexpr (TRIO) {
+        const unsigned ln = threadIdx.x & 31u;
+        primary = ln % 3u == 0u;
+        tix = ln < 3u * TRIO_ENVS_PER_WARP ? (tix >> 5) * TRIO_ENVS_PER_WARP + (int)(ln / 3u) : 0x3fffffff;
+    }
     int hi = p.n;
     if (p.part == 1) hi = *p.split;
     if (p.part == 2) tix += *p.split;
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             const uint64_t sseed = seed_of(p.seeds, p.seed, i);
             gen.init(sseed, p.env_off + (uint32_t)i, now_t);
             a = gen.next(sseed, p.env_off + (uint32_t)i, now_t);
-            if (p.act_out) reinterpret_cast<Act*>(p.act_out)[i] = a;
+            if (p.act_out && primary) reinterpret_cast<Act*>(p.act_out)[i] = a;
         } else {
             a = p.use_bcast ? ActIO<E>::bcast(p.bcast_action) : ActIO<E>::load(p.actions, i);
         }
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             if (p.ep_ret) {   // episode statistics (the caller-side bookkeeping of BasePlaySession.cs:58-69)
                 float ret = p.ep_ret[i] + r.reward;
                 if (r.done) { fin_ret = ret; fin_len = ept; ret = 0.0f; }
-                p.ep_ret[i] = ret;
+                if (primary) p.ep_ret[i] = ret;
             }
             if (AUTO_RESET && r.done) {
                 if constexpr (DEFER) {
@@ -344,19 +358,21 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
                 } else {
                     const int32_t ep = FusedReset<E>::value ? ep_ord : p.episode[i];
                     if (!r.did_reset) {
-                        if (p.terminal_obs) { float to[E::OD]; E::obs(s, to); store_obs<E::OD, false>(p.terminal_obs, (size_t)i, to); }
+                        if (p.terminal_obs && primary) { float to[E::OD]; E::obs(s, to); store_obs<E::OD, false>(p.terminal_obs, (size_t)i, to); }
+#ifndef GYMCUDA_PROBE_SKIP_RESET   // (timing probe only, never defined in the product build: what the in-kernel reset of a finished env costs the launch)
                         E::reset(s, seed, gid, (uint32_t)ep, now_t + 1, p.prm);
+#endif
                     }
-                    p.episode[i] = ep + 1;
+                    if (primary) p.episode[i] = ep + 1;
                 }
                 sbd = -1;
                 ept = 0;
             }
-            if (!deferred) E::store(p.state, p.aux, p.n, i, s);
+            if (!deferred && primary) E::store(p.state, p.aux, p.n, i, s);
             if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
-            if (LIMIT) p.ep_t[i] = ept;
+            if (LIMIT && primary) p.ep_t[i] = ept;
         }
-        if (!deferred) {
+        if (!deferred && primary) {
             float o[E::OD];
             E::obs(s, o);
             if (p.obs) store_obs<E::OD, false>(p.obs, (size_t)i, o);
@@ -365,9 +381,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             for (int r = 0; r < p.world; ++r)
                 store_obs<E::OD, false>(p.peer_obs[r], ((size_t)(p.gseq & 1u) * p.world + p.rank) * (size_t)p.n + (size_t)i, o);
         }
-        p.reward[i] = r.reward;
+        if (primary) p.reward[i] = r.reward;
         done_byte = (p.done_bits && trunc_only) ? (uint8_t)2 : (uint8_t)r.done;
         done = r.done != 0;
+        if constexpr (TRIO) { done = done && primary; invalid = invalid && primary; }   // one vote per env
     }
 
     // ---- envs whose step is long and uneven (LunarLander: FusedReset): WARP-granular epilogue, no CTA barrier -- a warp
@@ -379,7 +396,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
             const unsigned lane_w = threadIdx.x & 31;
             const unsigned mw = __ballot_sync(0xffffffffu, done);
             const unsigned miw = __ballot_sync(0xffffffffu, invalid);
-            if (tix < p.n) p.done[i] = done_byte;
+            if (tix < p.n && primary) p.done[i] = done_byte;
             if (miw != 0 && lane_w == 0) {
                 atomicAdd(&p.stats[1], (unsigned long long)__popc(miw));
                 *reinterpret_cast<volatile int*>(p.host_invalid) = 1;
@@ -415,9 +432,9 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs p) {
     if (lane == 0) warp_cnt[warp] = __popc(m);
     // the done bytes of the CTA go out as one 128 B line (32 lanes x 4 B) instead of four 32 B pieces: over PCIe
     // (zero-copy host buffers) every store instruction is a packet, and over HBM it is one full sector group
-    const bool packed = p.perm == nullptr && p.part == 0 && (reinterpret_cast<uintptr_t>(p.done) & 3u) == 0;
+    const bool packed = !TRIO && p.perm == nullptr && p.part == 0 && (reinterpret_cast<uintptr_t>(p.done) & 3u) == 0;
     if (packed) done_tile[threadIdx.x] = done_byte;
-    else if (tix < p.n) p.done[i] = done_byte;
+    else if (tix < p.n && primary) p.done[i] = done_byte;
     if (mi != 0 && lane == 0) {
         atomicAdd(&p.stats[1], (unsigned long long)__popc(mi));
         *reinterpret_cast<volatile int*>(p.host_invalid) = 1;
@@ -595,8 +612,13 @@ __device__ __forceinline__ void unroll8(F& f) {
 // fully unrolled: action-word and reset-refill boundaries fall only on chunk starts, so the per-step loop tests,
 // shifts and branches of the generic loop disappear; with HAS_SMALL (CartPole) a warp whose angles are all in
 // the polynomial range runs the chunk on step<true> (no range reduction, no branches around sincos).
-template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT, int BLOCK = ROLLOUT_BLOCK>
+// SUPPLIED (with ALL_OUT): the actions of every step come from the caller's `actions_in[k][n]` (gymcuda_step_many*) instead
+// of the policy stream and are not written back: the same chunked, 32-bit-indexed kernel, the eight action loads of a
+// chunk issued together at its start.  An action the env rejects leaves that env unstepped for that row (observation
+// unchanged, reward 0, done 0), as in step_kernel; a chunk that holds one runs step by step.
+template <class E, bool AUTO_RESET, bool LIMIT, bool ALL_OUT, int BLOCK = ROLLOUT_BLOCK, bool SUPPLIED = false>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
+    static_assert(ALL_OUT || !SUPPLIED, "the generic variant reads actions_in through a run-time test");
     using S = typename E::S;
     using Act = typename E::Act;
     const int tix = blockIdx.x * BLOCK + threadIdx.x;
@@ -619,9 +641,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
         const uint64_t seed = seed_of(p.seeds, p.seed, i);
         const uint32_t gid = p.env_off + (uint32_t)i;
         ActionGen<E> gen;
-        bool supplied = false;   // the actions come from the caller (gymcuda_step_many*), not from the policy stream
+        bool supplied = SUPPLIED;   // the actions come from the caller (gymcuda_step_many*), not from the policy stream
         if constexpr (!ALL_OUT) supplied = p.actions_in != nullptr;
         if (!supplied) gen.init(seed, gid, p.t);
+        const Act* const act_in = reinterpret_cast<const Act*>(p.actions_in);
         unsigned rejected = 0;
         const size_t n = (size_t)p.n;
         // next initial state, pre-generated: consumed at `done`, refilled for all lanes of the warp that
@@ -642,14 +665,21 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
         // limit_tag false: the caller has established that no lane can reach the time limit in this step (the
         // episode counter still runs); for an env that never terminates by itself (Pendulum) `done` is then a
         // compile-time 0 and the whole reset path drops out of the chunk
-        auto body = [&](int k, const Act a, auto small_tag, auto limit_tag) {
+        // rej_tag true (SUPPLIED only): this lane's action was rejected -- nothing but the stores happens for it
+        auto body = [&](int k, const Act a, auto small_tag, auto limit_tag, auto rej_tag) {
             constexpr bool SMALL = decltype(small_tag)::value;
             constexpr bool CHECK_LIMIT = LIMIT && decltype(limit_tag)::value;
+            constexpr bool MAY_REJECT = decltype(rej_tag)::value;
             const uint64_t t = p.t + (uint64_t)k;
-            StepOut r = StepSel<E, SMALL>::go(s, a, sbd, seed, gid, t);
+            StepOut r{0.0f, 0u};
             bool trunc_only = false;
-            if (LIMIT) ept += 1;
-            if (CHECK_LIMIT) { if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }
+            bool stepped = true;
+            if constexpr (MAY_REJECT) { stepped = E::valid(a); rejected += stepped ? 0u : 1u; }
+            if (stepped) {
+                r = StepSel<E, SMALL>::go(s, a, sbd, seed, gid, t);
+                if (LIMIT) ept += 1;
+                if (CHECK_LIMIT) { if (ept >= p.limit && !r.done) { r.done = 1u; trunc_only = true; } }
+            }
             if (STATS) ret += r.reward;
             if (r.done) {
                 episodes += 1;
@@ -685,7 +715,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
                 }
                 __stcs(reward_base + row, r.reward);
                 __stcs(done_base + row, (uint8_t)r.done);
-                __stcs(act_base + row, a);
+                if constexpr (!SUPPLIED) __stcs(act_base + row, a);
                 row += (uint32_t)p.n;
             } else {
                 const size_t idx = (size_t)k * n + (size_t)i;
@@ -705,7 +735,12 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
             // head: single steps until the absolute step index is a multiple of 8
             int head = (int)((8u - ((uint32_t)p.t & 7u)) & 7u);
             if (head > p.k_steps) head = p.k_steps;
-            for (; k < head; ++k) body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{}, std::true_type{});
+            constexpr bool MAY_REJECT = SUPPLIED && E::REJECT_INVALID;
+            using RejTag = std::integral_constant<bool, MAY_REJECT>;
+            for (; k < head; ++k) {
+                if constexpr (SUPPLIED) body(k, __ldcs(act_in + row), std::false_type{}, std::true_type{}, RejTag{});
+                else body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{}, std::true_type{}, std::false_type{});
+            }
 #pragma unroll 1
             for (; k + 8 <= p.k_steps; k += 8) {
                 const uint64_t tc = p.t + (uint64_t)k;
@@ -713,23 +748,44 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
                     E::reset(next, seed, gid, (uint32_t)ep, tc, p.prm);
                     have = 1;
                 }
+                Act acts[SUPPLIED ? 8 : 1];
+                if constexpr (SUPPLIED) {
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acts[j] = __ldcs(act_in + (row + (uint32_t)j * (uint32_t)p.n));
+                        if (MAY_REJECT) ok = ok && E::valid(acts[j]);
+                    }
+                    if constexpr (MAY_REJECT) {
+                        if (!__all_sync(__activemask(), ok)) {   // rare: a rejected action somewhere in the warp's chunk
+                            auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, acts[J], std::false_type{}, std::true_type{}, std::true_type{}); };
+                            unroll8<0>(f);
+                            continue;
+                        }
+                    }
+                }
+                // the action of step tc + J: the caller's, or draw J of the chunk
+                auto act_of = [&](auto jc) -> Act {
+                    constexpr int J = decltype(jc)::value;
+                    if constexpr (SUPPLIED) return acts[J]; else return gen.template at<J>(seed, gid, tc);
+                };
                 if constexpr (E::HAS_SMALL && AUTO_RESET) {
                     if (__all_sync(__activemask(), E::small_ok(s))) {
                         if constexpr (LIMIT) {
                             // no lane within 8 steps of the time limit (a reset only lowers the counter): the chunk
                             // runs without the per-step limit test
                             if (__all_sync(__activemask(), ept + 8 < p.limit)) {
-                                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::true_type{}, std::false_type{}); };
+                                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, act_of(jc), std::true_type{}, std::false_type{}, std::false_type{}); };
                                 unroll8<0>(f);
                                 continue;
                             }
                         }
-                        auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::true_type{}, std::true_type{}); };
+                        auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, act_of(jc), std::true_type{}, std::true_type{}, std::false_type{}); };
                         unroll8<0>(f);
                         continue;
                     }
                 }
-                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, gen.template at<J>(seed, gid, tc), std::false_type{}, std::true_type{}); };
+                auto f = [&](auto jc) { constexpr int J = decltype(jc)::value; body(k + J, act_of(jc), std::false_type{}, std::true_type{}, std::false_type{}); };
                 unroll8<0>(f);
             }
         }
@@ -755,21 +811,24 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
                 } else {
                     a = gen.next(seed, gid, p.t + (uint64_t)k);
                 }
+            } else if constexpr (SUPPLIED) {
+                a = __ldcs(act_in + row);
             } else {
                 a = gen.next(seed, gid, p.t + (uint64_t)k);
             }
+            using RejTag = std::integral_constant<bool, SUPPLIED && E::REJECT_INVALID>;
             if constexpr (ALL_OUT && E::HAS_SMALL && !E::ROLLOUT_CHUNK) {
                 // envs too large to unroll (Acrobot): the same warp vote, per step, picks the reduced-range step
-                if (__all_sync(__activemask(), E::small_ok(s))) { body(k, a, std::true_type{}, std::true_type{}); continue; }
+                if (__all_sync(__activemask(), E::small_ok(s))) { body(k, a, std::true_type{}, std::true_type{}, RejTag{}); continue; }
             }
-            body(k, a, std::false_type{}, std::true_type{});
+            body(k, a, std::false_type{}, std::true_type{}, RejTag{});
         }
         if (AUTO_RESET) p.episode[i] = ep;
         if (STATS && p.ep_ret) p.ep_ret[i] = ret;
         E::store(p.state, p.aux, p.n, i, s);
         if (E::HAS_SBD && !AUTO_RESET) p.sbd[i] = sbd;
         if (LIMIT) p.ep_t[i] = ept;
-        if constexpr (!ALL_OUT) {
+        if constexpr (!ALL_OUT || SUPPLIED) {
             if (rejected) {
                 atomicAdd(&p.stats[1], (unsigned long long)rejected);
                 *reinterpret_cast<volatile int*>(p.host_invalid) = 1;

@@ -63,8 +63,11 @@ __device__ __forceinline__ void store_lander(const Lander& L, float* __restrict_
 // LunarLander-v2, discrete (Discrete(4), LunarLanderEnv.cs:421) and continuous (Box(-1, 1, (2,)), :417)
 // ------------------------------------------------------------------------------------------------
 // HAS_PAIRS = false: the traits of the free-flight class of the contact partition (kernels.cuh)
-template <bool CONTINUOUS, bool HAS_PAIRS = true>
+// TRIO_ = true (contact class only): three lanes per lander inside the solver's iteration loops (lunar_core.cuh "TRIO");
+// step_kernel maps ten landers to a warp and lets the first lane of each trio do the global stores
+template <bool CONTINUOUS, bool HAS_PAIRS = true, bool TRIO_ = false>
 struct LunarLanderT {
+    static constexpr bool TRIO = TRIO_;
     static constexpr int SD = lunar::SD, AUX = lunar::AUXD + 2, AUXW = lunar::AUXD;
     static constexpr int OD = 8, AD = CONTINUOUS ? 2 : 1, ACTN = CONTINUOUS ? 0 : 4, DEFAULT_LIMIT = 0;
     static constexpr bool HAS_SBD = false;
@@ -104,12 +107,12 @@ struct LunarLanderT {
     // step with the auto-reset folded in (lunar_core.cuh step_autoreset); `ordinal` = the env's next RESET draw index
     __device__ static __forceinline__ StepOut step_ar(S& L, int32_t a, uint64_t seed, uint32_t gid, uint64_t t, bool allow, uint32_t ordinal) {
         const float none[2] = {0.0f, 0.0f};
-        const lunar::StepResult r = lunar::step_autoreset<HAS_PAIRS>(L, seed, gid, t, (int)a, none, allow, (uint64_t)ordinal);
+        const lunar::StepResult r = lunar::step_autoreset<HAS_PAIRS, TRIO_>(L, seed, gid, t, (int)a, none, allow, (uint64_t)ordinal);
         return StepOut{r.reward, (unsigned)(r.done != 0), (unsigned)r.did_reset};
     }
     __device__ static __forceinline__ StepOut step_ar(S& L, float2 a, uint64_t seed, uint32_t gid, uint64_t t, bool allow, uint32_t ordinal) {
         const float act[2] = {a.x, a.y};
-        const lunar::StepResult r = lunar::step_autoreset<HAS_PAIRS>(L, seed, gid, t, 0, act, allow, (uint64_t)ordinal);
+        const lunar::StepResult r = lunar::step_autoreset<HAS_PAIRS, TRIO_>(L, seed, gid, t, 0, act, allow, (uint64_t)ordinal);
         return StepOut{r.reward, (unsigned)(r.done != 0), (unsigned)r.did_reset};
     }
     __device__ static __forceinline__ void obs(const S& L, float* o) { lunar::observe(L, o); }

@@ -734,6 +734,40 @@ __device__ __forceinline__ bool joint_position(const Joint& J, float motor_mass,
     return position_error_sq <= LINEAR_SLOP_SQ_MAX && angular_error <= ANGULAR_SLOP;
 }
 
+// ---- three lanes per lander (TRIO) ------------------------------------------------------------------------------------
+// The contact class of the partition is latency-bound: ONE warp per sub-partition runs the dependent chain of 180 velocity
+// and up to 60 position iterations, and nothing but a shorter instruction stream per iteration shortens the launch.  In the
+// TRIO variant three neighbouring lanes (sub = 0, 1, 2 = fuselage, leg 0, leg 1) step the SAME lander: everything outside
+// the iteration loops is executed redundantly (identical inputs, identical results, no extra time in SIMT), and inside the
+// loops every lane keeps only ITS body and ITS manifold rows -- a lane runs one contact row per iteration instead of three.
+// A joint couples the fuselage with one leg: all three lanes fetch both bodies with shuffles and evaluate the joint (the
+// third lane is a clone of the leg's lane, so every lane's accumulators stay right), and each commits only its own body.
+// The order of operations per body is that of the plain loops (joint 1, joint 0, then the body's rows; rows of different
+// bodies commute): same bits.
+__device__ __forceinline__ float trio_get(unsigned tmask, float x, int src) { return __shfl_sync(tmask, x, src); }
+__device__ __forceinline__ V2 trio_get(unsigned tmask, V2 x, int src) { return mk(__shfl_sync(tmask, x.x, src), __shfl_sync(tmask, x.y, src)); }
+
+template <int ji>
+__device__ __forceinline__ void joint_velocity_trio(Joint& J, const JointWork& W, unsigned tmask, int base, int sub, V2& vm, float& wm) {
+    V2 vA = trio_get(tmask, vm, base), vB = trio_get(tmask, vm, base + 1 + ji);
+    float wA = trio_get(tmask, wm, base), wB = trio_get(tmask, wm, base + 1 + ji);
+    joint_velocity<ji>(J, W, vA, wA, vB, wB);
+    const bool isA = sub == 0, isB = sub == 1 + ji;
+    vm = isA ? vA : (isB ? vB : vm);
+    wm = isA ? wA : (isB ? wB : wm);
+}
+
+template <int ji, bool IN_RANGE>
+__device__ __forceinline__ bool joint_position_trio(const Joint& J, float motor_mass, unsigned tmask, int base, int sub, V2& cm, float& am) {
+    V2 cA = trio_get(tmask, cm, base), cB = trio_get(tmask, cm, base + 1 + ji);
+    float aA = trio_get(tmask, am, base), aB = trio_get(tmask, am, base + 1 + ji);
+    const bool ok = joint_position<ji, IN_RANGE>(J, motor_mass, cA, aA, cB, aB);
+    const bool isA = sub == 0, isB = sub == 1 + ji;
+    cm = isA ? cA : (isB ? cB : cm);
+    am = isA ? aA : (isB ? aB : am);
+    return ok;
+}
+
 // the touching manifolds of a step (creation order) and their island order
 struct Contacts { ActiveContact ac[MAXC]; int nc; uint32_t order; };
 
@@ -812,13 +846,17 @@ __device__ __forceinline__ void collide(Lander& L, Contacts& C) {
 #ifdef LUNAR_PHASE_CLOCKS
 __device__ long long g_lunar_phase[2][10][65536];
 #define LUNAR_PHASE(HP, k) do { const unsigned _t = blockIdx.x * blockDim.x + threadIdx.x; if (_t < 65536u) g_lunar_phase[(HP) ? 1 : 0][k][_t] = clock64(); } while (0)
+// slots 8 / 9: %globaltimer (ns, one clock for the whole GPU) at the start / end of the step -- when the two kernels of the partition really ran
+#define LUNAR_PHASE_NS(HP, k) do { const unsigned _t = blockIdx.x * blockDim.x + threadIdx.x; if (_t < 65536u) { unsigned long long _ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_ns)); g_lunar_phase[(HP) ? 1 : 0][k][_t] = (long long)_ns; } } while (0)
 #else
+#define LUNAR_PHASE_NS(HP, k) do {} while (0)
 #define LUNAR_PHASE(HP, k) do {} while (0)
 #endif
 
 // ---- Solve (b2Island::Solve) -- the island is always {fuselage, leg0, leg1} -- then the broad-phase update and ClearForces
-template <bool HAS_PAIRS>
+template <bool HAS_PAIRS, bool TRIO = false>
 __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
+    static_assert(HAS_PAIRS || !TRIO, "the free-flight class is throughput-bound: one lane per lander");
     const float h = DT;
     const float dt_ratio = (L.flags & F_FIRST_STEP) ? 0.0f : 1.0f;   // inv_dt0 * dt: 0 on a new World, then 50 * 0.02f = 1
     ActiveContact* ac = C.ac;
@@ -971,11 +1009,46 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
         // ---- velocity iterations: one branch-free loop body for every lane.  Register rows: the newest manifold of each body
         // (rows of different bodies commute: they share no variable); a body's older manifolds (a polygon astride a terrain
         // vertex) follow from local memory, in island order, skipped by the whole warp when no lane has one.
-        VelRow row[HAS_PAIRS ? 3 : 1];
+        // TRIO: lane `sub` of the trio keeps body `sub` (vm, wm / cm, am), its newest manifold (rm / pm) and its older ones (extra_m)
+        const unsigned tlane = TRIO ? (threadIdx.x & 31u) : 0u;
+        const int sub = (int)(tlane % 3u), tbase = (int)tlane - sub;
+        const unsigned tmask = 7u << tbase;
+        int mine = -1;            // TRIO: island entry of my body's newest manifold
+        uint32_t extra_m = 0u;    // TRIO: my body's older manifolds, island order
+        int nextra_m = 0;
+        VelRow row[(HAS_PAIRS && !TRIO) ? 3 : 1];
         uint32_t extra = 0u;   // island positions (4 bits each) of the manifolds that are not a body's newest
         int nextra = 0;
         bool warp_rows = false, warp_extra = false;
-        if (HAS_PAIRS) {
+        bool warp_row0 = true;   // some lane of the warp holds a fuselage row (an extra manifold of the fuselage implies a newest one)
+        if constexpr (TRIO) {
+            int first_of[3] = {-1, -1, -1};
+            for (int kk = 0; kk < nc; ++kk) {
+                const int k = (int)((order >> (4 * kk)) & 15u);
+                const int B = ac[k].body;
+                if (GETB(first_of, B) < 0) { SETB(first_of, B, k); }
+                else { extra |= (uint32_t)k << (4 * nextra++); if (B == sub) extra_m |= (uint32_t)k << (4 * nextra_m++); }
+            }
+            mine = GETB(first_of, sub);
+            VelRow& q = row[0];
+            q.count = 0; q.body = sub;
+            q.inv_mass = SHAPES[sub].inv_mass; q.inv_inertia = SHAPES[sub].inv_inertia;
+            q.normal = mk(0.0f, 1.0f); q.rb0 = q.rb1 = mk(0.0f, 0.0f);
+            q.ni0 = q.ni1 = q.ti0 = q.ti1 = q.nm0 = q.nm1 = q.tm0 = q.tm1 = q.friction = 0.0f;
+            q.k11 = q.k12 = q.k22 = q.i11 = q.i12 = q.i21 = q.i22 = 0.0f;
+            if (mine >= 0) {
+                const ActiveContact& cc = ac[mine];
+                q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
+                q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
+                q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
+                q.friction = cc.friction;
+                q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
+                q.count = cc.count;
+            }
+            const unsigned am = __activemask();
+            warp_rows = __ballot_sync(am, nc > 0) != 0u;
+            warp_extra = __ballot_sync(am, nextra > 0) != 0u;
+        } else if (HAS_PAIRS) {
             int first_of[3] = {-1, -1, -1};
             for (int kk = 0; kk < nc; ++kk) {
                 const int k = (int)((order >> (4 * kk)) & 15u);
@@ -1004,15 +1077,70 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
             const unsigned am = __activemask();
             warp_rows = __ballot_sync(am, nc > 0) != 0u;
             warp_extra = __ballot_sync(am, nextra > 0) != 0u;
+            warp_row0 = __ballot_sync(am, row[0].count > 0) != 0u;
         }
         LUNAR_PHASE(HAS_PAIRS, 3);
+        if constexpr (TRIO) {
+            V2 vm = GETB(v, sub); float wm = GETB(w, sub);
+            VelRow& rm = row[0];
+#pragma unroll 1
+            for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
+                joint_velocity_trio<1>(Jl[1], jw[1], tmask, tbase, sub, vm, wm);   // island order: leg 1's joint, then leg 0's
+                joint_velocity_trio<0>(Jl[0], jw[0], tmask, tbase, sub, vm, wm);
+                if (warp_rows) {
+                    velocity_row_select(rm, vm, wm);
+                    if (warp_extra) {
+                        for (int kk = 0; kk < nextra_m; ++kk) {
+                            ActiveContact& cc = ac[(extra_m >> (4 * kk)) & 15u];
+                            VelRow q;
+                            q.normal = cc.normal; q.rb0 = cc.p[0].rb; q.rb1 = cc.p[1].rb;
+                            q.ni0 = cc.p[0].normal_impulse; q.ni1 = cc.p[1].normal_impulse; q.ti0 = cc.p[0].tangent_impulse; q.ti1 = cc.p[1].tangent_impulse;
+                            q.nm0 = cc.p[0].normal_mass; q.nm1 = cc.p[1].normal_mass; q.tm0 = cc.p[0].tangent_mass; q.tm1 = cc.p[1].tangent_mass;
+                            q.friction = cc.friction;
+                            q.k11 = cc.k11; q.k12 = cc.k12; q.k22 = cc.k22; q.i11 = cc.nm11; q.i12 = cc.nm12; q.i21 = cc.nm21; q.i22 = cc.nm22;
+                            q.inv_mass = rm.inv_mass; q.inv_inertia = rm.inv_inertia;
+                            q.count = cc.count; q.body = sub;
+                            velocity_row_select(q, vm, wm);
+                            cc.p[0].normal_impulse = q.ni0; cc.p[0].tangent_impulse = q.ti0;
+                            cc.p[1].normal_impulse = q.ni1; cc.p[1].tangent_impulse = q.ti1;
+                        }
+                    }
+                }
+            }
+            // every lane gets every body's velocities and impulses back: the rest of the step is redundant again
+#pragma unroll
+            for (int B = 0; B < 3; ++B) { v[B] = trio_get(tmask, vm, tbase + B); w[B] = trio_get(tmask, wm, tbase + B); }
+            int first_of[3] = {-1, -1, -1};
+            for (int kk = nc - 1; kk >= 0; --kk) { const int k = (int)((order >> (4 * kk)) & 15u); SETB(first_of, ac[k].body, k); }
+#pragma unroll
+            for (int B = 0; B < 3; ++B) {
+                const float ni0 = trio_get(tmask, rm.ni0, tbase + B), ti0 = trio_get(tmask, rm.ti0, tbase + B);
+                const float ni1 = trio_get(tmask, rm.ni1, tbase + B), ti1 = trio_get(tmask, rm.ti1, tbase + B);
+                if (first_of[B] >= 0) {
+                    ActiveContact& cc = ac[first_of[B]];
+                    cc.p[0].normal_impulse = ni0; cc.p[0].tangent_impulse = ti0;
+                    cc.p[1].normal_impulse = ni1; cc.p[1].tangent_impulse = ti1;
+                }
+            }
+            for (int kk = 0; kk < nextra; ++kk) {   // (trio-uniform trip count)
+                ActiveContact& cc = ac[(extra >> (4 * kk)) & 15u];
+                const int src = tbase + cc.body;
+                cc.p[0].normal_impulse = trio_get(tmask, cc.p[0].normal_impulse, src); cc.p[0].tangent_impulse = trio_get(tmask, cc.p[0].tangent_impulse, src);
+                cc.p[1].normal_impulse = trio_get(tmask, cc.p[1].normal_impulse, src); cc.p[1].tangent_impulse = trio_get(tmask, cc.p[1].tangent_impulse, src);
+            }
+        } else {
+        // A fuselage manifold means a crash, and under auto-reset a crashed lander is re-created before the solve (step_autoreset):
+        // its island has no rows at all.  Warps in which no lane holds a fuselage row -- nearly all -- run the loop without it
+        // (one instance of the loop per case: each stays one basic block), a fifth fewer instructions per iteration.
+        auto velocity_iterations = [&](auto row0_tag) {
+        constexpr int B0 = decltype(row0_tag)::value ? 0 : 1;
 #pragma unroll 1
         for (int it = 0; it < VELOCITY_ITERATIONS; ++it) {
             joint_velocity<1>(Jl[1], jw[1], v[0], w[0], v[2], w[2]);   // island order: leg 1's joint, then leg 0's
             joint_velocity<0>(Jl[0], jw[0], v[0], w[0], v[1], w[1]);
             if (HAS_PAIRS && warp_rows) {
 #pragma unroll
-                for (int B = 0; B < 3; ++B) velocity_row_select(row[B], v[B], w[B]);
+                for (int B = B0; B < 3; ++B) velocity_row_select(row[B], v[B], w[B]);
                 if (warp_extra) {
                     for (int kk = 0; kk < nextra; ++kk) {
                         ActiveContact& cc = ac[(extra >> (4 * kk)) & 15u];
@@ -1034,6 +1162,8 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
                 }
             }
         }
+        };
+        if (HAS_PAIRS && warp_row0) velocity_iterations(std::true_type{}); else velocity_iterations(std::false_type{});
         if (HAS_PAIRS) {
             int first_of[3] = {-1, -1, -1};
             for (int kk = nc - 1; kk >= 0; --kk) { const int k = (int)((order >> (4 * kk)) & 15u); SETB(first_of, ac[k].body, k); }
@@ -1045,6 +1175,7 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
                     cc.p[1].normal_impulse = row[B].ni1; cc.p[1].tangent_impulse = row[B].ti1;
                 }
         }
+        }   // !TRIO
 
         LUNAR_PHASE(HAS_PAIRS, 4);
         // integrate positions
@@ -1070,8 +1201,18 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
         // ANGULAR_SLOP + 1 ulp, just above what joints_okay accepts), but after two or three iterations the
         // corrections round to nothing: once an iteration returns bit-identical coordinates, the remaining ones
         // would too, so the loop stops there -- same result as all 60, position_solved stays false.
-        PosRow prow[HAS_PAIRS ? 3 : 1];
-        if (HAS_PAIRS) {
+        PosRow prow[(HAS_PAIRS && !TRIO) ? 3 : 1];
+        if constexpr (TRIO) {
+            PosRow& q = prow[0];
+            q.count = 0; q.body = sub; q.type = MF_FACE_A;
+            q.centroid = SHAPES[sub].centroid; q.inv_mass = SHAPES[sub].inv_mass; q.inv_inertia = SHAPES[sub].inv_inertia;
+            q.local_normal = mk(0.0f, 1.0f); q.local_point = q.lp0 = q.lp1 = mk(0.0f, 0.0f);
+            if (mine >= 0) {
+                const Manifold& m = ac[mine].m;
+                q.local_normal = m.local_normal; q.local_point = m.local_point; q.lp0 = m.lp[0]; q.lp1 = m.lp[1];
+                q.type = m.type; q.count = m.count;
+            }
+        } else if (HAS_PAIRS) {
             int first_of[3] = {-1, -1, -1};
             for (int kk = nc - 1; kk >= 0; --kk) { const int k = (int)((order >> (4 * kk)) & 15u); SETB(first_of, ac[k].body, k); }
 #pragma unroll
@@ -1090,8 +1231,39 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
         // every body angle far inside the single-path range of the argument reduction (a step turns a body by at most pi / 2)?
         const bool small_angles = fabsf(a[0]) < 30000.0f && fabsf(a[1]) < 30000.0f && fabsf(a[2]) < 30000.0f;
         bool position_solved = false;
-        auto position_iterations = [&](auto in_range_tag) {
+        auto position_iterations_trio = [&](auto in_range_tag) {
             constexpr bool IN_RANGE = decltype(in_range_tag)::value;
+            V2 cm = GETB(c, sub); float am = GETB(a, sub);
+            const PosRow& m = prow[0];
+#pragma unroll 1
+            for (int it = 0; it < POSITION_ITERATIONS; ++it) {
+                const V2 c_in = cm; const float a_in = am;
+                float min_separation = 0.0f;
+                if (warp_rows) {
+                    position_point_select<IN_RANGE>(m.count > 0, m.type, m.local_normal, m.local_point, m.lp0, m.centroid, m.inv_mass, m.inv_inertia, cm, am, min_separation);
+                    position_point_select<IN_RANGE>(m.count > 1, m.type, m.local_normal, m.local_point, m.lp1, m.centroid, m.inv_mass, m.inv_inertia, cm, am, min_separation);
+                    if (warp_extra) {
+                        for (int kk = 0; kk < nextra_m; ++kk) {
+                            const ActiveContact& cc = ac[(extra_m >> (4 * kk)) & 15u];
+                            for (int j = 0; j < cc.m.count; ++j)
+                                position_point(cc.m.type, cc.m.local_normal, cc.m.local_point, cc.m.lp[j], m.centroid, m.inv_mass, m.inv_inertia, cm, am, min_separation);
+                        }
+                    }
+                }
+                // min over the island's points >= -3 linearSlop  <=>  every lane's own minimum is
+                const bool contacts_okay = __all_sync(tmask, min_separation >= -3.0f * LINEAR_SLOP) != 0;
+                const bool j1 = joint_position_trio<1, IN_RANGE>(Jl[1], jw[1].motor_mass, tmask, tbase, sub, cm, am);
+                const bool j0 = joint_position_trio<0, IN_RANGE>(Jl[0], jw[0].motor_mass, tmask, tbase, sub, cm, am);
+                if (contacts_okay && j1 && j0) { position_solved = true; break; }
+                const int moved = (__float_as_int(cm.x) ^ __float_as_int(c_in.x)) | (__float_as_int(cm.y) ^ __float_as_int(c_in.y)) | (__float_as_int(am) ^ __float_as_int(a_in));
+                if (__ballot_sync(tmask, moved != 0) == 0u) break;   // fixed point of the whole island
+            }
+#pragma unroll
+            for (int B = 0; B < 3; ++B) { c[B] = trio_get(tmask, cm, tbase + B); a[B] = trio_get(tmask, am, tbase + B); }
+        };
+        auto position_iterations = [&](auto in_range_tag, auto row0_tag) {
+            constexpr bool IN_RANGE = decltype(in_range_tag)::value;
+            constexpr int B0 = decltype(row0_tag)::value ? 0 : 1;
 #pragma unroll 1
             for (int it = 0; it < POSITION_ITERATIONS; ++it) {
                 const V2 c_in[3] = {c[0], c[1], c[2]};
@@ -1099,7 +1271,7 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
                 float min_separation = 0.0f;
                 if (HAS_PAIRS && warp_rows) {
 #pragma unroll
-                    for (int B = 0; B < 3; ++B) {
+                    for (int B = B0; B < 3; ++B) {
                         const PosRow& m = prow[B];
                         position_point_select<IN_RANGE>(m.count > 0, m.type, m.local_normal, m.local_point, m.lp0, m.centroid, m.inv_mass, m.inv_inertia, c[B], a[B], min_separation);
                         position_point_select<IN_RANGE>(m.count > 1, m.type, m.local_normal, m.local_point, m.lp1, m.centroid, m.inv_mass, m.inv_inertia, c[B], a[B], min_separation);
@@ -1127,7 +1299,9 @@ __device__ __forceinline__ void solve(Lander& L, Contacts& C) {
                 if (moved == 0) break;   // fixed point
             }
         };
-        if (small_angles) position_iterations(std::true_type{}); else position_iterations(std::false_type{});
+        if constexpr (TRIO) { if (small_angles) position_iterations_trio(std::true_type{}); else position_iterations_trio(std::false_type{}); }
+        else if (HAS_PAIRS && warp_row0) { if (small_angles) position_iterations(std::true_type{}, std::true_type{}); else position_iterations(std::false_type{}, std::true_type{}); }
+        else { if (small_angles) position_iterations(std::true_type{}, std::false_type{}); else position_iterations(std::false_type{}, std::false_type{}); }
         LUNAR_PHASE(HAS_PAIRS, 5);
 
         // copy back, store impulses (b2ContactSolver::StoreImpulses): slots in creation order
@@ -1379,9 +1553,10 @@ __device__ __forceinline__ void reset(Lander& L, uint64_t seed, uint32_t gid, ui
 // new episode's zero step: same outputs (reward -100, done, the observation after the zero step) and same state, one solve
 // instead of two.  Not taken when the old solve could still matter: the island could fall asleep in this very step (done with
 // +100 overrides -100, :767), or the caller wants the terminal observation (`allow` false).
-template <bool HAS_PAIRS = true>
+template <bool HAS_PAIRS = true, bool TRIO = false>
 __device__ __noinline__ StepResult step_autoreset(Lander& L, uint64_t seed, uint32_t gid, uint64_t t, int i_action, const float* c_action,
                                                   bool allow, uint64_t next_ordinal) {
+    LUNAR_PHASE_NS(HAS_PAIRS, 8);
     LUNAR_PHASE(HAS_PAIRS, 0);
     Powers pw = pre_physics(L, seed, gid, t, i_action, c_action);
     LUNAR_PHASE(HAS_PAIRS, 1);
@@ -1402,11 +1577,12 @@ __device__ __noinline__ StepResult step_autoreset(Lander& L, uint64_t seed, uint
             early = true;
         }
     }
-    solve<HAS_PAIRS>(L, C);                                                                   // :721-725
+    solve<HAS_PAIRS, TRIO>(L, C);                                                             // :721-725
     LUNAR_PHASE(HAS_PAIRS, 6);
     StepResult r = post_physics(L, pw);
     if (early) r = StepResult{-100.0f, 1, 1};
     LUNAR_PHASE(HAS_PAIRS, 7);
+    LUNAR_PHASE_NS(HAS_PAIRS, 9);
     return r;
 }
 

@@ -22,6 +22,22 @@ static void launch_step_t(bool auto_reset, bool limit, int grid, cudaStream_t s,
     else step_kernel<E, false, false><<<grid, STEP_BLOCK, 0, s>>>(a);
 }
 
+template <bool C>
+static void launch_step_trio(bool auto_reset, bool limit, int n, cudaStream_t s, const StepArgs& a) {
+    using E = LunarLanderT<C, true, true>;
+    const int warps = (n + TRIO_ENVS_PER_WARP - 1) / TRIO_ENVS_PER_WARP;
+    const int grid = (warps * 32 + STEP_BLOCK - 1) / STEP_BLOCK;
+    if (auto_reset && limit) step_kernel<E, true, true><<<grid, STEP_BLOCK, 0, s>>>(a);
+    else if (auto_reset) step_kernel<E, true, false><<<grid, STEP_BLOCK, 0, s>>>(a);
+    else if (limit) step_kernel<E, false, true><<<grid, STEP_BLOCK, 0, s>>>(a);
+    else step_kernel<E, false, false><<<grid, STEP_BLOCK, 0, s>>>(a);
+}
+
+cudaError_t lunar_launch_step_trio(bool continuous, bool auto_reset, bool limit, cudaStream_t s, const StepArgs& a) {
+    if (continuous) launch_step_trio<true>(auto_reset, limit, a.n, s, a); else launch_step_trio<false>(auto_reset, limit, a.n, s, a);
+    return cudaGetLastError();
+}
+
 cudaError_t lunar_launch_step(bool continuous, bool has_pairs, bool auto_reset, bool limit, int grid, cudaStream_t s, const StepArgs& a) {
     if (continuous) { if (has_pairs) launch_step_t<true, true>(auto_reset, limit, grid, s, a); else launch_step_t<true, false>(auto_reset, limit, grid, s, a); }
     else { if (has_pairs) launch_step_t<false, true>(auto_reset, limit, grid, s, a); else launch_step_t<false, false>(auto_reset, limit, grid, s, a); }

@@ -13,6 +13,8 @@ constexpr int LUNAR_AUX_DIM = 31;     // int32 words per lander in get_state / s
 // One env step.  has_pairs selects the kernel of the partition class (kernels.cuh "contact partition"); a.part / a.split
 // restrict the launch to that class.  grid = blocks of STEP_BLOCK threads.
 cudaError_t lunar_launch_step(bool continuous, bool has_pairs, bool auto_reset, bool limit, int grid, cudaStream_t stream, const StepArgs& a);
+// The contact class stepped by three lanes per lander (lunar_core.cuh "TRIO"): sizes its own grid (ten landers per warp) from a.n.
+cudaError_t lunar_launch_step_trio(bool continuous, bool auto_reset, bool limit, cudaStream_t stream, const StepArgs& a);
 cudaError_t lunar_launch_reset(bool continuous, int grid, cudaStream_t stream, const ResetArgs& a);
 cudaError_t lunar_launch_sample(bool continuous, int grid, cudaStream_t stream, const SampleArgs& a);
 cudaError_t lunar_launch_ctor(bool continuous, int grid, cudaStream_t stream, const ResetArgs& a);

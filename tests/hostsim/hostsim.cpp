@@ -102,6 +102,10 @@ static void launch(int grid, int block, F&& kernel_call) {
 
 template <class E, bool AR, bool LIM, bool ALL_OUT, int BLOCK>
 static void run_rollout(const RolloutArgs& a) {
+    // all_out + actions_in: the SUPPLIED variant (gymcuda_step_many* with every output requested)
+    if constexpr (ALL_OUT) {
+        if (a.actions_in) { launch((a.n + BLOCK - 1) / BLOCK, BLOCK, [&] { rollout_kernel<E, AR, LIM, true, BLOCK, true>(a); }); return; }
+    }
     launch((a.n + BLOCK - 1) / BLOCK, BLOCK, [&] { rollout_kernel<E, AR, LIM, ALL_OUT, BLOCK>(a); });
 }
 
@@ -117,9 +121,12 @@ static int rollout_dispatch(const RolloutArgs& a, int auto_reset, int all_out, i
 }
 
 
+static int g_trio = 0;   // LunarLander step launches run as the TRIO variant (three lanes per lander; SIMT executor only)
+
 template <class E>
 static int k_step(const StepArgs& a, int auto_reset) {
-    const int grid = (a.n + STEP_BLOCK - 1) / STEP_BLOCK;
+    int grid = (a.n + STEP_BLOCK - 1) / STEP_BLOCK;
+    if constexpr (TrioEnv<E>::value) grid = ((a.n + TRIO_ENVS_PER_WARP - 1) / TRIO_ENVS_PER_WARP * 32 + STEP_BLOCK - 1) / STEP_BLOCK;
     const bool lim = a.limit > 0;
     if (auto_reset && lim) launch(grid, STEP_BLOCK, [&] { step_kernel<E, true, true>(a); });
     else if (auto_reset) launch(grid, STEP_BLOCK, [&] { step_kernel<E, true, false>(a); });
@@ -213,6 +220,7 @@ int hostsim_rollout(int kind, void* state, int32_t* aux, int32_t* sbd, int32_t* 
 // per-env seeds of VecEnv.Seed(int[]) (VecEnv.cs:48-53) for every kernel launched from now on; null = the handle's one seed
 void hostsim_set_seeds(const int32_t* seeds) { g_seeds = seeds; }
 void hostsim_set_simt(int on) { g_simt = on ? 1 : 0; }
+void hostsim_set_trio(int on) { g_trio = on ? 1 : 0; }
 // thread scheduling order of the SIMT executor: 0 ascending, 1 descending, 2 pseudo-random (seeded)
 void hostsim_set_schedule(int policy, uint64_t seed) { simt::g_policy = policy; simt::g_rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull; }
 
@@ -264,8 +272,8 @@ int hostsim_step_kernel(int kind, void* state, int32_t* aux, int32_t* sbd, int32
         case 2: rc = k_step<MountainCar>(a, auto_reset); break;
         case 3: rc = k_step<MountainCarCont>(a, auto_reset); break;
         case 4: rc = k_step<Acrobot>(a, auto_reset); break;
-        case 5: rc = k_step<LunarLander>(a, auto_reset); break;
-        case 6: rc = k_step<LunarLanderCont>(a, auto_reset); break;
+        case 5: rc = g_trio ? k_step<LunarLanderT<false, true, true>>(a, auto_reset) : k_step<LunarLander>(a, auto_reset); break;
+        case 6: rc = g_trio ? k_step<LunarLanderT<true, true, true>>(a, auto_reset) : k_step<LunarLanderCont>(a, auto_reset); break;
     }
     if (rc == 0 && block_epilogue && done_idx != nullptr) {
         int32_t* cnt = blk_cnt.data(); const int32_t* tmp = tmp_idx.data();

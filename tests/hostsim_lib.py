@@ -27,6 +27,7 @@ def build():
     L.hostsim_ctor.argtypes = [I, V, V, I, U32, U64]
     L.hostsim_rollout.argtypes = [I, V, V, V, V, V, V, V, V, V, V, V, V, I, I, I, U32, U64, U64, I, I, I, I, F, F, F, I]
     L.hostsim_set_simt.argtypes = [I]
+    L.hostsim_set_trio.argtypes = [I]
     L.hostsim_set_terminal_obs.argtypes = [V]
     L.hostsim_set_actions_in.argtypes = [V, V]
     L.hostsim_set_seeds.argtypes = [V]
@@ -84,14 +85,13 @@ class HostSim:
         return obs, rew, done, bad
 
     def rollout(self, k, all_out=True, block=64, ep_ret=None, sums=None, done_bits=0, actions_in=None):
-        """actions_in [k][n](, ad): gymcuda_step_many* (the generic variant fed with the caller's actions; all_out must be False);
-        self.rollout_invalid then holds [host flag, rejected count]."""
+        """actions_in [k][n](, ad): gymcuda_step_many* (all_out False: the generic variant fed with the caller's actions; all_out
+        True: the chunked SUPPLIED variant); self.rollout_invalid then holds [host flag, rejected count]."""
         n = self.n
         obs = np.empty((k, n, self.od), np.float32); rew = np.empty((k, n), np.float32); done = np.empty((k, n), np.uint8)
         act = np.empty((k, n), np.int32) if self.actn > 0 else np.empty((k, n, self.ad), np.float32)
         stats = np.zeros(2, np.uint64)
         if actions_in is not None:
-            assert not all_out
             a_in = np.ascontiguousarray(actions_in); flag = np.zeros(1, np.int32)
             self.L.hostsim_set_actions_in(_p(a_in), _p(flag))
             act = None

@@ -69,6 +69,36 @@ def test_reset_and_free_running_policy_bit_exact(continuous):
     env.Close()
 
 
+def test_three_lanes_per_lander_variant_bit_exact():
+    """GYMCUDA_LUNAR_TRIO=1 (the contact class stepped by three lanes per lander, lunar_core.cuh "TRIO"; measured: no gain, so it
+    is off by default): the same free-running comparison with the oracle, in a process of its own because the switch is read once."""
+    import os, subprocess, sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle_lib as O, gymnet_b200 as G
+from test_gpu_lunar import pid
+n, k = 2048, 330
+env = G.LunarLanderVecEnv(n, seed=1000, env_id_offset=5, auto_reset=True, time_limit=300)
+ora = O.OracleEnv(O.LUNARLANDER, n, seed=1000, env_id_offset=5, auto_reset=True, time_limit=300, mode=O.MODE_F32)
+obs = env.ResetBatch(); assert np.array_equal(obs, ora.reset())
+rng = np.random.default_rng(3); touched = 0; episodes = 0
+for t in range(k):
+    a = np.where(rng.random(n) < 0.5, pid(obs), rng.integers(0, 4, n)).astype(np.int32)
+    obs, rew, done = env.StepBatch(a)
+    oobs, orew, odone = ora.step(a)
+    assert np.array_equal(obs, oobs) and np.array_equal(rew, orew) and np.array_equal(done, odone), t
+    touched += int((obs[:, 6:] > 0).any(axis=1).sum()); episodes += int((done != 0).sum())
+st, ax, tt = env.GetState(); ost, oax, ott = ora.get_state()
+assert tt == ott and np.array_equal(st, ost.astype(np.float32)) and np.array_equal(ax, oax)
+assert touched > 0 and episodes > 0
+print("TRIO-OK", touched, episodes)
+""" % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, GYMCUDA_LUNAR_TRIO="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "TRIO-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
 def test_rollout_random_with_auto_reset_bit_exact():
     n, k = 1024, 300
     env = G.LunarLanderVecEnv(n, seed=7, auto_reset=True, time_limit=200)

@@ -116,6 +116,33 @@ def test_step_many_equals_the_oracle_stepped_k_times(name, n, k):
     env.Close()
 
 
+@pytest.mark.parametrize("name,n", [("CartPole-v1", 65536), ("Pendulum-v1", 60000), ("MountainCar-v0", 70000)])
+def test_step_many_one_wave_shape_and_partial_outputs(name, n):
+    """gymcuda_step_many at a batch that takes the one-wave 512-thread shape of the chunked kernel (launched at an unaligned step
+    index: head, chunks, tail), and the same steps with only some outputs requested (the generic variant): both == the oracle."""
+    rng = np.random.default_rng(77)
+    o = O.OracleEnv(KINDS[name], n, seed=9, env_id_offset=11, auto_reset=True, mode=O.MODE_F32)
+    env = MAKE[name](n, seed=9, env_id_offset=11, auto_reset=True)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    L = N.lib()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    od = env.obs_dim
+    for kk, partial in ((3, False), (29, False), (13, True), (16, False)):
+        acts = np.stack([random_actions(env, rng, n) for _ in range(kk)])
+        obs = np.empty((kk, n, od), np.float32); rew = np.empty((kk, n), np.float32); done = np.empty((kk, n), np.uint8)
+        rc = L.gymcuda_step_many(env._h, kk, p(acts), None if partial else p(obs), p(rew), p(done))
+        assert rc == 0, L.gymcuda_last_error()
+        for j in range(kk):
+            wo, wr, wd = o.step(acts[j])
+            assert np.array_equal(rew[j], wr) and np.array_equal(done[j], wd), (name, kk, j)
+            if not partial:
+                assert np.array_equal(obs[j], wo), (name, kk, j)
+        st, aux, t = o.get_state()
+        gs, ga, gt = env.GetState()
+        assert gt == t and np.array_equal(gs, st.astype(np.float32))
+    env.Close()
+
+
 def test_step_many_rejects_invalid_actions_per_step():
     n, k = 500, 20
     rng = np.random.default_rng(5)

@@ -137,6 +137,70 @@ def test_step_kernel_compaction_statistics_and_packed_done(hs, name, kind, n, k)
     assert episodes > 0
 
 
+def _pid(s):
+    """The reference test's heuristic (tests/Gym.Tests/Envs/Aether/LunarLanderEnvironment.cs:102-150), discrete."""
+    angle_targ = np.clip(s[:, 0] * 0.5 + s[:, 2] * 1.0, -0.4, 0.4)
+    hover_targ = 0.55 * np.abs(s[:, 0])
+    angle_todo = (angle_targ - s[:, 4]) * 0.5 - s[:, 5] * 1.0
+    hover_todo = (hover_targ - s[:, 1]) * 0.5 - s[:, 3] * 0.5
+    legs = (s[:, 6] > 0) | (s[:, 7] > 0)
+    angle_todo = np.where(legs, 0.0, angle_todo)
+    hover_todo = np.where(legs, -s[:, 3] * 0.5, hover_todo)
+    a = np.zeros(len(s), np.int32)
+    a[angle_todo > 0.05] = 1
+    a[angle_todo < -0.05] = 3
+    a[(hover_todo > np.abs(angle_todo)) & (hover_todo > 0.05)] = 2
+    return a
+
+
+@pytest.mark.parametrize("kind,n,k,time_limit", [(O.LUNARLANDER, 47, 420, 0), (O.LUNARLANDER_CONT, 13, 150, 0)], ids=["LunarLander-v2", "LunarLanderContinuous-v2"])
+def test_lunar_step_kernel_three_lanes_per_lander(hs, request, kind, n, k, time_limit):
+    """step_kernel<LunarLanderT<C, true, TRIO>>: ten landers per warp, three lanes each (one body per lane inside the velocity /
+    position iterations, joints and exits exchanged with trio-masked shuffles and votes), lanes 30-31 idle, ragged last warp --
+    bit-identical to the oracle through free flight, touch-down on one and two legs, belly contact, rest, sleep and the fused
+    auto-reset (PID heuristic mixed with random actions so that every one of them occurs), with and without the partition's
+    thread -> env permutation."""
+    full = "ascending" in request.node.callspec.id     # the long run under one schedule, a short one (free flight) under the others
+    if not full:
+        if kind != O.LUNARLANDER:
+            pytest.skip("the continuous variant runs under one schedule")
+        k = 12
+    o, sim = pair(hs, kind, n, done_bits=True, time_limit=time_limit)
+    if sim.limit == 0:
+        sim.limit = 0x7fffffff
+    rng = np.random.default_rng(3)
+    obs = sim.reset_kernel(mask=np.zeros(n, np.uint8))           # observe only
+    hs.hostsim_set_trio(1)
+    try:
+        episodes = 0; legs = 0; asleep = 0
+        for t in range(k):
+            if kind == O.LUNARLANDER:
+                a = np.where(rng.random(n) < 0.8, _pid(obs), rng.integers(0, 4, n)).astype(np.int32)
+            else:
+                a = rng.uniform(-1, 1, (n, 2)).astype(F32)
+            oo, orr, od = o.step(a)
+            if full and t < (250 if kind == O.LUNARLANDER else 60):   # the descent: the per-thread body of the plain kernel (fast), in lockstep with the oracle
+                obs = sim.step(a)[0]
+                assert np.array_equal(obs, oo)
+                continue
+            perm = sim.partition()[0] if t % 2 == 0 else None
+            so, sr, sd, idx, flag = sim.step_kernel(a, perm=perm, done_bits=1)
+            assert flag == 0
+            assert np.array_equal(sd, od), "done differs at step %d" % t
+            assert np.array_equal(sr, orr), "reward differs at step %d" % t
+            assert np.array_equal(so, oo), "observation differs at step %d" % t
+            assert np.array_equal(np.sort(idx), np.nonzero(od)[0]), "compacted done list differs at step %d" % t
+            assert same_state(o, sim), "state differs at step %d" % t
+            episodes += int((od != 0).sum()); legs += int((oo[:, 6:] > 0).any(1).sum()); asleep += int((orr == 100.0).sum())
+            obs = so
+        if full:
+            assert episodes > 0 and legs > 0
+            if kind == O.LUNARLANDER:
+                assert asleep > 0          # a lander came to rest and fell asleep (+100)
+    finally:
+        hs.hostsim_set_trio(0)
+
+
 def test_step_kernel_rejects_invalid_actions_and_broadcasts(hs):
     n = 200
     o, sim = pair(hs, O.MOUNTAINCAR, n)
@@ -367,14 +431,23 @@ def test_step_kernel_terminal_observations(hs, name, kind, n, limit, k):
     assert seen > 0
 
 
-@pytest.mark.parametrize("name,kind,n", [("CartPole-v1", O.CARTPOLE, 100), ("Pendulum-v1", O.PENDULUM, 70), ("MountainCar-v0", O.MOUNTAINCAR, 64),
+@pytest.mark.parametrize("name,kind,n", [("CartPole-v1", O.CARTPOLE, 100), ("Pendulum-v1", O.PENDULUM, 72), ("MountainCar-v0", O.MOUNTAINCAR, 64),
                                          ("MountainCarContinuous-v0", O.MOUNTAINCAR_CONT, 33), ("Acrobot-v1", O.ACROBOT, 50)],
                          ids=["CartPole-v1", "Pendulum-v1", "MountainCar-v0", "MountainCarContinuous-v0", "Acrobot-v1"])
-def test_rollout_kernel_with_caller_supplied_actions(hs, name, kind, n):
-    """gymcuda_step_many*: the generic rollout variant fed from `actions_in` == k oracle steps with those actions (auto-reset,
-    default time limits); an invalid action leaves its env unstepped for that step, is counted and raises the host flag."""
+@pytest.mark.parametrize("shape", ["generic", "chunked64", "chunked512"])
+def test_rollout_kernel_with_caller_supplied_actions(hs, name, kind, n, shape):
+    """gymcuda_step_many*: the rollout kernel fed from `actions_in` -- the generic variant, and the chunked all-outputs SUPPLIED
+    variant in its 64- and 512-thread shapes (started at an unaligned step index: head, chunks, tail) -- == k oracle steps with
+    those actions (auto-reset, default time limits); an invalid action leaves its env unstepped for that step, is counted and
+    raises the host flag."""
+    if shape == "chunked512" and kind == O.ACROBOT:
+        pytest.skip("Acrobot has no 512-thread shape (ROLLOUT_CHUNK off)")
     rng = np.random.default_rng(23)
     o, sim = pair(hs, kind, n)
+    if shape != "generic":           # 3 warm-up steps: the chunked launch then starts at t = 3 (a 5-step head before the first chunk)
+        for _ in range(3):
+            a0 = np.ones(n, np.int32) if sim.actn > 0 else np.zeros((n, sim.ad), F32)
+            o.step(a0); sim.step(a0)
     k = 37
     if sim.actn > 0:
         acts = rng.integers(0, sim.actn, (k, n)).astype(np.int32)
@@ -387,7 +460,7 @@ def test_rollout_kernel_with_caller_supplied_actions(hs, name, kind, n):
             acts[bad] = 7
         else:
             acts[bad] = np.nan
-    obs, rew, done, _, episodes = sim.rollout(k, all_out=False, actions_in=acts)
+    obs, rew, done, _, episodes = sim.rollout(k, all_out=shape != "generic", block=512 if shape == "chunked512" else 64, actions_in=acts)
     want_eps = 0
     for j in range(k):
         wo, wr, wd = o.step(acts[j])
