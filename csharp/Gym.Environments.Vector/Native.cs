@@ -72,6 +72,8 @@ namespace Gym.Environments.Vector {
         [DllImport(Lib)] internal static extern int gymcuda_step_many(GymCudaHandle env, int kSteps, int[] actions, float[] obs, float[] reward, byte[] done);
         [DllImport(Lib)] internal static extern int gymcuda_step_many(GymCudaHandle env, int kSteps, float[] actions, float[] obs, float[] reward, byte[] done);
         [DllImport(Lib)] internal static extern int gymcuda_set_terminal_obs(GymCudaHandle env, IntPtr buffer);
+        internal static readonly IntPtr NoObs = new IntPtr(1);   // GYMCUDA_NO_OBS: gymcuda_step_device writes no observation copy
+        [DllImport(Lib)] internal static extern int gymcuda_obs_view_device(GymCudaHandle env, out IntPtr dObs);
         [DllImport(Lib)] internal static extern int gymcuda_box_sample_device(int device, IntPtr cudaStream, ulong seed, ulong index, IntPtr dLow, IntPtr dHigh, int dim, int count, int asInt, IntPtr dOut);
         [DllImport(Lib)] internal static extern int gymcuda_box_sample(int device, ulong seed, ulong index, float[] low, float[] high, int dim, int count, int asInt, float[] output);
         [DllImport(Lib)] internal static extern int gymcuda_rollout_random_device(GymCudaHandle env, int kSteps, IntPtr dObs, IntPtr dReward, IntPtr dDone, IntPtr dActions);

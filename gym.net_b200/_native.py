@@ -8,6 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+NO_OBS = 1   # GYMCUDA_NO_OBS: d_obs value that makes gymcuda_step_device write no observation copy
 # GYMCUDA_LIB: development aid -- load another build of the SAME library (kernel A/B experiments under tools/)
 LIB_PATH = os.environ.get("GYMCUDA_LIB") or os.path.join(HERE, "csrc", "libgymcuda.so")
 
@@ -62,6 +63,7 @@ SYMBOLS = {
     "gymcuda_step_many_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_step_many": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_set_terminal_obs": (_I, [_VP, _VP]),
+    "gymcuda_obs_view_device": (_I, [_VP, C.POINTER(C.c_void_p)]),
     "gymcuda_rollout_random_device": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_rollout_random": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "gymcuda_sample_actions": (_I, [_VP, _VP, _VP]),

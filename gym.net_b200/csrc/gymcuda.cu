@@ -212,7 +212,7 @@ static int check(const gymcuda_env* e) {
 template <class E>
 static cudaError_t launch_step(gymcuda_env* e, const StepArgs& a) {
     const bool ar = e->auto_reset, lim = e->limit > 0;
-    if (e->n >= STEP_BIG_BATCH) {   // a million envs and more: 1024-thread CTAs (kernels.cuh)
+    if (e->n >= STEP_BIG_BATCH) {   // a million envs and more (kernels.cuh)
         const int grid = (e->n + STEP_BLOCK_BIG - 1) / STEP_BLOCK_BIG;
         if (ar && lim) step_kernel<E, true, true, STEP_BLOCK_BIG><<<grid, STEP_BLOCK_BIG, 0, e->stream>>>(a);
         else if (ar) step_kernel<E, true, false, STEP_BLOCK_BIG><<<grid, STEP_BLOCK_BIG, 0, e->stream>>>(a);
@@ -797,10 +797,22 @@ int gymcuda_step_device(gymcuda_env* e, const void* d_actions, float* d_obs, flo
     ENTER(e);
     TRACE("step_device");
     if (!d_actions) return fail(GYMCUDA_EINVAL, "d_actions is null");
+    const bool no_obs = d_obs == GYMCUDA_NO_OBS;   // no observation copy: the caller reads the state in place (gymcuda_obs_view_device) or asks gymcuda_observe
+    if (no_obs) d_obs = nullptr;
     if (int rc = check_device_buffers(e, d_actions, d_obs, d_reward)) return rc;
     e->async_steps = true;
-    return step_launch(e, d_actions, 0, 0, d_obs ? d_obs : e->d_obs, d_reward ? d_reward : e->d_reward,
+    return step_launch(e, d_actions, 0, 0, no_obs ? nullptr : (d_obs ? d_obs : e->d_obs), d_reward ? d_reward : e->d_reward,
                        d_done ? d_done : e->d_done);
+}
+
+int gymcuda_obs_view_device(gymcuda_env* e, const float** d_obs) {
+    ENTER(e);
+    if (!d_obs) return fail(GYMCUDA_EINVAL, "d_obs is null");
+    const int k = e->cfg.env_kind;
+    if (k != GYMCUDA_CARTPOLE && k != GYMCUDA_MOUNTAINCAR && k != GYMCUDA_MOUNTAINCAR_CONT)
+        return fail(GYMCUDA_EINVAL, "the observation of this env kind is computed from its state: there is nothing to view in place");
+    *d_obs = reinterpret_cast<const float*>(e->d_state);
+    return GYMCUDA_OK;
 }
 
 int gymcuda_set_terminal_obs(gymcuda_env* e, float* buffer) {

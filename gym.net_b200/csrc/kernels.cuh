@@ -741,6 +741,14 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
                 if constexpr (SUPPLIED) body(k, __ldcs(act_in + row), std::false_type{}, std::true_type{}, RejTag{});
                 else body(k, gen.next(seed, gid, p.t + (uint64_t)k), std::false_type{}, std::true_type{}, std::false_type{});
             }
+            // SUPPLIED: the actions of the NEXT chunk are loaded while this one is stepped (two register sets of eight)
+            Act ahead[SUPPLIED ? 8 : 1];
+            if constexpr (SUPPLIED) {
+                if (k + 8 <= p.k_steps) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ahead[j] = __ldcs(act_in + (row + (uint32_t)j * (uint32_t)p.n));
+                }
+            }
 #pragma unroll 1
             for (; k + 8 <= p.k_steps; k += 8) {
                 const uint64_t tc = p.t + (uint64_t)k;
@@ -753,8 +761,12 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const RolloutArgs p) {
                     bool ok = true;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        acts[j] = __ldcs(act_in + (row + (uint32_t)j * (uint32_t)p.n));
+                        acts[j] = ahead[j];
                         if (MAY_REJECT) ok = ok && E::valid(acts[j]);
+                    }
+                    if (k + 16 <= p.k_steps) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ahead[j] = __ldcs(act_in + (row + (uint32_t)(8 + j) * (uint32_t)p.n));
                     }
                     if constexpr (MAY_REJECT) {
                         if (!__all_sync(__activemask(), ok)) {   // rare: a rejected action somewhere in the warp's chunk

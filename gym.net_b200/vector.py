@@ -295,6 +295,15 @@ class CudaVecEnv:
         N.check(self._L.gymcuda_step_device(self._h, C.c_void_p(d_actions), C.c_void_p(d_obs or 0),
                                             C.c_void_p(d_reward or 0), C.c_void_p(d_done or 0)))
 
+    NO_OBS = N.NO_OBS   # StepDevice(d_obs=NO_OBS): no observation copy (read them through ObsViewDevice, or call Observe)
+
+    def ObsViewDevice(self):
+        """Device pointer to [n][obs_dim] float32 = the current observations without a copy (the library's state array); only
+        for the env kinds whose observation is their state vector (CartPole, MountainCar, MountainCarContinuous)."""
+        p = C.c_void_p()
+        N.check(self._L.gymcuda_obs_view_device(self._h, C.byref(p)))
+        return p.value
+
     def RolloutRandomDevice(self, k_steps, d_obs=0, d_reward=0, d_done=0, d_actions=0):
         N.check(self._L.gymcuda_rollout_random_device(self._h, int(k_steps), C.c_void_p(d_obs or 0),
                                                       C.c_void_p(d_reward or 0), C.c_void_p(d_done or 0),

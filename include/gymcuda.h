@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GYMCUDA_VERSION 110 /* 0.1.10: round-2 additions (step_many, terminal obs, device clock, box sample, render); purely additive */
+#define GYMCUDA_VERSION 111 /* 0.1.11: round-2 additions (step_many, terminal obs, device clock, box sample, render, obs view); purely additive */
 
 typedef enum gymcuda_status {
     GYMCUDA_OK = 0,
@@ -134,6 +134,16 @@ int gymcuda_step(gymcuda_env* env, const void* actions, float* obs, float* rewar
  * 16 bytes, actions 4 bytes (8 for a 2-D Box), rewards 4; anything else is GYMCUDA_EINVAL. */
 int gymcuda_step_device(gymcuda_env* env, const void* d_actions, float* d_obs, float* d_reward,
                         uint8_t* d_done);
+/* d_obs = GYMCUDA_NO_OBS: the step writes no observation copy at all.  For the envs whose observation IS their state vector
+ * (CartPole: CartPoleEnv.cs:183 returns `state`; MountainCar, MountainCarContinuous) a learner on the device reads the
+ * current observations in place through gymcuda_obs_view_device -- the step then moves the 41 B per CartPole env step of
+ * SURVEY 8d (state read + written, action, reward, done) instead of 57.  For the other envs gymcuda_observe still
+ * recomputes the observations from the state on request. */
+#define GYMCUDA_NO_OBS ((float*)(uintptr_t)1)
+/* *d_obs = device pointer to [num_envs][obs_dim] float32 holding the current observations WITHOUT a copy (the library's
+ * state array), valid until gymcuda_destroy and always current on the handle's stream; GYMCUDA_EINVAL for an env kind
+ * whose observation is computed from its state (Pendulum, Acrobot, LunarLander). */
+int gymcuda_obs_view_device(gymcuda_env* env, const float** d_obs);
 /* Broadcast of one action to every env: the shipped IVecEnv.Step(int action) (IVecEnv.cs:14). */
 int gymcuda_step_broadcast(gymcuda_env* env, int32_t action, float* obs, float* reward, uint8_t* done);
 /* k_steps env steps with CALLER-SUPPLIED actions in ONE launch (the rollout kernel fed from `actions` [k_steps][num_envs]

@@ -39,7 +39,7 @@ def test_python_binding_covers_the_header():
 
 def test_version_and_config_default():
     L = N.lib()
-    assert L.gymcuda_version() == 110
+    assert L.gymcuda_version() == 111
     cfg = N.Config()
     assert L.gymcuda_config_default(C.byref(cfg), N.LUNARLANDER, 8) == 0
     assert cfg.struct_size == C.sizeof(N.Config)

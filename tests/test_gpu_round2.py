@@ -143,6 +143,79 @@ def test_step_many_one_wave_shape_and_partial_outputs(name, n):
     env.Close()
 
 
+@pytest.mark.parametrize("name", ["CartPole-v1", "MountainCar-v0", "MountainCarContinuous-v0"])
+def test_step_device_without_observation_copy_and_obs_view(name):
+    """gymcuda_step_device(d_obs = GYMCUDA_NO_OBS): no observation is written; gymcuda_obs_view_device points at the state
+    array, which IS the current observation of these env kinds -- equal to the oracle's observations after every step,
+    auto-resets included; Pendulum has no such view (EINVAL) and gymcuda_observe still recomputes."""
+    import torch
+    n = 3000
+    rng = np.random.default_rng(8)
+    limit = 50 if name == "MountainCarContinuous-v0" else 0      # (its episodes last 999 steps otherwise)
+    o = O.OracleEnv(KINDS[name], n, seed=4, auto_reset=True, mode=O.MODE_F32, time_limit=limit)
+    env = MAKE[name](n, seed=4, auto_reset=True, time_limit=limit)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    dev = torch.device("cuda", 0)
+    od = env.obs_dim
+    view = env.ObsViewDevice()
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rew = torch.empty(n, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
+    canary = torch.full((n, od), 7.0, device=dev)
+    seen = 0
+    for t in range(260):
+        a = random_actions(env, rng, n)
+        wo, wr, wd = o.step(a)
+        d_a = torch.from_numpy(a).to(dev)
+        env.StepDevice(d_a.data_ptr(), env.NO_OBS, rew.data_ptr(), done.data_ptr()); env.Sync()
+        got = np.empty((n, od), np.float32)
+        assert rt.cudaMemcpy(C.c_void_p(got.ctypes.data), C.c_void_p(view), C.c_size_t(got.nbytes), 2) == 0   # cudaMemcpyDeviceToHost
+        assert np.array_equal(got, wo) and np.array_equal(rew.cpu().numpy(), wr) and np.array_equal(done.cpu().numpy(), wd), t
+        seen += int(wd.sum())
+    assert seen > 0 and bool((canary == 7.0).all())
+    assert np.array_equal(env.Observe(), wo)
+    env.Close()
+    pend = G.PendulumVecEnv(8, seed=1, auto_reset=True); pend.ResetBatch()
+    with pytest.raises(ValueError):          # GYMCUDA_EINVAL (C#: ArgumentException)
+        pend.ObsViewDevice()
+    pend.Close()
+
+
+@pytest.mark.parametrize("name,limit", [("CartPole-v1", 0), ("MountainCar-v0", 9), ("Pendulum-v1", 7)])
+def test_million_env_batch(name, limit):
+    """Batches of 2^20 envs and more (their own launch shape, STEP_BLOCK_BIG): ragged size, == the oracle incl. auto-resets, the time limit firing for every env at once, the done list, and the
+    no-observation-copy mode."""
+    import torch
+    n = (1 << 20) + 77
+    rng = np.random.default_rng(12)
+    o = O.OracleEnv(KINDS[name], n, seed=6, env_id_offset=3, auto_reset=True, mode=O.MODE_F32, time_limit=limit)
+    env = MAKE[name](n, seed=6, env_id_offset=3, auto_reset=True, time_limit=limit)
+    assert np.array_equal(env.ResetBatch(), o.reset())
+    episodes = 0
+    for t in range(24):
+        a = random_actions(env, rng, n)
+        wo, wr, wd = o.step(a)
+        go, gr, gd = env.StepBatch(a)
+        assert np.array_equal(gd, wd) and np.array_equal(gr, wr) and np.array_equal(go, wo), (name, t)
+        episodes += int(wd.sum())
+        if t in (8, 20):
+            assert np.array_equal(np.sort(env.DoneIndices()), np.nonzero(wd)[0])
+    assert episodes > 0 and env.Stats()["episodes"] == episodes
+    if name != "Pendulum-v1":
+        dev = torch.device("cuda", 0)
+        rew = torch.empty(n, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
+        for t in range(6):
+            a = random_actions(env, rng, n)
+            wo, wr, wd = o.step(a)
+            d_a = torch.from_numpy(a).to(dev)
+            env.StepDevice(d_a.data_ptr(), env.NO_OBS, rew.data_ptr(), done.data_ptr()); env.Sync()
+            assert np.array_equal(done.cpu().numpy(), wd) and np.array_equal(rew.cpu().numpy(), wr)
+        assert np.array_equal(env.Observe(), wo)
+    st, aux, t = o.get_state()
+    gs, ga, gt = env.GetState()
+    assert gt == t and np.array_equal(gs, st.astype(np.float32))
+    env.Close()
+
+
 def test_step_many_rejects_invalid_actions_per_step():
     n, k = 500, 20
     rng = np.random.default_rng(5)
