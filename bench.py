@@ -12,8 +12,9 @@ One step writes num_envs * inner * 25 B = 839 MB >> the 126 MB L2, so no L2 flus
 The timed region is K launches right after the warm-up (one kernel timed alone: the regime of the burst copy
 behind MEASURED_PEAKS.json); `roofline.sustained` repeats the measurement after >= 0.6 s of continuous launches,
 next to a memset and a copy timed live in the same state.
-`e2e` is the same metric through the host-buffer C-ABI call (gymcuda_step) with pinned HOST action /
-obs / reward / done buffers: H2D + kernel + D2H inside the timed region, every step.
+`e2e` is the same metric, same bench step (`--inner` env steps of every env), through the host-buffer C-ABI call
+gymcuda_step_many with pinned HOST buffers: the caller's actions travel in and obs / reward / done travel out inside the
+timed region, every step; `e2e.per_step_call` is the one-env-step-per-call figure (gymcuda_step, the reference's Step()).
 After the headline, the same process measures the other BASELINE.json configs and appends them as `envs` to the one JSON
 line (SURVEY 8d configs 3-5 and the L2-busting 16 777 216-env CartPole step run), each with the roofline that binds it.
 Prints exactly one JSON line on rank 0.
@@ -534,7 +535,7 @@ def main():
         except Exception:
             pass
 
-    # ---- e2e: host buffers through gymcuda_step (H2D actions, kernel, D2H obs/reward/done), every step
+    # ---- host buffers through gymcuda_step (H2D actions, kernel, D2H obs/reward/done), one env step per call
     e2e_steps = args.e2e_steps
     h_act = torch.empty((n, ad), dtype=t_act.dtype).pin_memory()
     # obs | reward | done adjacent in one pinned block (what the C# shim pins): the library then needs one DMA
@@ -571,10 +572,58 @@ def main():
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e = {"value": world * n * e2e_steps / e2e_s, "unit": "env-steps/s",
-           "h2d_bytes_per_step": n * ad * 4, "d2h_bytes_per_step": n * (od * 4 + 4 + 1),
-           "api": "gymcuda_step (host buffers, pinned)", "steps": e2e_steps,
+    per_call = {"value": world * n * e2e_steps / e2e_s, "unit": "env-steps/s",
+                "h2d_bytes_per_call": n * ad * 4, "d2h_bytes_per_call": n * (od * 4 + 4 + 1),
+                "api": "gymcuda_step (host buffers, pinned): one env step of every env per call", "calls": e2e_steps}
+
+    # ---- e2e, the bench's own step: K env steps of every env per call through gymcuda_step_many with pinned HOST buffers --
+    # the caller's actions [K][n] travel in, obs / reward / done [K][n] travel out, every call; inside the call the action
+    # chunks, the chunk launches and the trajectory chunks are pipelined over PCIe's two directions (gymcuda.cu host_k_steps)
+    K = args.inner
+    hm_act = torch.empty((K, n, ad), dtype=t_act.dtype).pin_memory()
+    hm_obs = torch.empty((K, n, od), dtype=torch.float32).pin_memory()
+    hm_rew = torch.empty((K, n), dtype=torch.float32).pin_memory()
+    hm_done = torch.empty((K, n), dtype=torch.uint8).pin_memory()
+    if env.act_n > 0:
+        hm_act.numpy()[:] = rng.integers(0, env.act_n, (K, n, ad))
+    else:
+        hm_act.numpy()[:] = rng.uniform(-1, 1, (K, n, ad))
+    many_args = (env._h, C.c_int(K), C.c_void_p(hm_act.data_ptr()), C.c_void_p(hm_obs.data_ptr()),
+                 C.c_void_p(hm_rew.data_ptr()), C.c_void_p(hm_done.data_ptr()))
+
+    def e2e_many():
+        if L.gymcuda_step_many(*many_args) != 0:
+            raise RuntimeError(L.gymcuda_last_error())
+
+    for _ in range(max(3, args.warmup)):
+        e2e_many()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_many()
+    barrier()
+    many_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([many_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        many_s = float(tt.item())
+    h2d, d2h = K * n * ad * 4, K * n * (od * 4 + 4 + 1)
+    # the PCIe ceiling of that call, live: one bare device -> pinned-host DMA of the size of its observations
+    d_src = torch.empty((K, n, od), dtype=torch.float32, device=dev)
+    hm_obs.copy_(d_src, non_blocking=True); torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(); hm_obs.copy_(d_src, non_blocking=True); c1.record(); torch.cuda.synchronize()
+    dma_gbs = d_src.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del d_src
+    e2e = {"value": world * n * K * args.steps / many_s, "unit": "env-steps/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "gymcuda_step_many (host buffers, pinned): %d env steps of every env per call = one bench step, caller-supplied actions" % K,
+           "steps": args.steps, "ms_per_step": many_s / args.steps * 1e3,
+           "pcie_gbs_per_gpu": {"h2d": h2d * args.steps / many_s / 1e9, "d2h": d2h * args.steps / many_s / 1e9,
+                                "bare_d2h_dma_live": dma_gbs, "d2h_frac_of_bare_dma": d2h * args.steps / many_s / 1e9 / dma_gbs},
+           "per_step_call": per_call,
            "host_affinity": ("%d cores of the GPU's NUMA node" % len(host_cpus)) if host_cpus else "unchanged"}
+    del hm_act, hm_obs, hm_rew, hm_done
 
     # ---- N > 1 only, outside the headline timing: what the optional observation all-gather costs per step,
     # with NCCL after the step kernel and fused into it as NVLink peer stores (gymcuda_step_gather_device)

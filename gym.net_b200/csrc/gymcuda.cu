@@ -138,6 +138,8 @@ struct gymcuda_env {
     EnvParams prm;
     int32_t *d_perm, *d_block_free;   // LunarLander contact partition
     cudaStream_t side_stream;         // LunarLander: the kernel of the second partition class runs here, concurrently
+    cudaStream_t in_stream, out_stream;   // host-buffer k-step calls: action chunks travel in, trajectory chunks travel out while the next chunk is stepped (created on first use)
+    std::vector<cudaEvent_t> pipe_events; // their events (grow-only)
     cudaEvent_t ev_fork, ev_join;
     int sm_count;                     // multiprocessors of the device (launch heuristics)
     int auxw;   // int32 words per env in d_aux (LunarLander only)
@@ -389,6 +391,9 @@ int gymcuda_destroy(gymcuda_env* e) {
     cudaFree(e->g_local);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->side_stream) { cudaStreamSynchronize(e->side_stream); cudaStreamDestroy(e->side_stream); }
+    if (e->in_stream) { cudaStreamSynchronize(e->in_stream); cudaStreamDestroy(e->in_stream); }
+    if (e->out_stream) { cudaStreamSynchronize(e->out_stream); cudaStreamDestroy(e->out_stream); }
+    for (cudaEvent_t ev : e->pipe_events) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     cudaFree(e->d_state); cudaFree(e->d_sbd); cudaFree(e->d_ept); cudaFree(e->d_episode); cudaFree(e->d_seeds); cudaFree(e->d_aux); cudaFree(e->d_perm); cudaFree(e->d_block_free);
@@ -875,28 +880,91 @@ int gymcuda_step_many_device(gymcuda_env* e, int k_steps, const void* d_actions,
 
 static cudaError_t scratch_reserve(gymcuda_env* e, int slot, size_t bytes, void** out);
 
+// Host-buffer k-step calls as a three-stage pipeline over chunks of steps: the actions of chunk c + 1 travel to the device
+// (in_stream) and the trajectory of chunk c - 1 travels back (out_stream) while chunk c is stepped on the handle's stream.
+// PCIe is full duplex, so the call lasts about as long as its larger direction -- the trajectory -- alone.  The state is
+// carried between the chunk launches in device memory, so the result is that of one k-step launch (tests T4: k-split).
+// Chunk = a multiple of 8 steps (the chunked kernels' alignment) holding ~16 MB of trajectory.
+static int pipe_chunk_steps(const gymcuda_env* e, int k_steps) {
+    const size_t per_step = (size_t)e->n * ((size_t)e->ki.od * 4 + 4 + 1 + (size_t)e->ki.ad * 4);
+    size_t c = ((size_t)16 << 20) / (per_step ? per_step : 1);
+    c = (c + 7) / 8 * 8;
+    if (c < 8) c = 8;
+    // the first chunk ends on a multiple of 8 of the absolute step index, so that every later launch starts aligned
+    const size_t head = (size_t)((8u - ((unsigned)e->t & 7u)) & 7u);
+    size_t first = head ? head + (c > 8 ? c - 8 : 0) : c;
+    if (first > (size_t)k_steps) first = (size_t)k_steps;
+    return (int)first;   // (the caller uses c for the following chunks)
+}
+static cudaError_t pipe_prepare(gymcuda_env* e, size_t events) {
+    cudaError_t ce;
+    if (!e->in_stream && (ce = cudaStreamCreateWithFlags(&e->in_stream, cudaStreamNonBlocking)) != cudaSuccess) return ce;
+    if (!e->out_stream && (ce = cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking)) != cudaSuccess) return ce;
+    while (e->pipe_events.size() < events) {
+        cudaEvent_t ev;
+        if ((ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return ce;
+        e->pipe_events.push_back(ev);
+    }
+    return cudaSuccess;
+}
+
+// supplied = true: gymcuda_step_many (actions in, obs / reward / done out); false: gymcuda_rollout_random (everything out)
+static int host_k_steps(gymcuda_env* e, bool supplied, int k_steps, const void* actions_in, float* obs, float* reward, uint8_t* done, void* actions_out) {
+    const size_t n = (size_t)e->n, od = (size_t)e->ki.od, ab = (size_t)e->ki.ad * 4;
+    const size_t kn = (size_t)k_steps * n;
+    void *d_obs = nullptr, *d_reward = nullptr, *d_done = nullptr, *d_act = nullptr;
+#define HK_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    HK_TRY(scratch_reserve(e, 0, obs ? kn * od * 4 : 0, &d_obs));
+    HK_TRY(scratch_reserve(e, 1, reward ? kn * 4 : 0, &d_reward));
+    HK_TRY(scratch_reserve(e, 2, done ? kn : 0, &d_done));
+    HK_TRY(scratch_reserve(e, 3, (supplied || actions_out) ? kn * ab : 0, &d_act));
+    const int c_first = pipe_chunk_steps(e, k_steps);
+    int c_rest = (int)((((size_t)16 << 20) / (n * (od * 4 + 4 + 1 + ab)) + 7) / 8 * 8);
+    if (c_rest < 8) c_rest = 8;
+    const size_t chunks = 1 + (size_t)((k_steps - c_first) + c_rest - 1) / (size_t)c_rest;
+    HK_TRY(pipe_prepare(e, 2 * chunks + 1));
+    // everything queued on the handle's stream so far (earlier asynchronous steps, a pending H2D) precedes the pipeline
+    HK_TRY(cudaEventRecord(e->pipe_events[2 * chunks], e->stream));
+    HK_TRY(cudaStreamWaitEvent(e->in_stream, e->pipe_events[2 * chunks], 0));
+    HK_TRY(cudaStreamWaitEvent(e->out_stream, e->pipe_events[2 * chunks], 0));
+    size_t ci = 0;
+    for (int k0 = 0; k0 < k_steps; ++ci) {
+        const int kc = k0 == 0 ? c_first : (k_steps - k0 < c_rest ? k_steps - k0 : c_rest);
+        const size_t off = (size_t)k0 * n, cnt = (size_t)kc * n;
+        uint8_t* const d_act_c = d_act ? static_cast<uint8_t*>(d_act) + off * ab : nullptr;
+        if (supplied) {
+            HK_TRY(cudaMemcpyAsync(d_act_c, static_cast<const uint8_t*>(actions_in) + off * ab, cnt * ab, cudaMemcpyHostToDevice, e->in_stream));
+            HK_TRY(cudaEventRecord(e->pipe_events[2 * ci], e->in_stream));
+            HK_TRY(cudaStreamWaitEvent(e->stream, e->pipe_events[2 * ci], 0));
+        }
+        float* const d_obs_c = d_obs ? static_cast<float*>(d_obs) + off * od : nullptr;
+        float* const d_rew_c = d_reward ? static_cast<float*>(d_reward) + off : nullptr;
+        uint8_t* const d_done_c = d_done ? static_cast<uint8_t*>(d_done) + off : nullptr;
+        const int rc = supplied ? gymcuda_step_many_device(e, kc, d_act_c, d_obs_c, d_rew_c, d_done_c)
+                                : gymcuda_rollout_random_device(e, kc, d_obs_c, d_rew_c, d_done_c, d_act_c);
+        if (rc) { cudaStreamSynchronize(e->in_stream); cudaStreamSynchronize(e->out_stream); cudaStreamSynchronize(e->stream); return rc; }
+        HK_TRY(cudaEventRecord(e->pipe_events[2 * ci + 1], e->stream));
+        HK_TRY(cudaStreamWaitEvent(e->out_stream, e->pipe_events[2 * ci + 1], 0));
+        if (obs) HK_TRY(cudaMemcpyAsync(obs + off * od, d_obs_c, cnt * od * 4, cudaMemcpyDeviceToHost, e->out_stream));
+        if (reward) HK_TRY(cudaMemcpyAsync(reward + off, d_rew_c, cnt * 4, cudaMemcpyDeviceToHost, e->out_stream));
+        if (done) HK_TRY(cudaMemcpyAsync(done + off, d_done_c, cnt, cudaMemcpyDeviceToHost, e->out_stream));
+        if (!supplied && actions_out) HK_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(actions_out) + off * ab, d_act_c, cnt * ab, cudaMemcpyDeviceToHost, e->out_stream));
+        k0 += kc;
+    }
+    HK_TRY(cudaStreamSynchronize(e->out_stream));
+#undef HK_TRY
+    e->async_steps = false;   // synchronised below
+    return step_finish_host(e, nullptr, nullptr, nullptr);   // synchronise the handle's stream + report rejected actions
+}
+
 int gymcuda_step_many(gymcuda_env* e, int k_steps, const void* actions, float* obs, float* reward, uint8_t* done) {
     ENTER(e);
     TRACE("step_many");
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
     if (!actions) return fail(GYMCUDA_EINVAL, "actions is null");
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "Step() before Reset(): the reference dereferences a null state here (CartPoleEnv.cs:40,141)");
     if (int rc0 = drain_async_invalid(e)) return rc0;
-    const size_t kn = (size_t)k_steps * (size_t)e->n;
-    void *d_obs = nullptr, *d_reward = nullptr, *d_done = nullptr, *d_act = nullptr;
-#define SM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
-    SM_TRY(scratch_reserve(e, 0, obs ? kn * e->ki.od * 4 : 0, &d_obs));
-    SM_TRY(scratch_reserve(e, 1, reward ? kn * 4 : 0, &d_reward));
-    SM_TRY(scratch_reserve(e, 2, done ? kn : 0, &d_done));
-    SM_TRY(scratch_reserve(e, 3, kn * e->ki.ad * 4, &d_act));
-    SM_TRY(cudaMemcpyAsync(d_act, actions, kn * e->ki.ad * 4, cudaMemcpyHostToDevice, e->stream));
-    int rc = gymcuda_step_many_device(e, k_steps, d_act, (float*)d_obs, (float*)d_reward, (uint8_t*)d_done);
-    if (rc) return rc;
-    e->async_steps = false;   // synchronised below
-    if (obs) SM_TRY(cudaMemcpyAsync(obs, d_obs, kn * e->ki.od * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (reward) SM_TRY(cudaMemcpyAsync(reward, d_reward, kn * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (done) SM_TRY(cudaMemcpyAsync(done, d_done, kn, cudaMemcpyDeviceToHost, e->stream));
-#undef SM_TRY
-    return step_finish_host(e, nullptr, nullptr, nullptr);   // synchronise + report rejected actions
+    return host_k_steps(e, true, k_steps, actions, obs, reward, done, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -949,23 +1017,10 @@ static cudaError_t scratch_reserve(gymcuda_env* e, int slot, size_t bytes, void*
 
 int gymcuda_rollout_random(gymcuda_env* e, int k_steps, float* obs, float* reward, uint8_t* done, void* actions) {
     ENTER(e);
+    TRACE("rollout_random");
     if (k_steps <= 0) return fail(GYMCUDA_EINVAL, "k_steps must be > 0");
-    const size_t kn = (size_t)k_steps * (size_t)e->n;
-    void *d_obs = nullptr, *d_reward = nullptr, *d_done = nullptr, *d_act = nullptr;
-#define RB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); return fail(_e == cudaErrorMemoryAllocation ? GYMCUDA_ENOMEM : GYMCUDA_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
-    RB_TRY(scratch_reserve(e, 0, obs ? kn * e->ki.od * 4 : 0, &d_obs));
-    RB_TRY(scratch_reserve(e, 1, reward ? kn * 4 : 0, &d_reward));
-    RB_TRY(scratch_reserve(e, 2, done ? kn : 0, &d_done));
-    RB_TRY(scratch_reserve(e, 3, actions ? kn * e->ki.ad * 4 : 0, &d_act));
-    int rc = gymcuda_rollout_random_device(e, k_steps, (float*)d_obs, (float*)d_reward, (uint8_t*)d_done, d_act);
-    if (rc) return rc;
-    if (obs) RB_TRY(cudaMemcpyAsync(obs, d_obs, kn * e->ki.od * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (reward) RB_TRY(cudaMemcpyAsync(reward, d_reward, kn * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (done) RB_TRY(cudaMemcpyAsync(done, d_done, kn, cudaMemcpyDeviceToHost, e->stream));
-    if (actions) RB_TRY(cudaMemcpyAsync(actions, d_act, kn * e->ki.ad * 4, cudaMemcpyDeviceToHost, e->stream));
-    RB_TRY(cudaStreamSynchronize(e->stream));
-#undef RB_TRY
-    return GYMCUDA_OK;
+    if (!e->has_state) return fail(GYMCUDA_ESTATE, "rollout before Reset()");
+    return host_k_steps(e, false, k_steps, nullptr, obs, reward, done, actions);
 }
 
 // ------------------------------------------------------------------------------------------------
