@@ -148,8 +148,6 @@ struct gymcuda_env {
     uint8_t* d_out;          // obs | reward | done
     float *d_obs, *d_reward;
     uint8_t *d_done, *d_mask, *d_sample_mask;
-    const void* alias_host[4]; void* alias_dev[4];   // cache of mapped_alias()
-    unsigned alias_epoch;
     void* scratch[4]; size_t scratch_cap[4];   // device scratch of gymcuda_rollout_random (host buffers)
     volatile int* h_invalid; // mapped pinned flags: [0] set by the step kernel when it rejects an action,
     int* d_invalid_flag;     //                      [1] set by gather_wait_kernel on a timeout (1 + missing rank)
@@ -678,11 +676,6 @@ static int step_launch(gymcuda_env* e, const void* d_actions, int use_bcast, int
     return GYMCUDA_OK;
 }
 
-// Device-visible alias of a host pointer if (and only if) it is page-locked memory mapped into the
-// device address space (cudaHostAlloc / cudaHostRegister / gymcuda_host_alloc), else null.
-static std::atomic<unsigned> g_host_epoch{1};   // bumped by every (un)registration / pinned (de)allocation made through this library
-                                                // (handles may live on different host threads)
-
 static bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // What the kernels' vector accesses need: observations leave as 16 B (float4) or 8 B (float2) vectors, a 2-D Box action
@@ -697,22 +690,19 @@ static int check_device_buffers(const gymcuda_env* e, const void* actions, const
     return GYMCUDA_OK;
 }
 
-// `align`: a mapped buffer the kernel could not address with its vector accesses counts as not mapped (it is staged)
-static void* mapped_alias(gymcuda_env* e, const void* host, int slot, size_t align) {
+// Device-visible alias of a host pointer if (and only if) it is page-locked memory mapped into the device address space
+// (cudaHostAlloc / cudaHostRegister / gymcuda_host_alloc), else null.
+// `align`: a mapped buffer the kernel could not address with its vector accesses counts as not mapped (it is staged).
+// Asked anew on every call (a fraction of a microsecond next to a launch): a cached answer would outlive a buffer that was
+// unpinned or freed behind the library's back (raw cudaFreeHost / cudaHostUnregister, a torch tensor going away) and whose
+// address came back as pageable memory -- the kernel would then store through a stale device alias (ADVICE, round 1).
+static void* mapped_alias(gymcuda_env*, const void* host, int, size_t align) {
     if (!host || !is_aligned(host, align)) return nullptr;
-    const unsigned epoch = g_host_epoch.load(std::memory_order_acquire);
-    if (e->alias_epoch != epoch) {   // a buffer may have been registered or released since the answers were cached
-        for (int k = 0; k < 4; ++k) e->alias_host[k] = nullptr;
-        e->alias_epoch = epoch;
-    }
-    if (e->alias_host[slot] == host) return e->alias_dev[slot];
     cudaPointerAttributes at;
     void* dev = nullptr;
     if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) dev = at.devicePointer;
     else cudaGetLastError();   // pageable memory reports an error on old drivers: clear it
     if (dev && !is_aligned(dev, align)) dev = nullptr;
-    e->alias_host[slot] = host;
-    e->alias_dev[slot] = dev;
     return dev;
 }
 
@@ -1420,27 +1410,23 @@ int gymcuda_sync(gymcuda_env* e) {
 int gymcuda_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(GYMCUDA_EINVAL, "ptr is null");
     CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_free(void* ptr) {
     if (ptr) CU_TRY(cudaFreeHost(ptr));
-    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_register(void* ptr, size_t bytes) {
     if (!ptr || bytes == 0) return fail(GYMCUDA_EINVAL, "gymcuda_host_register: null pointer or empty range");
     CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
-    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 
 int gymcuda_host_unregister(void* ptr) {
     if (!ptr) return GYMCUDA_OK;
     CU_TRY(cudaHostUnregister(ptr));
-    g_host_epoch.fetch_add(1, std::memory_order_release);
     return GYMCUDA_OK;
 }
 

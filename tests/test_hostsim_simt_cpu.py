@@ -179,7 +179,7 @@ def test_lunar_step_kernel_three_lanes_per_lander(hs, request, kind, n, k, time_
             else:
                 a = rng.uniform(-1, 1, (n, 2)).astype(F32)
             oo, orr, od = o.step(a)
-            if full and t < (250 if kind == O.LUNARLANDER else 60):   # the descent: the per-thread body of the plain kernel (fast), in lockstep with the oracle
+            if full and t < (250 if kind == O.LUNARLANDER else 100):   # the descent: the per-thread body of the plain kernel (fast), in lockstep with the oracle
                 obs = sim.step(a)[0]
                 assert np.array_equal(obs, oo)
                 continue
