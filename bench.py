@@ -580,50 +580,64 @@ def main():
     # the caller's actions [K][n] travel in, obs / reward / done [K][n] travel out, every call; inside the call the action
     # chunks, the chunk launches and the trajectory chunks are pipelined over PCIe's two directions (gymcuda.cu host_k_steps)
     K = args.inner
-    hm_act = torch.empty((K, n, ad), dtype=t_act.dtype).pin_memory()
-    hm_obs = torch.empty((K, n, od), dtype=torch.float32).pin_memory()
-    hm_rew = torch.empty((K, n), dtype=torch.float32).pin_memory()
-    hm_done = torch.empty((K, n), dtype=torch.uint8).pin_memory()
-    if env.act_n > 0:
-        hm_act.numpy()[:] = rng.integers(0, env.act_n, (K, n, ad))
-    else:
-        hm_act.numpy()[:] = rng.uniform(-1, 1, (K, n, ad))
-    many_args = (env._h, C.c_int(K), C.c_void_p(hm_act.data_ptr()), C.c_void_p(hm_obs.data_ptr()),
-                 C.c_void_p(hm_rew.data_ptr()), C.c_void_p(hm_done.data_ptr()))
+    alloc_error = None
+    try:
+        hm_act = torch.empty((K, n, ad), dtype=t_act.dtype).pin_memory()
+        hm_obs = torch.empty((K, n, od), dtype=torch.float32).pin_memory()
+        hm_rew = torch.empty((K, n), dtype=torch.float32).pin_memory()
+        hm_done = torch.empty((K, n), dtype=torch.uint8).pin_memory()
+    except Exception as ex:   # the 840 MB of pinned host memory per rank could not be had
+        alloc_error = repr(ex)[:300]
+    if world > 1:   # every rank takes the same path (the timed loop below holds barriers)
+        flag = torch.tensor([0 if alloc_error is None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) and alloc_error is None:
+            alloc_error = "another rank could not allocate its pinned host buffers"
+    if alloc_error is None:
+        if env.act_n > 0:
+            hm_act.numpy()[:] = rng.integers(0, env.act_n, (K, n, ad))
+        else:
+            hm_act.numpy()[:] = rng.uniform(-1, 1, (K, n, ad))
+        many_args = (env._h, C.c_int(K), C.c_void_p(hm_act.data_ptr()), C.c_void_p(hm_obs.data_ptr()),
+                     C.c_void_p(hm_rew.data_ptr()), C.c_void_p(hm_done.data_ptr()))
 
-    def e2e_many():
-        if L.gymcuda_step_many(*many_args) != 0:
-            raise RuntimeError(L.gymcuda_last_error())
+        def e2e_many():
+            if L.gymcuda_step_many(*many_args) != 0:
+                raise RuntimeError(L.gymcuda_last_error())
 
-    for _ in range(max(3, args.warmup)):
-        e2e_many()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_many()
-    barrier()
-    many_s = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([many_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        many_s = float(tt.item())
-    h2d, d2h = K * n * ad * 4, K * n * (od * 4 + 4 + 1)
-    # the PCIe ceiling of that call, live: one bare device -> pinned-host DMA of the size of its observations
-    d_src = torch.empty((K, n, od), dtype=torch.float32, device=dev)
-    hm_obs.copy_(d_src, non_blocking=True); torch.cuda.synchronize()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record(); hm_obs.copy_(d_src, non_blocking=True); c1.record(); torch.cuda.synchronize()
-    dma_gbs = d_src.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    del d_src
-    e2e = {"value": world * n * K * args.steps / many_s, "unit": "env-steps/s",
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "gymcuda_step_many (host buffers, pinned): %d env steps of every env per call = one bench step, caller-supplied actions" % K,
-           "steps": args.steps, "ms_per_step": many_s / args.steps * 1e3,
-           "pcie_gbs_per_gpu": {"h2d": h2d * args.steps / many_s / 1e9, "d2h": d2h * args.steps / many_s / 1e9,
-                                "bare_d2h_dma_live": dma_gbs, "d2h_frac_of_bare_dma": d2h * args.steps / many_s / 1e9 / dma_gbs},
-           "per_step_call": per_call,
-           "host_affinity": ("%d cores of the GPU's NUMA node" % len(host_cpus)) if host_cpus else "unchanged"}
-    del hm_act, hm_obs, hm_rew, hm_done
+        for _ in range(max(3, args.warmup)):
+            e2e_many()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_many()
+        barrier()
+        many_s = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([many_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            many_s = float(tt.item())
+        h2d, d2h = K * n * ad * 4, K * n * (od * 4 + 4 + 1)
+        # the PCIe ceiling of that call, live: one bare device -> pinned-host DMA of the size of its observations
+        d_src = torch.empty((K, n, od), dtype=torch.float32, device=dev)
+        hm_obs.copy_(d_src, non_blocking=True); torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(); hm_obs.copy_(d_src, non_blocking=True); c1.record(); torch.cuda.synchronize()
+        dma_gbs = d_src.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del d_src
+        e2e = {"value": world * n * K * args.steps / many_s, "unit": "env-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "gymcuda_step_many (host buffers, pinned): %d env steps of every env per call = one bench step, caller-supplied actions" % K,
+               "steps": args.steps, "ms_per_step": many_s / args.steps * 1e3,
+               "pcie_gbs_per_gpu": {"h2d": h2d * args.steps / many_s / 1e9, "d2h": d2h * args.steps / many_s / 1e9,
+                                    "bare_d2h_dma_live": dma_gbs, "d2h_frac_of_bare_dma": d2h * args.steps / many_s / 1e9 / dma_gbs},
+               "per_step_call": per_call,
+               "host_affinity": ("%d cores of the GPU's NUMA node" % len(host_cpus)) if host_cpus else "unchanged"}
+        del hm_act, hm_obs, hm_rew, hm_done
+    else:   # the per-call figure stands in, and says so
+        e2e = dict(per_call, h2d_bytes_per_step=per_call["h2d_bytes_per_call"], d2h_bytes_per_step=per_call["d2h_bytes_per_call"],
+                   steps=e2e_steps, step_many_error=alloc_error,
+                   host_affinity=("%d cores of the GPU's NUMA node" % len(host_cpus)) if host_cpus else "unchanged")
 
     # ---- N > 1 only, outside the headline timing: what the optional observation all-gather costs per step,
     # with NCCL after the step kernel and fused into it as NVLink peer stores (gymcuda_step_gather_device)
