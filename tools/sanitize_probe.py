@@ -1,9 +1,17 @@
-"""Small pass over every kernel for compute-sanitizer (memcheck / racecheck)."""
+"""Small pass over every kernel for compute-sanitizer (memcheck / racecheck).
+   `python tools/sanitize_probe.py lunar` runs only the LunarLander contact loop (used with GYMCUDA_LUNAR_TRIO=1)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gymnet_b200 as G
 rng = np.random.default_rng(0)
+if len(sys.argv) > 1 and sys.argv[1] == "lunar":
+    ll = G.LunarLanderVecEnv(1500, seed=2, auto_reset=True, time_limit=300); obs = ll.ResetBatch()
+    for _ in range(120):
+        obs, r, d = ll.StepBatch(np.full(1500, 0, np.int32))
+    print("contacts", float((obs[:, 6:] > 0).any(1).mean()), "trio", os.environ.get("GYMCUDA_LUNAR_TRIO", "0"))
+    ll.Close()
+    sys.exit(0)
 for name, n in (("CartPole-v1", 3001), ("Pendulum-v1", 1025), ("MountainCar-v0", 515), ("MountainCarContinuous-v0", 515),
                 ("Acrobot-v1", 777), ("LunarLander-v2", 2500)):
     for auto in (False, True):
@@ -65,5 +73,23 @@ for name, n in (("CartPole-v1", 3001), ("Acrobot-v1", 777), ("LunarLander-v2", 7
         g.replay()
     torch.cuda.synchronize(); env.DoneIndices(); env.Stats(); env.SetDeviceClock(False)
     env.Close()
+# last session of round 2: step_many in the one-wave 512-thread shape from an unaligned step index (head, chunks with the next chunk's
+# actions prefetched, tail), a host call long enough for several pipelined chunks, rollouts through the same pipeline, no-observation-copy steps
+env = G.make("CartPole-v1", 57344 + 40, seed=5, auto_reset=True); env.ResetBatch()
+env.StepBatch(np.zeros(57344 + 40, np.int32))
+env.StepMany(rng.integers(0, 2, (45, 57344 + 40)).astype(np.int32))
+env.RolloutRandom(40)
+dev = torch.device("cuda", 0)
+a = torch.zeros(57344 + 40, dtype=torch.int32, device=dev); r = torch.empty(57344 + 40, device=dev); d = torch.empty(57344 + 40, dtype=torch.uint8, device=dev)
+for _ in range(3):
+    env.StepDevice(a.data_ptr(), env.NO_OBS, r.data_ptr(), d.data_ptr())
+env.Sync(); env.ObsViewDevice(); env.Observe(); env.Close()
+env = G.make("MountainCar-v0", 9000, seed=5, auto_reset=True, time_limit=11); env.ResetBatch()
+acts = rng.integers(0, 3, (300, 9000)).astype(np.int32); acts[17, 100] = 5
+try:
+    env.StepMany(acts)        # 300 x 9000 x 17 B = 46 MB: three pipelined chunks, one rejected action
+except G.InvalidActionError:
+    pass
+env.Close()
 G.Box(np.array([-2.0, 1.5, -np.inf, -np.inf], np.float32), np.array([3.0, np.inf, -4.0, np.inf], np.float32)).SampleBatch(5000, seed=1)
 print("sanitize probe done")
