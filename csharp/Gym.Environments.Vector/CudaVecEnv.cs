@@ -127,6 +127,15 @@ namespace Gym.Environments.Vector {
         }
         private GCHandle _terminalPin;
 
+        // Device-resident callers (a learner holding CUDA pointers, e.g. through TorchSharp): one asynchronous step on the handle's
+        // stream; dObs = NoObservationCopy skips the observation copy, the observations of the env kinds whose observation is their
+        // state vector (CartPoleEnv.cs:183) are then read in place at ObservationViewDevice.
+        public static readonly IntPtr NoObservationCopy = Native.NoObs;
+        public void StepDevice(IntPtr dActions, IntPtr dObs, IntPtr dReward, IntPtr dDone) {
+            Native.Check(Native.gymcuda_step_device(_h, dActions, dObs, dReward, dDone));
+        }
+        public IntPtr ObservationViewDevice { get { Native.Check(Native.gymcuda_obs_view_device(_h, out IntPtr p)); return p; } }
+
         public float[] Reset(byte[] mask) { Native.Check(Native.gymcuda_reset_masked(_h, mask, _obs)); return _obs; }
         public void RolloutRandom(int kSteps, float[] obs, float[] reward, byte[] done, int[] actions) {
             Native.Check(Native.gymcuda_rollout_random(_h, kSteps, obs, reward, done, actions));
